@@ -1,0 +1,64 @@
+// CPU debugging twin of the replica engine -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles asyncflow_b200/csrc/af_core.cuh (the SAME state machine the CUDA kernel
+// runs) for the host with a "warp" of one lane, so that the engine's event
+// semantics can be checked against oracle/des_port.py in the CPU-only test tier
+// (`pytest -m "not gpu"`) of a container that has no GPU.  It is built into
+// tests/host_twin/_build/ and loaded only by tests/; the product package
+// (asyncflow_b200/) cannot reach it and has no CPU fallback.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../asyncflow_b200/csrc/af_host_common.h"
+
+extern "C" const char* af_twin_last_error() {
+    static thread_local std::string e;
+    return e.c_str();
+}
+static std::string g_err;
+extern "C" const char* af_twin_error() { return g_err.c_str(); }
+
+extern "C" int af_twin_trace_tick_capacity(const AfScenario* sc) { return afh::trace_tick_capacity(*sc); }
+
+extern "C" double af_twin_hist_percentile(const uint32_t* hist, uint64_t n, double q) {
+    return afh::hist_percentile(hist, n, q);
+}
+
+extern "C" int af_twin_run(const AfScenario* sc, const AfSweep* sw, uint64_t sweep_first, const AfOptions* opt,
+                           uint64_t seed, uint64_t replica_begin, uint64_t n,
+                           AfReplicaStats* stats, uint32_t* sent, uint32_t* dropped, uint32_t* hist,
+                           uint32_t* thr, uint64_t* samp_sum, uint32_t* samp_max, double* trace_clocks,
+                           uint32_t* trace_series, uint32_t* trace_counts) {
+    if (!afh::validate(*sc, g_err)) return AF_ERR_INVALID;
+    afc::Layout L;
+    memset(&L, 0, sizeof L);
+    afh::make_layout(*sc, *opt, sw ? sw->n_columns : 0, L);
+    afc::Globals G;
+    memset(&G, 0, sizeof G);
+    G.edges = sc->edges; G.servers = sc->servers; G.endpoints = sc->endpoints; G.steps = sc->steps;
+    G.lb_edges = sc->lb_edges; G.spikes = sc->spike_marks; G.outages = sc->outage_marks;
+    if (sw) { G.sweep_cols = sw->columns; G.sweep_vals = sw->values; G.sweep_first = sweep_first; G.sweep_rows = sw->n_rows; }
+    std::vector<double> sp_t((size_t)(L.ev_total - L.ev_smem) + 1);
+    std::vector<uint64_t> sp_k((size_t)(L.ev_total - L.ev_smem) + 1);
+    std::vector<afc::ReqRec> sp_r((size_t)(L.rq_total - L.rq_smem) + 1);
+    std::vector<uint32_t> sp_n((size_t)(L.rq_total - L.rq_smem) + 1);
+    G.spill_ev_time = sp_t.data(); G.spill_ev_key = sp_k.data(); G.spill_rq_rec = sp_r.data(); G.spill_rq_next = sp_n.data();
+    G.stats = stats; G.edge_sent = sent; G.edge_dropped = dropped; G.hist = hist; G.thr = thr;
+    G.samp_sum = samp_sum; G.samp_max = samp_max; G.trace_clocks = trace_clocks; G.trace_series = trace_series;
+    G.trace_counts = trace_counts;
+    G.seed = seed; G.replica_begin = replica_begin; G.n_replicas = n;
+    std::vector<unsigned char> ws((size_t)L.warp_bytes + 64);
+    unsigned char* base = (unsigned char*)(((uintptr_t)ws.data() + 15) & ~(uintptr_t)15);
+    for (uint64_t r = 0; r < n; ++r) {
+        for (int32_t i = L.ev_smem; i < L.ev_total; ++i) sp_t[(size_t)(i - L.ev_smem)] = afr::u2d(afc::INF_BITS);
+        afc::Replica R(L, G);
+        R.bind(base, 0);
+        R.run(r);
+        if (L.collect_hist && stats) {
+            stats[r].p50 = afh::hist_percentile(hist + r * AF_HIST_BINS, stats[r].completed, 50.0);
+            stats[r].p95 = afh::hist_percentile(hist + r * AF_HIST_BINS, stats[r].completed, 95.0);
+            stats[r].p99 = afh::hist_percentile(hist + r * AF_HIST_BINS, stats[r].completed, 99.0);
+        }
+    }
+    return AF_OK;
+}

@@ -1,0 +1,81 @@
+"""Python face of the CPU debugging twin (tests/host_twin) -- TEST INFRASTRUCTURE ONLY.
+
+Runs the engine's state machine (asyncflow_b200/csrc/af_core.cuh compiled for the
+host, one-lane warp) so CPU-only tests can check event semantics against the
+oracle.  Never imported by the product package.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from asyncflow_b200 import _capi as K
+
+_DIR = Path(__file__).resolve().parent / "host_twin"
+_SO = _DIR / "_build" / "libaf_host_twin.so"
+_SRC = [_DIR / "af_host_twin.cpp"] + sorted((_DIR.parent.parent / "asyncflow_b200" / "csrc").glob("*.*h")) \
+    + [_DIR.parent.parent / "include" / "asyncflow_b200.h"]
+
+
+def build() -> Path:
+    newest = max(p.stat().st_mtime for p in _SRC)
+    if not _SO.exists() or _SO.stat().st_mtime < newest:
+        _SO.parent.mkdir(exist_ok=True)
+        subprocess.run(
+            ["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-x", "c++",
+             "-o", str(_SO), str(_DIR / "af_host_twin.cpp")], check=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(str(build()))
+        _lib.af_twin_error.restype = C.c_char_p
+        _lib.af_twin_hist_percentile.restype = C.c_double
+        _lib.af_twin_hist_percentile.argtypes = [C.c_void_p, C.c_uint64, C.c_double]
+        _lib.af_twin_trace_tick_capacity.argtypes = [C.POINTER(K.AfScenario)]
+        _lib.af_twin_run.argtypes = [
+            C.POINTER(K.AfScenario), C.POINTER(K.AfSweep), C.c_uint64, C.POINTER(K.AfOptions),
+            C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 10
+    return _lib
+
+
+def run(flat, *, seed: int, replica_begin: int = 0, n: int = 1, sweep=None, trace: int = 0,
+        clock_cap: int = 0, event_capacity: int = 0, request_capacity: int = 0) -> dict:
+    L = lib()
+    opt = K.AfOptions(event_capacity, request_capacity, 0, 0, 1, 1, trace, clock_cap)
+    T = flat.horizon_s
+    ne, nser = flat.n_edges, flat.n_series
+    tick_cap = L.af_twin_trace_tick_capacity(C.byref(flat.pod))
+    out = {
+        "stats": np.zeros(n, dtype=K.STATS_DTYPE),
+        "sent": np.zeros((n, ne), dtype=np.uint32),
+        "dropped": np.zeros((n, ne), dtype=np.uint32),
+        "hist": np.zeros((n, K.AF_HIST_BINS), dtype=np.uint32),
+        "thr": np.zeros((n, T), dtype=np.uint32),
+        "samp_sum": np.zeros((n, nser), dtype=np.uint64),
+        "samp_max": np.zeros((n, nser), dtype=np.uint32),
+        "trace_clocks": np.zeros((max(trace, 1), max(clock_cap, 1), 2), dtype=np.float64),
+        "trace_series": np.zeros((max(trace, 1), nser, tick_cap), dtype=np.uint32),
+        "trace_counts": np.zeros((max(n, 1), 2), dtype=np.uint32),
+    }
+    sw_p, keep = None, None
+    if sweep is not None:
+        sw, keep = sweep.pod(0, None)
+        sw_p = C.byref(sw)
+    rc = L.af_twin_run(C.byref(flat.pod), sw_p, 0, C.byref(opt), seed, replica_begin, n,
+                       *[out[k].ctypes.data for k in ("stats", "sent", "dropped", "hist", "thr",
+                                                      "samp_sum", "samp_max", "trace_clocks",
+                                                      "trace_series", "trace_counts")])
+    if rc != 0:
+        raise RuntimeError(L.af_twin_error().decode())
+    del keep
+    return out
