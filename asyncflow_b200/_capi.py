@@ -121,7 +121,7 @@ EXPORTS = [
     "af_engine_configure", "af_scenario_upload", "af_sweep_upload", "af_run", "af_sync",
     "af_last_run_ms", "af_launch_count", "af_fetch_stats", "af_fetch_edge_counts",
     "af_fetch_histograms", "af_fetch_throughput", "af_fetch_sampled", "af_fetch_trace_clocks",
-    "af_fetch_trace_series",
+    "af_fetch_trace_series", "af_reduce_histograms",
 ]
 
 _lib = None
@@ -159,6 +159,7 @@ def load() -> C.CDLL:
     lib.af_fetch_sampled.argtypes = [vp, vp, vp, u64]
     lib.af_fetch_trace_clocks.argtypes = [vp, u64, vp, u64, C.POINTER(u64)]
     lib.af_fetch_trace_series.argtypes = [vp, u64, vp, u64, C.POINTER(u64)]
+    lib.af_reduce_histograms.argtypes = [vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("af_abi_version",):

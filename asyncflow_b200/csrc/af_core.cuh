@@ -389,66 +389,59 @@ struct Replica {
         push(now + step[ep.step_begin + pk_step(r.pack)].dur, mk_payload(K_STEP_END, sidx, w));
     }
 
-    // the `for step in selected_endpoint.steps` loop from the current step (server.py:197-255)
-    AF_HD void run_steps(uint32_t slot, uint32_t sidx, ReqRec r) {
+    // the `for step in selected_endpoint.steps` loop from the current step (server.py:197-255).
+    // Returns true when no step is left (the caller then runs finish_request).
+    AF_HD bool run_steps(uint32_t slot, uint32_t sidx, ReqRec& r) {
         ServerS& S = server[sidx];
         const EndpointS ep = endpoint[pk_ep(r.pack)];
         uint32_t st = pk_step(r.pack);
-        if (st < ep.n_steps) {
-            const StepS sp = step[ep.step_begin + st];
-            if (sp.kind == AF_STEP_CPU) {
-                if (r.pack & PK_IO) { r.pack &= ~PK_IO; S.io_q -= 1; }
-                if (!(r.pack & PK_CORE)) {
-                    if (S.cpu_free > 0) { S.cpu_free -= 1; r.pack |= PK_CORE; }
-                    else {                          // cpu_req not triggered -> ready queue
-                        S.ready_q += 1;
-                        rq_set_pack(slot, r.pack);
-                        fifo_push(S.cpuq_head, S.cpuq_tail, slot);
-                        return;
-                    }
+        if (st >= ep.n_steps) return true;
+        const StepS sp = step[ep.step_begin + st];
+        if (sp.kind == AF_STEP_CPU) {
+            if (r.pack & PK_IO) { r.pack &= ~PK_IO; S.io_q -= 1; }
+            if (!(r.pack & PK_CORE)) {
+                if (S.cpu_free > 0) { S.cpu_free -= 1; r.pack |= PK_CORE; }
+                else {                              // cpu_req not triggered -> ready queue
+                    S.ready_q += 1;
+                    rq_set_pack(slot, r.pack);
+                    fifo_push(S.cpuq_head, S.cpuq_tail, slot);
+                    return false;
                 }
-                rq_set_pack(slot, r.pack);
-                push(now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
-            } else {
-                bool release = (r.pack & PK_CORE) != 0;
-                if (release) { r.pack &= ~PK_CORE; S.cpu_free += 1; }
-                if (!(r.pack & PK_IO)) { r.pack |= PK_IO; S.io_q += 1; }
-                rq_set_pack(slot, r.pack);
-                // SimPy order: the releasing request schedules its IO timeout before the
-                // woken waiter schedules its CPU timeout (see DESIGN.md "tie rule")
-                push(now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
-                if (release) grant_cpu_waiter(sidx);
             }
-            return;
+            rq_set_pack(slot, r.pack);
+            push(now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
+        } else {
+            bool release = (r.pack & PK_CORE) != 0;
+            if (release) { r.pack &= ~PK_CORE; S.cpu_free += 1; }
+            if (!(r.pack & PK_IO)) { r.pack |= PK_IO; S.io_q += 1; }
+            rq_set_pack(slot, r.pack);
+            // SimPy order: the releasing request schedules its IO timeout before the
+            // woken waiter schedules its CPU timeout (see DESIGN.md "tie rule")
+            push(now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
+            if (release) grant_cpu_waiter(sidx);
         }
-        finish_request(slot, sidx, r, ep);
-    }
-
-    AF_HD void start_after_ram(uint32_t slot, uint32_t sidx, const ReqRec& r, uint32_t total_ram) {
-        ServerS& S = server[sidx];
-        S.ram_free -= (int32_t)total_ram;
-        S.ram_in_use += (int32_t)total_ram;
-        run_steps(slot, sidx, r);
+        return false;
     }
 
     // server.py:257-276
-    AF_HD void finish_request(uint32_t slot, uint32_t sidx, ReqRec r, const EndpointS& ep) {
+    AF_HD void finish_request(uint32_t slot, uint32_t sidx, ReqRec r) {
         ServerS& S = server[sidx];
+        const uint32_t total_ram = endpoint[pk_ep(r.pack)].total_ram;
         // SimPy order of the pushes that follow a release (DESIGN.md "tie rule"):
         //   core + RAM : woken CPU waiter, then this request's edge, then RAM waiters
         //   core only  : this request's edge (Initialize is URGENT), then the CPU waiter
         bool had_core = (r.pack & PK_CORE) != 0;
         if (had_core) { r.pack &= ~PK_CORE; S.cpu_free += 1; }
-        if (had_core && ep.total_ram) grant_cpu_waiter(sidx);
+        if (had_core && total_ram) grant_cpu_waiter(sidx);
         if (r.pack & PK_IO) { r.pack &= ~PK_IO; S.io_q -= 1; }
-        if (ep.total_ram) {
-            S.ram_in_use -= (int32_t)ep.total_ram;
-            S.ram_free += (int32_t)ep.total_ram;
+        if (total_ram) {
+            S.ram_in_use -= (int32_t)total_ram;
+            S.ram_free += (int32_t)total_ram;
         }
         rq_set_pack(slot, r.pack);
         edge_send(slot, S.out_edge, r);
-        if (had_core && !ep.total_ram) grant_cpu_waiter(sidx);
-        if (ep.total_ram) {
+        if (had_core && !total_ram) grant_cpu_waiter(sidx);
+        if (total_ram) {
             // Container FIFO with head-of-line blocking
             while (S.ramq_head != NIL) {
                 uint32_t w = S.ramq_head;
@@ -456,7 +449,14 @@ struct Replica {
                 uint32_t need = endpoint[pk_ep(wr.pack)].total_ram;
                 if ((int32_t)need > S.ram_free) break;
                 fifo_pop(S.ramq_head, S.ramq_tail);
-                start_after_ram(w, sidx, wr, need);
+                S.ram_free -= (int32_t)need;
+                S.ram_in_use += (int32_t)need;
+                if (run_steps(w, sidx, wr)) {
+                    // an endpoint made of RAM steps only: it gives the memory straight back
+                    S.ram_in_use -= (int32_t)need;
+                    S.ram_free += (int32_t)need;
+                    edge_send(w, S.out_edge, wr);
+                }
             }
         }
     }
@@ -477,13 +477,14 @@ struct Replica {
         uint32_t total_ram = endpoint[ep_global].total_ram;
         if (total_ram) {
             if (S.ramq_head == NIL && (int32_t)total_ram <= S.ram_free) {
-                start_after_ram(slot, sidx, r, total_ram);
+                S.ram_free -= (int32_t)total_ram;
+                S.ram_in_use += (int32_t)total_ram;
             } else {
                 fifo_push(S.ramq_head, S.ramq_tail, slot);
+                return;
             }
-            return;
         }
-        run_steps(slot, sidx, r);
+        if (run_steps(slot, sidx, r)) finish_request(slot, sidx, r);
     }
 
     // -------------------------------------------------------------- client: completion
@@ -758,7 +759,7 @@ struct Replica {
             else if (kind == K_STEP_END) {
                 ReqRec r = rq_load(slot);
                 r.pack += 1u << 8;                   // next step
-                run_steps(slot, aux, r);
+                if (run_steps(slot, aux, r)) finish_request(slot, aux, r);
             }
             else if (kind == K_ARRIVAL) on_arrival();
             else if (kind == K_SPIKE) on_spike();

@@ -1,0 +1,514 @@
+// af_engine.cu -- sm_100a kernels and the C ABI of include/asyncflow_b200.h.
+//
+// Kernels:
+//   af_sim_kernel         one replica per warp, persistent CTAs pulling replica
+//                         indices from a global counter (skewed sweeps balance
+//                         themselves); per-warp workspace in shared memory with
+//                         spill tiers in HBM; the replica state machine is
+//                         af_core.cuh.
+//   af_percentile_kernel  HBM-bound pass over the per-replica latency histograms:
+//                         one warp per replica, coalesced 128-byte row reads, warp
+//                         prefix sums, numpy-"linear" p50/p95/p99.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+// (-fmad=false is part of the parity contract: see af_rng.cuh).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "af_host_common.h"
+
+// ---------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------
+__global__ void af_sim_kernel(const afc::Layout L, const afc::Globals G) {
+    extern __shared__ __align__(16) unsigned char af_smem[];
+    const int warp = (int)(threadIdx.x >> 5);
+    const int lane = (int)(threadIdx.x & 31u);
+    unsigned char* ws = af_smem + (size_t)warp * (size_t)L.warp_bytes;
+    const uint64_t warp_slot = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (uint64_t)warp;
+    afc::Replica R(L, G);
+    R.bind(ws, warp_slot);
+    for (;;) {
+        unsigned long long r = 0;
+        if (lane == 0) r = atomicAdd(G.work_counter, 1ull);
+        r = __shfl_sync(0xFFFFFFFFu, r, 0);
+        if (r >= G.n_replicas) break;
+        R.run((uint64_t)r);
+        __syncwarp();
+    }
+}
+
+// value of order statistic `rank` given the bin that holds it
+__device__ __forceinline__ double af_bin_value(int bin, uint64_t rank, uint64_t cum_before, uint32_t cnt) {
+    const long long base = (long long)((1023 + AF_HIST_MIN_EXP) << AF_HIST_SUB_BITS);
+    double lo = __longlong_as_double(((long long)bin + base) << (52 - AF_HIST_SUB_BITS));
+    double hi = __longlong_as_double(((long long)bin + 1 + base) << (52 - AF_HIST_SUB_BITS));
+    double frac = ((double)(rank - cum_before) + 0.5) / (double)cnt;
+    return lo + frac * (hi - lo);
+}
+
+__global__ void af_percentile_kernel(const uint32_t* __restrict__ hist, AfReplicaStats* __restrict__ stats,
+                                     uint64_t n_replicas) {
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = (int)(threadIdx.x & 31u);
+    if (warp >= n_replicas) return;
+    const uint32_t* row = hist + warp * AF_HIST_BINS;
+    const uint64_t n = stats[warp].completed;
+    // target order statistics (numpy linear interpolation between two neighbours)
+    const double qs[3] = {50.0, 95.0, 99.0};
+    uint64_t rank[6]; double frac[3]; double val[6];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double pos = n ? qs[i] / 100.0 * (double)(n - 1) : 0.0;
+        uint64_t lo = (uint64_t)floor(pos);
+        frac[i] = pos - (double)lo;
+        rank[2 * i] = lo;
+        rank[2 * i + 1] = (lo + 1 < n) ? lo + 1 : lo;
+        val[2 * i] = val[2 * i + 1] = 0.0;
+    }
+    uint64_t carry = 0;
+    for (int base = 0; base < AF_HIST_BINS; base += 32) {
+        uint32_t c = row[base + lane];                 // one coalesced 128-byte read per warp
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        uint64_t before = carry + (incl - c);
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            if (c && rank[i] >= before && rank[i] < before + c) val[i] = af_bin_value(base + lane, rank[i], before, c);
+        carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    // each target was found by exactly one lane: sum-reduce to share it
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double v = val[i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        val[i] = v;
+    }
+    if (lane == 0) {
+        const double nan = __longlong_as_double(0x7FF8000000000000ll);
+        double p[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            p[i] = n ? ((frac[i] == 0.0 || rank[2 * i + 1] == rank[2 * i]) ? val[2 * i]
+                                                                            : val[2 * i] + frac[i] * (val[2 * i + 1] - val[2 * i]))
+                     : nan;
+        stats[warp].p50 = p[0]; stats[warp].p95 = p[1]; stats[warp].p99 = p[2];
+    }
+}
+
+
+// Sum the per-replica latency histograms into one [AF_HIST_BINS] u64 histogram (the summary
+// block a rank contributes to the end-of-sweep NCCL all-gather).  HBM-bound: each block walks
+// a strip of replicas, a thread owns bins t, t+256, ... so every row read is coalesced.
+__global__ void af_hist_reduce_kernel(const uint32_t* __restrict__ hist, unsigned long long* __restrict__ total,
+                                      uint64_t n_replicas, uint64_t rows_per_block) {
+    uint64_t r0 = (uint64_t)blockIdx.x * rows_per_block;
+    uint64_t r1 = r0 + rows_per_block < n_replicas ? r0 + rows_per_block : n_replicas;
+    unsigned long long acc[AF_HIST_BINS / 256];
+#pragma unroll
+    for (int j = 0; j < AF_HIST_BINS / 256; ++j) acc[j] = 0;
+    for (uint64_t r = r0; r < r1; ++r) {
+        const uint32_t* row = hist + r * AF_HIST_BINS;
+#pragma unroll
+        for (int j = 0; j < AF_HIST_BINS / 256; ++j) acc[j] += row[j * 256 + threadIdx.x];
+    }
+#pragma unroll
+    for (int j = 0; j < AF_HIST_BINS / 256; ++j)
+        if (acc[j]) atomicAdd(&total[j * 256 + threadIdx.x], acc[j]);
+}
+
+// ---------------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct af_engine {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_sim = nullptr, ev_end = nullptr;
+    std::string err;
+    AfOptions opt{};
+    bool have_scenario = false;
+    AfScenario sc{};            // host copy; pointers repointed at the vectors below
+    std::vector<AfEdge> h_edges; std::vector<AfServer> h_servers; std::vector<AfEndpoint> h_eps;
+    std::vector<AfStep> h_steps; std::vector<int32_t> h_lb; std::vector<AfSpikeMark> h_spikes;
+    std::vector<AfOutageMark> h_outages;
+    DevBuf d_edges, d_servers, d_eps, d_steps, d_lb, d_spikes, d_outages;
+    // sweep
+    int32_t sweep_cols = 0; uint64_t sweep_rows = 0, sweep_first = 0;
+    DevBuf d_sweep_cols, d_sweep_vals;
+    // spill + outputs
+    DevBuf d_sp_evt, d_sp_evk, d_sp_rq, d_sp_nx;
+    DevBuf d_stats, d_sent, d_dropped, d_hist, d_thr, d_ssum, d_smax, d_tclk, d_tser, d_tcnt, d_counter, d_htot;
+    // last run
+    uint64_t last_n = 0; bool ran = false;
+    afc::Layout L{};
+    uint64_t launches = 0;
+    float ms_total = 0.f, ms_sim = 0.f; bool timing_valid = false;
+
+    int fail(int code, const std::string& m) { err = m; return code; }
+    int cuda_fail(cudaError_t e, const char* what) {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return AF_ERR_CUDA;
+    }
+};
+
+#define AF_CUDA(e_, call, what) do { cudaError_t _c = (call); if (_c != cudaSuccess) return (e_)->cuda_fail(_c, what); } while (0)
+
+template <class T>
+static int upload_vec(af_engine* e, DevBuf& d, const std::vector<T>& h, const char* what) {
+    AF_CUDA(e, d.ensure(h.size() * sizeof(T)), what);
+    if (!h.empty()) AF_CUDA(e, cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, e->stream), what);
+    return AF_OK;
+}
+
+extern "C" {
+
+int af_abi_version(void) { return AF_ABI_VERSION; }
+
+const char* af_last_error(const af_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int af_engine_create(int device, af_engine** out) {
+    if (!out) { g_create_error = "out is NULL"; return AF_ERR_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n);
+    if (ce != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "count is 0")
+                         + " (asyncflow_b200 has no CPU fallback)";
+        return AF_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device index out of range"; return AF_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(ce); return AF_ERR_CUDA; }
+    if (prop.major != 10) {
+        char b[160]; snprintf(b, sizeof b, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+        g_create_error = b; return AF_ERR_CUDA;
+    }
+    af_engine* e = new (std::nothrow) af_engine();
+    if (!e) { g_create_error = "host allocation failed"; return AF_ERR_NOMEM; }
+    e->device = device; e->sm_count = prop.multiProcessorCount; e->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if ((ce = cudaSetDevice(device)) != cudaSuccess || (ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess
+        || (ce = cudaEventCreate(&e->ev_begin)) != cudaSuccess || (ce = cudaEventCreate(&e->ev_sim)) != cudaSuccess
+        || (ce = cudaEventCreate(&e->ev_end)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(ce); delete e; return AF_ERR_CUDA;
+    }
+    e->opt.collect_histogram = 1; e->opt.collect_throughput = 1;
+    *out = e;
+    return AF_OK;
+}
+
+void af_engine_destroy(af_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    DevBuf* bufs[] = {&e->d_edges, &e->d_servers, &e->d_eps, &e->d_steps, &e->d_lb, &e->d_spikes, &e->d_outages,
+                      &e->d_sweep_cols, &e->d_sweep_vals, &e->d_sp_evt, &e->d_sp_evk, &e->d_sp_rq, &e->d_sp_nx,
+                      &e->d_stats, &e->d_sent, &e->d_dropped, &e->d_hist, &e->d_thr, &e->d_ssum, &e->d_smax,
+                      &e->d_tclk, &e->d_tser, &e->d_tcnt, &e->d_counter, &e->d_htot};
+    for (DevBuf* b : bufs) b->release();
+    cudaEventDestroy(e->ev_begin); cudaEventDestroy(e->ev_sim); cudaEventDestroy(e->ev_end);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int af_engine_configure(af_engine* e, const AfOptions* opt) {
+    if (!e || !opt) return AF_ERR_INVALID;
+    if (opt->event_capacity < 0 || opt->request_capacity < 0 || opt->warps_per_block < 0 || opt->warps_per_block > 32
+        || opt->trace_replicas < 0 || opt->trace_clock_capacity < 0)
+        return e->fail(AF_ERR_INVALID, "AfOptions: negative or out-of-range field");
+    e->opt = *opt;
+    return AF_OK;
+}
+
+int af_scenario_upload(af_engine* e, const AfScenario* s) {
+    if (!e || !s) return AF_ERR_INVALID;
+    std::string why;
+    if (!afh::validate(*s, why)) return e->fail(AF_ERR_INVALID, "scenario: " + why);
+    AF_CUDA(e, cudaSetDevice(e->device), "cudaSetDevice");
+    // wait for any run still reading the old tables
+    AF_CUDA(e, cudaStreamSynchronize(e->stream), "sync before upload");
+    e->sc = *s;
+    e->h_edges.assign(s->edges, s->edges + s->n_edges);
+    e->h_servers.assign(s->servers, s->servers + s->n_servers);
+    e->h_eps.assign(s->endpoints, s->endpoints + s->n_endpoints);
+    e->h_steps.assign(s->steps, s->steps + s->n_steps);
+    e->h_lb.assign(s->lb_edges, s->lb_edges + s->n_lb_edges);
+    e->h_spikes.assign(s->spike_marks, s->spike_marks + s->n_spike_marks);
+    e->h_outages.assign(s->outage_marks, s->outage_marks + s->n_outage_marks);
+    int rc;
+    if ((rc = upload_vec(e, e->d_edges, e->h_edges, "edges"))) return rc;
+    if ((rc = upload_vec(e, e->d_servers, e->h_servers, "servers"))) return rc;
+    if ((rc = upload_vec(e, e->d_eps, e->h_eps, "endpoints"))) return rc;
+    if ((rc = upload_vec(e, e->d_steps, e->h_steps, "steps"))) return rc;
+    if ((rc = upload_vec(e, e->d_lb, e->h_lb, "lb_edges"))) return rc;
+    if ((rc = upload_vec(e, e->d_spikes, e->h_spikes, "spike_marks"))) return rc;
+    if ((rc = upload_vec(e, e->d_outages, e->h_outages, "outage_marks"))) return rc;
+    AF_CUDA(e, cudaStreamSynchronize(e->stream), "scenario upload");
+    e->sc.edges = e->h_edges.data(); e->sc.servers = e->h_servers.data(); e->sc.endpoints = e->h_eps.data();
+    e->sc.steps = e->h_steps.data(); e->sc.lb_edges = e->h_lb.data(); e->sc.spike_marks = e->h_spikes.data();
+    e->sc.outage_marks = e->h_outages.data();
+    e->have_scenario = true;
+    e->sweep_cols = 0; e->sweep_rows = 0;     // a sweep belongs to the scenario it was built for
+    e->ran = false;
+    return AF_OK;
+}
+
+int af_sweep_upload(af_engine* e, const AfSweep* sw, uint64_t first_replica) {
+    if (!e) return AF_ERR_INVALID;
+    if (!e->have_scenario) return e->fail(AF_ERR_STATE, "af_sweep_upload before af_scenario_upload");
+    AF_CUDA(e, cudaSetDevice(e->device), "cudaSetDevice");
+    AF_CUDA(e, cudaStreamSynchronize(e->stream), "sync before sweep upload");
+    if (!sw || sw->n_columns == 0 || sw->n_rows == 0) { e->sweep_cols = 0; e->sweep_rows = 0; return AF_OK; }
+    if (!sw->columns || !sw->values) return e->fail(AF_ERR_INVALID, "sweep: null columns/values");
+    const AfScenario& s = e->sc;
+    for (int c = 0; c < sw->n_columns; ++c) {
+        int f = sw->columns[c].field, i = sw->columns[c].index, lim = 1;
+        switch (f) {
+        case AF_FIELD_USERS_MEAN: case AF_FIELD_USERS_SIGMA: case AF_FIELD_RATE_PER_USER: lim = 1; break;
+        case AF_FIELD_EDGE_MEAN: case AF_FIELD_EDGE_SIGMA: case AF_FIELD_EDGE_DROPOUT: lim = s.n_edges; break;
+        case AF_FIELD_SERVER_CPU_CORES: case AF_FIELD_SERVER_RAM_MB: lim = s.n_servers; break;
+        case AF_FIELD_STEP_DURATION: lim = s.n_steps; break;
+        case AF_FIELD_ENDPOINT_RAM: lim = s.n_endpoints; break;
+        case AF_FIELD_SPIKE_DELTA: lim = s.n_spike_marks; break;
+        default: return e->fail(AF_ERR_INVALID, "sweep: unknown field id");
+        }
+        if (i < 0 || i >= lim) return e->fail(AF_ERR_INVALID, "sweep: column index out of range");
+    }
+    size_t cb = (size_t)sw->n_columns * sizeof(AfSweepColumn), vb = (size_t)sw->n_columns * sw->n_rows * sizeof(double);
+    AF_CUDA(e, e->d_sweep_cols.ensure(cb), "sweep columns");
+    AF_CUDA(e, e->d_sweep_vals.ensure(vb), "sweep values");
+    AF_CUDA(e, cudaMemcpyAsync(e->d_sweep_cols.p, sw->columns, cb, cudaMemcpyHostToDevice, e->stream), "sweep columns H2D");
+    AF_CUDA(e, cudaMemcpyAsync(e->d_sweep_vals.p, sw->values, vb, cudaMemcpyHostToDevice, e->stream), "sweep values H2D");
+    AF_CUDA(e, cudaStreamSynchronize(e->stream), "sweep upload");
+    e->sweep_cols = sw->n_columns; e->sweep_rows = sw->n_rows; e->sweep_first = first_replica;
+    return AF_OK;
+}
+
+int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
+    if (!e) return AF_ERR_INVALID;
+    if (!e->have_scenario) return e->fail(AF_ERR_STATE, "af_run before af_scenario_upload");
+    if (end <= begin) return e->fail(AF_ERR_INVALID, "af_run: empty replica range");
+    AF_CUDA(e, cudaSetDevice(e->device), "cudaSetDevice");
+    const uint64_t n = end - begin;
+    afc::Layout& L = e->L;
+    memset(&L, 0, sizeof L);
+    afh::make_layout(e->sc, e->opt, e->sweep_cols, L);
+
+    // launch shape: persistent CTAs, as many warps per SM as shared memory allows
+    int wpb = e->opt.warps_per_block > 0 ? e->opt.warps_per_block : 4;
+    size_t smem = (size_t)wpb * (size_t)L.warp_bytes;
+    while (wpb > 1 && smem > (size_t)e->max_smem_optin) { --wpb; smem = (size_t)wpb * (size_t)L.warp_bytes; }
+    if (smem > (size_t)e->max_smem_optin)
+        return e->fail(AF_ERR_INVALID, "scenario tables do not fit in shared memory (one warp needs more than the 227 KB opt-in limit)");
+    AF_CUDA(e, cudaFuncSetAttribute(af_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute");
+    int bps = 0;
+    AF_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, af_sim_kernel, wpb * 32, smem), "occupancy");
+    if (bps < 1) return e->fail(AF_ERR_CUDA, "kernel cannot be resident (occupancy 0)");
+    if (e->opt.blocks_per_sm > 0 && e->opt.blocks_per_sm < bps) bps = e->opt.blocks_per_sm;
+    uint64_t grid = (uint64_t)e->sm_count * (uint64_t)bps;
+    uint64_t need_blocks = (n + wpb - 1) / wpb;
+    if (grid > need_blocks) grid = need_blocks;
+    const uint64_t warp_slots = grid * wpb;
+
+    // spill tiers and outputs (grow-only)
+    const uint64_t ev_sp = (uint64_t)(L.ev_total - L.ev_smem), rq_sp = (uint64_t)(L.rq_total - L.rq_smem);
+    AF_CUDA(e, e->d_sp_evt.ensure(warp_slots * ev_sp * 8 + 8), "spill events");
+    AF_CUDA(e, e->d_sp_evk.ensure(warp_slots * ev_sp * 8 + 8), "spill events");
+    AF_CUDA(e, e->d_sp_rq.ensure(warp_slots * rq_sp * 16 + 16), "spill requests");
+    AF_CUDA(e, e->d_sp_nx.ensure(warp_slots * rq_sp * 4 + 4), "spill requests");
+    const uint64_t ntr = (uint64_t)(L.trace_replicas < 0 ? 0 : L.trace_replicas) < n ? (uint64_t)L.trace_replicas : n;
+    L.trace_replicas = (int32_t)ntr;
+    AF_CUDA(e, e->d_stats.ensure(n * sizeof(AfReplicaStats)), "stats");
+    AF_CUDA(e, e->d_sent.ensure(n * L.n_edges * 4), "edge counts");
+    AF_CUDA(e, e->d_dropped.ensure(n * L.n_edges * 4), "edge counts");
+    AF_CUDA(e, e->d_ssum.ensure(n * L.n_series * 8), "sampled sums");
+    AF_CUDA(e, e->d_smax.ensure(n * L.n_series * 4), "sampled maxima");
+    AF_CUDA(e, e->d_counter.ensure(8), "work counter");
+    if (L.collect_hist) AF_CUDA(e, e->d_hist.ensure(n * AF_HIST_BINS * 4), "histograms");
+    if (L.collect_thr) AF_CUDA(e, e->d_thr.ensure(n * (uint64_t)L.horizon_s * 4), "throughput");
+    if (ntr) {
+        AF_CUDA(e, e->d_tclk.ensure(ntr * (uint64_t)L.trace_clock_cap * 16 + 16), "trace clocks");
+        AF_CUDA(e, e->d_tser.ensure(ntr * (uint64_t)L.n_series * (uint64_t)L.trace_tick_cap * 4 + 4), "trace series");
+    }
+    AF_CUDA(e, e->d_tcnt.ensure((ntr ? ntr : 1) * 8), "trace counts");
+
+    afc::Globals G;
+    memset(&G, 0, sizeof G);
+    G.edges = (const AfEdge*)e->d_edges.p; G.servers = (const AfServer*)e->d_servers.p;
+    G.endpoints = (const AfEndpoint*)e->d_eps.p; G.steps = (const AfStep*)e->d_steps.p;
+    G.lb_edges = (const int32_t*)e->d_lb.p; G.spikes = (const AfSpikeMark*)e->d_spikes.p;
+    G.outages = (const AfOutageMark*)e->d_outages.p;
+    G.sweep_cols = (const AfSweepColumn*)e->d_sweep_cols.p; G.sweep_vals = (const double*)e->d_sweep_vals.p;
+    G.sweep_first = e->sweep_first; G.sweep_rows = e->sweep_cols ? e->sweep_rows : 0;
+    G.spill_ev_time = (double*)e->d_sp_evt.p; G.spill_ev_key = (uint64_t*)e->d_sp_evk.p;
+    G.spill_rq_rec = (afc::ReqRec*)e->d_sp_rq.p; G.spill_rq_next = (uint32_t*)e->d_sp_nx.p;
+    G.stats = (AfReplicaStats*)e->d_stats.p; G.edge_sent = (uint32_t*)e->d_sent.p; G.edge_dropped = (uint32_t*)e->d_dropped.p;
+    G.hist = (uint32_t*)e->d_hist.p; G.thr = (uint32_t*)e->d_thr.p;
+    G.samp_sum = (uint64_t*)e->d_ssum.p; G.samp_max = (uint32_t*)e->d_smax.p;
+    G.trace_clocks = (double*)e->d_tclk.p; G.trace_series = (uint32_t*)e->d_tser.p; G.trace_counts = (uint32_t*)e->d_tcnt.p;
+    G.work_counter = (unsigned long long*)e->d_counter.p;
+    G.seed = seed; G.replica_begin = begin; G.n_replicas = n;
+
+    AF_CUDA(e, cudaEventRecord(e->ev_begin, e->stream), "event");
+    AF_CUDA(e, cudaMemsetAsync(e->d_counter.p, 0, 8, e->stream), "memset");
+    if (L.collect_hist) AF_CUDA(e, cudaMemsetAsync(e->d_hist.p, 0, n * AF_HIST_BINS * 4, e->stream), "memset hist");
+    if (L.collect_thr) AF_CUDA(e, cudaMemsetAsync(e->d_thr.p, 0, n * (uint64_t)L.horizon_s * 4, e->stream), "memset thr");
+    af_sim_kernel<<<(unsigned)grid, wpb * 32, smem, e->stream>>>(L, G);
+    AF_CUDA(e, cudaGetLastError(), "af_sim_kernel launch");
+    e->launches += 1;
+    AF_CUDA(e, cudaEventRecord(e->ev_sim, e->stream), "event");
+    if (L.collect_hist) {
+        unsigned blocks = (unsigned)((n * 32 + 255) / 256);
+        af_percentile_kernel<<<blocks, 256, 0, e->stream>>>((const uint32_t*)e->d_hist.p, (AfReplicaStats*)e->d_stats.p, n);
+        AF_CUDA(e, cudaGetLastError(), "af_percentile_kernel launch");
+        e->launches += 1;
+    }
+    AF_CUDA(e, cudaEventRecord(e->ev_end, e->stream), "event");
+    e->last_n = n; e->ran = true; e->timing_valid = false;
+    return AF_OK;
+}
+
+int af_sync(af_engine* e) {
+    if (!e) return AF_ERR_INVALID;
+    AF_CUDA(e, cudaSetDevice(e->device), "cudaSetDevice");
+    AF_CUDA(e, cudaStreamSynchronize(e->stream), "af_sync");
+    if (e->ran && !e->timing_valid) {
+        float a = 0.f, b = 0.f;
+        // begin -> end spans memsets + both kernels; begin -> sim spans memsets + the simulation kernel
+        if (cudaEventElapsedTime(&a, e->ev_begin, e->ev_end) == cudaSuccess
+            && cudaEventElapsedTime(&b, e->ev_begin, e->ev_sim) == cudaSuccess) {
+            e->ms_total = a; e->ms_sim = b; e->timing_valid = true;
+        }
+    }
+    return AF_OK;
+}
+
+int af_last_run_ms(af_engine* e, float* ms_total, float* ms_sim) {
+    if (!e) return AF_ERR_INVALID;
+    if (!e->ran) return e->fail(AF_ERR_STATE, "no run yet");
+    int rc = af_sync(e);
+    if (rc) return rc;
+    if (ms_total) *ms_total = e->ms_total;
+    if (ms_sim) *ms_sim = e->ms_sim;
+    return AF_OK;
+}
+
+uint64_t af_launch_count(const af_engine* e) { return e ? e->launches : 0; }
+
+static int fetch(af_engine* e, void* dst, const DevBuf& src, size_t bytes, uint64_t n, const char* what) {
+    if (!e || !dst) return AF_ERR_INVALID;
+    if (!e->ran) return e->fail(AF_ERR_STATE, "fetch before af_run");
+    if (n != e->last_n) return e->fail(AF_ERR_INVALID, "fetch: n differs from the last run's replica count");
+    AF_CUDA(e, cudaSetDevice(e->device), "cudaSetDevice");
+    AF_CUDA(e, cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, e->stream), what);
+    return af_sync(e);
+}
+
+int af_fetch_stats(af_engine* e, AfReplicaStats* out, uint64_t n) {
+    return fetch(e, out, e->d_stats, n * sizeof(AfReplicaStats), n, "stats D2H");
+}
+int af_fetch_edge_counts(af_engine* e, uint32_t* sent, uint32_t* dropped, uint64_t n) {
+    int rc = fetch(e, sent, e->d_sent, n * e->L.n_edges * 4, n, "edge sent D2H");
+    if (rc) return rc;
+    return fetch(e, dropped, e->d_dropped, n * e->L.n_edges * 4, n, "edge dropped D2H");
+}
+int af_fetch_histograms(af_engine* e, uint32_t* out, uint64_t n) {
+    if (e && e->ran && !e->L.collect_hist) return e->fail(AF_ERR_STATE, "histograms were not collected");
+    return fetch(e, out, e->d_hist, n * AF_HIST_BINS * 4, n, "hist D2H");
+}
+int af_fetch_throughput(af_engine* e, uint32_t* out, uint64_t n) {
+    if (e && e->ran && !e->L.collect_thr) return e->fail(AF_ERR_STATE, "throughput was not collected");
+    return fetch(e, out, e->d_thr, n * (uint64_t)e->L.horizon_s * 4, n, "throughput D2H");
+}
+int af_fetch_sampled(af_engine* e, uint64_t* sums, uint32_t* maxima, uint64_t n) {
+    int rc = fetch(e, sums, e->d_ssum, n * e->L.n_series * 8, n, "sampled sums D2H");
+    if (rc) return rc;
+    return fetch(e, maxima, e->d_smax, n * e->L.n_series * 4, n, "sampled maxima D2H");
+}
+
+int af_reduce_histograms(af_engine* e, uint64_t* out_bins) {
+    if (!e || !out_bins) return AF_ERR_INVALID;
+    if (!e->ran) return e->fail(AF_ERR_STATE, "reduce before af_run");
+    if (!e->L.collect_hist) return e->fail(AF_ERR_STATE, "histograms were not collected");
+    AF_CUDA(e, cudaSetDevice(e->device), "cudaSetDevice");
+    AF_CUDA(e, e->d_htot.ensure(AF_HIST_BINS * 8), "histogram total");
+    AF_CUDA(e, cudaMemsetAsync(e->d_htot.p, 0, AF_HIST_BINS * 8, e->stream), "memset");
+    const uint64_t n = e->last_n;
+    uint64_t blocks = (uint64_t)e->sm_count * 8;
+    if (blocks > n) blocks = n;
+    uint64_t rows = (n + blocks - 1) / blocks;
+    blocks = (n + rows - 1) / rows;
+    af_hist_reduce_kernel<<<(unsigned)blocks, 256, 0, e->stream>>>((const uint32_t*)e->d_hist.p,
+                                                                  (unsigned long long*)e->d_htot.p, n, rows);
+    AF_CUDA(e, cudaGetLastError(), "af_hist_reduce_kernel launch");
+    e->launches += 1;
+    AF_CUDA(e, cudaMemcpyAsync(out_bins, e->d_htot.p, AF_HIST_BINS * 8, cudaMemcpyDeviceToHost, e->stream), "hist total D2H");
+    AF_CUDA(e, cudaStreamSynchronize(e->stream), "af_reduce_histograms");
+    return AF_OK;
+}
+
+int af_fetch_trace_clocks(af_engine* e, uint64_t local, double* out, uint64_t cap_pairs, uint64_t* n_pairs) {
+    if (!e || !out || !n_pairs) return AF_ERR_INVALID;
+    if (!e->ran) return e->fail(AF_ERR_STATE, "fetch before af_run");
+    if (local >= (uint64_t)e->L.trace_replicas) return e->fail(AF_ERR_INVALID, "replica was not traced");
+    AF_CUDA(e, cudaSetDevice(e->device), "cudaSetDevice");
+    uint32_t cnt[2];
+    AF_CUDA(e, cudaMemcpyAsync(cnt, (uint32_t*)e->d_tcnt.p + local * 2, 8, cudaMemcpyDeviceToHost, e->stream), "trace counts");
+    AF_CUDA(e, cudaStreamSynchronize(e->stream), "trace counts");
+    uint64_t n = cnt[0];
+    if (n > (uint64_t)e->L.trace_clock_cap) n = (uint64_t)e->L.trace_clock_cap;
+    if (n > cap_pairs) n = cap_pairs;
+    *n_pairs = n;
+    if (n) AF_CUDA(e, cudaMemcpyAsync(out, (double*)e->d_tclk.p + local * (uint64_t)e->L.trace_clock_cap * 2, n * 16,
+                                      cudaMemcpyDeviceToHost, e->stream), "trace clocks");
+    return af_sync(e);
+}
+
+int af_fetch_trace_series(af_engine* e, uint64_t local, uint32_t* out, uint64_t cap_ticks, uint64_t* n_ticks) {
+    if (!e || !out || !n_ticks) return AF_ERR_INVALID;
+    if (!e->ran) return e->fail(AF_ERR_STATE, "fetch before af_run");
+    if (local >= (uint64_t)e->L.trace_replicas) return e->fail(AF_ERR_INVALID, "replica was not traced");
+    AF_CUDA(e, cudaSetDevice(e->device), "cudaSetDevice");
+    uint32_t cnt[2];
+    AF_CUDA(e, cudaMemcpyAsync(cnt, (uint32_t*)e->d_tcnt.p + local * 2, 8, cudaMemcpyDeviceToHost, e->stream), "trace counts");
+    AF_CUDA(e, cudaStreamSynchronize(e->stream), "trace counts");
+    uint64_t n = cnt[1];
+    if (n > (uint64_t)e->L.trace_tick_cap) n = (uint64_t)e->L.trace_tick_cap;
+    if (n > cap_ticks) n = cap_ticks;
+    *n_ticks = n;
+    const uint32_t* base = (const uint32_t*)e->d_tser.p + local * (uint64_t)e->L.n_series * (uint64_t)e->L.trace_tick_cap;
+    if (n) AF_CUDA(e, cudaMemcpy2DAsync(out, cap_ticks * 4, base, (size_t)e->L.trace_tick_cap * 4, n * 4, (size_t)e->L.n_series,
+                                        cudaMemcpyDeviceToHost, e->stream), "trace series");
+    return af_sync(e);
+}
+
+}  // extern "C"

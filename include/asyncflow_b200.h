@@ -221,6 +221,8 @@ int af_fetch_throughput(af_engine* e, uint32_t* out, uint64_t n);   /* [n][horiz
  *   j <  3*n_servers : server j/3, metric j%3 in {ready_queue_len, event_loop_io_sleep, ram_in_use}
  *   j >= 3*n_servers : edge j-3*n_servers, edge_concurrent_connection            */
 int af_fetch_sampled(af_engine* e, uint64_t* sums, uint32_t* maxima, uint64_t n);
+/* sum of the last run's per-replica histograms: out_bins[AF_HIST_BINS] (device reduction) */
+int af_reduce_histograms(af_engine* e, uint64_t* out_bins);
 /* full trace of one of the first `trace_replicas` replicas of the last run        */
 int af_fetch_trace_clocks(af_engine* e, uint64_t local_replica, double* start_finish,
                           uint64_t capacity_pairs, uint64_t* n_pairs);

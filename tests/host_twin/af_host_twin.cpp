@@ -62,3 +62,21 @@ extern "C" int af_twin_run(const AfScenario* sc, const AfSweep* sw, uint64_t swe
     }
     return AF_OK;
 }
+
+// sizeof() of every ABI struct as the C++ compiler lays it out (tests/test_capi.py)
+extern "C" int af_twin_sizeof(int which) {
+    switch (which) {
+    case 0: return (int)sizeof(AfEdge);
+    case 1: return (int)sizeof(AfServer);
+    case 2: return (int)sizeof(AfEndpoint);
+    case 3: return (int)sizeof(AfStep);
+    case 4: return (int)sizeof(AfSpikeMark);
+    case 5: return (int)sizeof(AfOutageMark);
+    case 6: return (int)sizeof(AfScenario);
+    case 7: return (int)sizeof(AfSweepColumn);
+    case 8: return (int)sizeof(AfSweep);
+    case 9: return (int)sizeof(AfOptions);
+    case 10: return (int)sizeof(AfReplicaStats);
+    default: return -1;
+    }
+}

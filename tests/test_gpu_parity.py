@@ -1,0 +1,195 @@
+"""GPU tier: the CUDA engine, called through the C ABI, against the oracle and the
+golden vectors (bit-exact), plus size-independent properties at BASELINE sizes."""
+
+from __future__ import annotations
+
+import des_port
+import numpy as np
+import pytest
+from helpers import (PARITY_CASES, SEED, assert_matches_oracle, check_against_golden, load_golden,
+                     load_scenario)
+
+from asyncflow_b200 import _capi as K
+from asyncflow_b200 import Engine, GpuSimulationRunner, SweepRunner, SweepSpec, flatten
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    with Engine(0) as e:
+        yield e
+
+
+def run_traced(eng, flat, begin, n, clock_cap=200000, **kw):
+    eng.upload(flat)
+    eng.configure(trace_replicas=n, trace_clock_capacity=clock_cap, **kw)
+    eng.run(SEED, begin, begin + n)
+    st = eng.stats()
+    sent, dropped = eng.edge_counts()
+    return st, sent, dropped
+
+
+@pytest.mark.parametrize("name", sorted(PARITY_CASES))
+def test_engine_reproduces_golden_vectors(eng, name):
+    gold = load_golden(name)
+    flat = flatten(load_scenario(name, gold["horizon"]))
+    for vec in gold["vectors"]:
+        st, sent, dropped = run_traced(eng, flat, vec["replica"], 1)
+        assert st[0]["flags"] == 0
+        check_against_golden(
+            vec, generated=int(st[0]["generated"]), completed=int(st[0]["completed"]),
+            clocks=eng.trace_clocks(0), edge_sent=dict(zip(flat.edge_ids, map(int, sent[0]))),
+            edge_dropped=dict(zip(flat.edge_ids, map(int, dropped[0]))),
+            throughput=eng.throughput()[0], series=eng.trace_series(0), flat=flat)
+
+
+@pytest.mark.parametrize("name", sorted(PARITY_CASES))
+def test_engine_matches_oracle_on_fresh_replicas(eng, name):
+    horizon = {"c1_my_service.yml": 10, "c3_lb_two_servers.yml": 12, "c4_lb8_events.yml": 245}.get(name)
+    payload = load_scenario(name, horizon)
+    flat = flatten(payload)
+    reps = [21, 22, 23] if not name.startswith("c4") else [21]
+    st, sent, dropped = run_traced(eng, flat, reps[0], len(reps))
+    thr, hist = eng.throughput(), eng.histograms()
+    ssum, smax = eng.sampled()
+    for i, rep in enumerate(reps):
+        o = des_port.simulate(payload, seed=SEED, replica=rep)
+        series = eng.trace_series(i)
+        assert_matches_oracle(o, flat, stats=st[i], clocks=eng.trace_clocks(i), sent=sent[i],
+                              dropped=dropped[i], series=series, throughput=thr[i], hist=hist[i])
+        np.testing.assert_array_equal(ssum[i], series.astype(np.uint64).sum(axis=1))
+        np.testing.assert_array_equal(smax[i], series.max(axis=1) if series.shape[1] else 0)
+
+
+def test_results_do_not_depend_on_batching_or_launch_shape(eng):
+    """Replica r is a function of (seed, r) only: one at a time == inside a batch of 300,
+    whatever the warps-per-block / occupancy."""
+    flat = flatten(load_scenario("mixed_lc.yml", 12))
+    eng.upload(flat)
+    eng.configure()
+    eng.run(SEED, 100, 400)
+    a = eng.stats().copy()
+    a_sent, a_drop = eng.edge_counts()
+    for wpb, bps in ((1, 1), (8, 0), (3, 2)):
+        eng.configure(warps_per_block=wpb, blocks_per_sm=bps)
+        eng.run(SEED, 100, 400)
+        b = eng.stats()
+        for f in ("generated", "completed", "n_events", "lat_sum", "lat_sumsq", "lat_min", "lat_max", "n_ticks", "p95"):
+            np.testing.assert_array_equal(a[f], b[f], err_msg=f)
+        np.testing.assert_array_equal(a_sent, eng.edge_counts()[0])
+    eng.configure()
+    eng.run(SEED, 250, 251)
+    one = eng.stats()[0]
+    for f in ("generated", "completed", "n_events", "lat_sum", "lat_min", "lat_max"):
+        assert one[f] == a[150][f]
+
+
+def test_sweep_rows_match_per_replica_oracle(eng):
+    base = load_scenario("c1_my_service.yml", 8)
+    flat = flatten(base)
+    users = [15.0, 90.0, 300.0, 700.0]
+    rtt = [0.001, 0.004, 0.02, 0.05]
+    spec = SweepSpec(flat, 4, {("users_mean",): users, ("edge_mean", "client-app"): rtt,
+                               ("server_ram_mb", "app-1"): [2048, 256, 512, 1024]})
+    eng.upload(flat)
+    eng.configure(trace_replicas=4, trace_clock_capacity=60000, request_capacity=60000)
+    eng.upload_sweep(spec, 0)
+    eng.run(SEED, 0, 4)
+    st = eng.stats()
+    sent, dropped = eng.edge_counts()
+    for i in range(4):
+        p = load_scenario("c1_my_service.yml", 8)
+        p["rqs_input"]["avg_active_users"]["mean"] = users[i]
+        p["topology_graph"]["edges"][1]["latency"]["mean"] = rtt[i]
+        p["topology_graph"]["nodes"]["servers"][0]["server_resources"]["ram_mb"] = [2048, 256, 512, 1024][i]
+        o = des_port.simulate(p, seed=SEED, replica=i)
+        assert_matches_oracle(o, flat, stats=st[i], clocks=eng.trace_clocks(i), sent=sent[i], dropped=dropped[i])
+    eng.upload_sweep(None)
+
+
+def test_overflow_is_reported_per_replica(eng):
+    flat = flatten(load_scenario("overload_single.yml"))
+    eng.upload(flat)
+    eng.configure(request_capacity=300)
+    eng.run(SEED, 0, 3)
+    assert (eng.stats()["flags"] & K.FLAG_REQUEST_OVERFLOW).all()
+    eng.configure()
+    eng.run(SEED, 0, 3)
+    assert (eng.stats()["flags"] == 0).all()
+
+
+def test_runner_api_mirrors_the_reference(eng, tmp_path):
+    payload = load_scenario("c1_my_service.yml", 10)
+    res = GpuSimulationRunner(env=None, simulation_input=payload, seed=SEED, replica=0).run()
+    o = des_port.simulate(payload, seed=SEED, replica=0)
+    np.testing.assert_array_equal(res.clocks, np.array(o["clocks"]).reshape(-1, 2))
+    st = res.get_latency_stats()
+    lat = res.latencies
+    assert st["total_requests"] == o["completed"] and st["p95"] == float(np.percentile(lat, 95))
+    ts, rps = res.get_throughput_series()
+    assert len(ts) == 10 and sum(rps) == o["completed"]
+    times, vals = res.get_series("ram_in_use", "app-1")
+    assert vals == o["server_series"]["app-1"]["ram_in_use"] and times[1] == 0.05
+    r2 = GpuSimulationRunner(simulation_input=payload)
+    r2.run()
+    with pytest.raises(RuntimeError):
+        r2.run()
+
+
+# ---- BASELINE-size properties (no oracle at this size) ----------------------------
+def test_c2_sweep_properties_at_full_size():
+    """configs[1]: 10 000 replicas of the README topology sweeping users 10..1000."""
+    n = 10_000
+    flat = flatten(load_scenario("c1_my_service.yml", 20))
+    users = np.linspace(10, 1000, n)
+    sw = SweepRunner(flat, n, {("users_mean",): users}, seed=SEED, throughput=True)
+    res = sw.run()
+    st = res.stats
+    assert not res.overflowed.any()
+    sent, dropped = res.edge_sent, res.edge_dropped
+    ge, ca, ac = (flat.edge_ids.index(e) for e in ("gen-client", "client-app", "app-client"))
+    # conservation: what the generator made went onto the first edge; every survivor of an edge
+    # is either still in flight at the horizon or went onto the next one
+    np.testing.assert_array_equal(sent[:, ge], st["generated"])
+    assert (sent[:, ca] <= sent[:, ge] - dropped[:, ge]).all()
+    assert (sent[:, ac] <= sent[:, ca] - dropped[:, ca]).all()
+    assert (st["completed"] <= sent[:, ac] - dropped[:, ac]).all()
+    np.testing.assert_array_equal(res.throughput.sum(axis=1), st["completed"])
+    # dropout is ~1 % per edge overall
+    assert abs(dropped[:, ge].sum() / sent[:, ge].sum() - 0.01) < 0.001
+    # arrivals scale with users (rate 100 rpm): generated ~ users * 100/60 * T
+    lo, hi = st["generated"][:500].mean(), st["generated"][-500:].mean()
+    assert 0.8 < lo / (users[:500].mean() * 100 / 60 * 20) < 1.2
+    assert 0.8 < hi / (users[-500:].mean() * 100 / 60 * 20) < 1.2
+    # the single core saturates at 500 req/s: overloaded replicas complete < 500 * T
+    assert st["completed"].max() <= 500 * 20
+    assert np.nanmedian(res.mean_latency[-500:]) > 10 * np.nanmedian(res.mean_latency[:500])
+    # stable replicas: latency floor = 2 ms CPU + 12 ms IO, percentiles ordered
+    assert (st["lat_min"][st["completed"] > 0] >= 0.014).all()
+    ok = st["completed"] > 10
+    assert (st["p50"][ok] <= st["p95"][ok]).all() and (st["p95"][ok] <= st["p99"][ok]).all()
+    assert (st["p99"][ok] <= st["lat_max"][ok] * 1.02).all()
+    # determinism: the same sweep again gives identical bits
+    again = sw.run()
+    np.testing.assert_array_equal(again.stats, st)
+    sw.close()
+
+
+def test_c3_statistics_match_reference_dashboard():
+    """configs[2] scenario at the reference's own parameters: the README dashboard reads
+    mean 0.024 / p50 0.023 / p95 0.034 / p99 0.040 s, 123.6 rps."""
+    flat = flatten(load_scenario("c3_lb_two_servers.yml", 600))
+    sw = SweepRunner(flat, 296, seed=SEED, throughput=True)
+    res = sw.run()
+    s = res.summary()
+    assert abs(s["mean_latency"] - 0.024) < 0.0008
+    assert abs(s["p50_mean"] - 0.023) < 0.0008
+    assert abs(s["p95_mean"] - 0.034) < 0.0012
+    assert abs(s["p99_mean"] - 0.040) < 0.0016
+    rps = res.completed.mean() / 600
+    assert abs(rps - 133.3 * 0.99 ** 4) < 1.5
+    # round robin keeps the two LB edges within one request of each other (no outages)
+    a, b = flat.edge_ids.index("lb-srv1"), flat.edge_ids.index("lb-srv2")
+    assert (np.abs(res.edge_sent[:, a].astype(np.int64) - res.edge_sent[:, b]) <= 1).all()
+    sw.close()
