@@ -180,11 +180,12 @@ struct Replica {
     uint64_t replica; uint64_t local; int lane;
     // clock + queue
     double now; double horizon; uint32_t seq;
-    int32_t ev_hw, ev_live, ev_last_free; uint32_t peak_ev;
+    int32_t ev_hw, ev_live, ev_last_free, ev_hole; uint32_t peak_ev;
     // request table
     uint32_t rq_free, rq_hw, rq_live, peak_rq;
     // generator (two clocks: the sampler's virtual one and the simulation's)
     double g_vnow, g_window_end, g_lam; uint32_t g_pos; uint32_t generated; bool g_done;
+    bool need_arrival; uint32_t arm_seq;
     // parameters that may be swept
     double users_mean, users_sigma, rate_per_user;
     // load balancer
@@ -255,38 +256,32 @@ struct Replica {
     }
 
     // -------------------------------------------------------------- event pool
-    // push: every lane executes it; the slot's owner lane is the only reader later.
-    AF_HD void push(double t, uint32_t payload) {
-        uint32_t s = seq++;
+    // An unsorted, lane-strided array: slot k belongs to lane k % 32.  push is O(1) -- it
+    // reuses the slot freed by the last pop, else a hole the last pop's scan noticed, else
+    // appends; pop is a warp arg-min over (time, seq).  Every lane executes push (same slot,
+    // same values), only the owner lane ever reads the slot back.
+    AF_HD void push_seq(double t, uint32_t payload, uint32_t s) {
         if (!(t < horizon)) return;   // env.run(until=T): events at >= T never fire
         int32_t slot;
         if (ev_last_free >= 0) { slot = ev_last_free; ev_last_free = -1; }
-        else if (ev_live == ev_hw) {
+        else if (ev_hole >= 0) { slot = ev_hole; ev_hole = -1; }
+        else {
             if (ev_hw >= L.ev_total) { flags |= AF_FLAG_EVENT_OVERFLOW; return; }
             slot = ev_hw++;
-        } else {
-            // a hole exists below the high-water mark: lanes look for it
-            int32_t mine = 0x7FFFFFFF;
-            for (int32_t k = lane; k < ev_hw; k += WARP)
-                if (evt_load(k) == INF_BITS) { mine = k; break; }
-#if AF_DEVICE_CODE
-            slot = (int32_t)w_min((uint32_t)mine);
-#else
-            slot = mine;
-#endif
         }
         ev_store(slot, afr::d2u(t), ((uint64_t)s << 32) | payload);
         ++ev_live;
         if ((uint32_t)ev_live > peak_ev) peak_ev = (uint32_t)ev_live;
     }
+    AF_HD void push(double t, uint32_t payload) { push_seq(t, payload, seq++); }
 
     // pop the (time, seq)-minimum; false when the pool is empty
     AF_HD bool pop(double& t, uint32_t& payload, uint32_t& ev_seq) {
         if (ev_live == 0) return false;
-        uint64_t bt = ~0ull, bk = ~0ull; int32_t bi = -1;
+        uint64_t bt = ~0ull, bk = ~0ull; int32_t bi = -1; int32_t hole = 0x7FFFFFFF;
         for (int32_t k = lane; k < ev_hw; k += WARP) {
             uint64_t tb = evt_load(k);
-            if (tb == INF_BITS) continue;
+            if (tb == INF_BITS) { if (k < hole) hole = k; continue; }
             uint64_t kk = evk_load(k);
             if (tb < bt || (tb == bt && kk < bk)) { bt = tb; bk = kk; bi = k; }
         }
@@ -304,17 +299,19 @@ struct Replica {
             b = w_ballot(cand);
         }
         int owner = __ffs((int)b) - 1;
-        uint32_t t_hi = w_shfl(hi, owner), t_lo = w_shfl(lo, owner);
         uint32_t k_hi = w_shfl((uint32_t)(bk >> 32), owner), k_lo = w_shfl((uint32_t)bk, owner);
         int32_t slot = (int32_t)w_shfl((uint32_t)bi, owner);
-        bt = ((uint64_t)t_hi << 32) | t_lo;
+        bt = ((uint64_t)mhi << 32) | mlo;
         bk = ((uint64_t)k_hi << 32) | k_lo;
+        hole = (int32_t)w_min((uint32_t)hole);
 #else
         int32_t slot = bi;
 #endif
         ev_mark_free(slot);
         --ev_live;
-        if (slot == ev_hw - 1) --ev_hw; else ev_last_free = slot;
+        if (slot == ev_hw - 1) { --ev_hw; ev_last_free = -1; }
+        else ev_last_free = slot;
+        ev_hole = hole < ev_hw ? hole : -1;
         t = afr::u2d(bt);
         payload = (uint32_t)bk;
         ev_seq = (uint32_t)(bk >> 32);
@@ -330,16 +327,9 @@ struct Replica {
             if (!(g_vnow < T)) return false;
             if (g_vnow >= g_window_end) {
                 g_window_end = g_vnow + (double)L.window_s;
-                afr::Src s = afr::make_gen(G.seed, replica, g_pos);
-                double users;
-                if (L.users_dist == AF_DIST_NORMAL) {
-                    double v = users_mean + users_sigma * afr::std_normal(s);
-                    users = v > 0.0 ? v : 0.0;      // truncated_gaussian_generator
-                } else {
-                    users = (double)afr::poisson(users_mean, s);
-                }
-                g_pos = s.pos;
-                g_lam = users * rate_per_user;
+                afr::GenDraw d = afr::gen_users(G.seed, replica, g_pos, L.users_dist, users_mean, users_sigma);
+                g_pos = d.pos;
+                g_lam = d.value * rate_per_user;
             }
             if (g_lam <= 0.0) { g_vnow = g_window_end; continue; }
             afr::Src s = afr::make_gen(G.seed, replica, g_pos);
@@ -359,19 +349,18 @@ struct Replica {
     // EdgeRuntime._deliver up to the timeout (edge.py:73-107)
     AF_HD void edge_send(uint32_t slot, uint32_t e, const ReqRec& r) {
         EdgeS& E = edge[e];
-        afr::Src s = afr::make_request(G.seed, replica, afr::P_EDGE, r.rid, pk_hops(r.pack));
-        s.load(0);
-        double u = afr::u53(s.w.x, s.w.y);
+        uint32_t s = seq++;                          // SimPy schedules the timeout here
+        afr::EdgeDraw d = afr::edge_draw(G.seed, replica, r.rid, pk_hops(r.pack), (int)(E.meta & 7u),
+                                         E.mean, E.sigma, E.dropout);
         E.sent += 1;
-        if (u < E.dropout) {                        // the request vanishes (edge.py:79-86)
+        if (d.u < E.dropout) {                      // the request vanishes (edge.py:79-86)
             E.dropped += 1;
             rq_release(slot);
             return;
         }
         E.conn += 1;
-        double transit = afr::sample_rv((int)(E.meta & 7u), E.mean, E.sigma, s);
-        double effective = transit + E.spike;      // spike read at SEND time (edge.py:94-106)
-        push(now + effective, mk_payload(K_DELIVER, e, slot));
+        double effective = d.transit + E.spike;    // spike read at SEND time (edge.py:94-106)
+        push_seq(now + effective, mk_payload(K_DELIVER, e, slot), s);
     }
 
     // -------------------------------------------------------------- server
@@ -558,15 +547,22 @@ struct Replica {
     AF_HD void on_arrival() {
         generated += 1;
         uint32_t slot = rq_alloc();
-        // the generator asks the sampler for the next gap right after transport():
-        // its timeout is pushed BEFORE the edge's delivery timeout (rqs_generator.py:103-119)
-        double gap;
-        if (!g_done && gen_next_gap(gap)) push(now + gap, mk_payload(K_ARRIVAL, 0, 0));
-        else g_done = true;
+        // the generator asks the sampler for the next gap right after transport(): its timeout is
+        // scheduled BEFORE the edge's delivery timeout (rqs_generator.py:103-119).  The seq is
+        // reserved here; the gap itself is drawn at the single arm_generator() site in run().
+        arm_seq = seq++;
+        need_arrival = true;
         if (slot == NIL) return;
         ReqRec r; r.t0 = now; r.rid = generated; r.pack = 1;  // record_hop(generator)
         rq_store(slot, r);
         edge_send(slot, (uint32_t)L.gen_edge, r);
+    }
+
+    AF_HD void arm_generator() {
+        need_arrival = false;
+        double gap;
+        if (!g_done && gen_next_gap(gap)) push_seq(now + gap, mk_payload(K_ARRIVAL, 0, 0), arm_seq);
+        else g_done = true;
     }
 
     // -------------------------------------------------------------- injection
@@ -725,7 +721,7 @@ struct Replica {
         lane = lane_id();
         load_params();
         now = 0.0; horizon = (double)L.horizon_s; seq = 0;
-        ev_hw = 0; ev_live = 0; ev_last_free = -1; peak_ev = 0;
+        ev_hw = 0; ev_live = 0; ev_last_free = -1; ev_hole = -1; peak_ev = 0;
         rq_free = NIL; rq_hw = 0; rq_live = 0; peak_rq = 0;
         g_vnow = 0.0; g_window_end = 0.0; g_lam = 0.0; g_pos = 0; generated = 0; g_done = false;
         lb_n = L.n_lb_edges;
@@ -742,15 +738,14 @@ struct Replica {
         if (L.n_outage > 0) {
             if (outage[0].fire == 0.0) on_outage(); else push(outage[0].fire, mk_payload(K_OUTAGE, 0, 0));
         }
-        {
-            double gap;
-            if (gen_next_gap(gap)) push(0.0 + gap, mk_payload(K_ARRIVAL, 0, 0)); else g_done = true;
-        }
+        arm_seq = seq++; need_arrival = true;
         tick_seq = seq++;
         tick_time = 0.0 + L.sample_period;
 
         double t; uint32_t payload, ev_seq;
-        while (pop(t, payload, ev_seq)) {
+        for (;;) {
+            if (need_arrival) arm_generator();
+            if (!pop(t, payload, ev_seq)) break;
             take_samples(t, ev_seq);
             now = t;
             ++n_events;

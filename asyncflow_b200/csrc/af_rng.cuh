@@ -21,7 +21,7 @@
 #define AF_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define AF_HD inline
-#define AF_HD_NOINLINE
+#define AF_HD_NOINLINE inline
 #endif
 
 namespace afr {
@@ -232,6 +232,39 @@ AF_HD double sample_rv(int dist, double mean, double sigma, Src& s) {
     if (dist == 2 /*LOG_NORMAL*/) return af_exp(mean + sigma * std_normal(s));
     if (dist == 4 /*UNIFORM*/) return s.next53();
     return (double)poisson(mean, s);  /* POISSON */
+}
+
+// One edge traversal's random numbers (reference runtime/actors/edge.py:78,90): the dropout
+// uniform and -- unless the request is dropped -- the latency variate.  Deliberately NOT
+// inlined: the engine sends requests from five places and the variate code is the bulk of the
+// kernel's instructions; one shared body keeps the hot loop inside the instruction cache.
+struct EdgeDraw { double u; double transit; };
+AF_HD_NOINLINE EdgeDraw edge_draw(uint64_t seed, uint64_t replica, uint32_t rid, uint32_t hop, int dist,
+                                  double mean, double sigma, double dropout) {
+    Src s = make_request(seed, replica, P_EDGE, rid, hop);
+    s.load(0);
+    EdgeDraw d;
+    d.u = u53(s.w.x, s.w.y);
+    d.transit = 0.0;
+    if (!(d.u < dropout)) d.transit = sample_rv(dist, mean, sigma, s);
+    return d;
+}
+
+// The generator's draws (samplers/poisson_poisson.py:58-71, gaussian_poisson.py:70-83); `pos`
+// is the index of the next uniform of the replica's sequential GEN stream.
+struct GenDraw { double value; uint32_t pos; };
+AF_HD_NOINLINE GenDraw gen_users(uint64_t seed, uint64_t replica, uint32_t pos, int users_dist, double mean,
+                                 double sigma) {
+    Src s = make_gen(seed, replica, pos);
+    GenDraw g;
+    if (users_dist == 1 /*NORMAL*/) {
+        double v = mean + sigma * std_normal(s);
+        g.value = v > 0.0 ? v : 0.0;        // truncated_gaussian_generator
+    } else {
+        g.value = (double)poisson(mean, s);
+    }
+    g.pos = s.pos;
+    return g;
 }
 
 }  // namespace afr

@@ -101,10 +101,11 @@ class Engine:
         self._check(self._lib.af_fetch_stats(self._h, out.ctypes.data, self._n), "af_fetch_stats")
         return out
 
-    def edge_counts(self) -> tuple[np.ndarray, np.ndarray]:
+    def edge_counts(self, sent: np.ndarray | None = None,
+                    dropped: np.ndarray | None = None) -> tuple[np.ndarray, np.ndarray]:
         ne = self.flat.n_edges
-        sent = np.empty((self._n, ne), dtype=np.uint32)
-        dropped = np.empty((self._n, ne), dtype=np.uint32)
+        sent = np.empty((self._n, ne), dtype=np.uint32) if sent is None else sent
+        dropped = np.empty((self._n, ne), dtype=np.uint32) if dropped is None else dropped
         self._check(self._lib.af_fetch_edge_counts(self._h, sent.ctypes.data, dropped.ctypes.data, self._n),
                     "af_fetch_edge_counts")
         return sent, dropped
@@ -114,15 +115,16 @@ class Engine:
         self._check(self._lib.af_fetch_histograms(self._h, out.ctypes.data, self._n), "af_fetch_histograms")
         return out
 
-    def throughput(self) -> np.ndarray:
-        out = np.empty((self._n, self.flat.horizon_s), dtype=np.uint32)
+    def throughput(self, out: np.ndarray | None = None) -> np.ndarray:
+        out = np.empty((self._n, self.flat.horizon_s), dtype=np.uint32) if out is None else out
         self._check(self._lib.af_fetch_throughput(self._h, out.ctypes.data, self._n), "af_fetch_throughput")
         return out
 
-    def sampled(self) -> tuple[np.ndarray, np.ndarray]:
+    def sampled(self, sums: np.ndarray | None = None,
+                maxima: np.ndarray | None = None) -> tuple[np.ndarray, np.ndarray]:
         ns = self.flat.n_series
-        sums = np.empty((self._n, ns), dtype=np.uint64)
-        maxima = np.empty((self._n, ns), dtype=np.uint32)
+        sums = np.empty((self._n, ns), dtype=np.uint64) if sums is None else sums
+        maxima = np.empty((self._n, ns), dtype=np.uint32) if maxima is None else maxima
         self._check(self._lib.af_fetch_sampled(self._h, sums.ctypes.data, maxima.ctypes.data, self._n),
                     "af_fetch_sampled")
         return sums, maxima

@@ -318,6 +318,20 @@ class SweepSpec:
         self._cols = (K.AfSweepColumn * max(1, len(cols)))(*[K.AfSweepColumn(f, i) for f, i in cols])
         self.columns = cols
 
+    def pin(self) -> None:
+        """Move the value table into page-locked host memory (needs torch + a CUDA device)."""
+        try:
+            import torch  # noqa: PLC0415  (plumbing only)
+        except ImportError:
+            return
+        if not torch.cuda.is_available() or self.values.size == 0:
+            return
+        t = torch.empty(self.values.shape, dtype=torch.float64, pin_memory=True)
+        arr = t.numpy()
+        arr[...] = self.values
+        self.values = arr
+        self._pin_keep = t
+
     def pod(self, first: int = 0, count: int | None = None) -> tuple[K.AfSweep, np.ndarray]:
         """AfSweep over rows ``[first, first+count)``; keep the returned array alive."""
         count = self.n_replicas - first if count is None else count
