@@ -132,11 +132,13 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        msg = (f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+    import os  # noqa: PLC0415
+    path = Path(os.environ.get("ASYNCFLOW_B200_LIB", LIB_PATH))   # override: kernel experiments only
+    if not path.exists():
+        msg = (f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; "
                "g.build()'` (nvcc, sm_100a).  asyncflow_b200 has no CPU fallback.")
         raise EngineUnavailable(msg)
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(path))
     vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
     lib.af_abi_version.restype = i32
     lib.af_engine_create.argtypes = [i32, C.POINTER(vp)]

@@ -35,9 +35,19 @@
 // Lanes differ only inside the few helpers that say so: the pending-event pool
 // is an unsorted, lane-strided array and pop-min is a warp arg-min
 // (redux.sync on the time words, then seq); per-entity loops (sampling, final
-// write-back, parameter load) are lane-strided.  The same source compiles for
-// the host with a warp of ONE lane (tests/host_twin -- a debugging twin used by
-// the CPU-only tests; it is NOT reachable from the product API).
+// write-back, parameter load) are lane-strided.
+//
+// Code-size rule (round-1 ncu capture, profiles/r01_*): with everything inlined
+// the kernel was 14 k instructions and 67 % of warp stalls were instruction-cache
+// misses -- every warp sits in a different handler.  So the replica's scalar
+// state lives in a per-warp struct in SHARED memory (`State`), the scenario
+// sizes / device pointers live in __constant__ memory, and every helper with
+// more than one call site is a real function (__noinline__) taking only
+// `State&`: one copy of each body, few live registers, more resident warps.
+//
+// The same source compiles for the host with a warp of ONE lane
+// (tests/host_twin -- a debugging twin used by the CPU-only tests; it is NOT
+// reachable from the product API).
 #pragma once
 #include "af_rng.cuh"
 #include "../../include/asyncflow_b200.h"
@@ -46,6 +56,14 @@
 #define AF_DEVICE_CODE 1
 #else
 #define AF_DEVICE_CODE 0
+#endif
+
+#if defined(__CUDACC__)
+#define AF_FN __host__ __device__ __noinline__       /* one shared body            */
+#define AF_IN __host__ __device__ __forceinline__    /* small, or single call site */
+#else
+#define AF_FN static
+#define AF_IN static inline
 #endif
 
 namespace afc {
@@ -57,15 +75,15 @@ constexpr uint64_t INF_BITS = 0x7FF0000000000000ull;
 enum : uint32_t { K_ARRIVAL = 0, K_DELIVER = 1, K_STEP_END = 2, K_SPIKE = 3, K_OUTAGE = 4 };
 constexpr uint32_t SLOT_BITS = 20, AUX_BITS = 9;
 constexpr uint32_t SLOT_MASK = (1u << SLOT_BITS) - 1, AUX_MASK = (1u << AUX_BITS) - 1;
-AF_HD uint32_t mk_payload(uint32_t kind, uint32_t aux, uint32_t slot) {
+AF_IN uint32_t mk_payload(uint32_t kind, uint32_t aux, uint32_t slot) {
     return (kind << 29) | (aux << SLOT_BITS) | slot;
 }
 
 // ---- request record pack: hops[0:8) step[8:16) ep[16:28) core[28] io[29] ----
 constexpr uint32_t PK_CORE = 1u << 28, PK_IO = 1u << 29;
-AF_HD uint32_t pk_hops(uint32_t p) { return p & 0xFFu; }
-AF_HD uint32_t pk_step(uint32_t p) { return (p >> 8) & 0xFFu; }
-AF_HD uint32_t pk_ep(uint32_t p) { return (p >> 16) & 0xFFFu; }
+AF_IN uint32_t pk_hops(uint32_t p) { return p & 0xFFu; }
+AF_IN uint32_t pk_step(uint32_t p) { return (p >> 8) & 0xFFu; }
+AF_IN uint32_t pk_ep(uint32_t p) { return (p >> 16) & 0xFFFu; }
 
 struct ReqRec { double t0; uint32_t rid; uint32_t pack; };          // 16 B
 
@@ -84,6 +102,38 @@ struct EndpointS { uint32_t step_begin, n_steps, total_ram, pad; }; // 16 B
 struct StepS { double dur; uint32_t kind, pad; };                   // 16 B
 struct SpikeS { double fire, delta; uint32_t edge, pad; };           // 24 B
 struct OutageS { double fire; int32_t lb_edge, down; };              // 16 B
+
+// The replica's scalar state: one per warp, at the start of the warp's workspace.
+struct State {
+    // views into this warp's workspace / spill regions
+    double* ev_time; uint64_t* ev_key; ReqRec* rq_rec; uint32_t* rq_next;
+    EdgeS* edge; ServerS* server; EndpointS* endpoint; StepS* step; uint32_t* lb;
+    SpikeS* spike; OutageS* outage; uint64_t* samp_sum; uint32_t* samp_max;
+    double* sp_ev_time; uint64_t* sp_ev_key; ReqRec* sp_rq_rec; uint32_t* sp_rq_next;
+    // identity
+    uint64_t replica, local;
+    // clock + pending-event pool
+    double now, horizon;
+    uint32_t seq;
+    int32_t ev_hw, ev_live, ev_last_free, ev_hole;
+    uint32_t peak_ev;
+    // request table
+    uint32_t rq_free, rq_hw, rq_live, peak_rq;
+    // generator (two clocks: the sampler's virtual one and the simulation's)
+    double g_vnow, g_window_end, g_lam;
+    uint32_t g_pos, generated, g_done, need_arrival, arm_seq;
+    // parameters that may be swept
+    double users_mean, users_sigma, rate_per_user;
+    // load balancer / timelines
+    int32_t lb_n, spike_cur, outage_cur;
+    // sampler
+    uint32_t tick_seq, n_ticks;
+    double tick_time;
+    // results
+    uint32_t completed, flags, traced, pad0;
+    uint64_t n_events;
+    double lat_sum, lat_sumsq, lat_min, lat_max;
+};
 
 // Everything the kernel needs to know about sizes; built on the host.
 struct Layout {
@@ -104,10 +154,10 @@ struct Layout {
     int32_t warp_bytes;
 };
 
-AF_HD int32_t align_up(int32_t x, int32_t a) { return (x + a - 1) / a * a; }
+AF_IN int32_t align_up(int32_t x, int32_t a) { return (x + a - 1) / a * a; }
 
 inline void layout_finalize(Layout& L) {
-    int32_t o = 0;
+    int32_t o = align_up((int32_t)sizeof(State), 16);
     L.off_ev_time = o;  o += 8 * L.ev_smem;
     L.off_ev_key = o;   o += 8 * L.ev_smem;
     L.off_rq_rec = o;   o += 16 * L.rq_smem;
@@ -140,6 +190,22 @@ struct Globals {
     uint64_t seed, replica_begin, n_replicas;
 };
 
+// Launch-wide constants: __constant__ memory on the device (every helper reads them
+// through the constant cache), plain globals in the host twin.
+#if defined(__CUDACC__)
+__constant__ Layout c_L;
+__constant__ Globals c_G;
+#endif
+#if AF_DEVICE_CODE
+#define AF_L c_L
+#define AF_G c_G
+#else
+static Layout h_L;
+static Globals h_G;
+#define AF_L h_L
+#define AF_G h_G
+#endif
+
 // ---- warp primitives (a warp of ONE lane on the host) ------------------------
 #if AF_DEVICE_CODE
 constexpr int WARP = 32;
@@ -152,640 +218,653 @@ __device__ __forceinline__ void w_sync() { __syncwarp(); }
 __device__ __forceinline__ void red_add_u32(uint32_t* p, uint32_t v) { atomicAdd(p, v); }
 #else
 constexpr int WARP = 1;
-inline int lane_id() { return 0; }
-inline uint32_t w_min(uint32_t v) { return v; }
-inline uint32_t w_ballot(bool p) { return p ? 1u : 0u; }
-inline uint32_t w_shfl(uint32_t v, int) { return v; }
-inline void w_sync() {}
-inline void red_add_u32(uint32_t* p, uint32_t v) { *p += v; }
+static inline int lane_id() { return 0; }
+static inline uint32_t w_min(uint32_t v) { return v; }
+static inline uint32_t w_ballot(bool p) { return p ? 1u : 0u; }
+static inline uint32_t w_shfl(uint32_t v, int) { return v; }
+static inline void w_sync() {}
+static inline void red_add_u32(uint32_t* p, uint32_t v) { *p += v; }
 #endif
-AF_HD int first_lane(uint32_t ballot) {
-#if AF_DEVICE_CODE
-    return __ffs((int)ballot) - 1;
-#else
-    (void)ballot; return 0;
-#endif
+
+// ---------------------------------------------------------------------------------
+// storage tiers: low slot numbers live in shared memory, the rest in the warp's HBM
+// spill region (overloaded replicas queue 10^4-10^5 requests)
+// ---------------------------------------------------------------------------------
+AF_IN ReqRec rq_load(const State& W, uint32_t s) {
+    return (int32_t)s < AF_L.rq_smem ? W.rq_rec[s] : W.sp_rq_rec[s - AF_L.rq_smem];
+}
+AF_IN void rq_store(State& W, uint32_t s, const ReqRec& r) {
+    if ((int32_t)s < AF_L.rq_smem) W.rq_rec[s] = r; else W.sp_rq_rec[s - AF_L.rq_smem] = r;
+}
+AF_IN void rq_set_pack(State& W, uint32_t s, uint32_t pack) {
+    if ((int32_t)s < AF_L.rq_smem) W.rq_rec[s].pack = pack; else W.sp_rq_rec[s - AF_L.rq_smem].pack = pack;
+}
+AF_IN uint32_t nx_load(const State& W, uint32_t s) {
+    return (int32_t)s < AF_L.rq_smem ? W.rq_next[s] : W.sp_rq_next[s - AF_L.rq_smem];
+}
+AF_IN void nx_store(State& W, uint32_t s, uint32_t v) {
+    if ((int32_t)s < AF_L.rq_smem) W.rq_next[s] = v; else W.sp_rq_next[s - AF_L.rq_smem] = v;
+}
+AF_IN uint64_t evt_load(const State& W, int32_t k) {
+    return afr::d2u(k < AF_L.ev_smem ? W.ev_time[k] : W.sp_ev_time[k - AF_L.ev_smem]);
+}
+AF_IN uint64_t evk_load(const State& W, int32_t k) {
+    return k < AF_L.ev_smem ? W.ev_key[k] : W.sp_ev_key[k - AF_L.ev_smem];
 }
 
-// ---- one replica --------------------------------------------------------------
-struct Replica {
-    const Layout& L;
-    const Globals& G;
-    // workspace views
-    double* ev_time; uint64_t* ev_key; ReqRec* rq_rec; uint32_t* rq_next;
-    EdgeS* edge; ServerS* server; EndpointS* endpoint; StepS* step; uint32_t* lb;
-    SpikeS* spike; OutageS* outage; uint64_t* samp_sum; uint32_t* samp_max;
-    double* sp_ev_time; uint64_t* sp_ev_key; ReqRec* sp_rq_rec; uint32_t* sp_rq_next;
-    // identity
-    uint64_t replica; uint64_t local; int lane;
-    // clock + queue
-    double now; double horizon; uint32_t seq;
-    int32_t ev_hw, ev_live, ev_last_free, ev_hole; uint32_t peak_ev;
-    // request table
-    uint32_t rq_free, rq_hw, rq_live, peak_rq;
-    // generator (two clocks: the sampler's virtual one and the simulation's)
-    double g_vnow, g_window_end, g_lam; uint32_t g_pos; uint32_t generated; bool g_done;
-    bool need_arrival; uint32_t arm_seq;
-    // parameters that may be swept
-    double users_mean, users_sigma, rate_per_user;
-    // load balancer
-    int32_t lb_n;
-    // timelines
-    int32_t spike_cur, outage_cur;
-    // sampler
-    double tick_time; uint32_t tick_seq; uint32_t n_ticks;
-    // results
-    uint32_t completed, flags; uint64_t n_events;
-    double lat_sum, lat_sumsq, lat_min, lat_max;
-    bool traced;
+// ---- request slots (free list threaded through rq_next) ------------------------
+AF_IN uint32_t rq_alloc(State& W) {
+    uint32_t s;
+    if (W.rq_free != NIL) { s = W.rq_free; W.rq_free = nx_load(W, s); }
+    else if ((int32_t)W.rq_hw < AF_L.rq_total) { s = W.rq_hw++; }
+    else { W.flags |= AF_FLAG_REQUEST_OVERFLOW; return NIL; }
+    uint32_t live = ++W.rq_live;
+    if (live > W.peak_rq) W.peak_rq = live;
+    return s;
+}
+AF_IN void rq_release(State& W, uint32_t s) { nx_store(W, s, W.rq_free); W.rq_free = s; --W.rq_live; }
 
-    AF_HD Replica(const Layout& l, const Globals& g) : L(l), G(g) {}
+// intrusive FIFOs (RAM waiters, CPU waiters) through the same `next` links
+AF_IN void fifo_push(State& W, uint32_t& head, uint32_t& tail, uint32_t s) {
+    nx_store(W, s, NIL);
+    if (tail == NIL) head = s; else nx_store(W, tail, s);
+    tail = s;
+}
+AF_IN uint32_t fifo_pop(State& W, uint32_t& head, uint32_t& tail) {
+    uint32_t s = head;
+    head = nx_load(W, s);
+    if (head == NIL) tail = NIL;
+    return s;
+}
 
-    // -------------------------------------------------------------- storage
-    AF_HD ReqRec rq_load(uint32_t s) const {
-        return (int32_t)s < L.rq_smem ? rq_rec[s] : sp_rq_rec[s - L.rq_smem];
+// ---------------------------------------------------------------------------------
+// pending-event pool: an unsorted, lane-strided array; slot k belongs to lane k % 32.
+// push is O(1) -- it reuses the slot freed by the last pop, else a hole the last pop's
+// scan noticed, else appends; pop is a warp arg-min over (time, seq).  Every lane
+// executes push (same slot, same values); only the owner lane reads the slot back.
+// ---------------------------------------------------------------------------------
+AF_FN void push_seq(State& W, double t, uint32_t payload, uint32_t s) {
+    if (!(t < W.horizon)) return;       // env.run(until=T): events at >= T never fire
+    int32_t slot;
+    if (W.ev_last_free >= 0) { slot = W.ev_last_free; W.ev_last_free = -1; }
+    else if (W.ev_hole >= 0) { slot = W.ev_hole; W.ev_hole = -1; }
+    else {
+        slot = W.ev_hw;
+        if (slot >= AF_L.ev_total) { W.flags |= AF_FLAG_EVENT_OVERFLOW; return; }
+        W.ev_hw = slot + 1;
     }
-    AF_HD void rq_store(uint32_t s, const ReqRec& r) {
-        if ((int32_t)s < L.rq_smem) rq_rec[s] = r; else sp_rq_rec[s - L.rq_smem] = r;
-    }
-    AF_HD void rq_set_pack(uint32_t s, uint32_t pack) {
-        if ((int32_t)s < L.rq_smem) rq_rec[s].pack = pack; else sp_rq_rec[s - L.rq_smem].pack = pack;
-    }
-    AF_HD uint32_t nx_load(uint32_t s) const {
-        return (int32_t)s < L.rq_smem ? rq_next[s] : sp_rq_next[s - L.rq_smem];
-    }
-    AF_HD void nx_store(uint32_t s, uint32_t v) {
-        if ((int32_t)s < L.rq_smem) rq_next[s] = v; else sp_rq_next[s - L.rq_smem] = v;
-    }
-    AF_HD uint64_t evt_load(int32_t k) const {
-        return afr::d2u(k < L.ev_smem ? ev_time[k] : sp_ev_time[k - L.ev_smem]);
-    }
-    AF_HD uint64_t evk_load(int32_t k) const {
-        return k < L.ev_smem ? ev_key[k] : sp_ev_key[k - L.ev_smem];
-    }
-    AF_HD void ev_store(int32_t k, uint64_t tbits, uint64_t key) {
-        if (k < L.ev_smem) { ev_time[k] = afr::u2d(tbits); ev_key[k] = key; }
-        else { sp_ev_time[k - L.ev_smem] = afr::u2d(tbits); sp_ev_key[k - L.ev_smem] = key; }
-    }
-    AF_HD void ev_mark_free(int32_t k) {
-        if (k < L.ev_smem) ev_time[k] = afr::u2d(INF_BITS); else sp_ev_time[k - L.ev_smem] = afr::u2d(INF_BITS);
-    }
+    uint64_t key = ((uint64_t)s << 32) | payload;
+    if (slot < AF_L.ev_smem) { W.ev_time[slot] = t; W.ev_key[slot] = key; }
+    else { W.sp_ev_time[slot - AF_L.ev_smem] = t; W.sp_ev_key[slot - AF_L.ev_smem] = key; }
+    uint32_t live = (uint32_t)(++W.ev_live);
+    if (live > W.peak_ev) W.peak_ev = live;
+}
+AF_IN void push(State& W, double t, uint32_t payload) { push_seq(W, t, payload, W.seq++); }
 
-    // -------------------------------------------------------------- request slots
-    AF_HD uint32_t rq_alloc() {
-        uint32_t s;
-        if (rq_free != NIL) { s = rq_free; rq_free = nx_load(s); }
-        else if ((int32_t)rq_hw < L.rq_total) { s = rq_hw++; }
-        else { flags |= AF_FLAG_REQUEST_OVERFLOW; return NIL; }
-        ++rq_live;
-        if (rq_live > peak_rq) peak_rq = rq_live;
-        return s;
+// pop the (time, seq)-minimum; false when the pool is empty (single call site)
+AF_IN bool pop(State& W, double& t, uint32_t& payload, uint32_t& ev_seq) {
+    if (W.ev_live == 0) return false;
+    const int lane = lane_id();
+    const int32_t hw = W.ev_hw;
+    uint64_t bt = ~0ull, bk = ~0ull; int32_t bi = -1; int32_t hole = 0x7FFFFFFF;
+    for (int32_t k = lane; k < hw; k += WARP) {
+        uint64_t tb = evt_load(W, k);
+        if (tb == INF_BITS) { if (k < hole) hole = k; continue; }
+        uint64_t kk = evk_load(W, k);
+        if (tb < bt || (tb == bt && kk < bk)) { bt = tb; bk = kk; bi = k; }
     }
-    AF_HD void rq_release(uint32_t s) { nx_store(s, rq_free); rq_free = s; --rq_live; }
-
-    AF_HD void fifo_push(uint32_t& head, uint32_t& tail, uint32_t s) {
-        nx_store(s, NIL);
-        if (tail == NIL) head = s; else nx_store(tail, s);
-        tail = s;
-    }
-    AF_HD uint32_t fifo_pop(uint32_t& head, uint32_t& tail) {
-        uint32_t s = head;
-        head = nx_load(s);
-        if (head == NIL) tail = NIL;
-        return s;
-    }
-
-    // -------------------------------------------------------------- event pool
-    // An unsorted, lane-strided array: slot k belongs to lane k % 32.  push is O(1) -- it
-    // reuses the slot freed by the last pop, else a hole the last pop's scan noticed, else
-    // appends; pop is a warp arg-min over (time, seq).  Every lane executes push (same slot,
-    // same values), only the owner lane ever reads the slot back.
-    AF_HD void push_seq(double t, uint32_t payload, uint32_t s) {
-        if (!(t < horizon)) return;   // env.run(until=T): events at >= T never fire
-        int32_t slot;
-        if (ev_last_free >= 0) { slot = ev_last_free; ev_last_free = -1; }
-        else if (ev_hole >= 0) { slot = ev_hole; ev_hole = -1; }
-        else {
-            if (ev_hw >= L.ev_total) { flags |= AF_FLAG_EVENT_OVERFLOW; return; }
-            slot = ev_hw++;
-        }
-        ev_store(slot, afr::d2u(t), ((uint64_t)s << 32) | payload);
-        ++ev_live;
-        if ((uint32_t)ev_live > peak_ev) peak_ev = (uint32_t)ev_live;
-    }
-    AF_HD void push(double t, uint32_t payload) { push_seq(t, payload, seq++); }
-
-    // pop the (time, seq)-minimum; false when the pool is empty
-    AF_HD bool pop(double& t, uint32_t& payload, uint32_t& ev_seq) {
-        if (ev_live == 0) return false;
-        uint64_t bt = ~0ull, bk = ~0ull; int32_t bi = -1; int32_t hole = 0x7FFFFFFF;
-        for (int32_t k = lane; k < ev_hw; k += WARP) {
-            uint64_t tb = evt_load(k);
-            if (tb == INF_BITS) { if (k < hole) hole = k; continue; }
-            uint64_t kk = evk_load(k);
-            if (tb < bt || (tb == bt && kk < bk)) { bt = tb; bk = kk; bi = k; }
-        }
 #if AF_DEVICE_CODE
-        uint32_t hi = (uint32_t)(bt >> 32), lo = (uint32_t)bt;
-        uint32_t mhi = w_min(hi);
-        bool cand = (hi == mhi) && bi >= 0;
-        uint32_t mlo = w_min(cand ? lo : 0xFFFFFFFFu);
-        cand = cand && lo == mlo;
-        uint32_t b = w_ballot(cand);
-        if (__popc(b) > 1) {          // equal times: the earlier push wins (SimPy eid order)
-            uint32_t sq = (uint32_t)(bk >> 32);
-            uint32_t msq = w_min(cand ? sq : 0xFFFFFFFFu);
-            cand = cand && sq == msq;
-            b = w_ballot(cand);
-        }
-        int owner = __ffs((int)b) - 1;
-        uint32_t k_hi = w_shfl((uint32_t)(bk >> 32), owner), k_lo = w_shfl((uint32_t)bk, owner);
-        int32_t slot = (int32_t)w_shfl((uint32_t)bi, owner);
-        bt = ((uint64_t)mhi << 32) | mlo;
-        bk = ((uint64_t)k_hi << 32) | k_lo;
-        hole = (int32_t)w_min((uint32_t)hole);
+    uint32_t hi = (uint32_t)(bt >> 32), lo = (uint32_t)bt;
+    uint32_t mhi = w_min(hi);
+    bool cand = (hi == mhi) && bi >= 0;
+    uint32_t mlo = w_min(cand ? lo : 0xFFFFFFFFu);
+    cand = cand && lo == mlo;
+    uint32_t b = w_ballot(cand);
+    if (__popc(b) > 1) {              // equal times: the earlier push wins (SimPy eid order)
+        uint32_t sq = (uint32_t)(bk >> 32);
+        uint32_t msq = w_min(cand ? sq : 0xFFFFFFFFu);
+        cand = cand && sq == msq;
+        b = w_ballot(cand);
+    }
+    int owner = __ffs((int)b) - 1;
+    uint32_t k_hi = w_shfl((uint32_t)(bk >> 32), owner), k_lo = w_shfl((uint32_t)bk, owner);
+    int32_t slot = (int32_t)w_shfl((uint32_t)bi, owner);
+    bt = ((uint64_t)mhi << 32) | mlo;
+    bk = ((uint64_t)k_hi << 32) | k_lo;
+    hole = (int32_t)w_min((uint32_t)hole);
 #else
-        int32_t slot = bi;
+    int32_t slot = bi;
 #endif
-        ev_mark_free(slot);
-        --ev_live;
-        if (slot == ev_hw - 1) { --ev_hw; ev_last_free = -1; }
-        else ev_last_free = slot;
-        ev_hole = hole < ev_hw ? hole : -1;
-        t = afr::u2d(bt);
-        payload = (uint32_t)bk;
-        ev_seq = (uint32_t)(bk >> 32);
-        return true;
-    }
+    if (slot < AF_L.ev_smem) W.ev_time[slot] = afr::u2d(INF_BITS);
+    else W.sp_ev_time[slot - AF_L.ev_smem] = afr::u2d(INF_BITS);
+    W.ev_live -= 1;
+    int32_t nhw = hw;
+    if (slot == hw - 1) { nhw = hw - 1; W.ev_hw = nhw; W.ev_last_free = -1; }
+    else W.ev_last_free = slot;
+    W.ev_hole = hole < nhw ? hole : -1;
+    t = afr::u2d(bt);
+    payload = (uint32_t)bk;
+    ev_seq = (uint32_t)(bk >> 32);
+    return true;
+}
 
-    // -------------------------------------------------------------- generator
-    // samplers/poisson_poisson.py:52-82 / gaussian_poisson.py:64-94.  Returns false
-    // when the sampler is exhausted; otherwise the next yielded gap.
-    AF_HD bool gen_next_gap(double& gap) {
-        const double T = horizon;
-        for (;;) {
-            if (!(g_vnow < T)) return false;
-            if (g_vnow >= g_window_end) {
-                g_window_end = g_vnow + (double)L.window_s;
-                afr::GenDraw d = afr::gen_users(G.seed, replica, g_pos, L.users_dist, users_mean, users_sigma);
-                g_pos = d.pos;
-                g_lam = d.value * rate_per_user;
+// ---------------------------------------------------------------------------------
+// generator: samplers/poisson_poisson.py:52-82 / gaussian_poisson.py:64-94.
+// Returns false when the sampler is exhausted; otherwise the next yielded gap.
+// ---------------------------------------------------------------------------------
+AF_IN bool gen_next_gap(State& W, double& gap) {
+    const double T = W.horizon;
+    double vnow = W.g_vnow, wend = W.g_window_end, lam = W.g_lam;
+    uint32_t pos = W.g_pos;
+    bool ok = false;
+    for (;;) {
+        if (!(vnow < T)) break;
+        if (vnow >= wend) {
+            wend = vnow + (double)AF_L.window_s;
+            afr::GenDraw d = afr::gen_users(AF_G.seed, W.replica, pos, AF_L.users_dist, W.users_mean, W.users_sigma);
+            pos = d.pos;
+            lam = d.value * W.rate_per_user;
+        }
+        if (lam <= 0.0) { vnow = wend; continue; }
+        afr::Src s = afr::make_gen(AF_G.seed, W.replica, pos);
+        double u = s.next53();
+        pos = s.pos;
+        if (u < 1e-15) u = 1e-15;                   // max(u, 1e-15)
+        double dt = afr::af_div(-afr::af_log(1.0 - u), lam);
+        if (vnow + dt > T) break;
+        if (vnow + dt >= wend) { vnow = wend; continue; }
+        vnow += dt;
+        gap = dt;
+        ok = true;
+        break;
+    }
+    W.g_vnow = vnow; W.g_window_end = wend; W.g_lam = lam; W.g_pos = pos;
+    return ok;
+}
+
+AF_IN void arm_generator(State& W) {
+    W.need_arrival = 0;
+    double gap;
+    if (!W.g_done && gen_next_gap(W, gap)) push_seq(W, W.now + gap, mk_payload(K_ARRIVAL, 0, 0), W.arm_seq);
+    else W.g_done = 1;
+}
+
+// ---------------------------------------------------------------------------------
+// edges: EdgeRuntime._deliver up to the timeout (edge.py:73-107)
+// ---------------------------------------------------------------------------------
+AF_FN void edge_send(State& W, uint32_t slot, uint32_t e, uint32_t rid, uint32_t hops) {
+    EdgeS& E = W.edge[e];
+    uint32_t s = W.seq++;                            // SimPy schedules the timeout here
+    const double dropout = E.dropout;
+    afr::EdgeDraw d = afr::edge_draw(AF_G.seed, W.replica, rid, hops, (int)(E.meta & 7u), E.mean, E.sigma, dropout);
+    E.sent += 1;
+    if (d.u < dropout) {                            // the request vanishes (edge.py:79-86)
+        E.dropped += 1;
+        rq_release(W, slot);
+        return;
+    }
+    E.conn += 1;
+    double effective = d.transit + E.spike;        // spike read at SEND time (edge.py:94-106)
+    push_seq(W, W.now + effective, mk_payload(K_DELIVER, e, slot), s);
+}
+
+// ---------------------------------------------------------------------------------
+// server
+// ---------------------------------------------------------------------------------
+// Container.put(1) processed -> head of the CPU get-queue resumes (server.py:222-231)
+AF_FN void grant_cpu_waiter(State& W, uint32_t sidx) {
+    ServerS& S = W.server[sidx];
+    if (S.cpuq_head == NIL) return;
+    uint32_t w = fifo_pop(W, S.cpuq_head, S.cpuq_tail);
+    S.cpu_free -= 1;
+    S.ready_q -= 1;
+    ReqRec r = rq_load(W, w);
+    r.pack |= PK_CORE;
+    rq_set_pack(W, w, r.pack);
+    const EndpointS ep = W.endpoint[pk_ep(r.pack)];
+    push(W, W.now + W.step[ep.step_begin + pk_step(r.pack)].dur, mk_payload(K_STEP_END, sidx, w));
+}
+
+// the `for step in selected_endpoint.steps` loop from the current step (server.py:197-255).
+// Returns the updated pack, with bit 31 set when no step is left (caller then finishes).
+constexpr uint32_t PK_DONE = 1u << 31;
+AF_FN uint32_t run_steps(State& W, uint32_t slot, uint32_t sidx, uint32_t pack) {
+    ServerS& S = W.server[sidx];
+    const EndpointS ep = W.endpoint[pk_ep(pack)];
+    uint32_t st = pk_step(pack);
+    if (st >= ep.n_steps) return pack | PK_DONE;
+    const StepS sp = W.step[ep.step_begin + st];
+    if (sp.kind == AF_STEP_CPU) {
+        if (pack & PK_IO) { pack &= ~PK_IO; S.io_q -= 1; }
+        if (!(pack & PK_CORE)) {
+            if (S.cpu_free > 0) { S.cpu_free -= 1; pack |= PK_CORE; }
+            else {                                  // cpu_req not triggered -> ready queue
+                S.ready_q += 1;
+                rq_set_pack(W, slot, pack);
+                fifo_push(W, S.cpuq_head, S.cpuq_tail, slot);
+                return pack;
             }
-            if (g_lam <= 0.0) { g_vnow = g_window_end; continue; }
-            afr::Src s = afr::make_gen(G.seed, replica, g_pos);
-            double u = s.next53();
-            g_pos = s.pos;
-            if (u < 1e-15) u = 1e-15;               // max(u, 1e-15)
-            double dt = afr::af_div(-afr::af_log(1.0 - u), g_lam);
-            if (g_vnow + dt > T) return false;
-            if (g_vnow + dt >= g_window_end) { g_vnow = g_window_end; continue; }
-            g_vnow += dt;
-            gap = dt;
-            return true;
+        }
+        rq_set_pack(W, slot, pack);
+        push(W, W.now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
+    } else {
+        bool release = (pack & PK_CORE) != 0;
+        if (release) { pack &= ~PK_CORE; S.cpu_free += 1; }
+        if (!(pack & PK_IO)) { pack |= PK_IO; S.io_q += 1; }
+        rq_set_pack(W, slot, pack);
+        // SimPy order: the releasing request schedules its IO timeout before the
+        // woken waiter schedules its CPU timeout (see DESIGN.md "tie rule")
+        push(W, W.now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
+        if (release) grant_cpu_waiter(W, sidx);
+    }
+    return pack;
+}
+
+// server.py:257-276
+AF_FN void finish_request(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, uint32_t pack) {
+    ServerS& S = W.server[sidx];
+    pack &= ~PK_DONE;
+    const uint32_t total_ram = W.endpoint[pk_ep(pack)].total_ram;
+    // SimPy order of the pushes that follow a release (DESIGN.md "tie rule"):
+    //   core + RAM : woken CPU waiter, then this request's edge, then RAM waiters
+    //   core only  : this request's edge (Initialize is URGENT), then the CPU waiter
+    bool had_core = (pack & PK_CORE) != 0;
+    if (had_core) { pack &= ~PK_CORE; S.cpu_free += 1; }
+    if (had_core && total_ram) grant_cpu_waiter(W, sidx);
+    if (pack & PK_IO) { pack &= ~PK_IO; S.io_q -= 1; }
+    if (total_ram) {
+        S.ram_in_use -= (int32_t)total_ram;
+        S.ram_free += (int32_t)total_ram;
+    }
+    rq_set_pack(W, slot, pack);
+    edge_send(W, slot, S.out_edge, rid, pk_hops(pack));
+    if (had_core && !total_ram) grant_cpu_waiter(W, sidx);
+    if (total_ram) {
+        // Container FIFO with head-of-line blocking
+        while (S.ramq_head != NIL) {
+            uint32_t w = S.ramq_head;
+            ReqRec wr = rq_load(W, w);
+            uint32_t need = W.endpoint[pk_ep(wr.pack)].total_ram;
+            if ((int32_t)need > S.ram_free) break;
+            fifo_pop(W, S.ramq_head, S.ramq_tail);
+            S.ram_free -= (int32_t)need;
+            S.ram_in_use += (int32_t)need;
+            uint32_t np = run_steps(W, w, sidx, wr.pack);
+            if (np & PK_DONE) {
+                // an endpoint made of RAM steps only: it gives the memory straight back
+                S.ram_in_use -= (int32_t)need;
+                S.ram_free += (int32_t)need;
+                edge_send(W, w, S.out_edge, wr.rid, pk_hops(np));
+            }
         }
     }
+}
 
-    // -------------------------------------------------------------- edges
-    // EdgeRuntime._deliver up to the timeout (edge.py:73-107)
-    AF_HD void edge_send(uint32_t slot, uint32_t e, const ReqRec& r) {
-        EdgeS& E = edge[e];
-        uint32_t s = seq++;                          // SimPy schedules the timeout here
-        afr::EdgeDraw d = afr::edge_draw(G.seed, replica, r.rid, pk_hops(r.pack), (int)(E.meta & 7u),
-                                         E.mean, E.sigma, E.dropout);
-        E.sent += 1;
-        if (d.u < E.dropout) {                      // the request vanishes (edge.py:79-86)
-            E.dropped += 1;
-            rq_release(slot);
+// ServerRuntime._dispatcher + head of _handle_request (server.py:88-149, 303-313)
+AF_IN void server_arrive(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, uint32_t pack) {
+    ServerS& S = W.server[sidx];
+    pack += 1;                                       // record_hop(SERVER)
+    uint32_t epi = 0;
+    const uint32_t n_ep = S.n_ep;
+    if (n_ep > 1) {
+        afr::Src s = afr::make_request(AF_G.seed, W.replica, afr::P_SERVER, rid, pk_hops(pack));
+        s.load(0);
+        epi = (uint32_t)(((uint64_t)s.w.x * n_ep) >> 32);
+    }
+    uint32_t ep_global = S.ep_begin + epi;
+    pack = (pack & 0xFFu) | (ep_global << 16);       // step 0, flags clear
+    rq_set_pack(W, slot, pack);
+    uint32_t total_ram = W.endpoint[ep_global].total_ram;
+    if (total_ram) {
+        if (S.ramq_head == NIL && (int32_t)total_ram <= S.ram_free) {
+            S.ram_free -= (int32_t)total_ram;
+            S.ram_in_use += (int32_t)total_ram;
+        } else {
+            fifo_push(W, S.ramq_head, S.ramq_tail, slot);
             return;
         }
-        E.conn += 1;
-        double effective = d.transit + E.spike;    // spike read at SEND time (edge.py:94-106)
-        push_seq(now + effective, mk_payload(K_DELIVER, e, slot), s);
     }
+    uint32_t np = run_steps(W, slot, sidx, pack);
+    if (np & PK_DONE) finish_request(W, slot, sidx, rid, np);
+}
 
-    // -------------------------------------------------------------- server
-    AF_HD void grant_cpu_waiter(uint32_t sidx) {
-        // Container.put(1) processed -> head of the CPU get-queue resumes (server.py:222-231)
-        ServerS& S = server[sidx];
-        if (S.cpuq_head == NIL) return;
-        uint32_t w = fifo_pop(S.cpuq_head, S.cpuq_tail);
-        S.cpu_free -= 1;
-        S.ready_q -= 1;
-        ReqRec r = rq_load(w);
-        r.pack |= PK_CORE;
-        rq_set_pack(w, r.pack);
-        const EndpointS& ep = endpoint[pk_ep(r.pack)];
-        push(now + step[ep.step_begin + pk_step(r.pack)].dur, mk_payload(K_STEP_END, sidx, w));
-    }
-
-    // the `for step in selected_endpoint.steps` loop from the current step (server.py:197-255).
-    // Returns true when no step is left (the caller then runs finish_request).
-    AF_HD bool run_steps(uint32_t slot, uint32_t sidx, ReqRec& r) {
-        ServerS& S = server[sidx];
-        const EndpointS ep = endpoint[pk_ep(r.pack)];
-        uint32_t st = pk_step(r.pack);
-        if (st >= ep.n_steps) return true;
-        const StepS sp = step[ep.step_begin + st];
-        if (sp.kind == AF_STEP_CPU) {
-            if (r.pack & PK_IO) { r.pack &= ~PK_IO; S.io_q -= 1; }
-            if (!(r.pack & PK_CORE)) {
-                if (S.cpu_free > 0) { S.cpu_free -= 1; r.pack |= PK_CORE; }
-                else {                              // cpu_req not triggered -> ready queue
-                    S.ready_q += 1;
-                    rq_set_pack(slot, r.pack);
-                    fifo_push(S.cpuq_head, S.cpuq_tail, slot);
-                    return false;
-                }
-            }
-            rq_set_pack(slot, r.pack);
-            push(now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
-        } else {
-            bool release = (r.pack & PK_CORE) != 0;
-            if (release) { r.pack &= ~PK_CORE; S.cpu_free += 1; }
-            if (!(r.pack & PK_IO)) { r.pack |= PK_IO; S.io_q += 1; }
-            rq_set_pack(slot, r.pack);
-            // SimPy order: the releasing request schedules its IO timeout before the
-            // woken waiter schedules its CPU timeout (see DESIGN.md "tie rule")
-            push(now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
-            if (release) grant_cpu_waiter(sidx);
+// ---------------------------------------------------------------------------------
+// client: completion (client.py:62-69 + analyzer.py:83-125)
+// ---------------------------------------------------------------------------------
+AF_IN void complete(State& W, uint32_t slot, double t0) {
+    const double now = W.now;
+    const double lat = now - t0;                     // finish - start (analyzer.py:86-89)
+    const uint32_t done = ++W.completed;
+    W.lat_sum += lat;
+    W.lat_sumsq += lat * lat;
+    if (lat < W.lat_min) W.lat_min = lat;
+    if (lat > W.lat_max) W.lat_max = lat;
+    const bool traced = W.traced != 0;
+    if (traced && (int32_t)(done - 1) >= AF_L.trace_clock_cap) W.flags |= AF_FLAG_TRACE_TRUNCATED;
+    if (lane_id() == 0) {
+        const uint64_t local = W.local;
+        if (AF_L.collect_hist) {
+            int32_t idx = (int32_t)(afr::d2u(lat) >> (52 - AF_HIST_SUB_BITS))
+                          - ((1023 + AF_HIST_MIN_EXP) << AF_HIST_SUB_BITS);
+            idx = idx < 0 ? 0 : (idx >= AF_HIST_BINS ? AF_HIST_BINS - 1 : idx);
+            red_add_u32(&AF_G.hist[local * AF_HIST_BINS + (uint32_t)idx], 1u);
         }
-        return false;
-    }
-
-    // server.py:257-276
-    AF_HD void finish_request(uint32_t slot, uint32_t sidx, ReqRec r) {
-        ServerS& S = server[sidx];
-        const uint32_t total_ram = endpoint[pk_ep(r.pack)].total_ram;
-        // SimPy order of the pushes that follow a release (DESIGN.md "tie rule"):
-        //   core + RAM : woken CPU waiter, then this request's edge, then RAM waiters
-        //   core only  : this request's edge (Initialize is URGENT), then the CPU waiter
-        bool had_core = (r.pack & PK_CORE) != 0;
-        if (had_core) { r.pack &= ~PK_CORE; S.cpu_free += 1; }
-        if (had_core && total_ram) grant_cpu_waiter(sidx);
-        if (r.pack & PK_IO) { r.pack &= ~PK_IO; S.io_q -= 1; }
-        if (total_ram) {
-            S.ram_in_use -= (int32_t)total_ram;
-            S.ram_free += (int32_t)total_ram;
+        if (AF_L.collect_thr) {
+            // bucket k counts (k, k+1] (analyzer.py:108-125)
+            int32_t b = (int32_t)ceil(now) - 1;
+            b = b < 0 ? 0 : b;
+            if (b < AF_L.horizon_s) red_add_u32(&AF_G.thr[local * (uint64_t)AF_L.horizon_s + (uint32_t)b], 1u);
         }
-        rq_set_pack(slot, r.pack);
-        edge_send(slot, S.out_edge, r);
-        if (had_core && !total_ram) grant_cpu_waiter(sidx);
-        if (total_ram) {
-            // Container FIFO with head-of-line blocking
-            while (S.ramq_head != NIL) {
-                uint32_t w = S.ramq_head;
-                ReqRec wr = rq_load(w);
-                uint32_t need = endpoint[pk_ep(wr.pack)].total_ram;
-                if ((int32_t)need > S.ram_free) break;
-                fifo_pop(S.ramq_head, S.ramq_tail);
-                S.ram_free -= (int32_t)need;
-                S.ram_in_use += (int32_t)need;
-                if (run_steps(w, sidx, wr)) {
-                    // an endpoint made of RAM steps only: it gives the memory straight back
-                    S.ram_in_use -= (int32_t)need;
-                    S.ram_free += (int32_t)need;
-                    edge_send(w, S.out_edge, wr);
-                }
+        if (traced && (int32_t)(done - 1) < AF_L.trace_clock_cap) {
+            double* p = AF_G.trace_clocks + (local * (uint64_t)AF_L.trace_clock_cap + (done - 1)) * 2;
+            p[0] = t0; p[1] = now;
+        }
+    }
+    w_sync();
+    rq_release(W, slot);
+}
+
+// ---------------------------------------------------------------------------------
+// deliveries: edge.py:110-116, then the target node's forwarder
+// ---------------------------------------------------------------------------------
+AF_IN void on_deliver(State& W, uint32_t slot, uint32_t e) {
+    EdgeS& E = W.edge[e];
+    E.conn -= 1;
+    const uint32_t meta = E.meta;
+    ReqRec r = rq_load(W, slot);
+    r.pack += 1;                                     // record_hop(edge)
+    uint32_t tk = (meta >> 3) & 3u;
+    if (tk == AF_TARGET_CLIENT) {
+        r.pack += 1;                                 // record_hop(client)
+        if (pk_hops(r.pack) > 3) { complete(W, slot, r.t0); return; }   // client.py:62
+        rq_set_pack(W, slot, r.pack);
+        edge_send(W, slot, (uint32_t)AF_L.client_edge, r.rid, pk_hops(r.pack));
+    } else if (tk == AF_TARGET_LB) {
+        r.pack += 1;                                 // record_hop(LB)
+        rq_set_pack(W, slot, r.pack);
+        uint32_t* lb = W.lb;
+        const int32_t n = W.lb_n;
+        uint32_t pick = lb[0];
+        if (AF_L.lb_algo == AF_LB_ROUND_ROBIN) {     // lb_algorithms.py:22-36
+            for (int32_t i = 1; i < n; ++i) lb[i - 1] = lb[i];
+            lb[n - 1] = pick;
+        } else {                                     // least_connections, :10-20 (first min wins)
+            uint32_t best = W.edge[pick].conn;
+            for (int32_t i = 1; i < n; ++i) {
+                uint32_t c = W.edge[lb[i]].conn;
+                if (c < best) { best = c; pick = lb[i]; }
             }
         }
+        edge_send(W, slot, pick, r.rid, pk_hops(r.pack));
+    } else {
+        server_arrive(W, slot, meta >> 5, r.rid, r.pack);
     }
+}
 
-    // ServerRuntime._dispatcher + head of _handle_request (server.py:88-149, 303-313)
-    AF_HD void server_arrive(uint32_t slot, uint32_t sidx, ReqRec r) {
-        ServerS& S = server[sidx];
-        r.pack += 1;                                 // record_hop(SERVER)
-        uint32_t epi = 0;
-        if (S.n_ep > 1) {
-            afr::Src s = afr::make_request(G.seed, replica, afr::P_SERVER, r.rid, pk_hops(r.pack));
-            s.load(0);
-            epi = (uint32_t)(((uint64_t)s.w.x * S.n_ep) >> 32);
+// ---------------------------------------------------------------------------------
+// arrivals (rqs_generator.py:97-119)
+// ---------------------------------------------------------------------------------
+AF_IN void on_arrival(State& W) {
+    const uint32_t rid = ++W.generated;
+    uint32_t slot = rq_alloc(W);
+    // the generator asks the sampler for the next gap right after transport(): its timeout is
+    // scheduled BEFORE the edge's delivery timeout.  The seq is reserved here; the gap itself
+    // is drawn at the single arm_generator() site in run_replica().
+    W.arm_seq = W.seq++;
+    W.need_arrival = 1;
+    if (slot == NIL) return;
+    ReqRec r; r.t0 = W.now; r.rid = rid; r.pack = 1;  // record_hop(generator)
+    rq_store(W, slot, r);
+    edge_send(W, slot, (uint32_t)AF_L.gen_edge, rid, 1u);
+}
+
+// ---------------------------------------------------------------------------------
+// event injection (injection.py:167-226): all marks of this instant, then re-arm
+// ---------------------------------------------------------------------------------
+AF_FN void on_spike(State& W) {
+    int32_t cur = W.spike_cur;
+    double t = W.spike[cur].fire;
+    while (cur < AF_L.n_spike && W.spike[cur].fire == t) {
+        const SpikeS m = W.spike[cur];
+        W.edge[m.edge].spike = W.edge[m.edge].spike + m.delta;
+        ++cur;
+    }
+    W.spike_cur = cur;
+    if (cur < AF_L.n_spike) push(W, W.spike[cur].fire, mk_payload(K_SPIKE, 0, 0));
+}
+AF_FN void on_outage(State& W) {
+    int32_t cur = W.outage_cur;
+    double t = W.outage[cur].fire;
+    uint32_t* lb = W.lb;
+    int32_t n = W.lb_n;
+    while (cur < AF_L.n_outage && W.outage[cur].fire == t) {
+        const OutageS m = W.outage[cur];
+        ++cur;
+        if (m.lb_edge < 0) continue;
+        int32_t at = -1;
+        for (int32_t i = 0; i < n; ++i) if (lb[i] == (uint32_t)m.lb_edge) { at = i; break; }
+        if (at >= 0) {                               // pop (DOWN) or move_to_end (UP)
+            for (int32_t i = at + 1; i < n; ++i) lb[i - 1] = lb[i];
+            --n;
         }
-        uint32_t ep_global = S.ep_begin + epi;
-        r.pack = (r.pack & 0xFFu) | (ep_global << 16); // step 0, flags clear
-        rq_set_pack(slot, r.pack);
-        uint32_t total_ram = endpoint[ep_global].total_ram;
-        if (total_ram) {
-            if (S.ramq_head == NIL && (int32_t)total_ram <= S.ram_free) {
-                S.ram_free -= (int32_t)total_ram;
-                S.ram_in_use += (int32_t)total_ram;
+        if (!m.down) lb[n++] = (uint32_t)m.lb_edge;
+    }
+    W.lb_n = n;
+    W.outage_cur = cur;
+    if (cur < AF_L.n_outage) push(W, W.outage[cur].fire, mk_payload(K_OUTAGE, 0, 0));
+}
+
+// ---------------------------------------------------------------------------------
+// sampled metrics: emit every collector tick ordered before (t, ev_seq) (collector.py:50-66)
+// ---------------------------------------------------------------------------------
+AF_FN void take_samples(State& W, double t, uint32_t ev_seq) {
+    const int lane = lane_id();
+    const int32_t n_series = AF_L.n_series, ns3 = 3 * AF_L.n_servers;
+    const bool srv_on = (AF_L.metrics_mask & 7u) == 7u;          // collector.py:60-63
+    const bool edge_on = (AF_L.metrics_mask & AF_METRIC_EDGE_CONN) != 0;
+    double tick = W.tick_time;
+    uint32_t tseq = W.tick_seq, nt = W.n_ticks, seq = W.seq;
+    const double horizon = W.horizon;
+    const bool traced = W.traced != 0;
+    while ((tick < t || (tick == t && tseq < ev_seq)) && tick < horizon) {
+        for (int32_t j = lane; j < n_series; j += WARP) {
+            uint32_t v;
+            if (j < ns3) {
+                if (!srv_on) continue;
+                const ServerS& S = W.server[j / 3];
+                int m = j % 3;
+                v = (uint32_t)(m == 0 ? S.ready_q : (m == 1 ? S.io_q : S.ram_in_use));
             } else {
-                fifo_push(S.ramq_head, S.ramq_tail, slot);
-                return;
+                if (!edge_on) continue;
+                v = W.edge[j - ns3].conn;
+            }
+            W.samp_sum[j] += v;
+            if (v > W.samp_max[j]) W.samp_max[j] = v;
+            if (traced && (int32_t)nt < AF_L.trace_tick_cap)
+                AF_G.trace_series[(W.local * (uint64_t)n_series + (uint32_t)j) * (uint64_t)AF_L.trace_tick_cap + nt] = v;
+        }
+        nt += 1;
+        tseq = seq++;                                 // the collector re-arms its timeout here
+        tick = tick + AF_L.sample_period;
+    }
+    w_sync();
+    W.tick_time = tick; W.tick_seq = tseq; W.n_ticks = nt; W.seq = seq;
+}
+
+// ---------------------------------------------------------------------------------
+// set-up / write-back (once per replica)
+// ---------------------------------------------------------------------------------
+AF_IN void bind(State& W, unsigned char* ws, uint64_t warp_slot) {
+    W.ev_time = (double*)(ws + AF_L.off_ev_time);
+    W.ev_key = (uint64_t*)(ws + AF_L.off_ev_key);
+    W.rq_rec = (ReqRec*)(ws + AF_L.off_rq_rec);
+    W.rq_next = (uint32_t*)(ws + AF_L.off_rq_next);
+    W.edge = (EdgeS*)(ws + AF_L.off_edge);
+    W.server = (ServerS*)(ws + AF_L.off_server);
+    W.endpoint = (EndpointS*)(ws + AF_L.off_endpoint);
+    W.step = (StepS*)(ws + AF_L.off_step);
+    W.lb = (uint32_t*)(ws + AF_L.off_lb);
+    W.spike = (SpikeS*)(ws + AF_L.off_spike);
+    W.outage = (OutageS*)(ws + AF_L.off_outage);
+    W.samp_sum = (uint64_t*)(ws + AF_L.off_samp_sum);
+    W.samp_max = (uint32_t*)(ws + AF_L.off_samp_max);
+    uint64_t ev_sp = (uint64_t)(AF_L.ev_total - AF_L.ev_smem), rq_sp = (uint64_t)(AF_L.rq_total - AF_L.rq_smem);
+    W.sp_ev_time = AF_G.spill_ev_time + warp_slot * ev_sp;
+    W.sp_ev_key = AF_G.spill_ev_key + warp_slot * ev_sp;
+    W.sp_rq_rec = AF_G.spill_rq_rec + warp_slot * rq_sp;
+    W.sp_rq_next = AF_G.spill_rq_next + warp_slot * rq_sp;
+}
+
+AF_FN void load_params(State& W) {
+    const int lane = lane_id();
+    for (int32_t i = lane; i < AF_L.n_edges; i += WARP) {
+        const AfEdge a = AF_G.edges[i];
+        EdgeS e;
+        e.mean = a.mean; e.sigma = a.sigma; e.dropout = a.dropout; e.spike = 0.0;
+        e.meta = (uint32_t)a.dist | ((uint32_t)a.target_kind << 3) | ((uint32_t)a.target_index << 5);
+        e.conn = 0; e.sent = 0; e.dropped = 0;
+        W.edge[i] = e;
+    }
+    for (int32_t i = lane; i < AF_L.n_servers; i += WARP) {
+        const AfServer a = AF_G.servers[i];
+        ServerS s;
+        s.cpu_free = a.cpu_cores; s.ram_free = a.ram_mb; s.ready_q = 0; s.io_q = 0; s.ram_in_use = 0;
+        s.ramq_head = s.ramq_tail = s.cpuq_head = s.cpuq_tail = NIL;
+        s.out_edge = (uint32_t)a.out_edge; s.ep_begin = (uint32_t)a.endpoint_begin; s.n_ep = (uint32_t)a.n_endpoints;
+        W.server[i] = s;
+    }
+    for (int32_t i = lane; i < AF_L.n_endpoints; i += WARP) {
+        const AfEndpoint a = AF_G.endpoints[i];
+        EndpointS e; e.step_begin = (uint32_t)a.step_begin; e.n_steps = (uint32_t)a.n_steps;
+        e.total_ram = (uint32_t)a.total_ram; e.pad = 0;
+        W.endpoint[i] = e;
+    }
+    for (int32_t i = lane; i < AF_L.n_steps; i += WARP) {
+        const AfStep a = AF_G.steps[i];
+        StepS s; s.dur = a.duration; s.kind = (uint32_t)a.kind; s.pad = 0;
+        W.step[i] = s;
+    }
+    for (int32_t i = lane; i < AF_L.n_lb_edges; i += WARP) W.lb[i] = (uint32_t)AF_G.lb_edges[i];
+    for (int32_t i = lane; i < AF_L.n_spike; i += WARP) {
+        const AfSpikeMark a = AF_G.spikes[i];
+        SpikeS s; s.fire = a.fire_time; s.delta = a.delta; s.edge = (uint32_t)a.edge; s.pad = 0;
+        W.spike[i] = s;
+    }
+    for (int32_t i = lane; i < AF_L.n_outage; i += WARP) {
+        const AfOutageMark a = AF_G.outages[i];
+        OutageS o; o.fire = a.fire_time; o.lb_edge = a.lb_edge; o.down = a.down;
+        W.outage[i] = o;
+    }
+    for (int32_t i = lane; i < AF_L.n_series; i += WARP) { W.samp_sum[i] = 0; W.samp_max[i] = 0; }
+    w_sync();
+    W.users_mean = AF_L.users_mean; W.users_sigma = AF_L.users_sigma; W.rate_per_user = AF_L.rate_per_user;
+    // sweep overrides of this replica (uniform: every lane applies every column)
+    const uint64_t replica = W.replica;
+    if (AF_L.n_sweep_cols > 0 && replica >= AF_G.sweep_first && replica - AF_G.sweep_first < AF_G.sweep_rows) {
+        const double* row = AF_G.sweep_vals + (replica - AF_G.sweep_first) * (uint64_t)AF_L.n_sweep_cols;
+        for (int32_t c = 0; c < AF_L.n_sweep_cols; ++c) {
+            const AfSweepColumn col = AF_G.sweep_cols[c];
+            double v = row[c];
+            switch (col.field) {
+            case AF_FIELD_USERS_MEAN: W.users_mean = v; break;
+            case AF_FIELD_USERS_SIGMA: W.users_sigma = v; break;
+            case AF_FIELD_RATE_PER_USER: W.rate_per_user = v; break;
+            case AF_FIELD_EDGE_MEAN: W.edge[col.index].mean = v; break;
+            case AF_FIELD_EDGE_SIGMA: W.edge[col.index].sigma = v; break;
+            case AF_FIELD_EDGE_DROPOUT: W.edge[col.index].dropout = v; break;
+            case AF_FIELD_SERVER_CPU_CORES: W.server[col.index].cpu_free = (int32_t)v; break;
+            case AF_FIELD_SERVER_RAM_MB: W.server[col.index].ram_free = (int32_t)v; break;
+            case AF_FIELD_STEP_DURATION: W.step[col.index].dur = v; break;
+            case AF_FIELD_ENDPOINT_RAM: W.endpoint[col.index].total_ram = (uint32_t)v; break;
+            case AF_FIELD_SPIKE_DELTA:
+                W.spike[col.index].delta = W.spike[col.index].delta < 0.0 ? -v : v; break;
+            default: break;
             }
         }
-        if (run_steps(slot, sidx, r)) finish_request(slot, sidx, r);
-    }
-
-    // -------------------------------------------------------------- client: completion
-    AF_HD void complete(uint32_t slot, const ReqRec& r) {
-        double lat = now - r.t0;                     // finish - start (analyzer.py:86-89)
-        completed += 1;
-        lat_sum += lat;
-        lat_sumsq += lat * lat;
-        if (lat < lat_min) lat_min = lat;
-        if (lat > lat_max) lat_max = lat;
-        if (lane == 0) {
-            if (L.collect_hist) {
-                int32_t idx = (int32_t)(afr::d2u(lat) >> (52 - AF_HIST_SUB_BITS))
-                              - ((1023 + AF_HIST_MIN_EXP) << AF_HIST_SUB_BITS);
-                idx = idx < 0 ? 0 : (idx >= AF_HIST_BINS ? AF_HIST_BINS - 1 : idx);
-                red_add_u32(&G.hist[local * AF_HIST_BINS + (uint32_t)idx], 1u);
-            }
-            if (L.collect_thr) {
-                // bucket k counts (k, k+1] (analyzer.py:108-125)
-                int32_t b = (int32_t)ceil(now) - 1;
-                b = b < 0 ? 0 : b;
-                if (b < L.horizon_s) red_add_u32(&G.thr[local * (uint64_t)L.horizon_s + (uint32_t)b], 1u);
-            }
-            if (traced) {
-                uint32_t i = completed - 1;
-                if ((int32_t)i < L.trace_clock_cap) {
-                    double* p = G.trace_clocks + (local * (uint64_t)L.trace_clock_cap + i) * 2;
-                    p[0] = r.t0; p[1] = now;
-                }
-            }
-        }
-        if (traced && (int32_t)(completed - 1) >= L.trace_clock_cap) flags |= AF_FLAG_TRACE_TRUNCATED;
-        rq_release(slot);
-    }
-
-    // -------------------------------------------------------------- deliveries
-    AF_HD void on_deliver(uint32_t slot, uint32_t e) {
-        EdgeS& E = edge[e];
-        E.conn -= 1;
-        ReqRec r = rq_load(slot);
-        r.pack += 1;                                 // record_hop(edge)
-        uint32_t tk = (E.meta >> 3) & 3u;
-        if (tk == AF_TARGET_CLIENT) {
-            r.pack += 1;                             // record_hop(client)
-            if (pk_hops(r.pack) > 3) { complete(slot, r); return; }     // client.py:62
-            rq_set_pack(slot, r.pack);
-            edge_send(slot, (uint32_t)L.client_edge, r);
-        } else if (tk == AF_TARGET_LB) {
-            r.pack += 1;                             // record_hop(LB)
-            rq_set_pack(slot, r.pack);
-            uint32_t pick;
-            if (L.lb_algo == AF_LB_ROUND_ROBIN) {    // lb_algorithms.py:22-36
-                pick = lb[0];
-                for (int32_t i = 1; i < lb_n; ++i) lb[i - 1] = lb[i];
-                lb[lb_n - 1] = pick;
-            } else {                                 // least_connections, :10-20 (first min wins)
-                pick = lb[0];
-                uint32_t best = edge[pick].conn;
-                for (int32_t i = 1; i < lb_n; ++i) {
-                    uint32_t c = edge[lb[i]].conn;
-                    if (c < best) { best = c; pick = lb[i]; }
-                }
-            }
-            edge_send(slot, pick, r);
-        } else {
-            server_arrive(slot, E.meta >> 5, r);
-        }
-    }
-
-    // -------------------------------------------------------------- arrivals
-    AF_HD void on_arrival() {
-        generated += 1;
-        uint32_t slot = rq_alloc();
-        // the generator asks the sampler for the next gap right after transport(): its timeout is
-        // scheduled BEFORE the edge's delivery timeout (rqs_generator.py:103-119).  The seq is
-        // reserved here; the gap itself is drawn at the single arm_generator() site in run().
-        arm_seq = seq++;
-        need_arrival = true;
-        if (slot == NIL) return;
-        ReqRec r; r.t0 = now; r.rid = generated; r.pack = 1;  // record_hop(generator)
-        rq_store(slot, r);
-        edge_send(slot, (uint32_t)L.gen_edge, r);
-    }
-
-    AF_HD void arm_generator() {
-        need_arrival = false;
-        double gap;
-        if (!g_done && gen_next_gap(gap)) push_seq(now + gap, mk_payload(K_ARRIVAL, 0, 0), arm_seq);
-        else g_done = true;
-    }
-
-    // -------------------------------------------------------------- injection
-    AF_HD void on_spike() {       // injection.py:167-198: all marks of this instant, then re-arm
-        double t = spike[spike_cur].fire;
-        while (spike_cur < L.n_spike && spike[spike_cur].fire == t) {
-            const SpikeS m = spike[spike_cur];
-            edge[m.edge].spike = edge[m.edge].spike + m.delta;
-            ++spike_cur;
-        }
-        if (spike_cur < L.n_spike) push(spike[spike_cur].fire, mk_payload(K_SPIKE, 0, 0));
-    }
-    AF_HD void on_outage() {      // injection.py:201-226
-        double t = outage[outage_cur].fire;
-        while (outage_cur < L.n_outage && outage[outage_cur].fire == t) {
-            const OutageS m = outage[outage_cur];
-            ++outage_cur;
-            if (m.lb_edge < 0) continue;
-            int32_t at = -1;
-            for (int32_t i = 0; i < lb_n; ++i) if (lb[i] == (uint32_t)m.lb_edge) { at = i; break; }
-            if (at >= 0) {                           // pop (DOWN) or move_to_end (UP)
-                for (int32_t i = at + 1; i < lb_n; ++i) lb[i - 1] = lb[i];
-                --lb_n;
-            }
-            if (!m.down) lb[lb_n++] = (uint32_t)m.lb_edge;
-        }
-        if (outage_cur < L.n_outage) push(outage[outage_cur].fire, mk_payload(K_OUTAGE, 0, 0));
-    }
-
-    // -------------------------------------------------------------- sampled metrics
-    AF_HD uint32_t series_value(int32_t j) const {
-        if (j < 3 * L.n_servers) {
-            const ServerS& S = server[j / 3];
-            int m = j % 3;
-            return (uint32_t)(m == 0 ? S.ready_q : (m == 1 ? S.io_q : S.ram_in_use));
-        }
-        return edge[j - 3 * L.n_servers].conn;
-    }
-    AF_HD bool series_enabled(int32_t j) const {
-        if (j < 3 * L.n_servers) return (L.metrics_mask & 7u) == 7u;   // collector.py:60-63
-        return (L.metrics_mask & AF_METRIC_EDGE_CONN) != 0;
-    }
-    // emit every collector tick ordered before (t, ev_seq)  (collector.py:50-66)
-    AF_HD void take_samples(double t, uint32_t ev_seq) {
-        while (tick_time < t || (tick_time == t && tick_seq < ev_seq)) {
-            if (!(tick_time < horizon)) return;
-            for (int32_t j = lane; j < L.n_series; j += WARP) {
-                if (!series_enabled(j)) continue;
-                uint32_t v = series_value(j);
-                samp_sum[j] += v;
-                if (v > samp_max[j]) samp_max[j] = v;
-                if (traced && (int32_t)n_ticks < L.trace_tick_cap)
-                    G.trace_series[(local * (uint64_t)L.n_series + (uint32_t)j) * (uint64_t)L.trace_tick_cap + n_ticks] = v;
-            }
-            n_ticks += 1;
-            tick_seq = seq++;                         // the collector re-arms its timeout here
-            tick_time = tick_time + L.sample_period;
-        }
-    }
-
-    // -------------------------------------------------------------- set-up
-    AF_HD void bind(unsigned char* ws, uint64_t warp_slot) {
-        ev_time = (double*)(ws + L.off_ev_time);
-        ev_key = (uint64_t*)(ws + L.off_ev_key);
-        rq_rec = (ReqRec*)(ws + L.off_rq_rec);
-        rq_next = (uint32_t*)(ws + L.off_rq_next);
-        edge = (EdgeS*)(ws + L.off_edge);
-        server = (ServerS*)(ws + L.off_server);
-        endpoint = (EndpointS*)(ws + L.off_endpoint);
-        step = (StepS*)(ws + L.off_step);
-        lb = (uint32_t*)(ws + L.off_lb);
-        spike = (SpikeS*)(ws + L.off_spike);
-        outage = (OutageS*)(ws + L.off_outage);
-        samp_sum = (uint64_t*)(ws + L.off_samp_sum);
-        samp_max = (uint32_t*)(ws + L.off_samp_max);
-        uint64_t ev_sp = (uint64_t)(L.ev_total - L.ev_smem), rq_sp = (uint64_t)(L.rq_total - L.rq_smem);
-        sp_ev_time = G.spill_ev_time + warp_slot * ev_sp;
-        sp_ev_key = G.spill_ev_key + warp_slot * ev_sp;
-        sp_rq_rec = G.spill_rq_rec + warp_slot * rq_sp;
-        sp_rq_next = G.spill_rq_next + warp_slot * rq_sp;
-    }
-
-    AF_HD void load_params() {
-        for (int32_t i = lane; i < L.n_edges; i += WARP) {
-            const AfEdge a = G.edges[i];
-            EdgeS e;
-            e.mean = a.mean; e.sigma = a.sigma; e.dropout = a.dropout; e.spike = 0.0;
-            e.meta = (uint32_t)a.dist | ((uint32_t)a.target_kind << 3) | ((uint32_t)a.target_index << 5);
-            e.conn = 0; e.sent = 0; e.dropped = 0;
-            edge[i] = e;
-        }
-        for (int32_t i = lane; i < L.n_servers; i += WARP) {
-            const AfServer a = G.servers[i];
-            ServerS s;
-            s.cpu_free = a.cpu_cores; s.ram_free = a.ram_mb; s.ready_q = 0; s.io_q = 0; s.ram_in_use = 0;
-            s.ramq_head = s.ramq_tail = s.cpuq_head = s.cpuq_tail = NIL;
-            s.out_edge = (uint32_t)a.out_edge; s.ep_begin = (uint32_t)a.endpoint_begin; s.n_ep = (uint32_t)a.n_endpoints;
-            server[i] = s;
-        }
-        for (int32_t i = lane; i < L.n_endpoints; i += WARP) {
-            const AfEndpoint a = G.endpoints[i];
-            EndpointS e; e.step_begin = (uint32_t)a.step_begin; e.n_steps = (uint32_t)a.n_steps;
-            e.total_ram = (uint32_t)a.total_ram; e.pad = 0;
-            endpoint[i] = e;
-        }
-        for (int32_t i = lane; i < L.n_steps; i += WARP) {
-            const AfStep a = G.steps[i];
-            StepS s; s.dur = a.duration; s.kind = (uint32_t)a.kind; s.pad = 0;
-            step[i] = s;
-        }
-        for (int32_t i = lane; i < L.n_lb_edges; i += WARP) lb[i] = (uint32_t)G.lb_edges[i];
-        for (int32_t i = lane; i < L.n_spike; i += WARP) {
-            const AfSpikeMark a = G.spikes[i];
-            SpikeS s; s.fire = a.fire_time; s.delta = a.delta; s.edge = (uint32_t)a.edge; s.pad = 0;
-            spike[i] = s;
-        }
-        for (int32_t i = lane; i < L.n_outage; i += WARP) {
-            const AfOutageMark a = G.outages[i];
-            OutageS o; o.fire = a.fire_time; o.lb_edge = a.lb_edge; o.down = a.down;
-            outage[i] = o;
-        }
-        for (int32_t i = lane; i < L.n_series; i += WARP) { samp_sum[i] = 0; samp_max[i] = 0; }
-        for (int32_t i = lane; i < L.ev_smem; i += WARP) ev_time[i] = afr::u2d(INF_BITS);
         w_sync();
-        users_mean = L.users_mean; users_sigma = L.users_sigma; rate_per_user = L.rate_per_user;
-        // sweep overrides of this replica (uniform: every lane applies every column)
-        if (L.n_sweep_cols > 0 && replica >= G.sweep_first && replica - G.sweep_first < G.sweep_rows) {
-            const double* row = G.sweep_vals + (replica - G.sweep_first) * (uint64_t)L.n_sweep_cols;
-            for (int32_t c = 0; c < L.n_sweep_cols; ++c) {
-                const AfSweepColumn col = G.sweep_cols[c];
-                double v = row[c];
-                switch (col.field) {
-                case AF_FIELD_USERS_MEAN: users_mean = v; break;
-                case AF_FIELD_USERS_SIGMA: users_sigma = v; break;
-                case AF_FIELD_RATE_PER_USER: rate_per_user = v; break;
-                case AF_FIELD_EDGE_MEAN: edge[col.index].mean = v; break;
-                case AF_FIELD_EDGE_SIGMA: edge[col.index].sigma = v; break;
-                case AF_FIELD_EDGE_DROPOUT: edge[col.index].dropout = v; break;
-                case AF_FIELD_SERVER_CPU_CORES: server[col.index].cpu_free = (int32_t)v; break;
-                case AF_FIELD_SERVER_RAM_MB: server[col.index].ram_free = (int32_t)v; break;
-                case AF_FIELD_STEP_DURATION: step[col.index].dur = v; break;
-                case AF_FIELD_ENDPOINT_RAM: endpoint[col.index].total_ram = (uint32_t)v; break;
-                case AF_FIELD_SPIKE_DELTA:
-                    spike[col.index].delta = spike[col.index].delta < 0.0 ? -v : v; break;
-                default: break;
-                }
-            }
-            w_sync();
-        }
     }
+}
 
-    // -------------------------------------------------------------- the replica
-    AF_HD void run(uint64_t local_index) {
-        local = local_index;
-        replica = G.replica_begin + local_index;
-        lane = lane_id();
-        load_params();
-        now = 0.0; horizon = (double)L.horizon_s; seq = 0;
-        ev_hw = 0; ev_live = 0; ev_last_free = -1; ev_hole = -1; peak_ev = 0;
-        rq_free = NIL; rq_hw = 0; rq_live = 0; peak_rq = 0;
-        g_vnow = 0.0; g_window_end = 0.0; g_lam = 0.0; g_pos = 0; generated = 0; g_done = false;
-        lb_n = L.n_lb_edges;
-        spike_cur = 0; outage_cur = 0;
-        n_ticks = 0; completed = 0; flags = 0; n_events = 0;
-        lat_sum = 0.0; lat_sumsq = 0.0; lat_min = afr::u2d(INF_BITS); lat_max = 0.0;
-        traced = (int64_t)local_index < (int64_t)L.trace_replicas;
-
-        // start order of the reference (simulation_runner.py:339-342, 301-336):
-        // spike timeline, outage timeline, generator, ..., collector
-        if (L.n_spike > 0) {
-            if (spike[0].fire == 0.0) on_spike(); else push(spike[0].fire, mk_payload(K_SPIKE, 0, 0));
-        }
-        if (L.n_outage > 0) {
-            if (outage[0].fire == 0.0) on_outage(); else push(outage[0].fire, mk_payload(K_OUTAGE, 0, 0));
-        }
-        arm_seq = seq++; need_arrival = true;
-        tick_seq = seq++;
-        tick_time = 0.0 + L.sample_period;
-
-        double t; uint32_t payload, ev_seq;
-        for (;;) {
-            if (need_arrival) arm_generator();
-            if (!pop(t, payload, ev_seq)) break;
-            take_samples(t, ev_seq);
-            now = t;
-            ++n_events;
-            uint32_t kind = payload >> 29, aux = (payload >> SLOT_BITS) & AUX_MASK, slot = payload & SLOT_MASK;
-            if (kind == K_DELIVER) on_deliver(slot, aux);
-            else if (kind == K_STEP_END) {
-                ReqRec r = rq_load(slot);
-                r.pack += 1u << 8;                   // next step
-                if (run_steps(slot, aux, r)) finish_request(slot, aux, r);
-            }
-            else if (kind == K_ARRIVAL) on_arrival();
-            else if (kind == K_SPIKE) on_spike();
-            else on_outage();
-            if (flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW)) break;
-        }
-        take_samples(horizon, 0u);                    // ticks strictly before the horizon
-        w_sync();
-        write_back();
+AF_FN void write_back(State& W) {
+    const int lane = lane_id();
+    const uint64_t local = W.local;
+    for (int32_t i = lane; i < AF_L.n_edges; i += WARP) {
+        AF_G.edge_sent[local * (uint64_t)AF_L.n_edges + (uint32_t)i] = W.edge[i].sent;
+        AF_G.edge_dropped[local * (uint64_t)AF_L.n_edges + (uint32_t)i] = W.edge[i].dropped;
     }
-
-    AF_HD void write_back() {
-        for (int32_t i = lane; i < L.n_edges; i += WARP) {
-            G.edge_sent[local * (uint64_t)L.n_edges + (uint32_t)i] = edge[i].sent;
-            G.edge_dropped[local * (uint64_t)L.n_edges + (uint32_t)i] = edge[i].dropped;
-        }
-        for (int32_t j = lane; j < L.n_series; j += WARP) {
-            G.samp_sum[local * (uint64_t)L.n_series + (uint32_t)j] = samp_sum[j];
-            G.samp_max[local * (uint64_t)L.n_series + (uint32_t)j] = samp_max[j];
-        }
-        if (lane == 0) {
-            AfReplicaStats st;
-            st.n_events = n_events; st.generated = generated; st.completed = completed;
-            st.flags = flags; st.n_ticks = n_ticks; st.peak_events = peak_ev; st.peak_requests = peak_rq;
-            st.lat_sum = lat_sum; st.lat_sumsq = lat_sumsq;
-            st.lat_min = completed ? lat_min : 0.0; st.lat_max = lat_max;
-            st.p50 = st.p95 = st.p99 = afr::u2d(0x7FF8000000000000ull);
-            G.stats[local] = st;
-            if (traced) { G.trace_counts[local * 2] = completed; G.trace_counts[local * 2 + 1] = n_ticks; }
-        }
+    for (int32_t j = lane; j < AF_L.n_series; j += WARP) {
+        AF_G.samp_sum[local * (uint64_t)AF_L.n_series + (uint32_t)j] = W.samp_sum[j];
+        AF_G.samp_max[local * (uint64_t)AF_L.n_series + (uint32_t)j] = W.samp_max[j];
     }
-};
+    if (lane == 0) {
+        AfReplicaStats st;
+        st.n_events = W.n_events; st.generated = W.generated; st.completed = W.completed;
+        st.flags = W.flags; st.n_ticks = W.n_ticks; st.peak_events = W.peak_ev; st.peak_requests = W.peak_rq;
+        st.lat_sum = W.lat_sum; st.lat_sumsq = W.lat_sumsq;
+        st.lat_min = W.completed ? W.lat_min : 0.0; st.lat_max = W.lat_max;
+        st.p50 = st.p95 = st.p99 = afr::u2d(0x7FF8000000000000ull);
+        AF_G.stats[local] = st;
+        if (W.traced) { AF_G.trace_counts[local * 2] = W.completed; AF_G.trace_counts[local * 2 + 1] = W.n_ticks; }
+    }
+    w_sync();
+}
+
+// ---------------------------------------------------------------------------------
+// the replica
+// ---------------------------------------------------------------------------------
+AF_IN void run_replica(State& W, uint64_t local_index) {
+    W.local = local_index;
+    W.replica = AF_G.replica_begin + local_index;
+    W.now = 0.0; W.horizon = (double)AF_L.horizon_s; W.seq = 0;
+    W.ev_hw = 0; W.ev_live = 0; W.ev_last_free = -1; W.ev_hole = -1; W.peak_ev = 0;
+    W.rq_free = NIL; W.rq_hw = 0; W.rq_live = 0; W.peak_rq = 0;
+    W.g_vnow = 0.0; W.g_window_end = 0.0; W.g_lam = 0.0; W.g_pos = 0; W.generated = 0; W.g_done = 0;
+    W.lb_n = AF_L.n_lb_edges;
+    W.spike_cur = 0; W.outage_cur = 0;
+    W.n_ticks = 0; W.completed = 0; W.flags = 0; W.n_events = 0;
+    W.lat_sum = 0.0; W.lat_sumsq = 0.0; W.lat_min = afr::u2d(INF_BITS); W.lat_max = 0.0;
+    W.traced = (int64_t)local_index < (int64_t)AF_L.trace_replicas ? 1u : 0u;
+    w_sync();
+    load_params(W);
+
+    // start order of the reference (simulation_runner.py:339-342, 301-336):
+    // spike timeline, outage timeline, generator, ..., collector
+    if (AF_L.n_spike > 0) {
+        if (W.spike[0].fire == 0.0) on_spike(W); else push(W, W.spike[0].fire, mk_payload(K_SPIKE, 0, 0));
+    }
+    if (AF_L.n_outage > 0) {
+        if (W.outage[0].fire == 0.0) on_outage(W); else push(W, W.outage[0].fire, mk_payload(K_OUTAGE, 0, 0));
+    }
+    W.arm_seq = W.seq++; W.need_arrival = 1;
+    W.tick_seq = W.seq++;
+    W.tick_time = 0.0 + AF_L.sample_period;
+
+    uint64_t n_events = 0;
+    double t; uint32_t payload, ev_seq;
+    for (;;) {
+        if (W.need_arrival) arm_generator(W);
+        if (!pop(W, t, payload, ev_seq)) break;
+        {
+            const double tick = W.tick_time;
+            if (tick < t || (tick == t && W.tick_seq < ev_seq)) take_samples(W, t, ev_seq);
+        }
+        W.now = t;
+        ++n_events;
+        uint32_t kind = payload >> 29, aux = (payload >> SLOT_BITS) & AUX_MASK, slot = payload & SLOT_MASK;
+        if (kind == K_DELIVER) on_deliver(W, slot, aux);
+        else if (kind == K_STEP_END) {
+            ReqRec r = rq_load(W, slot);
+            uint32_t np = run_steps(W, slot, aux, r.pack + (1u << 8));   // next step
+            if (np & PK_DONE) finish_request(W, slot, aux, r.rid, np);
+        }
+        else if (kind == K_ARRIVAL) on_arrival(W);
+        else if (kind == K_SPIKE) on_spike(W);
+        else on_outage(W);
+        if (W.flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW)) break;
+    }
+    W.n_events = n_events;
+    take_samples(W, W.horizon, 0u);                   // ticks strictly before the horizon
+    write_back(W);
+}
 
 }  // namespace afc

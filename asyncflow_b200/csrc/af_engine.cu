@@ -24,20 +24,21 @@
 // ---------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------
-__global__ void af_sim_kernel(const afc::Layout L, const afc::Globals G) {
+__global__ void af_sim_kernel() {
     extern __shared__ __align__(16) unsigned char af_smem[];
     const int warp = (int)(threadIdx.x >> 5);
     const int lane = (int)(threadIdx.x & 31u);
-    unsigned char* ws = af_smem + (size_t)warp * (size_t)L.warp_bytes;
+    unsigned char* ws = af_smem + (size_t)warp * (size_t)afc::c_L.warp_bytes;
     const uint64_t warp_slot = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (uint64_t)warp;
-    afc::Replica R(L, G);
-    R.bind(ws, warp_slot);
+    afc::State& W = *reinterpret_cast<afc::State*>(ws);
+    afc::bind(W, ws, warp_slot);
+    __syncwarp();
     for (;;) {
         unsigned long long r = 0;
-        if (lane == 0) r = atomicAdd(G.work_counter, 1ull);
+        if (lane == 0) r = atomicAdd(afc::c_G.work_counter, 1ull);
         r = __shfl_sync(0xFFFFFFFFu, r, 0);
-        if (r >= G.n_replicas) break;
-        R.run((uint64_t)r);
+        if (r >= afc::c_G.n_replicas) break;
+        afc::run_replica(W, (uint64_t)r);
         __syncwarp();
     }
 }
@@ -171,6 +172,7 @@ struct af_engine {
     // last run
     uint64_t last_n = 0; bool ran = false;
     afc::Layout L{};
+    afc::Globals G_host{};
     uint64_t launches = 0;
     float ms_total = 0.f, ms_sim = 0.f; bool timing_valid = false;
 
@@ -382,7 +384,10 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     AF_CUDA(e, cudaMemsetAsync(e->d_counter.p, 0, 8, e->stream), "memset");
     if (L.collect_hist) AF_CUDA(e, cudaMemsetAsync(e->d_hist.p, 0, n * AF_HIST_BINS * 4, e->stream), "memset hist");
     if (L.collect_thr) AF_CUDA(e, cudaMemsetAsync(e->d_thr.p, 0, n * (uint64_t)L.horizon_s * 4, e->stream), "memset thr");
-    af_sim_kernel<<<(unsigned)grid, wpb * 32, smem, e->stream>>>(L, G);
+    AF_CUDA(e, cudaMemcpyToSymbolAsync(afc::c_L, &L, sizeof L, 0, cudaMemcpyHostToDevice, e->stream), "layout -> constant memory");
+    e->G_host = G;   // keep the source alive until the async copy has been issued from pageable memory
+    AF_CUDA(e, cudaMemcpyToSymbolAsync(afc::c_G, &e->G_host, sizeof G, 0, cudaMemcpyHostToDevice, e->stream), "globals -> constant memory");
+    af_sim_kernel<<<(unsigned)grid, wpb * 32, smem, e->stream>>>();
     AF_CUDA(e, cudaGetLastError(), "af_sim_kernel launch");
     e->launches += 1;
     AF_CUDA(e, cudaEventRecord(e->ev_sim, e->stream), "event");

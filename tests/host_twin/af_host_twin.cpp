@@ -30,10 +30,10 @@ extern "C" int af_twin_run(const AfScenario* sc, const AfSweep* sw, uint64_t swe
                            uint32_t* thr, uint64_t* samp_sum, uint32_t* samp_max, double* trace_clocks,
                            uint32_t* trace_series, uint32_t* trace_counts) {
     if (!afh::validate(*sc, g_err)) return AF_ERR_INVALID;
-    afc::Layout L;
+    afc::Layout& L = afc::h_L;
     memset(&L, 0, sizeof L);
     afh::make_layout(*sc, *opt, sw ? sw->n_columns : 0, L);
-    afc::Globals G;
+    afc::Globals& G = afc::h_G;
     memset(&G, 0, sizeof G);
     G.edges = sc->edges; G.servers = sc->servers; G.endpoints = sc->endpoints; G.steps = sc->steps;
     G.lb_edges = sc->lb_edges; G.spikes = sc->spike_marks; G.outages = sc->outage_marks;
@@ -50,10 +50,9 @@ extern "C" int af_twin_run(const AfScenario* sc, const AfSweep* sw, uint64_t swe
     std::vector<unsigned char> ws((size_t)L.warp_bytes + 64);
     unsigned char* base = (unsigned char*)(((uintptr_t)ws.data() + 15) & ~(uintptr_t)15);
     for (uint64_t r = 0; r < n; ++r) {
-        for (int32_t i = L.ev_smem; i < L.ev_total; ++i) sp_t[(size_t)(i - L.ev_smem)] = afr::u2d(afc::INF_BITS);
-        afc::Replica R(L, G);
-        R.bind(base, 0);
-        R.run(r);
+        afc::State& W = *reinterpret_cast<afc::State*>(base);
+        afc::bind(W, base, 0);
+        afc::run_replica(W, r);
         if (L.collect_hist && stats) {
             stats[r].p50 = afh::hist_percentile(hist + r * AF_HIST_BINS, stats[r].completed, 50.0);
             stats[r].p95 = afh::hist_percentile(hist + r * AF_HIST_BINS, stats[r].completed, 95.0);
