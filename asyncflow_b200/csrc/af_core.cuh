@@ -66,6 +66,14 @@
 #define AF_IN static inline
 #endif
 
+// Tell the compiler that a pointer is into shared memory so that the helpers (which only
+// see a generic `State&`) emit LDS/STS instead of generic LD/ST.
+#if AF_DEVICE_CODE
+#define AF_SHARED(p) __builtin_assume(__isShared(p))
+#else
+#define AF_SHARED(p) ((void)0)
+#endif
+
 namespace afc {
 
 constexpr uint32_t NIL = 0xFFFFFFFFu;
@@ -284,6 +292,7 @@ AF_IN uint32_t fifo_pop(State& W, uint32_t& head, uint32_t& tail) {
 // executes push (same slot, same values); only the owner lane reads the slot back.
 // ---------------------------------------------------------------------------------
 AF_FN void push_seq(State& W, double t, uint32_t payload, uint32_t s) {
+    AF_SHARED(&W);
     if (!(t < W.horizon)) return;       // env.run(until=T): events at >= T never fire
     int32_t slot;
     if (W.ev_last_free >= 0) { slot = W.ev_last_free; W.ev_last_free = -1; }
@@ -393,6 +402,7 @@ AF_IN void arm_generator(State& W) {
 // edges: EdgeRuntime._deliver up to the timeout (edge.py:73-107)
 // ---------------------------------------------------------------------------------
 AF_FN void edge_send(State& W, uint32_t slot, uint32_t e, uint32_t rid, uint32_t hops) {
+    AF_SHARED(&W);
     EdgeS& E = W.edge[e];
     uint32_t s = W.seq++;                            // SimPy schedules the timeout here
     const double dropout = E.dropout;
@@ -413,6 +423,7 @@ AF_FN void edge_send(State& W, uint32_t slot, uint32_t e, uint32_t rid, uint32_t
 // ---------------------------------------------------------------------------------
 // Container.put(1) processed -> head of the CPU get-queue resumes (server.py:222-231)
 AF_FN void grant_cpu_waiter(State& W, uint32_t sidx) {
+    AF_SHARED(&W);
     ServerS& S = W.server[sidx];
     if (S.cpuq_head == NIL) return;
     uint32_t w = fifo_pop(W, S.cpuq_head, S.cpuq_tail);
@@ -429,6 +440,7 @@ AF_FN void grant_cpu_waiter(State& W, uint32_t sidx) {
 // Returns the updated pack, with bit 31 set when no step is left (caller then finishes).
 constexpr uint32_t PK_DONE = 1u << 31;
 AF_FN uint32_t run_steps(State& W, uint32_t slot, uint32_t sidx, uint32_t pack) {
+    AF_SHARED(&W);
     ServerS& S = W.server[sidx];
     const EndpointS ep = W.endpoint[pk_ep(pack)];
     uint32_t st = pk_step(pack);
@@ -462,6 +474,7 @@ AF_FN uint32_t run_steps(State& W, uint32_t slot, uint32_t sidx, uint32_t pack) 
 
 // server.py:257-276
 AF_FN void finish_request(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, uint32_t pack) {
+    AF_SHARED(&W);
     ServerS& S = W.server[sidx];
     pack &= ~PK_DONE;
     const uint32_t total_ram = W.endpoint[pk_ep(pack)].total_ram;
@@ -622,6 +635,7 @@ AF_IN void on_arrival(State& W) {
 // event injection (injection.py:167-226): all marks of this instant, then re-arm
 // ---------------------------------------------------------------------------------
 AF_FN void on_spike(State& W) {
+    AF_SHARED(&W);
     int32_t cur = W.spike_cur;
     double t = W.spike[cur].fire;
     while (cur < AF_L.n_spike && W.spike[cur].fire == t) {
@@ -633,6 +647,7 @@ AF_FN void on_spike(State& W) {
     if (cur < AF_L.n_spike) push(W, W.spike[cur].fire, mk_payload(K_SPIKE, 0, 0));
 }
 AF_FN void on_outage(State& W) {
+    AF_SHARED(&W);
     int32_t cur = W.outage_cur;
     double t = W.outage[cur].fire;
     uint32_t* lb = W.lb;
@@ -658,6 +673,7 @@ AF_FN void on_outage(State& W) {
 // sampled metrics: emit every collector tick ordered before (t, ev_seq) (collector.py:50-66)
 // ---------------------------------------------------------------------------------
 AF_FN void take_samples(State& W, double t, uint32_t ev_seq) {
+    AF_SHARED(&W);
     const int lane = lane_id();
     const int32_t n_series = AF_L.n_series, ns3 = 3 * AF_L.n_servers;
     const bool srv_on = (AF_L.metrics_mask & 7u) == 7u;          // collector.py:60-63
@@ -716,6 +732,7 @@ AF_IN void bind(State& W, unsigned char* ws, uint64_t warp_slot) {
 }
 
 AF_FN void load_params(State& W) {
+    AF_SHARED(&W);
     const int lane = lane_id();
     for (int32_t i = lane; i < AF_L.n_edges; i += WARP) {
         const AfEdge a = AF_G.edges[i];
@@ -786,6 +803,7 @@ AF_FN void load_params(State& W) {
 }
 
 AF_FN void write_back(State& W) {
+    AF_SHARED(&W);
     const int lane = lane_id();
     const uint64_t local = W.local;
     for (int32_t i = lane; i < AF_L.n_edges; i += WARP) {
