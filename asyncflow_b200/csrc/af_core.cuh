@@ -113,10 +113,8 @@ struct OutageS { double fire; int32_t lb_edge, down; };              // 16 B
 
 // The replica's scalar state: one per warp, at the start of the warp's workspace.
 struct State {
-    // views into this warp's workspace / spill regions
-    double* ev_time; uint64_t* ev_key; ReqRec* rq_rec; uint32_t* rq_next;
-    EdgeS* edge; ServerS* server; EndpointS* endpoint; StepS* step; uint32_t* lb;
-    SpikeS* spike; OutageS* outage; uint64_t* samp_sum; uint32_t* samp_max;
+    // this warp's HBM spill regions (the shared-memory tables sit at fixed offsets
+    // behind this struct: see tbl_*() below -- 32-bit shared addresses, no pointer loads)
     double* sp_ev_time; uint64_t* sp_ev_key; ReqRec* sp_rq_rec; uint32_t* sp_rq_next;
     // identity
     uint64_t replica, local;
@@ -214,6 +212,25 @@ static Globals h_G;
 #define AF_G h_G
 #endif
 
+
+// Shared-memory tables of the warp: fixed byte offsets (Layout) behind its State.
+#define AF_TBL(name, type, off)                                                    \
+    AF_IN type* name(State& W) { return reinterpret_cast<type*>(reinterpret_cast<unsigned char*>(&W) + AF_L.off); } \
+    AF_IN const type* name(const State& W) { return reinterpret_cast<const type*>(reinterpret_cast<const unsigned char*>(&W) + AF_L.off); }
+AF_TBL(tbl_ev_time, double, off_ev_time)
+AF_TBL(tbl_ev_key, uint64_t, off_ev_key)
+AF_TBL(tbl_rq_rec, ReqRec, off_rq_rec)
+AF_TBL(tbl_rq_next, uint32_t, off_rq_next)
+AF_TBL(tbl_edge, EdgeS, off_edge)
+AF_TBL(tbl_server, ServerS, off_server)
+AF_TBL(tbl_endpoint, EndpointS, off_endpoint)
+AF_TBL(tbl_step, StepS, off_step)
+AF_TBL(tbl_lb, uint32_t, off_lb)
+AF_TBL(tbl_spike, SpikeS, off_spike)
+AF_TBL(tbl_outage, OutageS, off_outage)
+AF_TBL(tbl_samp_sum, uint64_t, off_samp_sum)
+AF_TBL(tbl_samp_max, uint32_t, off_samp_max)
+
 // ---- warp primitives (a warp of ONE lane on the host) ------------------------
 #if AF_DEVICE_CODE
 constexpr int WARP = 32;
@@ -239,25 +256,25 @@ static inline void red_add_u32(uint32_t* p, uint32_t v) { *p += v; }
 // spill region (overloaded replicas queue 10^4-10^5 requests)
 // ---------------------------------------------------------------------------------
 AF_IN ReqRec rq_load(const State& W, uint32_t s) {
-    return (int32_t)s < AF_L.rq_smem ? W.rq_rec[s] : W.sp_rq_rec[s - AF_L.rq_smem];
+    return (int32_t)s < AF_L.rq_smem ? tbl_rq_rec(W)[s] : W.sp_rq_rec[s - AF_L.rq_smem];
 }
 AF_IN void rq_store(State& W, uint32_t s, const ReqRec& r) {
-    if ((int32_t)s < AF_L.rq_smem) W.rq_rec[s] = r; else W.sp_rq_rec[s - AF_L.rq_smem] = r;
+    if ((int32_t)s < AF_L.rq_smem) tbl_rq_rec(W)[s] = r; else W.sp_rq_rec[s - AF_L.rq_smem] = r;
 }
 AF_IN void rq_set_pack(State& W, uint32_t s, uint32_t pack) {
-    if ((int32_t)s < AF_L.rq_smem) W.rq_rec[s].pack = pack; else W.sp_rq_rec[s - AF_L.rq_smem].pack = pack;
+    if ((int32_t)s < AF_L.rq_smem) tbl_rq_rec(W)[s].pack = pack; else W.sp_rq_rec[s - AF_L.rq_smem].pack = pack;
 }
 AF_IN uint32_t nx_load(const State& W, uint32_t s) {
-    return (int32_t)s < AF_L.rq_smem ? W.rq_next[s] : W.sp_rq_next[s - AF_L.rq_smem];
+    return (int32_t)s < AF_L.rq_smem ? tbl_rq_next(W)[s] : W.sp_rq_next[s - AF_L.rq_smem];
 }
 AF_IN void nx_store(State& W, uint32_t s, uint32_t v) {
-    if ((int32_t)s < AF_L.rq_smem) W.rq_next[s] = v; else W.sp_rq_next[s - AF_L.rq_smem] = v;
+    if ((int32_t)s < AF_L.rq_smem) tbl_rq_next(W)[s] = v; else W.sp_rq_next[s - AF_L.rq_smem] = v;
 }
 AF_IN uint64_t evt_load(const State& W, int32_t k) {
-    return afr::d2u(k < AF_L.ev_smem ? W.ev_time[k] : W.sp_ev_time[k - AF_L.ev_smem]);
+    return afr::d2u(k < AF_L.ev_smem ? tbl_ev_time(W)[k] : W.sp_ev_time[k - AF_L.ev_smem]);
 }
 AF_IN uint64_t evk_load(const State& W, int32_t k) {
-    return k < AF_L.ev_smem ? W.ev_key[k] : W.sp_ev_key[k - AF_L.ev_smem];
+    return k < AF_L.ev_smem ? tbl_ev_key(W)[k] : W.sp_ev_key[k - AF_L.ev_smem];
 }
 
 // ---- request slots (free list threaded through rq_next) ------------------------
@@ -303,7 +320,7 @@ AF_FN void push_seq(State& W, double t, uint32_t payload, uint32_t s) {
         W.ev_hw = slot + 1;
     }
     uint64_t key = ((uint64_t)s << 32) | payload;
-    if (slot < AF_L.ev_smem) { W.ev_time[slot] = t; W.ev_key[slot] = key; }
+    if (slot < AF_L.ev_smem) { tbl_ev_time(W)[slot] = t; tbl_ev_key(W)[slot] = key; }
     else { W.sp_ev_time[slot - AF_L.ev_smem] = t; W.sp_ev_key[slot - AF_L.ev_smem] = key; }
     uint32_t live = (uint32_t)(++W.ev_live);
     if (live > W.peak_ev) W.peak_ev = live;
@@ -344,7 +361,7 @@ AF_IN bool pop(State& W, double& t, uint32_t& payload, uint32_t& ev_seq) {
 #else
     int32_t slot = bi;
 #endif
-    if (slot < AF_L.ev_smem) W.ev_time[slot] = afr::u2d(INF_BITS);
+    if (slot < AF_L.ev_smem) tbl_ev_time(W)[slot] = afr::u2d(INF_BITS);
     else W.sp_ev_time[slot - AF_L.ev_smem] = afr::u2d(INF_BITS);
     W.ev_live -= 1;
     int32_t nhw = hw;
@@ -403,7 +420,7 @@ AF_IN void arm_generator(State& W) {
 // ---------------------------------------------------------------------------------
 AF_FN void edge_send(State& W, uint32_t slot, uint32_t e, uint32_t rid, uint32_t hops) {
     AF_SHARED(&W);
-    EdgeS& E = W.edge[e];
+    EdgeS& E = tbl_edge(W)[e];
     uint32_t s = W.seq++;                            // SimPy schedules the timeout here
     const double dropout = E.dropout;
     afr::EdgeDraw d = afr::edge_draw(AF_G.seed, W.replica, rid, hops, (int)(E.meta & 7u), E.mean, E.sigma, dropout);
@@ -424,7 +441,7 @@ AF_FN void edge_send(State& W, uint32_t slot, uint32_t e, uint32_t rid, uint32_t
 // Container.put(1) processed -> head of the CPU get-queue resumes (server.py:222-231)
 AF_FN void grant_cpu_waiter(State& W, uint32_t sidx) {
     AF_SHARED(&W);
-    ServerS& S = W.server[sidx];
+    ServerS& S = tbl_server(W)[sidx];
     if (S.cpuq_head == NIL) return;
     uint32_t w = fifo_pop(W, S.cpuq_head, S.cpuq_tail);
     S.cpu_free -= 1;
@@ -432,8 +449,8 @@ AF_FN void grant_cpu_waiter(State& W, uint32_t sidx) {
     ReqRec r = rq_load(W, w);
     r.pack |= PK_CORE;
     rq_set_pack(W, w, r.pack);
-    const EndpointS ep = W.endpoint[pk_ep(r.pack)];
-    push(W, W.now + W.step[ep.step_begin + pk_step(r.pack)].dur, mk_payload(K_STEP_END, sidx, w));
+    const EndpointS ep = tbl_endpoint(W)[pk_ep(r.pack)];
+    push(W, W.now + tbl_step(W)[ep.step_begin + pk_step(r.pack)].dur, mk_payload(K_STEP_END, sidx, w));
 }
 
 // the `for step in selected_endpoint.steps` loop from the current step (server.py:197-255).
@@ -441,11 +458,11 @@ AF_FN void grant_cpu_waiter(State& W, uint32_t sidx) {
 constexpr uint32_t PK_DONE = 1u << 31;
 AF_FN uint32_t run_steps(State& W, uint32_t slot, uint32_t sidx, uint32_t pack) {
     AF_SHARED(&W);
-    ServerS& S = W.server[sidx];
-    const EndpointS ep = W.endpoint[pk_ep(pack)];
+    ServerS& S = tbl_server(W)[sidx];
+    const EndpointS ep = tbl_endpoint(W)[pk_ep(pack)];
     uint32_t st = pk_step(pack);
     if (st >= ep.n_steps) return pack | PK_DONE;
-    const StepS sp = W.step[ep.step_begin + st];
+    const StepS sp = tbl_step(W)[ep.step_begin + st];
     if (sp.kind == AF_STEP_CPU) {
         if (pack & PK_IO) { pack &= ~PK_IO; S.io_q -= 1; }
         if (!(pack & PK_CORE)) {
@@ -475,9 +492,9 @@ AF_FN uint32_t run_steps(State& W, uint32_t slot, uint32_t sidx, uint32_t pack) 
 // server.py:257-276
 AF_FN void finish_request(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, uint32_t pack) {
     AF_SHARED(&W);
-    ServerS& S = W.server[sidx];
+    ServerS& S = tbl_server(W)[sidx];
     pack &= ~PK_DONE;
-    const uint32_t total_ram = W.endpoint[pk_ep(pack)].total_ram;
+    const uint32_t total_ram = tbl_endpoint(W)[pk_ep(pack)].total_ram;
     // SimPy order of the pushes that follow a release (DESIGN.md "tie rule"):
     //   core + RAM : woken CPU waiter, then this request's edge, then RAM waiters
     //   core only  : this request's edge (Initialize is URGENT), then the CPU waiter
@@ -497,7 +514,7 @@ AF_FN void finish_request(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, 
         while (S.ramq_head != NIL) {
             uint32_t w = S.ramq_head;
             ReqRec wr = rq_load(W, w);
-            uint32_t need = W.endpoint[pk_ep(wr.pack)].total_ram;
+            uint32_t need = tbl_endpoint(W)[pk_ep(wr.pack)].total_ram;
             if ((int32_t)need > S.ram_free) break;
             fifo_pop(W, S.ramq_head, S.ramq_tail);
             S.ram_free -= (int32_t)need;
@@ -515,7 +532,7 @@ AF_FN void finish_request(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, 
 
 // ServerRuntime._dispatcher + head of _handle_request (server.py:88-149, 303-313)
 AF_IN void server_arrive(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, uint32_t pack) {
-    ServerS& S = W.server[sidx];
+    ServerS& S = tbl_server(W)[sidx];
     pack += 1;                                       // record_hop(SERVER)
     uint32_t epi = 0;
     const uint32_t n_ep = S.n_ep;
@@ -527,7 +544,7 @@ AF_IN void server_arrive(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, u
     uint32_t ep_global = S.ep_begin + epi;
     pack = (pack & 0xFFu) | (ep_global << 16);       // step 0, flags clear
     rq_set_pack(W, slot, pack);
-    uint32_t total_ram = W.endpoint[ep_global].total_ram;
+    uint32_t total_ram = tbl_endpoint(W)[ep_global].total_ram;
     if (total_ram) {
         if (S.ramq_head == NIL && (int32_t)total_ram <= S.ram_free) {
             S.ram_free -= (int32_t)total_ram;
@@ -581,7 +598,7 @@ AF_IN void complete(State& W, uint32_t slot, double t0) {
 // deliveries: edge.py:110-116, then the target node's forwarder
 // ---------------------------------------------------------------------------------
 AF_IN void on_deliver(State& W, uint32_t slot, uint32_t e) {
-    EdgeS& E = W.edge[e];
+    EdgeS& E = tbl_edge(W)[e];
     E.conn -= 1;
     const uint32_t meta = E.meta;
     ReqRec r = rq_load(W, slot);
@@ -595,16 +612,16 @@ AF_IN void on_deliver(State& W, uint32_t slot, uint32_t e) {
     } else if (tk == AF_TARGET_LB) {
         r.pack += 1;                                 // record_hop(LB)
         rq_set_pack(W, slot, r.pack);
-        uint32_t* lb = W.lb;
+        uint32_t* lb = tbl_lb(W);
         const int32_t n = W.lb_n;
         uint32_t pick = lb[0];
         if (AF_L.lb_algo == AF_LB_ROUND_ROBIN) {     // lb_algorithms.py:22-36
             for (int32_t i = 1; i < n; ++i) lb[i - 1] = lb[i];
             lb[n - 1] = pick;
         } else {                                     // least_connections, :10-20 (first min wins)
-            uint32_t best = W.edge[pick].conn;
+            uint32_t best = tbl_edge(W)[pick].conn;
             for (int32_t i = 1; i < n; ++i) {
-                uint32_t c = W.edge[lb[i]].conn;
+                uint32_t c = tbl_edge(W)[lb[i]].conn;
                 if (c < best) { best = c; pick = lb[i]; }
             }
         }
@@ -637,23 +654,23 @@ AF_IN void on_arrival(State& W) {
 AF_FN void on_spike(State& W) {
     AF_SHARED(&W);
     int32_t cur = W.spike_cur;
-    double t = W.spike[cur].fire;
-    while (cur < AF_L.n_spike && W.spike[cur].fire == t) {
-        const SpikeS m = W.spike[cur];
-        W.edge[m.edge].spike = W.edge[m.edge].spike + m.delta;
+    double t = tbl_spike(W)[cur].fire;
+    while (cur < AF_L.n_spike && tbl_spike(W)[cur].fire == t) {
+        const SpikeS m = tbl_spike(W)[cur];
+        tbl_edge(W)[m.edge].spike = tbl_edge(W)[m.edge].spike + m.delta;
         ++cur;
     }
     W.spike_cur = cur;
-    if (cur < AF_L.n_spike) push(W, W.spike[cur].fire, mk_payload(K_SPIKE, 0, 0));
+    if (cur < AF_L.n_spike) push(W, tbl_spike(W)[cur].fire, mk_payload(K_SPIKE, 0, 0));
 }
 AF_FN void on_outage(State& W) {
     AF_SHARED(&W);
     int32_t cur = W.outage_cur;
-    double t = W.outage[cur].fire;
-    uint32_t* lb = W.lb;
+    double t = tbl_outage(W)[cur].fire;
+    uint32_t* lb = tbl_lb(W);
     int32_t n = W.lb_n;
-    while (cur < AF_L.n_outage && W.outage[cur].fire == t) {
-        const OutageS m = W.outage[cur];
+    while (cur < AF_L.n_outage && tbl_outage(W)[cur].fire == t) {
+        const OutageS m = tbl_outage(W)[cur];
         ++cur;
         if (m.lb_edge < 0) continue;
         int32_t at = -1;
@@ -666,7 +683,7 @@ AF_FN void on_outage(State& W) {
     }
     W.lb_n = n;
     W.outage_cur = cur;
-    if (cur < AF_L.n_outage) push(W, W.outage[cur].fire, mk_payload(K_OUTAGE, 0, 0));
+    if (cur < AF_L.n_outage) push(W, tbl_outage(W)[cur].fire, mk_payload(K_OUTAGE, 0, 0));
 }
 
 // ---------------------------------------------------------------------------------
@@ -687,15 +704,15 @@ AF_FN void take_samples(State& W, double t, uint32_t ev_seq) {
             uint32_t v;
             if (j < ns3) {
                 if (!srv_on) continue;
-                const ServerS& S = W.server[j / 3];
+                const ServerS& S = tbl_server(W)[j / 3];
                 int m = j % 3;
                 v = (uint32_t)(m == 0 ? S.ready_q : (m == 1 ? S.io_q : S.ram_in_use));
             } else {
                 if (!edge_on) continue;
-                v = W.edge[j - ns3].conn;
+                v = tbl_edge(W)[j - ns3].conn;
             }
-            W.samp_sum[j] += v;
-            if (v > W.samp_max[j]) W.samp_max[j] = v;
+            tbl_samp_sum(W)[j] += v;
+            if (v > tbl_samp_max(W)[j]) tbl_samp_max(W)[j] = v;
             if (traced && (int32_t)nt < AF_L.trace_tick_cap)
                 AF_G.trace_series[(W.local * (uint64_t)n_series + (uint32_t)j) * (uint64_t)AF_L.trace_tick_cap + nt] = v;
         }
@@ -711,19 +728,7 @@ AF_FN void take_samples(State& W, double t, uint32_t ev_seq) {
 // set-up / write-back (once per replica)
 // ---------------------------------------------------------------------------------
 AF_IN void bind(State& W, unsigned char* ws, uint64_t warp_slot) {
-    W.ev_time = (double*)(ws + AF_L.off_ev_time);
-    W.ev_key = (uint64_t*)(ws + AF_L.off_ev_key);
-    W.rq_rec = (ReqRec*)(ws + AF_L.off_rq_rec);
-    W.rq_next = (uint32_t*)(ws + AF_L.off_rq_next);
-    W.edge = (EdgeS*)(ws + AF_L.off_edge);
-    W.server = (ServerS*)(ws + AF_L.off_server);
-    W.endpoint = (EndpointS*)(ws + AF_L.off_endpoint);
-    W.step = (StepS*)(ws + AF_L.off_step);
-    W.lb = (uint32_t*)(ws + AF_L.off_lb);
-    W.spike = (SpikeS*)(ws + AF_L.off_spike);
-    W.outage = (OutageS*)(ws + AF_L.off_outage);
-    W.samp_sum = (uint64_t*)(ws + AF_L.off_samp_sum);
-    W.samp_max = (uint32_t*)(ws + AF_L.off_samp_max);
+    (void)ws;
     uint64_t ev_sp = (uint64_t)(AF_L.ev_total - AF_L.ev_smem), rq_sp = (uint64_t)(AF_L.rq_total - AF_L.rq_smem);
     W.sp_ev_time = AF_G.spill_ev_time + warp_slot * ev_sp;
     W.sp_ev_key = AF_G.spill_ev_key + warp_slot * ev_sp;
@@ -740,7 +745,7 @@ AF_FN void load_params(State& W) {
         e.mean = a.mean; e.sigma = a.sigma; e.dropout = a.dropout; e.spike = 0.0;
         e.meta = (uint32_t)a.dist | ((uint32_t)a.target_kind << 3) | ((uint32_t)a.target_index << 5);
         e.conn = 0; e.sent = 0; e.dropped = 0;
-        W.edge[i] = e;
+        tbl_edge(W)[i] = e;
     }
     for (int32_t i = lane; i < AF_L.n_servers; i += WARP) {
         const AfServer a = AF_G.servers[i];
@@ -748,31 +753,31 @@ AF_FN void load_params(State& W) {
         s.cpu_free = a.cpu_cores; s.ram_free = a.ram_mb; s.ready_q = 0; s.io_q = 0; s.ram_in_use = 0;
         s.ramq_head = s.ramq_tail = s.cpuq_head = s.cpuq_tail = NIL;
         s.out_edge = (uint32_t)a.out_edge; s.ep_begin = (uint32_t)a.endpoint_begin; s.n_ep = (uint32_t)a.n_endpoints;
-        W.server[i] = s;
+        tbl_server(W)[i] = s;
     }
     for (int32_t i = lane; i < AF_L.n_endpoints; i += WARP) {
         const AfEndpoint a = AF_G.endpoints[i];
         EndpointS e; e.step_begin = (uint32_t)a.step_begin; e.n_steps = (uint32_t)a.n_steps;
         e.total_ram = (uint32_t)a.total_ram; e.pad = 0;
-        W.endpoint[i] = e;
+        tbl_endpoint(W)[i] = e;
     }
     for (int32_t i = lane; i < AF_L.n_steps; i += WARP) {
         const AfStep a = AF_G.steps[i];
         StepS s; s.dur = a.duration; s.kind = (uint32_t)a.kind; s.pad = 0;
-        W.step[i] = s;
+        tbl_step(W)[i] = s;
     }
-    for (int32_t i = lane; i < AF_L.n_lb_edges; i += WARP) W.lb[i] = (uint32_t)AF_G.lb_edges[i];
+    for (int32_t i = lane; i < AF_L.n_lb_edges; i += WARP) tbl_lb(W)[i] = (uint32_t)AF_G.lb_edges[i];
     for (int32_t i = lane; i < AF_L.n_spike; i += WARP) {
         const AfSpikeMark a = AF_G.spikes[i];
         SpikeS s; s.fire = a.fire_time; s.delta = a.delta; s.edge = (uint32_t)a.edge; s.pad = 0;
-        W.spike[i] = s;
+        tbl_spike(W)[i] = s;
     }
     for (int32_t i = lane; i < AF_L.n_outage; i += WARP) {
         const AfOutageMark a = AF_G.outages[i];
         OutageS o; o.fire = a.fire_time; o.lb_edge = a.lb_edge; o.down = a.down;
-        W.outage[i] = o;
+        tbl_outage(W)[i] = o;
     }
-    for (int32_t i = lane; i < AF_L.n_series; i += WARP) { W.samp_sum[i] = 0; W.samp_max[i] = 0; }
+    for (int32_t i = lane; i < AF_L.n_series; i += WARP) { tbl_samp_sum(W)[i] = 0; tbl_samp_max(W)[i] = 0; }
     w_sync();
     W.users_mean = AF_L.users_mean; W.users_sigma = AF_L.users_sigma; W.rate_per_user = AF_L.rate_per_user;
     // sweep overrides of this replica (uniform: every lane applies every column)
@@ -786,15 +791,15 @@ AF_FN void load_params(State& W) {
             case AF_FIELD_USERS_MEAN: W.users_mean = v; break;
             case AF_FIELD_USERS_SIGMA: W.users_sigma = v; break;
             case AF_FIELD_RATE_PER_USER: W.rate_per_user = v; break;
-            case AF_FIELD_EDGE_MEAN: W.edge[col.index].mean = v; break;
-            case AF_FIELD_EDGE_SIGMA: W.edge[col.index].sigma = v; break;
-            case AF_FIELD_EDGE_DROPOUT: W.edge[col.index].dropout = v; break;
-            case AF_FIELD_SERVER_CPU_CORES: W.server[col.index].cpu_free = (int32_t)v; break;
-            case AF_FIELD_SERVER_RAM_MB: W.server[col.index].ram_free = (int32_t)v; break;
-            case AF_FIELD_STEP_DURATION: W.step[col.index].dur = v; break;
-            case AF_FIELD_ENDPOINT_RAM: W.endpoint[col.index].total_ram = (uint32_t)v; break;
+            case AF_FIELD_EDGE_MEAN: tbl_edge(W)[col.index].mean = v; break;
+            case AF_FIELD_EDGE_SIGMA: tbl_edge(W)[col.index].sigma = v; break;
+            case AF_FIELD_EDGE_DROPOUT: tbl_edge(W)[col.index].dropout = v; break;
+            case AF_FIELD_SERVER_CPU_CORES: tbl_server(W)[col.index].cpu_free = (int32_t)v; break;
+            case AF_FIELD_SERVER_RAM_MB: tbl_server(W)[col.index].ram_free = (int32_t)v; break;
+            case AF_FIELD_STEP_DURATION: tbl_step(W)[col.index].dur = v; break;
+            case AF_FIELD_ENDPOINT_RAM: tbl_endpoint(W)[col.index].total_ram = (uint32_t)v; break;
             case AF_FIELD_SPIKE_DELTA:
-                W.spike[col.index].delta = W.spike[col.index].delta < 0.0 ? -v : v; break;
+                tbl_spike(W)[col.index].delta = tbl_spike(W)[col.index].delta < 0.0 ? -v : v; break;
             default: break;
             }
         }
@@ -807,12 +812,12 @@ AF_FN void write_back(State& W) {
     const int lane = lane_id();
     const uint64_t local = W.local;
     for (int32_t i = lane; i < AF_L.n_edges; i += WARP) {
-        AF_G.edge_sent[local * (uint64_t)AF_L.n_edges + (uint32_t)i] = W.edge[i].sent;
-        AF_G.edge_dropped[local * (uint64_t)AF_L.n_edges + (uint32_t)i] = W.edge[i].dropped;
+        AF_G.edge_sent[local * (uint64_t)AF_L.n_edges + (uint32_t)i] = tbl_edge(W)[i].sent;
+        AF_G.edge_dropped[local * (uint64_t)AF_L.n_edges + (uint32_t)i] = tbl_edge(W)[i].dropped;
     }
     for (int32_t j = lane; j < AF_L.n_series; j += WARP) {
-        AF_G.samp_sum[local * (uint64_t)AF_L.n_series + (uint32_t)j] = W.samp_sum[j];
-        AF_G.samp_max[local * (uint64_t)AF_L.n_series + (uint32_t)j] = W.samp_max[j];
+        AF_G.samp_sum[local * (uint64_t)AF_L.n_series + (uint32_t)j] = tbl_samp_sum(W)[j];
+        AF_G.samp_max[local * (uint64_t)AF_L.n_series + (uint32_t)j] = tbl_samp_max(W)[j];
     }
     if (lane == 0) {
         AfReplicaStats st;
@@ -848,10 +853,10 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
     // start order of the reference (simulation_runner.py:339-342, 301-336):
     // spike timeline, outage timeline, generator, ..., collector
     if (AF_L.n_spike > 0) {
-        if (W.spike[0].fire == 0.0) on_spike(W); else push(W, W.spike[0].fire, mk_payload(K_SPIKE, 0, 0));
+        if (tbl_spike(W)[0].fire == 0.0) on_spike(W); else push(W, tbl_spike(W)[0].fire, mk_payload(K_SPIKE, 0, 0));
     }
     if (AF_L.n_outage > 0) {
-        if (W.outage[0].fire == 0.0) on_outage(W); else push(W, W.outage[0].fire, mk_payload(K_OUTAGE, 0, 0));
+        if (tbl_outage(W)[0].fire == 0.0) on_outage(W); else push(W, tbl_outage(W)[0].fire, mk_payload(K_OUTAGE, 0, 0));
     }
     W.arm_seq = W.seq++; W.need_arrival = 1;
     W.tick_seq = W.seq++;

@@ -338,7 +338,9 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     afh::make_layout(e->sc, e->opt, e->sweep_cols, L);
 
     // launch shape: persistent CTAs, as many warps per SM as shared memory allows
+    // the kernel is compiled for CTAs of at most 4 warps (__launch_bounds__(128, AF_MIN_BLOCKS))
     int wpb = e->opt.warps_per_block > 0 ? e->opt.warps_per_block : 4;
+    if (wpb > 4) wpb = 4;
     size_t smem = (size_t)wpb * (size_t)L.warp_bytes;
     while (wpb > 1 && smem > (size_t)e->max_smem_optin) { --wpb; smem = (size_t)wpb * (size_t)L.warp_bytes; }
     if (smem > (size_t)e->max_smem_optin)

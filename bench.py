@@ -79,17 +79,38 @@ def _cpu_one(args):
     return r["completed"], r["heap_events"]
 
 
+_POOL = None
+
+
+def _noop(_):
+    return 0
+
+
+def cpu_pool(cores: int):
+    """A warm process pool (fork + imports are NOT part of what gets timed)."""
+    global _POOL
+    if _POOL is None and cores > 1:
+        import multiprocessing as mp
+        _POOL = mp.get_context("fork").Pool(cores)
+        _POOL.map(_noop, range(cores * 4))
+    return _POOL
+
+
+def cpu_pool_close() -> None:
+    global _POOL
+    if _POOL is not None:
+        _POOL.close()
+        _POOL.join()
+        _POOL = None
+
+
 def cpu_path(payload, replica_ids, total, cores: int):
     """Simulate `replica_ids` with the reference's CPU path on `cores` processes."""
-    import multiprocessing as mp
     rtt, sig = sweep_rows(np.asarray(replica_ids), total)
     jobs = [(payload, SEED, int(r), m, s) for r, m, s in zip(replica_ids, rtt, sig)]
+    pool = cpu_pool(cores)
     t0 = time.perf_counter()
-    if cores > 1:
-        with mp.get_context("fork").Pool(cores) as pool:
-            out = pool.map(_cpu_one, jobs, chunksize=1)
-    else:
-        out = [_cpu_one(j) for j in jobs]
+    out = pool.map(_cpu_one, jobs, chunksize=1) if pool is not None else [_cpu_one(j) for j in jobs]
     dt = time.perf_counter() - t0
     return sum(c for c, _ in out), sum(h for _, h in out), dt
 
@@ -165,7 +186,7 @@ def run_reference(a) -> None:
     cores = os.cpu_count() or 1
     total = a.replicas * a.gpus
     payload = workload(a.replicas, a.horizon)
-    per_step = max(cores, min(2 * cores, 64))
+    per_step = 4 * cores                                  # ~4 replicas per core and step
     ids = spaced(total, per_step * (a.steps + a.warmup))
     chunks = [ids[i::(a.steps + a.warmup)] for i in range(a.steps + a.warmup)]
     for c in chunks[: a.warmup]:
@@ -204,6 +225,8 @@ def run_ours(a) -> None:
     import torch.distributed as dist
 
     from asyncflow_b200 import SweepRunner, flatten
+    from asyncflow_b200._capi import STATS_DTYPE as res_dtype
+    from asyncflow_b200.distributed import all_gather_summary, summary_block
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -227,28 +250,19 @@ def run_ours(a) -> None:
     sw = SweepRunner(flat, a.replicas, cols, seed=SEED, device=local, histogram=True, throughput=False)
     eng = sw.engine()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    summary_dev = torch.zeros(2048 + 4, dtype=torch.int64, device="cuda")
-    gathered = [torch.zeros_like(summary_dev) for _ in range(world)] if world > 1 else None
 
     def launch():
         eng.configure(request_capacity=sw.request_capacity, event_capacity=sw.event_capacity,
                       histogram=True, throughput=False)
         eng.run(SEED, begin, begin + a.replicas)
 
+    empty_stats = np.zeros(0, dtype=res_dtype)
+
     def summarise(res_stats=None):
-        """This rank's summary block; all-gathered over NVLink when world > 1."""
-        hist = eng.reduced_histogram()
-        blk = np.zeros(2048 + 4, dtype=np.int64)
-        blk[:2048] = hist.astype(np.int64)
-        if res_stats is not None:
-            blk[2048] = int(res_stats["completed"].sum())
-            blk[2049] = int(res_stats["generated"].sum())
-            blk[2050] = int(res_stats["n_events"].sum())
-        summary_dev.copy_(torch.from_numpy(blk), non_blocking=False)
-        if world > 1:
-            dist.all_gather(gathered, summary_dev)
-            return torch.stack(gathered).sum(0)
-        return summary_dev
+        """This rank's summary block (device-reduced histogram + totals), all-gathered over
+        NCCL when world > 1 -- the sweep's only collective."""
+        ints, flts = summary_block(empty_stats if res_stats is None else res_stats, eng.reduced_histogram())
+        return all_gather_summary(ints, flts, device="cuda" if world > 1 else None)
 
     def barrier():
         if world > 1:
@@ -266,7 +280,7 @@ def run_ours(a) -> None:
         eng.upload_sweep(sw.spec, begin, row_first=0, row_count=a.replicas)
         launch()
         res = sw.collect(begin)
-        summarise(res.stats)
+        res.global_summary = summarise(res.stats)
         return res
 
     # sweep rows resident for the `value` steps
@@ -327,6 +341,9 @@ def run_ours(a) -> None:
         "events_per_s": events * a.steps / (dev_ms / 1e3),
         "wall_ms_per_step_resident": wall_resident / a.steps * 1e3,
         "replicas_overflowed": overflow,
+        "latency_all_replicas": {"mean_s": res.global_summary.mean_latency, "p50_s": res.global_summary.percentile(50),
+                                 "p95_s": res.global_summary.percentile(95), "p99_s": res.global_summary.percentile(99),
+                                 "source": "merged (all-gathered) histogram"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(sw.spec.values.nbytes),
                 "d2h_bytes_per_step": int(sw.d2h_bytes + (2048 * 8)), "ms_per_step": wall_e2e / a.steps * 1e3},
         "gpu_launches": int(launches),
@@ -339,7 +356,8 @@ def run_ours(a) -> None:
     }
     if world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        k = max(cores, min(3 * cores, 48))
+        k = 8 * cores                                     # ~8 replicas per core: 10-30 s of CPU work
+        cpu_path(payload, spaced(total, cores), total, cores)   # untimed: page in the interpreter state
         n, h, dt = cpu_path(payload, spaced(total, k), total, cores)
         out["cpu_baseline"] = {
             "value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
@@ -362,10 +380,13 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    try:
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_ours(a)
+    finally:
+        cpu_pool_close()
 
 
 if __name__ == "__main__":

@@ -161,7 +161,7 @@ typedef struct AfSweep {
 typedef struct AfOptions {
     int32_t event_capacity;      /* pending timed events per replica (0 = default) */
     int32_t request_capacity;    /* in-flight requests per replica   (0 = default) */
-    int32_t warps_per_block;     /* 0 = default                                    */
+    int32_t warps_per_block;     /* 1..4 (0 = default 4; larger values are clamped) */
     int32_t blocks_per_sm;       /* 0 = as many as fit                             */
     int32_t collect_histogram;   /* latency histogram per replica (AF_HIST_BINS)   */
     int32_t collect_throughput;  /* completions per 1-s bucket per replica         */

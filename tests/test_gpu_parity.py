@@ -71,7 +71,7 @@ def test_results_do_not_depend_on_batching_or_launch_shape(eng):
     eng.run(SEED, 100, 400)
     a = eng.stats().copy()
     a_sent, a_drop = eng.edge_counts()
-    for wpb, bps in ((1, 1), (8, 0), (3, 2)):
+    for wpb, bps in ((1, 1), (8, 0), (3, 2), (2, 5)):
         eng.configure(warps_per_block=wpb, blocks_per_sm=bps)
         eng.run(SEED, 100, 400)
         b = eng.stats()

@@ -48,7 +48,7 @@ def lib() -> C.CDLL:
     return _lib
 
 
-def run(flat, *, seed: int, replica_begin: int = 0, n: int = 1, sweep=None, trace: int = 0,
+def run(flat, *, seed: int, replica_begin: int = 0, n: int = 1, sweep=None, sweep_first: int = 0, trace: int = 0,
         clock_cap: int = 0, event_capacity: int = 0, request_capacity: int = 0) -> dict:
     L = lib()
     opt = K.AfOptions(event_capacity, request_capacity, 0, 0, 1, 1, trace, clock_cap)
@@ -69,9 +69,10 @@ def run(flat, *, seed: int, replica_begin: int = 0, n: int = 1, sweep=None, trac
     }
     sw_p, keep = None, None
     if sweep is not None:
-        sw, keep = sweep.pod(0, None)
+        # rows [sweep_first, end) of the table describe replicas sweep_first, sweep_first+1, ...
+        sw, keep = sweep.pod(sweep_first, None)
         sw_p = C.byref(sw)
-    rc = L.af_twin_run(C.byref(flat.pod), sw_p, 0, C.byref(opt), seed, replica_begin, n,
+    rc = L.af_twin_run(C.byref(flat.pod), sw_p, sweep_first, C.byref(opt), seed, replica_begin, n,
                        *[out[k].ctypes.data for k in ("stats", "sent", "dropped", "hist", "thr",
                                                       "samp_sum", "samp_max", "trace_clocks",
                                                       "trace_series", "trace_counts")])
