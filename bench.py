@@ -172,7 +172,8 @@ def profiled_traffic(config_key: str):
     if p.exists():
         try:
             d = json.loads(p.read_text())
-            return d.get(config_key)
+            entry = d.get(config_key)
+            return None if entry is None else entry.get("dram_bytes_per_launch")
         except ValueError:
             return None
     return None
