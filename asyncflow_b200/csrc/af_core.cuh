@@ -24,11 +24,20 @@
 //   take_samples       metrics/collector.py:50-66
 //   complete           client.py:62-69 + metrics/analyzer.py:83-125
 //
-// Ordering rule: events pop by (time, seq); seq is the per-replica push counter,
-// the analogue of SimPy's eid.  Ticks of the sampled-metric collector are not
-// queued: state is piecewise constant between events, so the samples that fall
-// before an event are emitted lazily just before it (they carry a seq too, so
-// ties are ordered as SimPy would).
+// Ordering rule (DESIGN.md "tie rule").  SimPy orders by (time, priority, eid).  Timed
+// events live in the pending-event pool and pop by (time, seq), seq being the per-replica
+// scheduling counter (SimPy's eid).  Step durations are deterministic, so different
+// requests DO reach the same instant (e.g. 3 ms CPU + 8 ms IO + 1 ms CPU == 12 ms IO), and
+// what happens at such an instant depends on SimPy's zero-delay events: a Store put, a
+// Container get/put or a process resume is itself an event that is queued BEHIND everything
+// already scheduled for that instant.  The engine therefore keeps a small FIFO of zero-delay
+// continuation items (the "now-queue": I_PUT, I_GOT, I_CLIENT_LOOP, I_RAM_OK, I_CPU_OK,
+// I_CPU_PUT, I_RAM_PUT -- one per SimPy event that carries an observable effect), each with
+// its own seq, and always runs the smallest seq among {now-queue front, pool events of the
+// current instant}.  URGENT events (process Initialize) run at the end of the item that
+// created them, as in SimPy.  Collector ticks are not queued: state is piecewise constant
+// between timed events, so the samples that fall before an event are emitted lazily just
+// before it (they carry a seq too).
 //
 // Execution model: ALL 32 lanes of the warp run this code redundantly on the
 // same replica (warp-uniform control flow, identical values in every lane).
@@ -74,6 +83,14 @@
 #define AF_SHARED(p) ((void)0)
 #endif
 
+// Host-twin debugging aid: compile the twin with -DAF_TRACE_HOST to log every handled event.
+#if defined(AF_TRACE_HOST) && !AF_DEVICE_CODE
+#include <stdio.h>
+#define AF_TRACE(...) fprintf(stderr, __VA_ARGS__)
+#else
+#define AF_TRACE(...) ((void)0)
+#endif
+
 namespace afc {
 
 constexpr uint32_t NIL = 0xFFFFFFFFu;
@@ -101,10 +118,11 @@ struct EdgeS {            // 48 B
     uint32_t meta;        // dist[0:3) | target_kind[3:5) | target_index[5:)
     uint32_t conn, sent, dropped;
 };
-struct ServerS {          // 48 B
+struct ServerS {          // 64 B
     int32_t cpu_free, ram_free, ready_q, io_q, ram_in_use;
     uint32_t ramq_head, ramq_tail, cpuq_head, cpuq_tail;
     uint32_t out_edge, ep_begin, n_ep;
+    uint32_t inbox_head, inbox_tail, get_pending, pad;   // the server's Store + its dispatcher's pending get()
 };
 struct EndpointS { uint32_t step_begin, n_steps, total_ram, pad; }; // 16 B
 struct StepS { double dur; uint32_t kind, pad; };                   // 16 B
@@ -123,6 +141,10 @@ struct State {
     uint32_t seq;
     int32_t ev_hw, ev_live, ev_last_free, ev_hole;
     uint32_t peak_ev;
+    // zero-delay continuation FIFO (ring of NQ_CAP items) + "the pool may hold an event of this instant"
+    uint32_t nq_head, nq_tail, tie_now;
+    // Stores of the client and the load balancer (servers keep theirs in ServerS)
+    uint32_t cl_head, cl_tail, cl_pending, lb_head, lb_tail, lb_pending;
     // request table
     uint32_t rq_free, rq_hw, rq_live, peak_rq;
     // generator (two clocks: the sampler's virtual one and the simulation's)
@@ -156,9 +178,11 @@ struct Layout {
     int32_t trace_replicas, trace_clock_cap, trace_tick_cap;
     // byte offsets inside the per-warp workspace
     int32_t off_ev_time, off_ev_key, off_rq_rec, off_rq_next, off_edge, off_server,
-            off_endpoint, off_step, off_lb, off_spike, off_outage, off_samp_sum, off_samp_max;
+            off_endpoint, off_step, off_lb, off_spike, off_outage, off_samp_sum, off_samp_max, off_nq;
     int32_t warp_bytes;
 };
+
+constexpr int32_t NQ_CAP = 64;   // now-queue capacity (power of two)
 
 AF_IN int32_t align_up(int32_t x, int32_t a) { return (x + a - 1) / a * a; }
 
@@ -166,9 +190,10 @@ inline void layout_finalize(Layout& L) {
     int32_t o = align_up((int32_t)sizeof(State), 16);
     L.off_ev_time = o;  o += 8 * L.ev_smem;
     L.off_ev_key = o;   o += 8 * L.ev_smem;
+    L.off_nq = o;       o += 8 * NQ_CAP;
     L.off_rq_rec = o;   o += 16 * L.rq_smem;
     L.off_edge = o;     o += 48 * L.n_edges;
-    L.off_server = o;   o += 48 * L.n_servers;
+    L.off_server = o;   o += 64 * L.n_servers;
     L.off_endpoint = o; o += 16 * L.n_endpoints;
     L.off_step = o;     o += 16 * L.n_steps;
     L.off_spike = o;    o += 24 * L.n_spike;
@@ -230,6 +255,7 @@ AF_TBL(tbl_spike, SpikeS, off_spike)
 AF_TBL(tbl_outage, OutageS, off_outage)
 AF_TBL(tbl_samp_sum, uint64_t, off_samp_sum)
 AF_TBL(tbl_samp_max, uint32_t, off_samp_max)
+AF_TBL(tbl_nq, uint64_t, off_nq)
 
 // ---- warp primitives (a warp of ONE lane on the host) ------------------------
 #if AF_DEVICE_CODE
@@ -311,6 +337,7 @@ AF_IN uint32_t fifo_pop(State& W, uint32_t& head, uint32_t& tail) {
 AF_FN void push_seq(State& W, double t, uint32_t payload, uint32_t s) {
     AF_SHARED(&W);
     if (!(t < W.horizon)) return;       // env.run(until=T): events at >= T never fire
+    if (t == W.now) W.tie_now = 1;      // a zero-delay timeout: it competes with the now-queue
     int32_t slot;
     if (W.ev_last_free >= 0) { slot = W.ev_last_free; W.ev_last_free = -1; }
     else if (W.ev_hole >= 0) { slot = W.ev_hole; W.ev_hole = -1; }
@@ -327,8 +354,10 @@ AF_FN void push_seq(State& W, double t, uint32_t payload, uint32_t s) {
 }
 AF_IN void push(State& W, double t, uint32_t payload) { push_seq(W, t, payload, W.seq++); }
 
-// pop the (time, seq)-minimum; false when the pool is empty (single call site)
-AF_IN bool pop(State& W, double& t, uint32_t& payload, uint32_t& ev_seq) {
+// The (time, seq)-minimum of the pool, without removing it.  `more` = at least one other
+// event carries the same time.  False when the pool is empty.  (single call site)
+struct PoolMin { uint64_t tbits, key; int32_t slot, hole; bool more; };
+AF_IN bool pool_scan(State& W, PoolMin& m) {
     if (W.ev_live == 0) return false;
     const int lane = lane_id();
     const int32_t hw = W.ev_hw;
@@ -346,7 +375,8 @@ AF_IN bool pop(State& W, double& t, uint32_t& payload, uint32_t& ev_seq) {
     uint32_t mlo = w_min(cand ? lo : 0xFFFFFFFFu);
     cand = cand && lo == mlo;
     uint32_t b = w_ballot(cand);
-    if (__popc(b) > 1) {              // equal times: the earlier push wins (SimPy eid order)
+    bool more = __popc(b) > 1;
+    if (more) {                       // equal times: the earlier push wins (SimPy eid order)
         uint32_t sq = (uint32_t)(bk >> 32);
         uint32_t msq = w_min(cand ? sq : 0xFFFFFFFFu);
         cand = cand && sq == msq;
@@ -354,24 +384,44 @@ AF_IN bool pop(State& W, double& t, uint32_t& payload, uint32_t& ev_seq) {
     }
     int owner = __ffs((int)b) - 1;
     uint32_t k_hi = w_shfl((uint32_t)(bk >> 32), owner), k_lo = w_shfl((uint32_t)bk, owner);
-    int32_t slot = (int32_t)w_shfl((uint32_t)bi, owner);
-    bt = ((uint64_t)mhi << 32) | mlo;
-    bk = ((uint64_t)k_hi << 32) | k_lo;
-    hole = (int32_t)w_min((uint32_t)hole);
+    m.slot = (int32_t)w_shfl((uint32_t)bi, owner);
+    m.tbits = ((uint64_t)mhi << 32) | mlo;
+    m.key = ((uint64_t)k_hi << 32) | k_lo;
+    m.hole = (int32_t)w_min((uint32_t)hole);
+    if (!more && hw > WARP) {
+        // a lane holding several slots may hide a second event of the same instant
+        bool dup = false;
+        for (int32_t k = lane; k < hw; k += WARP) dup = dup || (k != m.slot && evt_load(W, k) == m.tbits);
+        more = w_ballot(dup) != 0;
+    }
+    m.more = more;
 #else
-    int32_t slot = bi;
+    m.slot = bi; m.tbits = bt; m.key = bk; m.hole = hole;
+    bool more = false;
+    for (int32_t k = 0; k < hw; ++k) more = more || (k != bi && evt_load(W, k) == bt);
+    m.more = more;
 #endif
+    return true;
+}
+AF_IN void pool_remove(State& W, const PoolMin& m) {
+    const int32_t hw = W.ev_hw, slot = m.slot;
     if (slot < AF_L.ev_smem) tbl_ev_time(W)[slot] = afr::u2d(INF_BITS);
     else W.sp_ev_time[slot - AF_L.ev_smem] = afr::u2d(INF_BITS);
     W.ev_live -= 1;
     int32_t nhw = hw;
     if (slot == hw - 1) { nhw = hw - 1; W.ev_hw = nhw; W.ev_last_free = -1; }
     else W.ev_last_free = slot;
-    W.ev_hole = hole < nhw ? hole : -1;
-    t = afr::u2d(bt);
-    payload = (uint32_t)bk;
-    ev_seq = (uint32_t)(bk >> 32);
-    return true;
+    W.ev_hole = m.hole < nhw ? m.hole : -1;
+}
+
+// ---- now-queue: FIFO of zero-delay continuation items (seq << 32 | kind:3 aux:9 slot:20) ----
+enum : uint32_t { I_PUT = 0, I_GOT = 1, I_CLIENT_LOOP = 2, I_RAM_OK = 3, I_CPU_OK = 4, I_CPU_PUT = 5, I_RAM_PUT = 6 };
+constexpr uint32_t NODE_CLIENT = 0, NODE_LB = 1, NODE_SERVER0 = 2;   // `aux` of I_PUT / I_GOT
+AF_IN void nq_push(State& W, uint32_t kind, uint32_t aux, uint32_t slot) {
+    uint32_t tail = W.nq_tail;
+    if (tail - W.nq_head >= (uint32_t)NQ_CAP) { W.flags |= AF_FLAG_EVENT_OVERFLOW; return; }
+    tbl_nq(W)[tail & (NQ_CAP - 1)] = ((uint64_t)(W.seq++) << 32) | mk_payload(kind, aux, slot);
+    W.nq_tail = tail + 1;
 }
 
 // ---------------------------------------------------------------------------------
@@ -416,12 +466,13 @@ AF_IN void arm_generator(State& W) {
 }
 
 // ---------------------------------------------------------------------------------
-// edges: EdgeRuntime._deliver up to the timeout (edge.py:73-107)
+// edges: EdgeRuntime.transport -> Initialize (URGENT) -> _deliver up to its timeout
+// (edge.py:73-107).  Called at the END of the item that called transport().
 // ---------------------------------------------------------------------------------
 AF_FN void edge_send(State& W, uint32_t slot, uint32_t e, uint32_t rid, uint32_t hops) {
     AF_SHARED(&W);
     EdgeS& E = tbl_edge(W)[e];
-    uint32_t s = W.seq++;                            // SimPy schedules the timeout here
+    uint32_t s = W.seq++;                            // the timeout's place in SimPy's eid order
     const double dropout = E.dropout;
     afr::EdgeDraw d = afr::edge_draw(AF_G.seed, W.replica, rid, hops, (int)(E.meta & 7u), E.mean, E.sigma, dropout);
     E.sent += 1;
@@ -436,126 +487,135 @@ AF_FN void edge_send(State& W, uint32_t slot, uint32_t e, uint32_t rid, uint32_t
 }
 
 // ---------------------------------------------------------------------------------
-// server
+// Stores (mailboxes).  Store.put appends at once and schedules the put event (I_PUT); the
+// consumer's pending get() is served when THAT event is processed (-> I_GOT); a consumer
+// that calls get() on a non-empty store is served at once (-> I_GOT).   SURVEY.md App. A
 // ---------------------------------------------------------------------------------
-// Container.put(1) processed -> head of the CPU get-queue resumes (server.py:222-231)
-AF_FN void grant_cpu_waiter(State& W, uint32_t sidx) {
-    AF_SHARED(&W);
-    ServerS& S = tbl_server(W)[sidx];
-    if (S.cpuq_head == NIL) return;
-    uint32_t w = fifo_pop(W, S.cpuq_head, S.cpuq_tail);
-    S.cpu_free -= 1;
-    S.ready_q -= 1;
-    ReqRec r = rq_load(W, w);
-    r.pack |= PK_CORE;
-    rq_set_pack(W, w, r.pack);
-    const EndpointS ep = tbl_endpoint(W)[pk_ep(r.pack)];
-    push(W, W.now + tbl_step(W)[ep.step_begin + pk_step(r.pack)].dur, mk_payload(K_STEP_END, sidx, w));
+struct Inbox { uint32_t* head; uint32_t* tail; uint32_t* pending; };
+AF_IN Inbox inbox_of(State& W, uint32_t node) {
+    if (node == NODE_CLIENT) return Inbox{&W.cl_head, &W.cl_tail, &W.cl_pending};
+    if (node == NODE_LB) return Inbox{&W.lb_head, &W.lb_tail, &W.lb_pending};
+    ServerS& S = tbl_server(W)[node - NODE_SERVER0];
+    return Inbox{&S.inbox_head, &S.inbox_tail, &S.get_pending};
+}
+// `yield box.get()` of the node's consumer process
+AF_IN void consumer_get(State& W, uint32_t node) {
+    Inbox b = inbox_of(W, node);
+    if (*b.head != NIL) { uint32_t it = fifo_pop(W, *b.head, *b.tail); nq_push(W, I_GOT, node, it); }
+    else *b.pending = 1;
 }
 
-// the `for step in selected_endpoint.steps` loop from the current step (server.py:197-255).
-// Returns the updated pack, with bit 31 set when no step is left (caller then finishes).
-constexpr uint32_t PK_DONE = 1u << 31;
-AF_FN uint32_t run_steps(State& W, uint32_t slot, uint32_t sidx, uint32_t pack) {
+// ---------------------------------------------------------------------------------
+// server: Container semantics (FIFO, head-of-line blocking; level changes at CALL time,
+// waiters are woken when the put/get EVENT is processed or a new request walks the queue)
+// ---------------------------------------------------------------------------------
+// Container._trigger_get over the CPU queue: grant heads while a core is free
+// (returns true when `watch` was among the granted: its get is "triggered" at the call)
+AF_IN bool cpu_walk(State& W, ServerS& S, uint32_t sidx, uint32_t watch) {
+    bool hit = false;
+    while (S.cpuq_head != NIL && S.cpu_free > 0) {
+        uint32_t w = fifo_pop(W, S.cpuq_head, S.cpuq_tail);
+        S.cpu_free -= 1;
+        hit = hit || w == watch;
+        nq_push(W, I_CPU_OK, sidx, w);
+    }
+    return hit;
+}
+// ... over the RAM queue: grant heads while they fit, stop at the first that does not
+AF_IN void ram_walk(State& W, ServerS& S, uint32_t sidx) {
+    while (S.ramq_head != NIL) {
+        uint32_t w = S.ramq_head;
+        uint32_t need = tbl_endpoint(W)[pk_ep(rq_load(W, w).pack)].total_ram;
+        if ((int32_t)need > S.ram_free) break;
+        fifo_pop(W, S.ramq_head, S.ramq_tail);
+        S.ram_free -= (int32_t)need;
+        nq_push(W, I_RAM_OK, sidx, w);
+    }
+}
+
+constexpr uint32_t PK_WAIT = 1u << 30;   // the request sits in the ready queue (server.py:215-217)
+
+// The `for step in selected_endpoint.steps` loop (server.py:197-255) from the request's current
+// step up to its next yield, and the tail of the handler (server.py:257-276).
+AF_FN void run_steps(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, uint32_t pack) {
     AF_SHARED(&W);
     ServerS& S = tbl_server(W)[sidx];
     const EndpointS ep = tbl_endpoint(W)[pk_ep(pack)];
-    uint32_t st = pk_step(pack);
-    if (st >= ep.n_steps) return pack | PK_DONE;
-    const StepS sp = tbl_step(W)[ep.step_begin + st];
-    if (sp.kind == AF_STEP_CPU) {
-        if (pack & PK_IO) { pack &= ~PK_IO; S.io_q -= 1; }
-        if (!(pack & PK_CORE)) {
-            if (S.cpu_free > 0) { S.cpu_free -= 1; pack |= PK_CORE; }
-            else {                                  // cpu_req not triggered -> ready queue
-                S.ready_q += 1;
-                rq_set_pack(W, slot, pack);
+    const uint32_t st = pk_step(pack);
+    if (st < ep.n_steps) {
+        const StepS sp = tbl_step(W)[ep.step_begin + st];
+        if (sp.kind == AF_STEP_CPU) {
+            if (pack & PK_IO) { pack &= ~PK_IO; S.io_q -= 1; }
+            if (!(pack & PK_CORE)) {                 // cpu_req = CPU.get(1); yield cpu_req
                 fifo_push(W, S.cpuq_head, S.cpuq_tail, slot);
-                return pack;
+                if (!cpu_walk(W, S, sidx, slot)) { pack |= PK_WAIT; S.ready_q += 1; }   // not cpu_req.triggered
+                rq_set_pack(W, slot, pack);
+                return;
             }
+            rq_set_pack(W, slot, pack);
+            push(W, W.now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
+        } else {
+            if (pack & PK_CORE) {                    // yield CPU.put(1): level rises NOW
+                S.cpu_free += 1;
+                rq_set_pack(W, slot, pack);
+                nq_push(W, I_CPU_PUT, sidx, slot);
+                return;
+            }
+            if (!(pack & PK_IO)) { pack |= PK_IO; S.io_q += 1; }
+            rq_set_pack(W, slot, pack);
+            push(W, W.now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
         }
-        rq_set_pack(W, slot, pack);
-        push(W, W.now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
-    } else {
-        bool release = (pack & PK_CORE) != 0;
-        if (release) { pack &= ~PK_CORE; S.cpu_free += 1; }
-        if (!(pack & PK_IO)) { pack |= PK_IO; S.io_q += 1; }
-        rq_set_pack(W, slot, pack);
-        // SimPy order: the releasing request schedules its IO timeout before the
-        // woken waiter schedules its CPU timeout (see DESIGN.md "tie rule")
-        push(W, W.now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
-        if (release) grant_cpu_waiter(W, sidx);
+        return;
     }
-    return pack;
-}
-
-// server.py:257-276
-AF_FN void finish_request(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, uint32_t pack) {
-    AF_SHARED(&W);
-    ServerS& S = tbl_server(W)[sidx];
-    pack &= ~PK_DONE;
-    const uint32_t total_ram = tbl_endpoint(W)[pk_ep(pack)].total_ram;
-    // SimPy order of the pushes that follow a release (DESIGN.md "tie rule"):
-    //   core + RAM : woken CPU waiter, then this request's edge, then RAM waiters
-    //   core only  : this request's edge (Initialize is URGENT), then the CPU waiter
-    bool had_core = (pack & PK_CORE) != 0;
-    if (had_core) { pack &= ~PK_CORE; S.cpu_free += 1; }
-    if (had_core && total_ram) grant_cpu_waiter(W, sidx);
+    // end of the endpoint
+    if (pack & PK_CORE) {                            // yield CPU.put(1)
+        S.cpu_free += 1;
+        rq_set_pack(W, slot, pack);
+        nq_push(W, I_CPU_PUT, sidx, slot);
+        return;
+    }
     if (pack & PK_IO) { pack &= ~PK_IO; S.io_q -= 1; }
-    if (total_ram) {
-        S.ram_in_use -= (int32_t)total_ram;
-        S.ram_free += (int32_t)total_ram;
-    }
     rq_set_pack(W, slot, pack);
-    edge_send(W, slot, S.out_edge, rid, pk_hops(pack));
-    if (had_core && !total_ram) grant_cpu_waiter(W, sidx);
-    if (total_ram) {
-        // Container FIFO with head-of-line blocking
-        while (S.ramq_head != NIL) {
-            uint32_t w = S.ramq_head;
-            ReqRec wr = rq_load(W, w);
-            uint32_t need = tbl_endpoint(W)[pk_ep(wr.pack)].total_ram;
-            if ((int32_t)need > S.ram_free) break;
-            fifo_pop(W, S.ramq_head, S.ramq_tail);
-            S.ram_free -= (int32_t)need;
-            S.ram_in_use += (int32_t)need;
-            uint32_t np = run_steps(W, w, sidx, wr.pack);
-            if (np & PK_DONE) {
-                // an endpoint made of RAM steps only: it gives the memory straight back
-                S.ram_in_use -= (int32_t)need;
-                S.ram_free += (int32_t)need;
-                edge_send(W, w, S.out_edge, wr.rid, pk_hops(np));
-            }
-        }
+    if (ep.total_ram) {                              // yield RAM.put(total_ram): level rises NOW
+        S.ram_in_use -= (int32_t)ep.total_ram;
+        S.ram_free += (int32_t)ep.total_ram;
+        nq_push(W, I_RAM_PUT, sidx, slot);
+        return;
     }
+    edge_send(W, slot, S.out_edge, rid, pk_hops(pack));
 }
 
-// ServerRuntime._dispatcher + head of _handle_request (server.py:88-149, 303-313)
-AF_IN void server_arrive(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, uint32_t pack) {
+// the CPU.put(1) event of `slot` is processed: waiters are re-examined, then the request goes on
+AF_IN void on_cpu_put(State& W, uint32_t slot, uint32_t sidx) {
     ServerS& S = tbl_server(W)[sidx];
-    pack += 1;                                       // record_hop(SERVER)
+    cpu_walk(W, S, sidx, NIL);
+    ReqRec r = rq_load(W, slot);
+    run_steps(W, slot, sidx, r.rid, r.pack & ~PK_CORE);   // core_locked = False; same step again
+}
+
+// ServerRuntime._dispatcher resumed with `slot` (server.py:303-313), then the head of
+// _handle_request (server.py:88-149), which runs as an URGENT Initialize right after
+AF_IN void server_got(State& W, uint32_t slot, uint32_t sidx) {
+    consumer_get(W, NODE_SERVER0 + sidx);            // the dispatcher loops back to get() first
+    ServerS& S = tbl_server(W)[sidx];
+    ReqRec r = rq_load(W, slot);
+    uint32_t pack = r.pack + 1;                      // record_hop(SERVER)
     uint32_t epi = 0;
     const uint32_t n_ep = S.n_ep;
     if (n_ep > 1) {
-        afr::Src s = afr::make_request(AF_G.seed, W.replica, afr::P_SERVER, rid, pk_hops(pack));
-        s.load(0);
-        epi = (uint32_t)(((uint64_t)s.w.x * n_ep) >> 32);
+        afr::Src src = afr::make_request(AF_G.seed, W.replica, afr::P_SERVER, r.rid, pk_hops(pack));
+        src.load(0);
+        epi = (uint32_t)(((uint64_t)src.w.x * n_ep) >> 32);
     }
-    uint32_t ep_global = S.ep_begin + epi;
+    const uint32_t ep_global = S.ep_begin + epi;
     pack = (pack & 0xFFu) | (ep_global << 16);       // step 0, flags clear
     rq_set_pack(W, slot, pack);
-    uint32_t total_ram = tbl_endpoint(W)[ep_global].total_ram;
-    if (total_ram) {
-        if (S.ramq_head == NIL && (int32_t)total_ram <= S.ram_free) {
-            S.ram_free -= (int32_t)total_ram;
-            S.ram_in_use += (int32_t)total_ram;
-        } else {
-            fifo_push(W, S.ramq_head, S.ramq_tail, slot);
-            return;
-        }
+    if (tbl_endpoint(W)[ep_global].total_ram) {      // yield RAM.get(total_ram)
+        fifo_push(W, S.ramq_head, S.ramq_tail, slot);
+        ram_walk(W, S, sidx);
+        return;
     }
-    uint32_t np = run_steps(W, slot, sidx, pack);
-    if (np & PK_DONE) finish_request(W, slot, sidx, rid, np);
+    run_steps(W, slot, sidx, r.rid, pack);
 }
 
 // ---------------------------------------------------------------------------------
@@ -595,45 +655,85 @@ AF_IN void complete(State& W, uint32_t slot, double t0) {
 }
 
 // ---------------------------------------------------------------------------------
-// deliveries: edge.py:110-116, then the target node's forwarder
+// one zero-delay item (single call site in run_replica)
 // ---------------------------------------------------------------------------------
+AF_IN void run_item(State& W, uint32_t item) {
+    const uint32_t kind = item >> 29, aux = (item >> SLOT_BITS) & AUX_MASK, slot = item & SLOT_MASK;
+    AF_TRACE("it t=%.17g kind=%u aux=%u slot=%u\n", W.now, kind, aux, slot);
+    if (kind == I_PUT) {                             // a StorePut event is processed
+        Inbox b = inbox_of(W, aux);
+        if (*b.pending) { *b.pending = 0; nq_push(W, I_GOT, aux, fifo_pop(W, *b.head, *b.tail)); }
+    } else if (kind == I_GOT) {                      // the node's consumer resumes with `slot`
+        if (aux >= NODE_SERVER0) { server_got(W, slot, aux - NODE_SERVER0); return; }
+        ReqRec r = rq_load(W, slot);
+        r.pack += 1;                                 // record_hop(client / LB)
+        if (aux == NODE_CLIENT) {
+            if (pk_hops(r.pack) > 3) {               // client.py:62: back from the servers
+                complete(W, slot, r.t0);
+                nq_push(W, I_CLIENT_LOOP, 0, 0);     // yield completed_box.put(state)
+                return;
+            }
+            rq_set_pack(W, slot, r.pack);
+            consumer_get(W, NODE_CLIENT);
+            edge_send(W, slot, (uint32_t)AF_L.client_edge, r.rid, pk_hops(r.pack));
+        } else {
+            rq_set_pack(W, slot, r.pack);
+            uint32_t* lb = tbl_lb(W);
+            const int32_t n = W.lb_n;
+            uint32_t pick = lb[0];
+            if (AF_L.lb_algo == AF_LB_ROUND_ROBIN) { // lb_algorithms.py:22-36
+                for (int32_t i = 1; i < n; ++i) lb[i - 1] = lb[i];
+                lb[n - 1] = pick;
+            } else {                                 // least_connections, :10-20 (first min wins)
+                uint32_t best = tbl_edge(W)[pick].conn;
+                for (int32_t i = 1; i < n; ++i) {
+                    uint32_t c = tbl_edge(W)[lb[i]].conn;
+                    if (c < best) { best = c; pick = lb[i]; }
+                }
+            }
+            consumer_get(W, NODE_LB);
+            edge_send(W, slot, pick, r.rid, pk_hops(r.pack));
+        }
+    } else if (kind == I_CLIENT_LOOP) {
+        consumer_get(W, NODE_CLIENT);
+    } else if (kind == I_RAM_OK) {                   // the RAM get event is processed: the handler resumes
+        ServerS& S = tbl_server(W)[aux];
+        ReqRec r = rq_load(W, slot);
+        S.ram_in_use += (int32_t)tbl_endpoint(W)[pk_ep(r.pack)].total_ram;
+        run_steps(W, slot, aux, r.rid, r.pack);
+    } else if (kind == I_CPU_OK) {                   // the CPU get event is processed
+        ServerS& S = tbl_server(W)[aux];
+        ReqRec r = rq_load(W, slot);
+        if (r.pack & PK_WAIT) { r.pack &= ~PK_WAIT; S.ready_q -= 1; }
+        run_steps(W, slot, aux, r.rid, r.pack | PK_CORE);
+    } else if (kind == I_CPU_PUT) {
+        on_cpu_put(W, slot, aux);
+    } else {                                         // I_RAM_PUT: waiters first, then forward
+        ServerS& S = tbl_server(W)[aux];
+        ram_walk(W, S, aux);
+        ReqRec r = rq_load(W, slot);
+        edge_send(W, slot, S.out_edge, r.rid, pk_hops(r.pack));
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// timed events
+// ---------------------------------------------------------------------------------
+// edge.py:110-116: the edge's timeout fired
 AF_IN void on_deliver(State& W, uint32_t slot, uint32_t e) {
     EdgeS& E = tbl_edge(W)[e];
     E.conn -= 1;
     const uint32_t meta = E.meta;
     ReqRec r = rq_load(W, slot);
-    r.pack += 1;                                     // record_hop(edge)
-    uint32_t tk = (meta >> 3) & 3u;
-    if (tk == AF_TARGET_CLIENT) {
-        r.pack += 1;                                 // record_hop(client)
-        if (pk_hops(r.pack) > 3) { complete(W, slot, r.t0); return; }   // client.py:62
-        rq_set_pack(W, slot, r.pack);
-        edge_send(W, slot, (uint32_t)AF_L.client_edge, r.rid, pk_hops(r.pack));
-    } else if (tk == AF_TARGET_LB) {
-        r.pack += 1;                                 // record_hop(LB)
-        rq_set_pack(W, slot, r.pack);
-        uint32_t* lb = tbl_lb(W);
-        const int32_t n = W.lb_n;
-        uint32_t pick = lb[0];
-        if (AF_L.lb_algo == AF_LB_ROUND_ROBIN) {     // lb_algorithms.py:22-36
-            for (int32_t i = 1; i < n; ++i) lb[i - 1] = lb[i];
-            lb[n - 1] = pick;
-        } else {                                     // least_connections, :10-20 (first min wins)
-            uint32_t best = tbl_edge(W)[pick].conn;
-            for (int32_t i = 1; i < n; ++i) {
-                uint32_t c = tbl_edge(W)[lb[i]].conn;
-                if (c < best) { best = c; pick = lb[i]; }
-            }
-        }
-        edge_send(W, slot, pick, r.rid, pk_hops(r.pack));
-    } else {
-        server_arrive(W, slot, meta >> 5, r.rid, r.pack);
-    }
+    rq_set_pack(W, slot, r.pack + 1);                // record_hop(edge)
+    const uint32_t tk = (meta >> 3) & 3u;
+    const uint32_t node = tk == AF_TARGET_CLIENT ? NODE_CLIENT : (tk == AF_TARGET_LB ? NODE_LB : NODE_SERVER0 + (meta >> 5));
+    Inbox b = inbox_of(W, node);
+    fifo_push(W, *b.head, *b.tail, slot);            // Store.put: items.append now ...
+    nq_push(W, I_PUT, node, slot);                   // ... the put event is processed later
 }
 
-// ---------------------------------------------------------------------------------
-// arrivals (rqs_generator.py:97-119)
-// ---------------------------------------------------------------------------------
+// rqs_generator.py:97-119
 AF_IN void on_arrival(State& W) {
     const uint32_t rid = ++W.generated;
     uint32_t slot = rq_alloc(W);
@@ -753,6 +853,7 @@ AF_FN void load_params(State& W) {
         s.cpu_free = a.cpu_cores; s.ram_free = a.ram_mb; s.ready_q = 0; s.io_q = 0; s.ram_in_use = 0;
         s.ramq_head = s.ramq_tail = s.cpuq_head = s.cpuq_tail = NIL;
         s.out_edge = (uint32_t)a.out_edge; s.ep_begin = (uint32_t)a.endpoint_begin; s.n_ep = (uint32_t)a.n_endpoints;
+        s.inbox_head = s.inbox_tail = NIL; s.get_pending = 1; s.pad = 0;
         tbl_server(W)[i] = s;
     }
     for (int32_t i = lane; i < AF_L.n_endpoints; i += WARP) {
@@ -840,6 +941,8 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
     W.replica = AF_G.replica_begin + local_index;
     W.now = 0.0; W.horizon = (double)AF_L.horizon_s; W.seq = 0;
     W.ev_hw = 0; W.ev_live = 0; W.ev_last_free = -1; W.ev_hole = -1; W.peak_ev = 0;
+    W.nq_head = 0; W.nq_tail = 0; W.tie_now = 0;
+    W.cl_head = W.cl_tail = NIL; W.cl_pending = 1; W.lb_head = W.lb_tail = NIL; W.lb_pending = 1;
     W.rq_free = NIL; W.rq_hw = 0; W.rq_live = 0; W.peak_rq = 0;
     W.g_vnow = 0.0; W.g_window_end = 0.0; W.g_lam = 0.0; W.g_pos = 0; W.generated = 0; W.g_done = 0;
     W.lb_n = AF_L.n_lb_edges;
@@ -863,10 +966,33 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
     W.tick_time = 0.0 + AF_L.sample_period;
 
     uint64_t n_events = 0;
-    double t; uint32_t payload, ev_seq;
     for (;;) {
         if (W.need_arrival) arm_generator(W);
-        if (!pop(W, t, payload, ev_seq)) break;
+        const bool have_item = W.nq_head != W.nq_tail;
+        if (have_item && !W.tie_now) {               // fast path: nothing else lives at this instant
+            uint32_t item = (uint32_t)tbl_nq(W)[W.nq_head & (NQ_CAP - 1)];
+            W.nq_head += 1;
+            run_item(W, item);
+            if (W.flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW)) break;
+            continue;
+        }
+        PoolMin m;
+        const bool have_ev = pool_scan(W, m);
+        if (have_item) {
+            const uint64_t front = tbl_nq(W)[W.nq_head & (NQ_CAP - 1)];
+            const bool same_t = have_ev && m.tbits == afr::d2u(W.now);
+            if (!(same_t && (uint32_t)(m.key >> 32) < (uint32_t)(front >> 32))) {
+                if (!same_t) W.tie_now = 0;
+                W.nq_head += 1;
+                run_item(W, (uint32_t)front);
+                if (W.flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW)) break;
+                continue;
+            }
+        } else if (!have_ev) break;
+        pool_remove(W, m);
+        const double t = afr::u2d(m.tbits);
+        const uint32_t payload = (uint32_t)m.key, ev_seq = (uint32_t)(m.key >> 32);
+        W.tie_now = m.more ? 1u : 0u;
         {
             const double tick = W.tick_time;
             if (tick < t || (tick == t && W.tick_seq < ev_seq)) take_samples(W, t, ev_seq);
@@ -874,11 +1000,12 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
         W.now = t;
         ++n_events;
         uint32_t kind = payload >> 29, aux = (payload >> SLOT_BITS) & AUX_MASK, slot = payload & SLOT_MASK;
+        AF_TRACE("ev t=%.17g seq=%u kind=%u aux=%u slot=%u rid=%u\n", t, ev_seq, kind, aux, slot,
+                 kind == K_DELIVER || kind == K_STEP_END ? rq_load(W, slot).rid : 0u);
         if (kind == K_DELIVER) on_deliver(W, slot, aux);
         else if (kind == K_STEP_END) {
             ReqRec r = rq_load(W, slot);
-            uint32_t np = run_steps(W, slot, aux, r.pack + (1u << 8));   // next step
-            if (np & PK_DONE) finish_request(W, slot, aux, r.rid, np);
+            run_steps(W, slot, aux, r.rid, r.pack + (1u << 8));   // the timeout fired: next step
         }
         else if (kind == K_ARRIVAL) on_arrival(W);
         else if (kind == K_SPIKE) on_spike(W);

@@ -37,6 +37,8 @@ CASES = {
     "overload_single.yml": (None, [0, 5]),
     "chain_two_servers.yml": (None, [0, 4]),
     "poisson_ties.yml": (None, [0, 5]),
+    "tie_cpu_io.yml": (None, [1, 6]),
+    "c5_multihop32.yml": (8, [1]),
 }
 FULL_CLOCKS_MAX = 1500
 

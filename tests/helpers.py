@@ -19,7 +19,8 @@ SERVER_SERIES = ("ready_queue_len", "event_loop_io_sleep", "ram_in_use")
 PARITY_CASES = {
     "c1_my_service.yml": 20, "c3_lb_two_servers.yml": 30, "c4_lb8_events.yml": 250,
     "ev_spikes_outages.yml": None, "mixed_lc.yml": None, "overload_single.yml": None,
-    "chain_two_servers.yml": None, "poisson_ties.yml": None,
+    "chain_two_servers.yml": None, "poisson_ties.yml": None, "tie_cpu_io.yml": None,
+    "c5_multihop32.yml": 8,
 }
 
 

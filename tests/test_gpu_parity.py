@@ -46,7 +46,8 @@ def test_engine_reproduces_golden_vectors(eng, name):
 
 @pytest.mark.parametrize("name", sorted(PARITY_CASES))
 def test_engine_matches_oracle_on_fresh_replicas(eng, name):
-    horizon = {"c1_my_service.yml": 10, "c3_lb_two_servers.yml": 12, "c4_lb8_events.yml": 245}.get(name)
+    horizon = {"c1_my_service.yml": 10, "c3_lb_two_servers.yml": 12, "c4_lb8_events.yml": 245,
+               "c5_multihop32.yml": 6}.get(name)
     payload = load_scenario(name, horizon)
     flat = flatten(payload)
     reps = [21, 22, 23] if not name.startswith("c4") else [21]

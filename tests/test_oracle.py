@@ -41,7 +41,8 @@ def test_python_and_c_rng_backends_give_identical_runs():
 @pytest.mark.skipif(not ref_harness.reference_available(), reason="/root/reference not on this box")
 @pytest.mark.parametrize("name", sorted(PARITY_CASES))
 def test_port_equals_unmodified_reference_actors(name):
-    horizon = {"c1_my_service.yml": 12, "c3_lb_two_servers.yml": 15, "c4_lb8_events.yml": 245}.get(name)
+    horizon = {"c1_my_service.yml": 12, "c3_lb_two_servers.yml": 15, "c4_lb8_events.yml": 245,
+               "c5_multihop32.yml": 5}.get(name)
     payload = load_scenario(name, horizon)
     for rep in (1, 9):
         r = ref_harness.run_reference(payload, seed=SEED, replica=rep)
