@@ -27,7 +27,7 @@ FIELDS = {
     "edge_dropout": 5, "server_cpu_cores": 6, "server_ram_mb": 7, "step_duration": 8,
     "endpoint_ram": 9, "spike_delta": 10,
 }
-FLAG_EVENT_OVERFLOW, FLAG_REQUEST_OVERFLOW, FLAG_TRACE_TRUNCATED = 1, 2, 4
+FLAG_EVENT_OVERFLOW, FLAG_REQUEST_OVERFLOW, FLAG_TRACE_TRUNCATED, FLAG_NOWQ_OVERFLOW = 1, 2, 4, 8
 
 
 class AfEdge(C.Structure):

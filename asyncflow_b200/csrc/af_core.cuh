@@ -182,7 +182,7 @@ struct Layout {
     int32_t warp_bytes;
 };
 
-constexpr int32_t NQ_CAP = 64;   // now-queue capacity (power of two)
+constexpr int32_t NQ_CAP = 128;   // now-queue capacity (power of two)
 
 AF_IN int32_t align_up(int32_t x, int32_t a) { return (x + a - 1) / a * a; }
 
@@ -417,9 +417,16 @@ AF_IN void pool_remove(State& W, const PoolMin& m) {
 // ---- now-queue: FIFO of zero-delay continuation items (seq << 32 | kind:3 aux:9 slot:20) ----
 enum : uint32_t { I_PUT = 0, I_GOT = 1, I_CLIENT_LOOP = 2, I_RAM_OK = 3, I_CPU_OK = 4, I_CPU_PUT = 5, I_RAM_PUT = 6 };
 constexpr uint32_t NODE_CLIENT = 0, NODE_LB = 1, NODE_SERVER0 = 2;   // `aux` of I_PUT / I_GOT
-AF_IN void nq_push(State& W, uint32_t kind, uint32_t aux, uint32_t slot) {
+// Fast path.  When the now-queue is empty and no pool event shares the current instant, an
+// item pushed as the LAST action of the running item would be the very next thing to run:
+// its effect may be applied at once (same state transitions, no ring round trip).  This is
+// what keeps the common no-tie case as cheap as an inlined cascade.
+AF_IN bool can_fuse(const State& W) { return W.nq_head == W.nq_tail && W.tie_now == 0; }
+
+AF_FN void nq_push(State& W, uint32_t kind, uint32_t aux, uint32_t slot) {
+    AF_SHARED(&W);
     uint32_t tail = W.nq_tail;
-    if (tail - W.nq_head >= (uint32_t)NQ_CAP) { W.flags |= AF_FLAG_EVENT_OVERFLOW; return; }
+    if (tail - W.nq_head >= (uint32_t)NQ_CAP) { W.flags |= AF_FLAG_NOWQ_OVERFLOW; return; }
     tbl_nq(W)[tail & (NQ_CAP - 1)] = ((uint64_t)(W.seq++) << 32) | mk_payload(kind, aux, slot);
     W.nq_tail = tail + 1;
 }
@@ -499,7 +506,8 @@ AF_IN Inbox inbox_of(State& W, uint32_t node) {
     return Inbox{&S.inbox_head, &S.inbox_tail, &S.get_pending};
 }
 // `yield box.get()` of the node's consumer process
-AF_IN void consumer_get(State& W, uint32_t node) {
+AF_FN void consumer_get(State& W, uint32_t node) {
+    AF_SHARED(&W);
     Inbox b = inbox_of(W, node);
     if (*b.head != NIL) { uint32_t it = fifo_pop(W, *b.head, *b.tail); nq_push(W, I_GOT, node, it); }
     else *b.pending = 1;
@@ -541,22 +549,30 @@ AF_FN void run_steps(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, uint3
     AF_SHARED(&W);
     ServerS& S = tbl_server(W)[sidx];
     const EndpointS ep = tbl_endpoint(W)[pk_ep(pack)];
-    const uint32_t st = pk_step(pack);
-    if (st < ep.n_steps) {
-        const StepS sp = tbl_step(W)[ep.step_begin + st];
-        if (sp.kind == AF_STEP_CPU) {
-            if (pack & PK_IO) { pack &= ~PK_IO; S.io_q -= 1; }
-            if (!(pack & PK_CORE)) {                 // cpu_req = CPU.get(1); yield cpu_req
-                fifo_push(W, S.cpuq_head, S.cpuq_tail, slot);
-                if (!cpu_walk(W, S, sidx, slot)) { pack |= PK_WAIT; S.ready_q += 1; }   // not cpu_req.triggered
+    for (;;) {
+        const uint32_t st = pk_step(pack);
+        if (st < ep.n_steps) {
+            const StepS sp = tbl_step(W)[ep.step_begin + st];
+            if (sp.kind == AF_STEP_CPU) {
+                if (pack & PK_IO) { pack &= ~PK_IO; S.io_q -= 1; }
+                if (!(pack & PK_CORE)) {             // cpu_req = CPU.get(1); yield cpu_req
+                    if (S.cpuq_head == NIL && S.cpu_free > 0 && can_fuse(W)) {
+                        S.cpu_free -= 1;             // granted, and its get event would run next
+                        pack |= PK_CORE;
+                    } else {
+                        fifo_push(W, S.cpuq_head, S.cpuq_tail, slot);
+                        if (!cpu_walk(W, S, sidx, slot)) { pack |= PK_WAIT; S.ready_q += 1; }   // not cpu_req.triggered
+                        rq_set_pack(W, slot, pack);
+                        return;
+                    }
+                }
                 rq_set_pack(W, slot, pack);
+                push(W, W.now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
                 return;
             }
-            rq_set_pack(W, slot, pack);
-            push(W, W.now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
-        } else {
             if (pack & PK_CORE) {                    // yield CPU.put(1): level rises NOW
                 S.cpu_free += 1;
+                if (can_fuse(W)) { cpu_walk(W, S, sidx, NIL); pack &= ~PK_CORE; continue; }
                 rq_set_pack(W, slot, pack);
                 nq_push(W, I_CPU_PUT, sidx, slot);
                 return;
@@ -564,25 +580,27 @@ AF_FN void run_steps(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, uint3
             if (!(pack & PK_IO)) { pack |= PK_IO; S.io_q += 1; }
             rq_set_pack(W, slot, pack);
             push(W, W.now + sp.dur, mk_payload(K_STEP_END, sidx, slot));
+            return;
         }
-        return;
-    }
-    // end of the endpoint
-    if (pack & PK_CORE) {                            // yield CPU.put(1)
-        S.cpu_free += 1;
+        // end of the endpoint (server.py:257-276)
+        if (pack & PK_CORE) {                        // yield CPU.put(1)
+            S.cpu_free += 1;
+            if (can_fuse(W)) { cpu_walk(W, S, sidx, NIL); pack &= ~PK_CORE; continue; }
+            rq_set_pack(W, slot, pack);
+            nq_push(W, I_CPU_PUT, sidx, slot);
+            return;
+        }
+        if (pack & PK_IO) { pack &= ~PK_IO; S.io_q -= 1; }
         rq_set_pack(W, slot, pack);
-        nq_push(W, I_CPU_PUT, sidx, slot);
+        if (ep.total_ram) {                          // yield RAM.put(total_ram): level rises NOW
+            S.ram_in_use -= (int32_t)ep.total_ram;
+            S.ram_free += (int32_t)ep.total_ram;
+            if (!can_fuse(W)) { nq_push(W, I_RAM_PUT, sidx, slot); return; }
+            ram_walk(W, S, sidx);                    // the put event would run next: waiters, then forward
+        }
+        edge_send(W, slot, S.out_edge, rid, pk_hops(pack));
         return;
     }
-    if (pack & PK_IO) { pack &= ~PK_IO; S.io_q -= 1; }
-    rq_set_pack(W, slot, pack);
-    if (ep.total_ram) {                              // yield RAM.put(total_ram): level rises NOW
-        S.ram_in_use -= (int32_t)ep.total_ram;
-        S.ram_free += (int32_t)ep.total_ram;
-        nq_push(W, I_RAM_PUT, sidx, slot);
-        return;
-    }
-    edge_send(W, slot, S.out_edge, rid, pk_hops(pack));
 }
 
 // the CPU.put(1) event of `slot` is processed: waiters are re-examined, then the request goes on
@@ -595,7 +613,8 @@ AF_IN void on_cpu_put(State& W, uint32_t slot, uint32_t sidx) {
 
 // ServerRuntime._dispatcher resumed with `slot` (server.py:303-313), then the head of
 // _handle_request (server.py:88-149), which runs as an URGENT Initialize right after
-AF_IN void server_got(State& W, uint32_t slot, uint32_t sidx) {
+AF_FN void server_got(State& W, uint32_t slot, uint32_t sidx) {
+    AF_SHARED(&W);
     consumer_get(W, NODE_SERVER0 + sidx);            // the dispatcher loops back to get() first
     ServerS& S = tbl_server(W)[sidx];
     ReqRec r = rq_load(W, slot);
@@ -610,10 +629,15 @@ AF_IN void server_got(State& W, uint32_t slot, uint32_t sidx) {
     const uint32_t ep_global = S.ep_begin + epi;
     pack = (pack & 0xFFu) | (ep_global << 16);       // step 0, flags clear
     rq_set_pack(W, slot, pack);
-    if (tbl_endpoint(W)[ep_global].total_ram) {      // yield RAM.get(total_ram)
-        fifo_push(W, S.ramq_head, S.ramq_tail, slot);
-        ram_walk(W, S, sidx);
-        return;
+    const uint32_t total_ram = tbl_endpoint(W)[ep_global].total_ram;
+    if (total_ram) {                                 // yield RAM.get(total_ram)
+        if (!(S.ramq_head == NIL && (int32_t)total_ram <= S.ram_free && can_fuse(W))) {
+            fifo_push(W, S.ramq_head, S.ramq_tail, slot);
+            ram_walk(W, S, sidx);
+            return;
+        }
+        S.ram_free -= (int32_t)total_ram;            // granted, and its get event would run next
+        S.ram_in_use += (int32_t)total_ram;
     }
     run_steps(W, slot, sidx, r.rid, pack);
 }
@@ -621,7 +645,8 @@ AF_IN void server_got(State& W, uint32_t slot, uint32_t sidx) {
 // ---------------------------------------------------------------------------------
 // client: completion (client.py:62-69 + analyzer.py:83-125)
 // ---------------------------------------------------------------------------------
-AF_IN void complete(State& W, uint32_t slot, double t0) {
+AF_FN void complete(State& W, uint32_t slot, double t0) {
+    AF_SHARED(&W);
     const double now = W.now;
     const double lat = now - t0;                     // finish - start (analyzer.py:86-89)
     const uint32_t done = ++W.completed;
@@ -655,6 +680,45 @@ AF_IN void complete(State& W, uint32_t slot, double t0) {
 }
 
 // ---------------------------------------------------------------------------------
+// a node's consumer process resumes with `slot` (the StoreGet event is processed):
+// client.py:43-71, load_balancer.py:60-72 + routing/lb_algorithms.py:10-36, server.py:303-313
+// ---------------------------------------------------------------------------------
+AF_FN void node_got(State& W, uint32_t node, uint32_t slot) {
+    AF_SHARED(&W);
+    if (node >= NODE_SERVER0) { server_got(W, slot, node - NODE_SERVER0); return; }
+    ReqRec r = rq_load(W, slot);
+    r.pack += 1;                                     // record_hop(client / LB)
+    if (node == NODE_CLIENT) {
+        if (pk_hops(r.pack) > 3) {                   // client.py:62: back from the servers
+            complete(W, slot, r.t0);
+            if (can_fuse(W)) consumer_get(W, NODE_CLIENT);
+            else nq_push(W, I_CLIENT_LOOP, 0, 0);    // yield completed_box.put(state)
+            return;
+        }
+        rq_set_pack(W, slot, r.pack);
+        consumer_get(W, NODE_CLIENT);
+        edge_send(W, slot, (uint32_t)AF_L.client_edge, r.rid, pk_hops(r.pack));
+        return;
+    }
+    rq_set_pack(W, slot, r.pack);
+    uint32_t* lb = tbl_lb(W);
+    const int32_t n = W.lb_n;
+    uint32_t pick = lb[0];
+    if (AF_L.lb_algo == AF_LB_ROUND_ROBIN) {         // lb_algorithms.py:22-36
+        for (int32_t i = 1; i < n; ++i) lb[i - 1] = lb[i];
+        lb[n - 1] = pick;
+    } else {                                         // least_connections, :10-20 (first min wins)
+        uint32_t best = tbl_edge(W)[pick].conn;
+        for (int32_t i = 1; i < n; ++i) {
+            uint32_t c = tbl_edge(W)[lb[i]].conn;
+            if (c < best) { best = c; pick = lb[i]; }
+        }
+    }
+    consumer_get(W, NODE_LB);
+    edge_send(W, slot, pick, r.rid, pk_hops(r.pack));
+}
+
+// ---------------------------------------------------------------------------------
 // one zero-delay item (single call site in run_replica)
 // ---------------------------------------------------------------------------------
 AF_IN void run_item(State& W, uint32_t item) {
@@ -663,37 +727,8 @@ AF_IN void run_item(State& W, uint32_t item) {
     if (kind == I_PUT) {                             // a StorePut event is processed
         Inbox b = inbox_of(W, aux);
         if (*b.pending) { *b.pending = 0; nq_push(W, I_GOT, aux, fifo_pop(W, *b.head, *b.tail)); }
-    } else if (kind == I_GOT) {                      // the node's consumer resumes with `slot`
-        if (aux >= NODE_SERVER0) { server_got(W, slot, aux - NODE_SERVER0); return; }
-        ReqRec r = rq_load(W, slot);
-        r.pack += 1;                                 // record_hop(client / LB)
-        if (aux == NODE_CLIENT) {
-            if (pk_hops(r.pack) > 3) {               // client.py:62: back from the servers
-                complete(W, slot, r.t0);
-                nq_push(W, I_CLIENT_LOOP, 0, 0);     // yield completed_box.put(state)
-                return;
-            }
-            rq_set_pack(W, slot, r.pack);
-            consumer_get(W, NODE_CLIENT);
-            edge_send(W, slot, (uint32_t)AF_L.client_edge, r.rid, pk_hops(r.pack));
-        } else {
-            rq_set_pack(W, slot, r.pack);
-            uint32_t* lb = tbl_lb(W);
-            const int32_t n = W.lb_n;
-            uint32_t pick = lb[0];
-            if (AF_L.lb_algo == AF_LB_ROUND_ROBIN) { // lb_algorithms.py:22-36
-                for (int32_t i = 1; i < n; ++i) lb[i - 1] = lb[i];
-                lb[n - 1] = pick;
-            } else {                                 // least_connections, :10-20 (first min wins)
-                uint32_t best = tbl_edge(W)[pick].conn;
-                for (int32_t i = 1; i < n; ++i) {
-                    uint32_t c = tbl_edge(W)[lb[i]].conn;
-                    if (c < best) { best = c; pick = lb[i]; }
-                }
-            }
-            consumer_get(W, NODE_LB);
-            edge_send(W, slot, pick, r.rid, pk_hops(r.pack));
-        }
+    } else if (kind == I_GOT) {
+        node_got(W, aux, slot);
     } else if (kind == I_CLIENT_LOOP) {
         consumer_get(W, NODE_CLIENT);
     } else if (kind == I_RAM_OK) {                   // the RAM get event is processed: the handler resumes
@@ -729,6 +764,10 @@ AF_IN void on_deliver(State& W, uint32_t slot, uint32_t e) {
     const uint32_t tk = (meta >> 3) & 3u;
     const uint32_t node = tk == AF_TARGET_CLIENT ? NODE_CLIENT : (tk == AF_TARGET_LB ? NODE_LB : NODE_SERVER0 + (meta >> 5));
     Inbox b = inbox_of(W, node);
+    if (*b.pending && *b.head == NIL && can_fuse(W)) {
+        node_got(W, node, slot);                     // put -> pending get -> resume, nothing in between
+        return;
+    }
     fifo_push(W, *b.head, *b.tail, slot);            // Store.put: items.append now ...
     nq_push(W, I_PUT, node, slot);                   // ... the put event is processed later
 }
@@ -973,7 +1012,7 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
             uint32_t item = (uint32_t)tbl_nq(W)[W.nq_head & (NQ_CAP - 1)];
             W.nq_head += 1;
             run_item(W, item);
-            if (W.flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW)) break;
+            if (W.flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW | AF_FLAG_NOWQ_OVERFLOW)) break;
             continue;
         }
         PoolMin m;
@@ -985,7 +1024,7 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
                 if (!same_t) W.tie_now = 0;
                 W.nq_head += 1;
                 run_item(W, (uint32_t)front);
-                if (W.flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW)) break;
+                if (W.flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW | AF_FLAG_NOWQ_OVERFLOW)) break;
                 continue;
             }
         } else if (!have_ev) break;
@@ -1010,7 +1049,7 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
         else if (kind == K_ARRIVAL) on_arrival(W);
         else if (kind == K_SPIKE) on_spike(W);
         else on_outage(W);
-        if (W.flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW)) break;
+        if (W.flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW | AF_FLAG_NOWQ_OVERFLOW)) break;
     }
     W.n_events = n_events;
     take_samples(W, W.horizon, 0u);                   // ticks strictly before the horizon

@@ -39,7 +39,7 @@ def summary_block(stats: np.ndarray, reduced_hist: np.ndarray | None) -> tuple[n
     t[1] = int(stats["generated"].sum())
     t[2] = int(stats["n_events"].sum())
     t[3] = int(stats.shape[0])
-    t[4] = int(((stats["flags"] & (K.FLAG_EVENT_OVERFLOW | K.FLAG_REQUEST_OVERFLOW)) != 0).sum())
+    t[4] = int(((stats["flags"] & (K.FLAG_EVENT_OVERFLOW | K.FLAG_REQUEST_OVERFLOW | K.FLAG_NOWQ_OVERFLOW)) != 0).sum())
     t[5] = int(stats["n_ticks"].sum())
     flts = np.array([float(stats["lat_sum"].sum()), float(stats["lat_sumsq"].sum()),
                      float(stats["lat_min"][stats["completed"] > 0].min()) if (stats["completed"] > 0).any() else np.inf,

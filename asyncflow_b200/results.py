@@ -176,7 +176,7 @@ class SweepResults:
 
     @property
     def overflowed(self) -> np.ndarray:
-        return (self.stats["flags"] & (K.FLAG_EVENT_OVERFLOW | K.FLAG_REQUEST_OVERFLOW)) != 0
+        return (self.stats["flags"] & (K.FLAG_EVENT_OVERFLOW | K.FLAG_REQUEST_OVERFLOW | K.FLAG_NOWQ_OVERFLOW)) != 0
 
     @property
     def mean_latency(self) -> np.ndarray:

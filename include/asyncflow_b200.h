@@ -174,7 +174,8 @@ typedef struct AfOptions {
 #define AF_HIST_MIN_EXP (-20)
 
 /* AfReplicaStats.flags */
-enum { AF_FLAG_EVENT_OVERFLOW = 1, AF_FLAG_REQUEST_OVERFLOW = 2, AF_FLAG_TRACE_TRUNCATED = 4 };
+enum { AF_FLAG_EVENT_OVERFLOW = 1, AF_FLAG_REQUEST_OVERFLOW = 2, AF_FLAG_TRACE_TRUNCATED = 4,
+       AF_FLAG_NOWQ_OVERFLOW = 8 /* > 128 zero-delay continuations pending at one instant */ };
 
 typedef struct AfReplicaStats {
     uint64_t n_events;           /* timed events processed                          */
