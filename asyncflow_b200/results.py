@@ -208,6 +208,31 @@ class SweepResults:
         t = np.maximum(self.stats["n_ticks"], 1).astype(np.float64)[:, None]
         return self.samp_sum.astype(np.float64) / t
 
+    def confidence_interval(self, what: str = "mean", select: np.ndarray | None = None,
+                            level: float = 0.95) -> tuple[float, float, float]:
+        """Monte-Carlo estimate over replicas of a per-replica statistic (``"mean"``, ``"p50"``,
+        ``"p95"``, ``"p99"``, ``"completed"``, ``"generated"``): ``(estimate, lo, hi)`` with a normal
+        ``level`` interval on the mean across the selected replicas (reference ROADMAP.md:23-27)."""
+        if what == "mean":
+            x = self.mean_latency
+        elif what in ("p50", "p95", "p99", "completed", "generated", "lat_min", "lat_max"):
+            x = self.stats[what].astype(np.float64)
+        else:
+            msg = f"unknown statistic {what!r}"
+            raise KeyError(msg)
+        if select is not None:
+            x = x[select]
+        x = x[np.isfinite(x)]
+        if x.size == 0:
+            return float("nan"), float("nan"), float("nan")
+        m = float(x.mean())
+        if x.size == 1:
+            return m, m, m
+        from statistics import NormalDist  # noqa: PLC0415
+        z = NormalDist().inv_cdf(0.5 + level / 2.0)
+        half = z * float(x.std(ddof=1)) / float(np.sqrt(x.size))
+        return m, m - half, m + half
+
     def summary(self) -> dict[str, float]:
         ok = self.completed > 0
         tot_c = int(self.completed.sum())
