@@ -91,6 +91,9 @@
 #define AF_TRACE(...) ((void)0)
 #endif
 
+#define AF_LIKELY(x) __builtin_expect(!!(x), 1)
+#define AF_UNLIKELY(x) __builtin_expect(!!(x), 0)
+
 namespace afc {
 
 constexpr uint32_t NIL = 0xFFFFFFFFu;
@@ -122,12 +125,13 @@ struct ServerS {          // 64 B
     int32_t cpu_free, ram_free, ready_q, io_q, ram_in_use;
     uint32_t ramq_head, ramq_tail, cpuq_head, cpuq_tail;
     uint32_t out_edge, ep_begin, n_ep;
-    uint32_t inbox_head, inbox_tail, get_pending, pad;   // the server's Store + its dispatcher's pending get()
+    uint32_t pad[4];
 };
 struct EndpointS { uint32_t step_begin, n_steps, total_ram, pad; }; // 16 B
 struct StepS { double dur; uint32_t kind, pad; };                   // 16 B
 struct SpikeS { double fire, delta; uint32_t edge, pad; };           // 24 B
 struct OutageS { double fire; int32_t lb_edge, down; };              // 16 B
+struct InboxS { uint32_t head, tail, pending, pad; };                // 16 B: a node's Store + its consumer's pending get()
 
 // The replica's scalar state: one per warp, at the start of the warp's workspace.
 struct State {
@@ -142,9 +146,7 @@ struct State {
     int32_t ev_hw, ev_live, ev_last_free, ev_hole;
     uint32_t peak_ev;
     // zero-delay continuation FIFO (ring of NQ_CAP items) + "the pool may hold an event of this instant"
-    uint32_t nq_head, nq_tail, tie_now;
-    // Stores of the client and the load balancer (servers keep theirs in ServerS)
-    uint32_t cl_head, cl_tail, cl_pending, lb_head, lb_tail, lb_pending;
+    uint32_t nq_head, nq_tail, busy;   // busy = 2 * (items in the now-queue) + (pool may hold an event of this instant)
     // request table
     uint32_t rq_free, rq_hw, rq_live, peak_rq;
     // generator (two clocks: the sampler's virtual one and the simulation's)
@@ -178,7 +180,7 @@ struct Layout {
     int32_t trace_replicas, trace_clock_cap, trace_tick_cap;
     // byte offsets inside the per-warp workspace
     int32_t off_ev_time, off_ev_key, off_rq_rec, off_rq_next, off_edge, off_server,
-            off_endpoint, off_step, off_lb, off_spike, off_outage, off_samp_sum, off_samp_max, off_nq;
+            off_endpoint, off_step, off_lb, off_spike, off_outage, off_samp_sum, off_samp_max, off_nq, off_inbox;
     int32_t warp_bytes;
 };
 
@@ -191,6 +193,7 @@ inline void layout_finalize(Layout& L) {
     L.off_ev_time = o;  o += 8 * L.ev_smem;
     L.off_ev_key = o;   o += 8 * L.ev_smem;
     L.off_nq = o;       o += 8 * NQ_CAP;
+    L.off_inbox = o;    o += 16 * (L.n_servers + 2);
     L.off_rq_rec = o;   o += 16 * L.rq_smem;
     L.off_edge = o;     o += 48 * L.n_edges;
     L.off_server = o;   o += 64 * L.n_servers;
@@ -256,6 +259,7 @@ AF_TBL(tbl_outage, OutageS, off_outage)
 AF_TBL(tbl_samp_sum, uint64_t, off_samp_sum)
 AF_TBL(tbl_samp_max, uint32_t, off_samp_max)
 AF_TBL(tbl_nq, uint64_t, off_nq)
+AF_TBL(tbl_inbox, InboxS, off_inbox)
 
 // ---- warp primitives (a warp of ONE lane on the host) ------------------------
 #if AF_DEVICE_CODE
@@ -281,26 +285,34 @@ static inline void red_add_u32(uint32_t* p, uint32_t v) { *p += v; }
 // storage tiers: low slot numbers live in shared memory, the rest in the warp's HBM
 // spill region (overloaded replicas queue 10^4-10^5 requests)
 // ---------------------------------------------------------------------------------
+// AF_NO_SPILL: build variant for launches whose capacities fit the shared-memory tiers
+// (every spill branch disappears; the host only selects it when ev_total <= ev_smem and
+// rq_total <= rq_smem).
+#if defined(AF_NO_SPILL)
+#define AF_IN_SMEM(idx, cap) true
+#else
+#define AF_IN_SMEM(idx, cap) AF_LIKELY((int32_t)(idx) < (cap))
+#endif
 AF_IN ReqRec rq_load(const State& W, uint32_t s) {
-    return (int32_t)s < AF_L.rq_smem ? tbl_rq_rec(W)[s] : W.sp_rq_rec[s - AF_L.rq_smem];
+    return AF_IN_SMEM(s, AF_L.rq_smem) ? tbl_rq_rec(W)[s] : W.sp_rq_rec[s - AF_L.rq_smem];
 }
 AF_IN void rq_store(State& W, uint32_t s, const ReqRec& r) {
-    if ((int32_t)s < AF_L.rq_smem) tbl_rq_rec(W)[s] = r; else W.sp_rq_rec[s - AF_L.rq_smem] = r;
+    if (AF_IN_SMEM(s, AF_L.rq_smem)) tbl_rq_rec(W)[s] = r; else W.sp_rq_rec[s - AF_L.rq_smem] = r;
 }
 AF_IN void rq_set_pack(State& W, uint32_t s, uint32_t pack) {
-    if ((int32_t)s < AF_L.rq_smem) tbl_rq_rec(W)[s].pack = pack; else W.sp_rq_rec[s - AF_L.rq_smem].pack = pack;
+    if (AF_IN_SMEM(s, AF_L.rq_smem)) tbl_rq_rec(W)[s].pack = pack; else W.sp_rq_rec[s - AF_L.rq_smem].pack = pack;
 }
 AF_IN uint32_t nx_load(const State& W, uint32_t s) {
-    return (int32_t)s < AF_L.rq_smem ? tbl_rq_next(W)[s] : W.sp_rq_next[s - AF_L.rq_smem];
+    return AF_IN_SMEM(s, AF_L.rq_smem) ? tbl_rq_next(W)[s] : W.sp_rq_next[s - AF_L.rq_smem];
 }
 AF_IN void nx_store(State& W, uint32_t s, uint32_t v) {
-    if ((int32_t)s < AF_L.rq_smem) tbl_rq_next(W)[s] = v; else W.sp_rq_next[s - AF_L.rq_smem] = v;
+    if (AF_IN_SMEM(s, AF_L.rq_smem)) tbl_rq_next(W)[s] = v; else W.sp_rq_next[s - AF_L.rq_smem] = v;
 }
 AF_IN uint64_t evt_load(const State& W, int32_t k) {
-    return afr::d2u(k < AF_L.ev_smem ? tbl_ev_time(W)[k] : W.sp_ev_time[k - AF_L.ev_smem]);
+    return afr::d2u(AF_IN_SMEM(k, AF_L.ev_smem) ? tbl_ev_time(W)[k] : W.sp_ev_time[k - AF_L.ev_smem]);
 }
 AF_IN uint64_t evk_load(const State& W, int32_t k) {
-    return k < AF_L.ev_smem ? tbl_ev_key(W)[k] : W.sp_ev_key[k - AF_L.ev_smem];
+    return AF_IN_SMEM(k, AF_L.ev_smem) ? tbl_ev_key(W)[k] : W.sp_ev_key[k - AF_L.ev_smem];
 }
 
 // ---- request slots (free list threaded through rq_next) ------------------------
@@ -316,12 +328,14 @@ AF_IN uint32_t rq_alloc(State& W) {
 AF_IN void rq_release(State& W, uint32_t s) { nx_store(W, s, W.rq_free); W.rq_free = s; --W.rq_live; }
 
 // intrusive FIFOs (RAM waiters, CPU waiters) through the same `next` links
-AF_IN void fifo_push(State& W, uint32_t& head, uint32_t& tail, uint32_t s) {
+AF_FN void fifo_push(State& W, uint32_t& head, uint32_t& tail, uint32_t s) {
+    AF_SHARED(&W); AF_SHARED(&head); AF_SHARED(&tail);
     nx_store(W, s, NIL);
     if (tail == NIL) head = s; else nx_store(W, tail, s);
     tail = s;
 }
-AF_IN uint32_t fifo_pop(State& W, uint32_t& head, uint32_t& tail) {
+AF_FN uint32_t fifo_pop(State& W, uint32_t& head, uint32_t& tail) {
+    AF_SHARED(&W); AF_SHARED(&head); AF_SHARED(&tail);
     uint32_t s = head;
     head = nx_load(W, s);
     if (head == NIL) tail = NIL;
@@ -337,7 +351,7 @@ AF_IN uint32_t fifo_pop(State& W, uint32_t& head, uint32_t& tail) {
 AF_FN void push_seq(State& W, double t, uint32_t payload, uint32_t s) {
     AF_SHARED(&W);
     if (!(t < W.horizon)) return;       // env.run(until=T): events at >= T never fire
-    if (t == W.now) W.tie_now = 1;      // a zero-delay timeout: it competes with the now-queue
+    if (AF_UNLIKELY(t == W.now)) W.busy |= 1u;   // a zero-delay timeout: it competes with the now-queue
     int32_t slot;
     if (W.ev_last_free >= 0) { slot = W.ev_last_free; W.ev_last_free = -1; }
     else if (W.ev_hole >= 0) { slot = W.ev_hole; W.ev_hole = -1; }
@@ -347,7 +361,7 @@ AF_FN void push_seq(State& W, double t, uint32_t payload, uint32_t s) {
         W.ev_hw = slot + 1;
     }
     uint64_t key = ((uint64_t)s << 32) | payload;
-    if (slot < AF_L.ev_smem) { tbl_ev_time(W)[slot] = t; tbl_ev_key(W)[slot] = key; }
+    if (AF_IN_SMEM(slot, AF_L.ev_smem)) { tbl_ev_time(W)[slot] = t; tbl_ev_key(W)[slot] = key; }
     else { W.sp_ev_time[slot - AF_L.ev_smem] = t; W.sp_ev_key[slot - AF_L.ev_smem] = key; }
     uint32_t live = (uint32_t)(++W.ev_live);
     if (live > W.peak_ev) W.peak_ev = live;
@@ -362,6 +376,7 @@ AF_IN bool pool_scan(State& W, PoolMin& m) {
     const int lane = lane_id();
     const int32_t hw = W.ev_hw;
     uint64_t bt = ~0ull, bk = ~0ull; int32_t bi = -1; int32_t hole = 0x7FFFFFFF;
+#pragma unroll 1
     for (int32_t k = lane; k < hw; k += WARP) {
         uint64_t tb = evt_load(W, k);
         if (tb == INF_BITS) { if (k < hole) hole = k; continue; }
@@ -405,7 +420,7 @@ AF_IN bool pool_scan(State& W, PoolMin& m) {
 }
 AF_IN void pool_remove(State& W, const PoolMin& m) {
     const int32_t hw = W.ev_hw, slot = m.slot;
-    if (slot < AF_L.ev_smem) tbl_ev_time(W)[slot] = afr::u2d(INF_BITS);
+    if (AF_IN_SMEM(slot, AF_L.ev_smem)) tbl_ev_time(W)[slot] = afr::u2d(INF_BITS);
     else W.sp_ev_time[slot - AF_L.ev_smem] = afr::u2d(INF_BITS);
     W.ev_live -= 1;
     int32_t nhw = hw;
@@ -421,7 +436,7 @@ constexpr uint32_t NODE_CLIENT = 0, NODE_LB = 1, NODE_SERVER0 = 2;   // `aux` of
 // item pushed as the LAST action of the running item would be the very next thing to run:
 // its effect may be applied at once (same state transitions, no ring round trip).  This is
 // what keeps the common no-tie case as cheap as an inlined cascade.
-AF_IN bool can_fuse(const State& W) { return W.nq_head == W.nq_tail && W.tie_now == 0; }
+AF_IN bool can_fuse(const State& W) { return AF_LIKELY(W.busy == 0); }
 
 AF_FN void nq_push(State& W, uint32_t kind, uint32_t aux, uint32_t slot) {
     AF_SHARED(&W);
@@ -429,6 +444,7 @@ AF_FN void nq_push(State& W, uint32_t kind, uint32_t aux, uint32_t slot) {
     if (tail - W.nq_head >= (uint32_t)NQ_CAP) { W.flags |= AF_FLAG_NOWQ_OVERFLOW; return; }
     tbl_nq(W)[tail & (NQ_CAP - 1)] = ((uint64_t)(W.seq++) << 32) | mk_payload(kind, aux, slot);
     W.nq_tail = tail + 1;
+    W.busy += 2u;
 }
 
 // ---------------------------------------------------------------------------------
@@ -498,19 +514,12 @@ AF_FN void edge_send(State& W, uint32_t slot, uint32_t e, uint32_t rid, uint32_t
 // consumer's pending get() is served when THAT event is processed (-> I_GOT); a consumer
 // that calls get() on a non-empty store is served at once (-> I_GOT).   SURVEY.md App. A
 // ---------------------------------------------------------------------------------
-struct Inbox { uint32_t* head; uint32_t* tail; uint32_t* pending; };
-AF_IN Inbox inbox_of(State& W, uint32_t node) {
-    if (node == NODE_CLIENT) return Inbox{&W.cl_head, &W.cl_tail, &W.cl_pending};
-    if (node == NODE_LB) return Inbox{&W.lb_head, &W.lb_tail, &W.lb_pending};
-    ServerS& S = tbl_server(W)[node - NODE_SERVER0];
-    return Inbox{&S.inbox_head, &S.inbox_tail, &S.get_pending};
-}
 // `yield box.get()` of the node's consumer process
 AF_FN void consumer_get(State& W, uint32_t node) {
     AF_SHARED(&W);
-    Inbox b = inbox_of(W, node);
-    if (*b.head != NIL) { uint32_t it = fifo_pop(W, *b.head, *b.tail); nq_push(W, I_GOT, node, it); }
-    else *b.pending = 1;
+    InboxS& b = tbl_inbox(W)[node];
+    if (AF_UNLIKELY(b.head != NIL)) { uint32_t it = fifo_pop(W, b.head, b.tail); nq_push(W, I_GOT, node, it); }
+    else b.pending = 1;
 }
 
 // ---------------------------------------------------------------------------------
@@ -519,7 +528,8 @@ AF_FN void consumer_get(State& W, uint32_t node) {
 // ---------------------------------------------------------------------------------
 // Container._trigger_get over the CPU queue: grant heads while a core is free
 // (returns true when `watch` was among the granted: its get is "triggered" at the call)
-AF_IN bool cpu_walk(State& W, ServerS& S, uint32_t sidx, uint32_t watch) {
+AF_FN bool cpu_walk(State& W, ServerS& S, uint32_t sidx, uint32_t watch) {
+    AF_SHARED(&W); AF_SHARED(&S);
     bool hit = false;
     while (S.cpuq_head != NIL && S.cpu_free > 0) {
         uint32_t w = fifo_pop(W, S.cpuq_head, S.cpuq_tail);
@@ -530,7 +540,8 @@ AF_IN bool cpu_walk(State& W, ServerS& S, uint32_t sidx, uint32_t watch) {
     return hit;
 }
 // ... over the RAM queue: grant heads while they fit, stop at the first that does not
-AF_IN void ram_walk(State& W, ServerS& S, uint32_t sidx) {
+AF_FN void ram_walk(State& W, ServerS& S, uint32_t sidx) {
+    AF_SHARED(&W); AF_SHARED(&S);
     while (S.ramq_head != NIL) {
         uint32_t w = S.ramq_head;
         uint32_t need = tbl_endpoint(W)[pk_ep(rq_load(W, w).pack)].total_ram;
@@ -709,6 +720,7 @@ AF_FN void node_got(State& W, uint32_t node, uint32_t slot) {
         lb[n - 1] = pick;
     } else {                                         // least_connections, :10-20 (first min wins)
         uint32_t best = tbl_edge(W)[pick].conn;
+#pragma unroll 1
         for (int32_t i = 1; i < n; ++i) {
             uint32_t c = tbl_edge(W)[lb[i]].conn;
             if (c < best) { best = c; pick = lb[i]; }
@@ -725,8 +737,8 @@ AF_IN void run_item(State& W, uint32_t item) {
     const uint32_t kind = item >> 29, aux = (item >> SLOT_BITS) & AUX_MASK, slot = item & SLOT_MASK;
     AF_TRACE("it t=%.17g kind=%u aux=%u slot=%u\n", W.now, kind, aux, slot);
     if (kind == I_PUT) {                             // a StorePut event is processed
-        Inbox b = inbox_of(W, aux);
-        if (*b.pending) { *b.pending = 0; nq_push(W, I_GOT, aux, fifo_pop(W, *b.head, *b.tail)); }
+        InboxS& b = tbl_inbox(W)[aux];
+        if (b.pending) { b.pending = 0; nq_push(W, I_GOT, aux, fifo_pop(W, b.head, b.tail)); }
     } else if (kind == I_GOT) {
         node_got(W, aux, slot);
     } else if (kind == I_CLIENT_LOOP) {
@@ -763,12 +775,12 @@ AF_IN void on_deliver(State& W, uint32_t slot, uint32_t e) {
     rq_set_pack(W, slot, r.pack + 1);                // record_hop(edge)
     const uint32_t tk = (meta >> 3) & 3u;
     const uint32_t node = tk == AF_TARGET_CLIENT ? NODE_CLIENT : (tk == AF_TARGET_LB ? NODE_LB : NODE_SERVER0 + (meta >> 5));
-    Inbox b = inbox_of(W, node);
-    if (*b.pending && *b.head == NIL && can_fuse(W)) {
+    if (can_fuse(W)) {                               // (implies: every inbox empty, every consumer in get())
         node_got(W, node, slot);                     // put -> pending get -> resume, nothing in between
         return;
     }
-    fifo_push(W, *b.head, *b.tail, slot);            // Store.put: items.append now ...
+    InboxS& b = tbl_inbox(W)[node];
+    fifo_push(W, b.head, b.tail, slot);              // Store.put: items.append now ...
     nq_push(W, I_PUT, node, slot);                   // ... the put event is processed later
 }
 
@@ -892,7 +904,7 @@ AF_FN void load_params(State& W) {
         s.cpu_free = a.cpu_cores; s.ram_free = a.ram_mb; s.ready_q = 0; s.io_q = 0; s.ram_in_use = 0;
         s.ramq_head = s.ramq_tail = s.cpuq_head = s.cpuq_tail = NIL;
         s.out_edge = (uint32_t)a.out_edge; s.ep_begin = (uint32_t)a.endpoint_begin; s.n_ep = (uint32_t)a.n_endpoints;
-        s.inbox_head = s.inbox_tail = NIL; s.get_pending = 1; s.pad = 0;
+        s.pad[0] = s.pad[1] = s.pad[2] = s.pad[3] = 0;
         tbl_server(W)[i] = s;
     }
     for (int32_t i = lane; i < AF_L.n_endpoints; i += WARP) {
@@ -918,6 +930,7 @@ AF_FN void load_params(State& W) {
         tbl_outage(W)[i] = o;
     }
     for (int32_t i = lane; i < AF_L.n_series; i += WARP) { tbl_samp_sum(W)[i] = 0; tbl_samp_max(W)[i] = 0; }
+    for (int32_t i = lane; i < AF_L.n_servers + 2; i += WARP) { InboxS b; b.head = b.tail = NIL; b.pending = 1; b.pad = 0; tbl_inbox(W)[i] = b; }
     w_sync();
     W.users_mean = AF_L.users_mean; W.users_sigma = AF_L.users_sigma; W.rate_per_user = AF_L.rate_per_user;
     // sweep overrides of this replica (uniform: every lane applies every column)
@@ -980,8 +993,7 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
     W.replica = AF_G.replica_begin + local_index;
     W.now = 0.0; W.horizon = (double)AF_L.horizon_s; W.seq = 0;
     W.ev_hw = 0; W.ev_live = 0; W.ev_last_free = -1; W.ev_hole = -1; W.peak_ev = 0;
-    W.nq_head = 0; W.nq_tail = 0; W.tie_now = 0;
-    W.cl_head = W.cl_tail = NIL; W.cl_pending = 1; W.lb_head = W.lb_tail = NIL; W.lb_pending = 1;
+    W.nq_head = 0; W.nq_tail = 0; W.busy = 0;
     W.rq_free = NIL; W.rq_hw = 0; W.rq_live = 0; W.peak_rq = 0;
     W.g_vnow = 0.0; W.g_window_end = 0.0; W.g_lam = 0.0; W.g_pos = 0; W.generated = 0; W.g_done = 0;
     W.lb_n = AF_L.n_lb_edges;
@@ -1007,10 +1019,12 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
     uint64_t n_events = 0;
     for (;;) {
         if (W.need_arrival) arm_generator(W);
-        const bool have_item = W.nq_head != W.nq_tail;
-        if (have_item && !W.tie_now) {               // fast path: nothing else lives at this instant
+        const uint32_t busy = W.busy;
+        const bool have_item = busy >= 2u;
+        if (have_item && !(busy & 1u)) {             // no pool event shares this instant: just drain
             uint32_t item = (uint32_t)tbl_nq(W)[W.nq_head & (NQ_CAP - 1)];
             W.nq_head += 1;
+            W.busy = busy - 2u;
             run_item(W, item);
             if (W.flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW | AF_FLAG_NOWQ_OVERFLOW)) break;
             continue;
@@ -1021,7 +1035,7 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
             const uint64_t front = tbl_nq(W)[W.nq_head & (NQ_CAP - 1)];
             const bool same_t = have_ev && m.tbits == afr::d2u(W.now);
             if (!(same_t && (uint32_t)(m.key >> 32) < (uint32_t)(front >> 32))) {
-                if (!same_t) W.tie_now = 0;
+                W.busy = (same_t ? busy : (busy & ~1u)) - 2u;
                 W.nq_head += 1;
                 run_item(W, (uint32_t)front);
                 if (W.flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW | AF_FLAG_NOWQ_OVERFLOW)) break;
@@ -1031,7 +1045,7 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
         pool_remove(W, m);
         const double t = afr::u2d(m.tbits);
         const uint32_t payload = (uint32_t)m.key, ev_seq = (uint32_t)(m.key >> 32);
-        W.tie_now = m.more ? 1u : 0u;
+        W.busy = (W.busy & ~1u) | (m.more ? 1u : 0u);
         {
             const double tick = W.tick_time;
             if (tick < t || (tick == t && W.tick_seq < ev_seq)) take_samples(W, t, ev_seq);
