@@ -376,12 +376,14 @@ AF_IN bool pool_scan(State& W, PoolMin& m) {
     const int lane = lane_id();
     const int32_t hw = W.ev_hw;
     uint64_t bt = ~0ull, bk = ~0ull; int32_t bi = -1; int32_t hole = 0x7FFFFFFF;
+    bool dup = false;                 // this lane holds two events at ITS earliest time
 #pragma unroll 1
     for (int32_t k = lane; k < hw; k += WARP) {
         uint64_t tb = evt_load(W, k);
         if (tb == INF_BITS) { if (k < hole) hole = k; continue; }
         uint64_t kk = evk_load(W, k);
-        if (tb < bt || (tb == bt && kk < bk)) { bt = tb; bk = kk; bi = k; }
+        if (tb < bt) { bt = tb; bk = kk; bi = k; dup = false; }
+        else if (tb == bt) { dup = true; if (kk < bk) { bk = kk; bi = k; } }
     }
 #if AF_DEVICE_CODE
     uint32_t hi = (uint32_t)(bt >> 32), lo = (uint32_t)bt;
@@ -390,8 +392,8 @@ AF_IN bool pool_scan(State& W, PoolMin& m) {
     uint32_t mlo = w_min(cand ? lo : 0xFFFFFFFFu);
     cand = cand && lo == mlo;
     uint32_t b = w_ballot(cand);
-    bool more = __popc(b) > 1;
-    if (more) {                       // equal times: the earlier push wins (SimPy eid order)
+    const bool more = __popc(b) > 1 || w_ballot(cand && dup) != 0;
+    if (__popc(b) > 1) {              // equal times: the earlier push wins (SimPy eid order)
         uint32_t sq = (uint32_t)(bk >> 32);
         uint32_t msq = w_min(cand ? sq : 0xFFFFFFFFu);
         cand = cand && sq == msq;
@@ -403,18 +405,9 @@ AF_IN bool pool_scan(State& W, PoolMin& m) {
     m.tbits = ((uint64_t)mhi << 32) | mlo;
     m.key = ((uint64_t)k_hi << 32) | k_lo;
     m.hole = (int32_t)w_min((uint32_t)hole);
-    if (!more && hw > WARP) {
-        // a lane holding several slots may hide a second event of the same instant
-        bool dup = false;
-        for (int32_t k = lane; k < hw; k += WARP) dup = dup || (k != m.slot && evt_load(W, k) == m.tbits);
-        more = w_ballot(dup) != 0;
-    }
     m.more = more;
 #else
-    m.slot = bi; m.tbits = bt; m.key = bk; m.hole = hole;
-    bool more = false;
-    for (int32_t k = 0; k < hw; ++k) more = more || (k != bi && evt_load(W, k) == bt);
-    m.more = more;
+    m.slot = bi; m.tbits = bt; m.key = bk; m.hole = hole; m.more = dup;
 #endif
     return true;
 }
@@ -515,11 +508,15 @@ AF_FN void edge_send(State& W, uint32_t slot, uint32_t e, uint32_t rid, uint32_t
 // that calls get() on a non-empty store is served at once (-> I_GOT).   SURVEY.md App. A
 // ---------------------------------------------------------------------------------
 // `yield box.get()` of the node's consumer process
-AF_FN void consumer_get(State& W, uint32_t node) {
+AF_FN void consumer_get_slow(State& W, uint32_t node) {
     AF_SHARED(&W);
     InboxS& b = tbl_inbox(W)[node];
-    if (AF_UNLIKELY(b.head != NIL)) { uint32_t it = fifo_pop(W, b.head, b.tail); nq_push(W, I_GOT, node, it); }
-    else b.pending = 1;
+    uint32_t it = fifo_pop(W, b.head, b.tail);
+    nq_push(W, I_GOT, node, it);
+}
+AF_IN void consumer_get(State& W, uint32_t node) {
+    InboxS& b = tbl_inbox(W)[node];
+    if (AF_UNLIKELY(b.head != NIL)) consumer_get_slow(W, node); else b.pending = 1;
 }
 
 // ---------------------------------------------------------------------------------
@@ -583,7 +580,7 @@ AF_FN void run_steps(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, uint3
             }
             if (pack & PK_CORE) {                    // yield CPU.put(1): level rises NOW
                 S.cpu_free += 1;
-                if (can_fuse(W)) { cpu_walk(W, S, sidx, NIL); pack &= ~PK_CORE; continue; }
+                if (can_fuse(W)) { if (AF_UNLIKELY(S.cpuq_head != NIL)) cpu_walk(W, S, sidx, NIL); pack &= ~PK_CORE; continue; }
                 rq_set_pack(W, slot, pack);
                 nq_push(W, I_CPU_PUT, sidx, slot);
                 return;
@@ -596,7 +593,7 @@ AF_FN void run_steps(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, uint3
         // end of the endpoint (server.py:257-276)
         if (pack & PK_CORE) {                        // yield CPU.put(1)
             S.cpu_free += 1;
-            if (can_fuse(W)) { cpu_walk(W, S, sidx, NIL); pack &= ~PK_CORE; continue; }
+            if (can_fuse(W)) { if (AF_UNLIKELY(S.cpuq_head != NIL)) cpu_walk(W, S, sidx, NIL); pack &= ~PK_CORE; continue; }
             rq_set_pack(W, slot, pack);
             nq_push(W, I_CPU_PUT, sidx, slot);
             return;
@@ -607,7 +604,7 @@ AF_FN void run_steps(State& W, uint32_t slot, uint32_t sidx, uint32_t rid, uint3
             S.ram_in_use -= (int32_t)ep.total_ram;
             S.ram_free += (int32_t)ep.total_ram;
             if (!can_fuse(W)) { nq_push(W, I_RAM_PUT, sidx, slot); return; }
-            ram_walk(W, S, sidx);                    // the put event would run next: waiters, then forward
+            if (AF_UNLIKELY(S.ramq_head != NIL)) ram_walk(W, S, sidx);   // the put event would run next: waiters, then forward
         }
         edge_send(W, slot, S.out_edge, rid, pk_hops(pack));
         return;
@@ -624,8 +621,7 @@ AF_IN void on_cpu_put(State& W, uint32_t slot, uint32_t sidx) {
 
 // ServerRuntime._dispatcher resumed with `slot` (server.py:303-313), then the head of
 // _handle_request (server.py:88-149), which runs as an URGENT Initialize right after
-AF_FN void server_got(State& W, uint32_t slot, uint32_t sidx) {
-    AF_SHARED(&W);
+AF_IN void server_got(State& W, uint32_t slot, uint32_t sidx) {
     consumer_get(W, NODE_SERVER0 + sidx);            // the dispatcher loops back to get() first
     ServerS& S = tbl_server(W)[sidx];
     ReqRec r = rq_load(W, slot);
@@ -656,8 +652,7 @@ AF_FN void server_got(State& W, uint32_t slot, uint32_t sidx) {
 // ---------------------------------------------------------------------------------
 // client: completion (client.py:62-69 + analyzer.py:83-125)
 // ---------------------------------------------------------------------------------
-AF_FN void complete(State& W, uint32_t slot, double t0) {
-    AF_SHARED(&W);
+AF_IN void complete(State& W, uint32_t slot, double t0) {
     const double now = W.now;
     const double lat = now - t0;                     // finish - start (analyzer.py:86-89)
     const uint32_t done = ++W.completed;
