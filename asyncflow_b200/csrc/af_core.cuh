@@ -348,6 +348,19 @@ AF_FN uint32_t fifo_pop(State& W, uint32_t& head, uint32_t& tail) {
 // scan noticed, else appends; pop is a warp arg-min over (time, seq).  Every lane
 // executes push (same slot, same values); only the owner lane reads the slot back.
 // ---------------------------------------------------------------------------------
+// slow path of push: the high-water mark reached the capacity although holes may exist below it
+AF_FN int32_t pool_find_hole(State& W) {
+    AF_SHARED(&W);
+    const int lane = lane_id();
+    const int32_t hw = W.ev_hw;
+    int32_t mine = 0x7FFFFFFF;
+#pragma unroll 1
+    for (int32_t k = lane; k < hw; k += WARP)
+        if (evt_load(W, k) == INF_BITS) { mine = k; break; }
+    mine = (int32_t)w_min((uint32_t)mine);
+    return mine == 0x7FFFFFFF ? -1 : mine;
+}
+
 AF_FN void push_seq(State& W, double t, uint32_t payload, uint32_t s) {
     AF_SHARED(&W);
     if (!(t < W.horizon)) return;       // env.run(until=T): events at >= T never fire
@@ -357,8 +370,10 @@ AF_FN void push_seq(State& W, double t, uint32_t payload, uint32_t s) {
     else if (W.ev_hole >= 0) { slot = W.ev_hole; W.ev_hole = -1; }
     else {
         slot = W.ev_hw;
-        if (slot >= AF_L.ev_total) { W.flags |= AF_FLAG_EVENT_OVERFLOW; return; }
-        W.ev_hw = slot + 1;
+        if (AF_UNLIKELY(slot >= AF_L.ev_total)) {
+            slot = pool_find_hole(W);
+            if (slot < 0) { W.flags |= AF_FLAG_EVENT_OVERFLOW; return; }
+        } else W.ev_hw = slot + 1;
     }
     uint64_t key = ((uint64_t)s << 32) | payload;
     if (AF_IN_SMEM(slot, AF_L.ev_smem)) { tbl_ev_time(W)[slot] = t; tbl_ev_key(W)[slot] = key; }

@@ -1,0 +1,25 @@
+"""Randomised parity: the engine's state machine (CPU twin) vs the oracle, bit for bit, on
+scenarios built to tie (deterministic step durations), queue (CPU and RAM) and branch."""
+
+from __future__ import annotations
+
+import des_port
+import fuzz
+import pytest
+import twin
+from helpers import SEED, assert_matches_oracle
+
+from asyncflow_b200.flatten import flatten
+
+
+@pytest.mark.parametrize("seed", range(100, 124))
+def test_twin_equals_oracle_on_random_scenarios(seed):
+    payload = fuzz.scenario(seed)
+    flat = flatten(payload)
+    o = des_port.simulate(payload, seed=SEED, replica=seed)
+    r = twin.run(flat, seed=SEED, replica_begin=seed, n=1, trace=1, clock_cap=100000, request_capacity=200000)
+    st = r["stats"][0]
+    n, nt = int(st["completed"]), int(st["n_ticks"])
+    assert st["flags"] == 0
+    assert_matches_oracle(o, flat, stats=st, clocks=r["trace_clocks"][0, :n], sent=r["sent"][0],
+                          dropped=r["dropped"][0], series=r["trace_series"][0][:, :nt], throughput=r["thr"][0])
