@@ -543,6 +543,7 @@ AF_IN void consumer_get(State& W, uint32_t node) {
 AF_FN bool cpu_walk(State& W, ServerS& S, uint32_t sidx, uint32_t watch) {
     AF_SHARED(&W); AF_SHARED(&S);
     bool hit = false;
+#pragma unroll 1
     while (S.cpuq_head != NIL && S.cpu_free > 0) {
         uint32_t w = fifo_pop(W, S.cpuq_head, S.cpuq_tail);
         S.cpu_free -= 1;
@@ -554,6 +555,7 @@ AF_FN bool cpu_walk(State& W, ServerS& S, uint32_t sidx, uint32_t watch) {
 // ... over the RAM queue: grant heads while they fit, stop at the first that does not
 AF_FN void ram_walk(State& W, ServerS& S, uint32_t sidx) {
     AF_SHARED(&W); AF_SHARED(&S);
+#pragma unroll 1
     while (S.ramq_head != NIL) {
         uint32_t w = S.ramq_head;
         uint32_t need = tbl_endpoint(W)[pk_ep(rq_load(W, w).pack)].total_ram;
@@ -726,6 +728,7 @@ AF_FN void node_got(State& W, uint32_t node, uint32_t slot) {
     const int32_t n = W.lb_n;
     uint32_t pick = lb[0];
     if (AF_L.lb_algo == AF_LB_ROUND_ROBIN) {         // lb_algorithms.py:22-36
+#pragma unroll 1
         for (int32_t i = 1; i < n; ++i) lb[i - 1] = lb[i];
         lb[n - 1] = pick;
     } else {                                         // least_connections, :10-20 (first min wins)
@@ -816,6 +819,7 @@ AF_FN void on_spike(State& W) {
     AF_SHARED(&W);
     int32_t cur = W.spike_cur;
     double t = tbl_spike(W)[cur].fire;
+#pragma unroll 1
     while (cur < AF_L.n_spike && tbl_spike(W)[cur].fire == t) {
         const SpikeS m = tbl_spike(W)[cur];
         tbl_edge(W)[m.edge].spike = tbl_edge(W)[m.edge].spike + m.delta;
@@ -830,13 +834,16 @@ AF_FN void on_outage(State& W) {
     double t = tbl_outage(W)[cur].fire;
     uint32_t* lb = tbl_lb(W);
     int32_t n = W.lb_n;
+#pragma unroll 1
     while (cur < AF_L.n_outage && tbl_outage(W)[cur].fire == t) {
         const OutageS m = tbl_outage(W)[cur];
         ++cur;
         if (m.lb_edge < 0) continue;
         int32_t at = -1;
+#pragma unroll 1
         for (int32_t i = 0; i < n; ++i) if (lb[i] == (uint32_t)m.lb_edge) { at = i; break; }
         if (at >= 0) {                               // pop (DOWN) or move_to_end (UP)
+#pragma unroll 1
             for (int32_t i = at + 1; i < n; ++i) lb[i - 1] = lb[i];
             --n;
         }
@@ -860,7 +867,9 @@ AF_FN void take_samples(State& W, double t, uint32_t ev_seq) {
     uint32_t tseq = W.tick_seq, nt = W.n_ticks, seq = W.seq;
     const double horizon = W.horizon;
     const bool traced = W.traced != 0;
+#pragma unroll 1
     while ((tick < t || (tick == t && tseq < ev_seq)) && tick < horizon) {
+#pragma unroll 1
         for (int32_t j = lane; j < n_series; j += WARP) {
             uint32_t v;
             if (j < ns3) {
@@ -900,6 +909,7 @@ AF_IN void bind(State& W, unsigned char* ws, uint64_t warp_slot) {
 AF_FN void load_params(State& W) {
     AF_SHARED(&W);
     const int lane = lane_id();
+#pragma unroll 1
     for (int32_t i = lane; i < AF_L.n_edges; i += WARP) {
         const AfEdge a = AF_G.edges[i];
         EdgeS e;
@@ -908,6 +918,7 @@ AF_FN void load_params(State& W) {
         e.conn = 0; e.sent = 0; e.dropped = 0;
         tbl_edge(W)[i] = e;
     }
+#pragma unroll 1
     for (int32_t i = lane; i < AF_L.n_servers; i += WARP) {
         const AfServer a = AF_G.servers[i];
         ServerS s;
@@ -917,29 +928,36 @@ AF_FN void load_params(State& W) {
         s.pad[0] = s.pad[1] = s.pad[2] = s.pad[3] = 0;
         tbl_server(W)[i] = s;
     }
+#pragma unroll 1
     for (int32_t i = lane; i < AF_L.n_endpoints; i += WARP) {
         const AfEndpoint a = AF_G.endpoints[i];
         EndpointS e; e.step_begin = (uint32_t)a.step_begin; e.n_steps = (uint32_t)a.n_steps;
         e.total_ram = (uint32_t)a.total_ram; e.pad = 0;
         tbl_endpoint(W)[i] = e;
     }
+#pragma unroll 1
     for (int32_t i = lane; i < AF_L.n_steps; i += WARP) {
         const AfStep a = AF_G.steps[i];
         StepS s; s.dur = a.duration; s.kind = (uint32_t)a.kind; s.pad = 0;
         tbl_step(W)[i] = s;
     }
+#pragma unroll 1
     for (int32_t i = lane; i < AF_L.n_lb_edges; i += WARP) tbl_lb(W)[i] = (uint32_t)AF_G.lb_edges[i];
+#pragma unroll 1
     for (int32_t i = lane; i < AF_L.n_spike; i += WARP) {
         const AfSpikeMark a = AF_G.spikes[i];
         SpikeS s; s.fire = a.fire_time; s.delta = a.delta; s.edge = (uint32_t)a.edge; s.pad = 0;
         tbl_spike(W)[i] = s;
     }
+#pragma unroll 1
     for (int32_t i = lane; i < AF_L.n_outage; i += WARP) {
         const AfOutageMark a = AF_G.outages[i];
         OutageS o; o.fire = a.fire_time; o.lb_edge = a.lb_edge; o.down = a.down;
         tbl_outage(W)[i] = o;
     }
+#pragma unroll 1
     for (int32_t i = lane; i < AF_L.n_series; i += WARP) { tbl_samp_sum(W)[i] = 0; tbl_samp_max(W)[i] = 0; }
+#pragma unroll 1
     for (int32_t i = lane; i < AF_L.n_servers + 2; i += WARP) { InboxS b; b.head = b.tail = NIL; b.pending = 1; b.pad = 0; tbl_inbox(W)[i] = b; }
     w_sync();
     W.users_mean = AF_L.users_mean; W.users_sigma = AF_L.users_sigma; W.rate_per_user = AF_L.rate_per_user;
@@ -947,6 +965,7 @@ AF_FN void load_params(State& W) {
     const uint64_t replica = W.replica;
     if (AF_L.n_sweep_cols > 0 && replica >= AF_G.sweep_first && replica - AF_G.sweep_first < AF_G.sweep_rows) {
         const double* row = AF_G.sweep_vals + (replica - AF_G.sweep_first) * (uint64_t)AF_L.n_sweep_cols;
+#pragma unroll 1
         for (int32_t c = 0; c < AF_L.n_sweep_cols; ++c) {
             const AfSweepColumn col = AF_G.sweep_cols[c];
             double v = row[c];
@@ -974,10 +993,12 @@ AF_FN void write_back(State& W) {
     AF_SHARED(&W);
     const int lane = lane_id();
     const uint64_t local = W.local;
+#pragma unroll 1
     for (int32_t i = lane; i < AF_L.n_edges; i += WARP) {
         AF_G.edge_sent[local * (uint64_t)AF_L.n_edges + (uint32_t)i] = tbl_edge(W)[i].sent;
         AF_G.edge_dropped[local * (uint64_t)AF_L.n_edges + (uint32_t)i] = tbl_edge(W)[i].dropped;
     }
+#pragma unroll 1
     for (int32_t j = lane; j < AF_L.n_series; j += WARP) {
         AF_G.samp_sum[local * (uint64_t)AF_L.n_series + (uint32_t)j] = tbl_samp_sum(W)[j];
         AF_G.samp_max[local * (uint64_t)AF_L.n_series + (uint32_t)j] = tbl_samp_max(W)[j];

@@ -194,3 +194,20 @@ def test_c3_statistics_match_reference_dashboard():
     a, b = flat.edge_ids.index("lb-srv1"), flat.edge_ids.index("lb-srv2")
     assert (np.abs(res.edge_sent[:, a].astype(np.int64) - res.edge_sent[:, b]) <= 1).all()
     sw.close()
+
+
+@pytest.mark.parametrize("seed", [101, 107, 111, 113, 118, 122])
+def test_engine_equals_oracle_on_random_tie_prone_scenarios(eng, seed):
+    """tests/fuzz.py: deterministic step durations that tie, CPU/RAM queueing, every distribution."""
+    import fuzz
+    payload = fuzz.scenario(seed)
+    flat = flatten(payload)
+    eng.upload(flat)
+    eng.configure(trace_replicas=1, trace_clock_capacity=100000, request_capacity=200000)
+    eng.run(SEED, seed, seed + 1)
+    st = eng.stats()
+    sent, dropped = eng.edge_counts()
+    assert st[0]["flags"] == 0
+    o = des_port.simulate(payload, seed=SEED, replica=seed)
+    assert_matches_oracle(o, flat, stats=st[0], clocks=eng.trace_clocks(0), sent=sent[0], dropped=dropped[0],
+                          series=eng.trace_series(0), throughput=eng.throughput()[0])
