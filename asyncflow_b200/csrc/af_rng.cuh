@@ -38,7 +38,8 @@ AF_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
-AF_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+// (one shared body: Philox and log are used from four places; see the code-size rule in af_core.cuh)
+AF_HD_NOINLINE U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
@@ -90,7 +91,7 @@ AF_HD double af_div(double a, double b) {
 }
 
 // ln(x), finite normal x > 0 (fdlibm e_log.c scheme; see oracle/afrng.py:af_log)
-AF_HD double af_log(double x) {
+AF_HD_NOINLINE double af_log(double x) {
     const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
                  Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
                  Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
