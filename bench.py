@@ -187,7 +187,7 @@ def run_reference(a) -> None:
     cores = os.cpu_count() or 1
     total = a.replicas * a.gpus
     payload = workload(a.replicas, a.horizon)
-    per_step = 4 * cores                                  # ~4 replicas per core and step
+    per_step = 2 * cores                                  # ~2 replicas per core and step (~15 s)
     ids = spaced(total, per_step * (a.steps + a.warmup))
     chunks = [ids[i::(a.steps + a.warmup)] for i in range(a.steps + a.warmup)]
     for c in chunks[: a.warmup]:
@@ -357,7 +357,7 @@ def run_ours(a) -> None:
     }
     if world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        k = 8 * cores                                     # ~8 replicas per core: 10-30 s of CPU work
+        k = 3 * cores                                     # ~3 replicas per core: 10-30 s of CPU work
         cpu_path(payload, spaced(total, cores), total, cores)   # untimed: page in the interpreter state
         n, h, dt = cpu_path(payload, spaced(total, k), total, cores)
         out["cpu_baseline"] = {
