@@ -113,3 +113,22 @@ def all_gather_summary(ints: np.ndarray, flts: np.ndarray, device: str | None = 
         replicas=int(tot[:, 3].sum()), overflowed=int(tot[:, 4].sum()),
         lat_sum=float(all_f[:, 0].sum()), lat_min=float(all_f[:, 2].min()), lat_max=float(all_f[:, 3].max()),
         per_rank_completed=[int(x) for x in tot[:, 0]])
+
+
+def run_sharded(runner, *, with_histogram: bool = True):
+    """Run ``runner`` (a :class:`~asyncflow_b200.runner.SweepRunner` built for the WHOLE sweep)
+    on this rank's replica range and all-gather the summaries.
+
+    One process per GPU (``torchrun``); call ``torch.distributed.init_process_group("nccl")``
+    first.  Returns ``(local SweepResults, GlobalSummary)``; the per-replica rows of other
+    ranks stay on those ranks -- only the summary block crosses NVLink.
+    """
+    import torch.distributed as dist  # noqa: PLC0415
+
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    begin, end = shard_bounds(runner.n_replicas, rank, world)
+    res = runner.run(begin, end)
+    hist = runner.engine().reduced_histogram() if (with_histogram and runner.histogram) else None
+    ints, flts = summary_block(res.stats, hist)
+    return res, all_gather_summary(ints, flts)

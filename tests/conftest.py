@@ -20,6 +20,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _native_code_is_built():
+    """A fresh checkout has no .so files (they are git-ignored): build them once per session."""
+    lib = ROOT / "asyncflow_b200" / "_lib" / "libasyncflow_b200.so"
+    if not lib.exists():
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 @pytest.fixture(scope="session")
 def scenarios_dir() -> Path:
     return ROOT / "tests" / "scenarios"

@@ -211,3 +211,15 @@ def test_engine_equals_oracle_on_random_tie_prone_scenarios(eng, seed):
     o = des_port.simulate(payload, seed=SEED, replica=seed)
     assert_matches_oracle(o, flat, stats=st[0], clocks=eng.trace_clocks(0), sent=sent[0], dropped=dropped[0],
                           series=eng.trace_series(0), throughput=eng.throughput()[0])
+
+
+def test_run_sharded_world_of_one_equals_plain_run():
+    from asyncflow_b200.distributed import run_sharded
+    flat = flatten(load_scenario("c1_my_service.yml", 8))
+    sw = SweepRunner(flat, 64, {("users_mean",): np.linspace(20, 200, 64)}, seed=SEED)
+    res, glob = run_sharded(sw)
+    assert glob.replicas == 64 and glob.completed == int(res.completed.sum())
+    assert int(glob.histogram.sum()) == glob.completed
+    lat_all = glob.percentile(95)
+    assert res.stats["p95"].min() <= lat_all <= res.stats["p95"].max()
+    sw.close()
