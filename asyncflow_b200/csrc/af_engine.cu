@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -159,6 +160,12 @@ struct DevBuf {
 
 thread_local std::string g_create_error;
 
+// The launch parameters live in __constant__ memory, which is per device, not per engine: a
+// second engine on the same device must not overwrite them while the first one's kernel runs.
+constexpr int kMaxDevices = 64;
+std::mutex g_const_mutex;
+af_engine* g_const_owner[kMaxDevices] = {};
+
 }  // namespace
 
 struct af_engine {
@@ -244,6 +251,10 @@ void af_engine_destroy(af_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    {
+        std::lock_guard<std::mutex> lock(g_const_mutex);
+        if (g_const_owner[e->device % kMaxDevices] == e) g_const_owner[e->device % kMaxDevices] = nullptr;
+    }
     DevBuf* bufs[] = {&e->d_edges, &e->d_servers, &e->d_eps, &e->d_steps, &e->d_lb, &e->d_spikes, &e->d_outages,
                       &e->d_sweep_cols, &e->d_sweep_vals, &e->d_sp_evt, &e->d_sp_evk, &e->d_sp_rq, &e->d_sp_nx,
                       &e->d_stats, &e->d_sent, &e->d_dropped, &e->d_hist, &e->d_thr, &e->d_ssum, &e->d_smax,
@@ -398,6 +409,12 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     AF_CUDA(e, cudaMemsetAsync(e->d_counter.p, 0, 8, e->stream), "memset");
     if (L.collect_hist) AF_CUDA(e, cudaMemsetAsync(e->d_hist.p, 0, n * AF_HIST_BINS * 4, e->stream), "memset hist");
     if (L.collect_thr) AF_CUDA(e, cudaMemsetAsync(e->d_thr.p, 0, n * (uint64_t)L.horizon_s * 4, e->stream), "memset thr");
+    {   // serialise against another engine that may still be running on this device
+        std::lock_guard<std::mutex> lock(g_const_mutex);
+        af_engine*& owner = g_const_owner[e->device % kMaxDevices];
+        if (owner && owner != e) AF_CUDA(e, cudaStreamSynchronize(owner->stream), "waiting for the device's previous engine");
+        owner = e;
+    }
     AF_CUDA(e, cudaMemcpyToSymbolAsync(afc::c_L, &L, sizeof L, 0, cudaMemcpyHostToDevice, e->stream), "layout -> constant memory");
     e->G_host = G;   // keep the source alive until the async copy has been issued from pageable memory
     AF_CUDA(e, cudaMemcpyToSymbolAsync(afc::c_G, &e->G_host, sizeof G, 0, cudaMemcpyHostToDevice, e->stream), "globals -> constant memory");

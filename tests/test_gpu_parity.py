@@ -223,3 +223,17 @@ def test_run_sharded_world_of_one_equals_plain_run():
     lat_all = glob.percentile(95)
     assert res.stats["p95"].min() <= lat_all <= res.stats["p95"].max()
     sw.close()
+
+
+def test_two_engines_on_one_device_do_not_disturb_each_other():
+    """Launch parameters are in __constant__ memory (per device): a second engine has to wait."""
+    fa, fb = flatten(load_scenario("c1_my_service.yml", 10)), flatten(load_scenario("c3_lb_two_servers.yml", 8))
+    with Engine(0) as a, Engine(0) as b:
+        a.upload(fa); b.upload(fb)
+        a.configure(); b.configure()
+        a.run(SEED, 0, 2000); b.run(SEED, 0, 2000)      # b is launched while a may still be running
+        sa, sb = a.stats().copy(), b.stats().copy()
+        a.run(SEED, 0, 2000); a.sync(); b.run(SEED, 0, 2000); b.sync()
+        np.testing.assert_array_equal(a.stats(), sa)
+        np.testing.assert_array_equal(b.stats(), sb)
+    assert sa["completed"].sum() > 0 and sb["completed"].sum() > 0
