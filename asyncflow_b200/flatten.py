@@ -124,7 +124,8 @@ def flatten(payload: Any) -> FlatScenario:
     window = int(gen.get("user_sampling_window") or 60)
     horizon = int(ss.get("total_simulation_time") or 3600)
     period = float(ss.get("sample_period_s") or 0.01)
-    enabled = [_s(m) for m in (ss.get("enabled_sample_metrics") or ALL_SAMPLED)]
+    esm = ss.get("enabled_sample_metrics")
+    enabled = [_s(m) for m in (ALL_SAMPLED if esm is None else esm)]   # an explicit empty set disables sampling
     mask = 0
     for m in enabled:
         mask |= K.METRIC_BITS.get(m, 0)

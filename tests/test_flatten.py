@@ -56,6 +56,15 @@ def test_defaults_follow_the_schema():
     assert e.dist == K.DIST["normal"] and e.sigma == e.mean == 0.002
 
 
+def test_explicitly_empty_metric_set_disables_sampling():
+    d = load_scenario("c1_my_service.yml")
+    d["sim_settings"]["enabled_sample_metrics"] = []
+    assert flatten(d).pod.metrics_mask == 0
+    d["sim_settings"]["enabled_sample_metrics"] = ["ram_in_use", "edge_concurrent_connection"]
+    f = flatten(d)
+    assert f.pod.metrics_mask == 4 | 8
+
+
 def test_sweep_spec_columns():
     f = flatten(load_scenario("c3_lb_two_servers.yml"))
     n = 5

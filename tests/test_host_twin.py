@@ -106,3 +106,20 @@ def test_histogram_percentile_matches_numpy_within_two_percent():
         got = twin.lib().af_twin_hist_percentile(hist.ctypes.data, len(lat), q)
         exact = float(np.percentile(lat, q))
         assert abs(got - exact) < 0.01 * exact
+
+
+def test_partial_metric_sets_follow_the_collector_rule():
+    """collector.py:60-66: server series are recorded only if ALL THREE are enabled; edges on their own."""
+    payload = load_scenario("c1_my_service.yml", 6)
+    payload["sim_settings"]["enabled_sample_metrics"] = ["ram_in_use", "edge_concurrent_connection"]
+    flat = flatten(payload)
+    o = des_port.simulate(payload, seed=SEED, replica=3)
+    r = twin.run(flat, seed=SEED, replica_begin=3, n=1, trace=1, clock_cap=20000)
+    st = r["stats"][0]
+    n, nt = int(st["completed"]), int(st["n_ticks"])
+    np.testing.assert_array_equal(r["trace_clocks"][0, :n], np.array(o["clocks"]).reshape(-1, 2))
+    assert o["server_series"]["app-1"] == {"ram_in_use": []}
+    assert (r["samp_sum"][0][:3] == 0).all()                       # the server triple is off
+    conn = np.array(o["edge_series"]["gen-client"]["edge_concurrent_connection"], dtype=np.uint32)
+    assert nt == len(conn)
+    np.testing.assert_array_equal(r["trace_series"][0][3, :nt], conn)
