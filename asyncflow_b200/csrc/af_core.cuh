@@ -125,7 +125,8 @@ struct ServerS {          // 64 B
     int32_t cpu_free, ram_free, ready_q, io_q, ram_in_use;
     uint32_t ramq_head, ramq_tail, cpuq_head, cpuq_tail;
     uint32_t out_edge, ep_begin, n_ep;
-    uint32_t pad[4];
+    uint32_t ramq_head_need;   // total_ram of the request at the head of the RAM queue (valid when ramq_head != NIL)
+    uint32_t pad[3];
 };
 struct EndpointS { uint32_t step_begin, n_steps, total_ram, pad; }; // 16 B
 struct StepS { double dur; uint32_t kind, pad; };                   // 16 B
@@ -557,13 +558,19 @@ AF_FN void ram_walk(State& W, ServerS& S, uint32_t sidx) {
     AF_SHARED(&W); AF_SHARED(&S);
 #pragma unroll 1
     while (S.ramq_head != NIL) {
-        uint32_t w = S.ramq_head;
-        uint32_t need = tbl_endpoint(W)[pk_ep(rq_load(W, w).pack)].total_ram;
+        const uint32_t need = S.ramq_head_need;      // kept beside the queue: no trip to the waiter's record
         if ((int32_t)need > S.ram_free) break;
-        fifo_pop(W, S.ramq_head, S.ramq_tail);
+        uint32_t w = fifo_pop(W, S.ramq_head, S.ramq_tail);
+        if (S.ramq_head != NIL) S.ramq_head_need = tbl_endpoint(W)[pk_ep(rq_load(W, S.ramq_head).pack)].total_ram;
         S.ram_free -= (int32_t)need;
         nq_push(W, I_RAM_OK, sidx, w);
     }
+}
+// RAM.get(total_ram) of a request that cannot be served at once: join the queue, walk it
+AF_IN void ram_enqueue(State& W, ServerS& S, uint32_t sidx, uint32_t slot, uint32_t total_ram) {
+    if (S.ramq_head == NIL) S.ramq_head_need = total_ram;
+    fifo_push(W, S.ramq_head, S.ramq_tail, slot);
+    ram_walk(W, S, sidx);
 }
 
 constexpr uint32_t PK_WAIT = 1u << 30;   // the request sits in the ready queue (server.py:215-217)
@@ -638,10 +645,9 @@ AF_IN void on_cpu_put(State& W, uint32_t slot, uint32_t sidx) {
 
 // ServerRuntime._dispatcher resumed with `slot` (server.py:303-313), then the head of
 // _handle_request (server.py:88-149), which runs as an URGENT Initialize right after
-AF_IN void server_got(State& W, uint32_t slot, uint32_t sidx) {
+AF_IN void server_got(State& W, uint32_t slot, uint32_t sidx, const ReqRec& r) {
     consumer_get(W, NODE_SERVER0 + sidx);            // the dispatcher loops back to get() first
     ServerS& S = tbl_server(W)[sidx];
-    ReqRec r = rq_load(W, slot);
     uint32_t pack = r.pack + 1;                      // record_hop(SERVER)
     uint32_t epi = 0;
     const uint32_t n_ep = S.n_ep;
@@ -656,8 +662,7 @@ AF_IN void server_got(State& W, uint32_t slot, uint32_t sidx) {
     const uint32_t total_ram = tbl_endpoint(W)[ep_global].total_ram;
     if (total_ram) {                                 // yield RAM.get(total_ram)
         if (!(S.ramq_head == NIL && (int32_t)total_ram <= S.ram_free && can_fuse(W))) {
-            fifo_push(W, S.ramq_head, S.ramq_tail, slot);
-            ram_walk(W, S, sidx);
+            ram_enqueue(W, S, sidx, slot, total_ram);
             return;
         }
         S.ram_free -= (int32_t)total_ram;            // granted, and its get event would run next
@@ -706,10 +711,10 @@ AF_IN void complete(State& W, uint32_t slot, double t0) {
 // a node's consumer process resumes with `slot` (the StoreGet event is processed):
 // client.py:43-71, load_balancer.py:60-72 + routing/lb_algorithms.py:10-36, server.py:303-313
 // ---------------------------------------------------------------------------------
-AF_FN void node_got(State& W, uint32_t node, uint32_t slot) {
+AF_FN void node_got(State& W, uint32_t node, uint32_t slot, double t0, uint32_t rid, uint32_t pack_in) {
     AF_SHARED(&W);
-    if (node >= NODE_SERVER0) { server_got(W, slot, node - NODE_SERVER0); return; }
-    ReqRec r = rq_load(W, slot);
+    ReqRec r; r.t0 = t0; r.rid = rid; r.pack = pack_in;   // the record as the caller already holds it
+    if (node >= NODE_SERVER0) { server_got(W, slot, node - NODE_SERVER0, r); return; }
     r.pack += 1;                                     // record_hop(client / LB)
     if (node == NODE_CLIENT) {
         if (pk_hops(r.pack) > 3) {                   // client.py:62: back from the servers
@@ -753,7 +758,7 @@ AF_IN void run_item(State& W, uint32_t item) {
         InboxS& b = tbl_inbox(W)[aux];
         if (b.pending) { b.pending = 0; nq_push(W, I_GOT, aux, fifo_pop(W, b.head, b.tail)); }
     } else if (kind == I_GOT) {
-        node_got(W, aux, slot);
+        { ReqRec r = rq_load(W, slot); node_got(W, aux, slot, r.t0, r.rid, r.pack); }
     } else if (kind == I_CLIENT_LOOP) {
         consumer_get(W, NODE_CLIENT);
     } else if (kind == I_RAM_OK) {                   // the RAM get event is processed: the handler resumes
@@ -785,13 +790,14 @@ AF_IN void on_deliver(State& W, uint32_t slot, uint32_t e) {
     E.conn -= 1;
     const uint32_t meta = E.meta;
     ReqRec r = rq_load(W, slot);
-    rq_set_pack(W, slot, r.pack + 1);                // record_hop(edge)
+    r.pack += 1;                                     // record_hop(edge)
     const uint32_t tk = (meta >> 3) & 3u;
     const uint32_t node = tk == AF_TARGET_CLIENT ? NODE_CLIENT : (tk == AF_TARGET_LB ? NODE_LB : NODE_SERVER0 + (meta >> 5));
     if (can_fuse(W)) {                               // (implies: every inbox empty, every consumer in get())
-        node_got(W, node, slot);                     // put -> pending get -> resume, nothing in between
-        return;
+        node_got(W, node, slot, r.t0, r.rid, r.pack);   // put -> pending get -> resume, nothing in between
+        return;                                      // (the consumer stores the record's new pack itself)
     }
+    rq_set_pack(W, slot, r.pack);
     InboxS& b = tbl_inbox(W)[node];
     fifo_push(W, b.head, b.tail, slot);              // Store.put: items.append now ...
     nq_push(W, I_PUT, node, slot);                   // ... the put event is processed later
@@ -925,7 +931,7 @@ AF_FN void load_params(State& W) {
         s.cpu_free = a.cpu_cores; s.ram_free = a.ram_mb; s.ready_q = 0; s.io_q = 0; s.ram_in_use = 0;
         s.ramq_head = s.ramq_tail = s.cpuq_head = s.cpuq_tail = NIL;
         s.out_edge = (uint32_t)a.out_edge; s.ep_begin = (uint32_t)a.endpoint_begin; s.n_ep = (uint32_t)a.n_endpoints;
-        s.pad[0] = s.pad[1] = s.pad[2] = s.pad[3] = 0;
+        s.ramq_head_need = 0; s.pad[0] = s.pad[1] = s.pad[2] = 0;
         tbl_server(W)[i] = s;
     }
 #pragma unroll 1

@@ -14,9 +14,15 @@ ap.add_argument("--wpb", type=int, default=0)
 ap.add_argument("--bps", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--sweep", default="rtt")
+ap.add_argument("--no-metrics", action="store_true")
+ap.add_argument("--users", type=float, default=0.0)
 a = ap.parse_args()
 d = yaml.safe_load((ROOT / "tests" / "scenarios" / a.scenario).read_text())
 d["sim_settings"]["total_simulation_time"] = a.horizon
+if a.no_metrics:
+    d["sim_settings"]["enabled_sample_metrics"] = []
+if a.users > 0:
+    d["rqs_input"]["avg_active_users"]["mean"] = a.users
 flat = flatten(d)
 n = a.replicas
 sweep = None
