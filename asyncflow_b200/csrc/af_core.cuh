@@ -349,7 +349,26 @@ AF_FN uint32_t fifo_pop(State& W, uint32_t& head, uint32_t& tail) {
 // scan noticed, else appends; pop is a warp arg-min over (time, seq).  Every lane
 // executes push (same slot, same values); only the owner lane reads the slot back.
 // ---------------------------------------------------------------------------------
-// slow path of push: the high-water mark reached the capacity although holes may exist below it
+// Pool hygiene (both out of line, both rare).  push takes the slot of the last pop, then a hole the
+// last scan noticed, then APPENDS; under bursts that lets the high-water mark run ahead of the live
+// count and -- because fresh events keep landing at the top -- it never comes back: overloaded
+// replicas were scanning ~750 slots for ~20 live events (round-1 finding).  So: once the slack
+// exceeds POOL_SLACK, push fills the lowest hole instead, and popping the top slot pulls the mark
+// down to the highest occupied slot.
+constexpr int32_t POOL_SLACK = 8;
+AF_FN int32_t pool_top(State& W) {
+    AF_SHARED(&W);
+    const int lane = lane_id();
+    const int32_t hw = W.ev_hw;
+    int32_t mine = -1;
+#pragma unroll 1
+    for (int32_t k = lane; k < hw; k += WARP)
+        if (evt_load(W, k) != INF_BITS) mine = k;
+#if AF_DEVICE_CODE
+    mine = (int32_t)__reduce_max_sync(AF_FULL, (uint32_t)(mine + 1)) - 1;
+#endif
+    return mine;
+}
 AF_FN int32_t pool_find_hole(State& W) {
     AF_SHARED(&W);
     const int lane = lane_id();
@@ -371,10 +390,12 @@ AF_FN void push_seq(State& W, double t, uint32_t payload, uint32_t s) {
     else if (W.ev_hole >= 0) { slot = W.ev_hole; W.ev_hole = -1; }
     else {
         slot = W.ev_hw;
-        if (AF_UNLIKELY(slot >= AF_L.ev_total)) {
-            slot = pool_find_hole(W);
-            if (slot < 0) { W.flags |= AF_FLAG_EVENT_OVERFLOW; return; }
-        } else W.ev_hw = slot + 1;
+        if (AF_UNLIKELY(slot - W.ev_live > POOL_SLACK)) {
+            slot = pool_find_hole(W);                // fragmented: fill the lowest hole instead of appending --
+        } else {                                     // a fresh event at the top would keep every later scan long
+            if (AF_UNLIKELY(slot >= AF_L.ev_total)) { W.flags |= AF_FLAG_EVENT_OVERFLOW; return; }
+            W.ev_hw = slot + 1;
+        }
     }
     uint64_t key = ((uint64_t)s << 32) | payload;
     if (AF_IN_SMEM(slot, AF_L.ev_smem)) { tbl_ev_time(W)[slot] = t; tbl_ev_key(W)[slot] = key; }
@@ -433,7 +454,12 @@ AF_IN void pool_remove(State& W, const PoolMin& m) {
     else W.sp_ev_time[slot - AF_L.ev_smem] = afr::u2d(INF_BITS);
     W.ev_live -= 1;
     int32_t nhw = hw;
-    if (slot == hw - 1) { nhw = hw - 1; W.ev_hw = nhw; W.ev_last_free = -1; }
+    if (slot == hw - 1) {
+        nhw = hw - 1;
+        W.ev_hw = nhw;
+        if (AF_UNLIKELY(nhw - W.ev_live > POOL_SLACK)) { nhw = pool_top(W) + 1; W.ev_hw = nhw; }
+        W.ev_last_free = -1;
+    }
     else W.ev_last_free = slot;
     W.ev_hole = m.hole < nhw ? m.hole : -1;
 }
