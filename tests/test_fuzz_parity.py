@@ -12,7 +12,7 @@ from helpers import SEED, assert_matches_oracle
 from asyncflow_b200.flatten import flatten
 
 
-@pytest.mark.parametrize("seed", range(100, 124))
+@pytest.mark.parametrize("seed", range(100, 170))
 def test_twin_equals_oracle_on_random_scenarios(seed):
     payload = fuzz.scenario(seed)
     flat = flatten(payload)

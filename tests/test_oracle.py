@@ -69,3 +69,24 @@ def test_reference_statistics_match_published_dashboard():
     assert abs(st["mean"] - 0.024) < 0.001
     assert abs(st["p95"] - 0.034) < 0.002
     assert abs(st["p99"] - 0.040) < 0.003
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="/root/reference not on this box")
+@pytest.mark.parametrize("seed", range(100, 130))
+def test_port_equals_reference_on_random_tie_prone_scenarios(seed):
+    """tests/fuzz.py scenarios (deterministic ties, queueing, every distribution, events): the port
+    must reproduce the unmodified reference actors bit for bit -- the fuzz tests then compare the
+    engine with the port."""
+    import fuzz
+    payload = fuzz.scenario(seed)
+    r = ref_harness.run_reference(payload, seed=SEED, replica=seed)
+    o = des_port.simulate(payload, seed=SEED, replica=seed)
+    for k in ("generated", "completed", "clocks", "edge_sent", "edge_dropped"):
+        assert r[k] == o[k], k
+    for sid, ser in r["server_series"].items():
+        for k, v in ser.items():
+            assert list(v) == list(o["server_series"][sid][k]), (sid, k)
+    for eid, ser in r["edge_series"].items():
+        for k, v in ser.items():
+            assert list(v) == list(o["edge_series"][eid][k]), (eid, k)
