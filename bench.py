@@ -157,6 +157,30 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def latency_delta_vs_reference(device: int):
+    """BASELINE.json's second half: p50/p95/p99 latency delta vs the SimPy reference.  The reference
+    side is tests/golden/reference_numpy_stats.json (the unmodified reference on its own numpy RNG,
+    96 replicas of C3 at the reference's parameters, 60 s horizon: oracle/make_reference_stats.py);
+    the engine side is a 4096-replica run of the same scenario, outside the timed region."""
+    from asyncflow_b200 import SweepRunner, flatten
+    fx = ROOT / "tests" / "golden" / "reference_numpy_stats.json"
+    if not fx.exists():
+        return None
+    ref = json.loads(fx.read_text())["c3_lb_two_servers.yml"]
+    payload = yaml.safe_load((ROOT / "tests" / "scenarios" / "c3_lb_two_servers.yml").read_text())
+    payload["sim_settings"]["total_simulation_time"] = ref["horizon"]
+    sw = SweepRunner(flatten(payload), 4096, seed=SEED + 1, device=device)
+    st = sw.run().stats
+    sw.close()
+    mine = {"mean": float((st["lat_sum"] / st["completed"]).mean()), "median": float(st["p50"].mean()),
+            "p95": float(st["p95"].mean()), "p99": float(st["p99"].mean())}
+    return {"scenario": "c3_lb_two_servers.yml (reference parameters, horizon %d s)" % ref["horizon"],
+            "reference": "unmodified AsyncFlow actors, numpy PCG64, %d replicas" % ref["replicas"],
+            "engine_replicas": 4096,
+            "delta_pct": {k: 100.0 * (mine[k] - ref["mean"][k]) / ref["mean"][k] for k in mine},
+            "reference_s": {k: ref["mean"][k] for k in mine}, "engine_s": mine}
+
+
 def hbm_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -355,6 +379,7 @@ def run_ours(a) -> None:
                      "traffic": profiled_traffic(f"c3_r{a.replicas}_t{a.horizon}"),
                      "note": "latency/issue-bound state machine: HBM fraction is not the limiter (DESIGN.md 'Roofline')"},
     }
+    out["latency_delta_vs_reference"] = latency_delta_vs_reference(local)
     if world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
         k = 3 * cores                                     # ~3 replicas per core: 10-30 s of CPU work
