@@ -5,24 +5,25 @@
 // src/asyncflow/runtime/simulation_runner.py:369) popping (time, prio, eid)
 // tuples and resuming the AsyncFlow actor generators.  Here every actor is a
 // branch of one state machine and only events that carry simulated delay are
-// queued (6-7 per request instead of SimPy's 25-30); each
-// zero-delay SimPy cascade (Initialize / Store put+get / Container put+get /
-// process exit) is executed inline by the handler of the timed event that
-// starts it, in the order SimPy would have produced:
+// queued in the pending-event pool (6-7 per request instead of SimPy's 25-30,
+// SURVEY.md 8a); SimPy's zero-delay events (Store put/get, Container put/get,
+// process resume) are continuation items of a small FIFO that is bypassed
+// whenever nothing else shares the instant (see the ordering rule below):
 //
-//   handler            reference being replaced
-//   -----------------  ----------------------------------------------------------
-//   gen_next_gap       samplers/poisson_poisson.py:52-82, gaussian_poisson.py:64-94
-//   on_arrival         runtime/actors/rqs_generator.py:97-119
-//   edge_send          runtime/actors/edge.py:73-107 (dropout, latency, spike)
-//   on_deliver         edge.py:110-116 + client.py:43-71 + load_balancer.py:60-72
-//                      + routing/lb_algorithms.py:10-36 + server.py:303-313
-//   server_arrive      runtime/actors/server.py:88-149 (endpoint pick, RAM first)
-//   run_steps          server.py:197-255 (lazy CPU lock, IO queue)
-//   finish_request     server.py:257-276 (release core, RAM, forward)
-//   on_spike/on_outage runtime/events/injection.py:167-226
-//   take_samples       metrics/collector.py:50-66
-//   complete           client.py:62-69 + metrics/analyzer.py:83-125
+//   code here           reference being replaced
+//   ------------------  ---------------------------------------------------------
+//   gen_next_gap        samplers/poisson_poisson.py:52-82, gaussian_poisson.py:64-94
+//   on_arrival          runtime/actors/rqs_generator.py:97-119
+//   edge_send           runtime/actors/edge.py:73-107 (dropout, latency, spike)
+//   on_deliver          edge.py:110-116 (timeout fired: connection closes, Store.put)
+//   node_got            client.py:43-71, load_balancer.py:60-72 + routing/lb_algorithms.py:10-36,
+//                       server.py:303-313 (the node's consumer process resumes)
+//   server_got          runtime/actors/server.py:88-149 (endpoint pick, RAM first)
+//   run_steps           server.py:197-276 (lazy CPU lock, IO queue, release, forward)
+//   cpu_walk, ram_walk  simpy Container._trigger_get (FIFO, head-of-line blocking)
+//   on_spike/on_outage  runtime/events/injection.py:167-226
+//   take_samples        metrics/collector.py:50-66
+//   complete            client.py:62-69 + metrics/analyzer.py:83-125
 //
 // Ordering rule (DESIGN.md "tie rule").  SimPy orders by (time, priority, eid).  Timed
 // events live in the pending-event pool and pop by (time, seq), seq being the per-replica
