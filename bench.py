@@ -260,6 +260,9 @@ def run_ours(a) -> None:
         sys.exit("bench.py: no CUDA device (asyncflow_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout carries the JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     total = a.replicas * world
     begin = rank * a.replicas
