@@ -224,7 +224,7 @@ def run_reference(a) -> None:
     value = comp / dt
     sample = (f"{len(chunks[0])} replicas/step spaced over the sweep, horizon {a.horizon}s, "
               f"{cores} processes (multiprocessing), oracle/des_port.py on oracle/simpy_shim")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -232,7 +232,7 @@ def run_reference(a) -> None:
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "heap_events_per_s": ev / dt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def config_dict(a) -> dict:
@@ -260,9 +260,6 @@ def run_ours(a) -> None:
         sys.exit("bench.py: no CUDA device (asyncflow_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout carries the JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     total = a.replicas * world
     begin = rank * a.replicas
@@ -393,9 +390,27 @@ def run_ours(a) -> None:
             "sample": f"{k} replicas spaced over the sweep, horizon {a.horizon}s, {cores} processes, "
                       f"oracle/des_port.py on oracle/simpy_shim ({dt:.1f} s)",
             "heap_events_per_s": h / dt}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_FD = None
+
+
+def claim_stdout() -> None:
+    """Keep stdout for the ONE JSON line: native libraries write there too (NCCL prints its version
+    banner with printf at communicator creation), so fd 1 is pointed at stderr for the run and the
+    result goes to the saved descriptor."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj: dict) -> None:
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(obj) + "\n").encode())
 
 
 def main() -> None:
@@ -409,6 +424,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
+    claim_stdout()
     try:
         if a.impl == "reference":
             run_reference(a)
