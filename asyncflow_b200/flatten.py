@@ -286,6 +286,7 @@ class SweepSpec:
 
     def __init__(self, flat: FlatScenario, n_replicas: int, columns: dict[tuple, Any]) -> None:
         self.n_replicas = int(n_replicas)
+        self.selectors: list[tuple[tuple, np.ndarray]] = []
         cols: list[tuple[int, int]] = []
         vals: list[np.ndarray] = []
         for sel, v in columns.items():
@@ -310,6 +311,7 @@ class SweepSpec:
             else:
                 msg = f"unknown sweep field {name!r}"
                 raise KeyError(msg)
+            self.selectors.append((sel, arr))
             for t in targets:
                 cols.append((K.FIELDS[name], t))
                 vals.append(arr)
@@ -318,6 +320,55 @@ class SweepSpec:
                        else np.zeros((self.n_replicas, 0)))
         self._cols = (K.AfSweepColumn * max(1, len(cols)))(*[K.AfSweepColumn(f, i) for f, i in cols])
         self.columns = cols
+
+    def payload_for(self, payload: Any, replica: int) -> dict:
+        """The scenario of ONE replica of the sweep as a plain YAML-shaped dict.
+
+        Feeding the result to the reference's ``SimulationRunner`` (or to a one-replica
+        ``GpuSimulationRunner``) simulates exactly what row ``replica`` of the sweep simulates;
+        it is how a sweep point is handed back to the reference for inspection, and how the parity
+        tests build the oracle's input.  ``payload`` is the base scenario the sweep was made from.
+        """
+        import copy  # noqa: PLC0415
+
+        p = copy.deepcopy(_as_dict(payload))
+        topo = p["topology_graph"]
+        edges = {e["id"]: e for e in topo["edges"]}
+        servers = {s["id"]: s for s in topo["nodes"]["servers"]}
+        # endpoint_ram rewrites the step list, so it goes last (step selectors use original indices)
+        for sel, arr in sorted(self.selectors, key=lambda sa: sa[0][0] == "endpoint_ram"):
+            name, v = sel[0], float(arr[replica])
+            if name == "users_mean":
+                p["rqs_input"]["avg_active_users"]["mean"] = v
+            elif name == "users_sigma":
+                p["rqs_input"]["avg_active_users"]["variance"] = v
+            elif name == "rate_per_user":
+                p["rqs_input"]["avg_request_per_minute_per_user"]["mean"] = v * 60.0
+            elif name == "edge_mean":
+                edges[sel[1]]["latency"]["mean"] = v
+            elif name == "edge_sigma":
+                edges[sel[1]]["latency"]["variance"] = v
+            elif name == "edge_dropout":
+                edges[sel[1]]["dropout_rate"] = v
+            elif name == "server_cpu_cores":
+                servers[sel[1]].setdefault("server_resources", {})["cpu_cores"] = int(v)
+            elif name == "server_ram_mb":
+                servers[sel[1]].setdefault("server_resources", {})["ram_mb"] = int(v)
+            elif name == "step_duration":
+                op = servers[sel[1]]["endpoints"][int(sel[2])]["steps"][int(sel[3])]["step_operation"]
+                (k, _), = op.items()
+                op[k] = v
+            elif name == "endpoint_ram":
+                ep = servers[sel[1]]["endpoints"][int(sel[2])]
+                rest = [st for st in ep["steps"] if _s(st["kind"]) not in RAM_KINDS]
+                if int(v) > 0:      # total RAM is reserved up front, so one RAM step says it all
+                    rest.append({"kind": "ram", "step_operation": {"necessary_ram": int(v)}})
+                ep["steps"] = rest
+            elif name == "spike_delta":
+                for ev in p.get("events") or []:
+                    if ev["event_id"] == sel[1]:
+                        ev["start"]["spike_s"] = v
+        return p
 
     def pin(self) -> None:
         """Move the value table into page-locked host memory (needs torch + a CUDA device)."""

@@ -94,3 +94,43 @@ def scenario(seed: int) -> dict:
     if events:
         doc["events"] = events
     return doc
+
+
+def sweep_columns(seed: int, payload: dict, n: int) -> dict:
+    """Random per-replica overrides covering every AF_FIELD_* of the C ABI, for ``n`` replicas."""
+    rng = random.Random(seed * 7919 + 1)
+    topo = payload["topology_graph"]
+    cols: dict[tuple, list] = {}
+    if rng.random() < 0.7:
+        cols[("users_mean",)] = [rng.choice([30, 80, 200, 350]) for _ in range(n)]
+    if payload["rqs_input"]["avg_active_users"].get("distribution") == "normal" and rng.random() < 0.7:
+        cols[("users_sigma",)] = [rng.choice([5.0, 20.0, 60.0]) for _ in range(n)]
+    if rng.random() < 0.4:
+        cols[("rate_per_user",)] = [rng.choice([0.5, 1.0, 2.0]) for _ in range(n)]
+    for e in topo["edges"]:
+        r = rng.random()
+        dist = e["latency"].get("distribution") or "poisson"
+        if r < 0.3 and dist != "uniform":
+            cols[("edge_mean", e["id"])] = [rng.choice([0.001, 0.002, 0.005, 0.02]) if dist != "poisson"
+                                            else rng.choice([0.1, 0.4]) for _ in range(n)]
+        if 0.2 < r < 0.5 and dist in ("normal", "log_normal"):
+            cols[("edge_sigma", e["id"])] = [rng.choice([0.0005, 0.002, 0.2]) for _ in range(n)]
+        if r > 0.8:
+            cols[("edge_dropout", e["id"])] = [rng.choice([0.0, 0.02, 0.2]) for _ in range(n)]
+    for s in topo["nodes"]["servers"]:
+        if rng.random() < 0.4:
+            cols[("server_cpu_cores", s["id"])] = [rng.choice([1, 2, 4]) for _ in range(n)]
+        if rng.random() < 0.4:
+            cols[("server_ram_mb", s["id"])] = [rng.choice([256, 300, 2048]) for _ in range(n)]
+        for j, ep in enumerate(s["endpoints"]):
+            if rng.random() < 0.3:
+                cols[("endpoint_ram", s["id"], j)] = [rng.choice([0, 32, 128, 256]) for _ in range(n)]
+            for k, st in enumerate(ep["steps"]):
+                if st["kind"] != "ram" and rng.random() < 0.25:
+                    cols[("step_duration", s["id"], j, k)] = [rng.choice(DUR) for _ in range(n)]
+    for ev in payload.get("events") or []:
+        if "spike_s" in ev["start"] and rng.random() < 0.6:
+            cols[("spike_delta", ev["event_id"])] = [rng.choice([0.001, 0.004, 0.03]) for _ in range(n)]
+    if not cols:
+        cols[("users_mean",)] = [rng.choice([30, 80, 200]) for _ in range(n)]
+    return cols

@@ -78,6 +78,45 @@ def test_sweep_spec_columns():
         SweepSpec(f, n, {("bogus",): 1.0})
 
 
+def test_payload_for_spells_out_one_sweep_row():
+    base = load_scenario("c4_lb8_events.yml")
+    f = flatten(base)
+    ev = next(e["event_id"] for e in base["events"] if "spike_s" in e["start"])
+    spec = SweepSpec(f, 3, {("users_mean",): [10, 20, 30], ("rate_per_user",): [0.5, 1.0, 2.0],
+                            ("edge_mean", "client-lb"): [0.001, 0.002, 0.003], ("edge_dropout", "client-lb"): 0.0,
+                            ("server_cpu_cores", "srv-3"): [1, 2, 4], ("endpoint_ram", "srv-3", 0): [64, 0, 512],
+                            ("step_duration", "srv-3", 0, 0): [0.001, 0.002, 0.004], ("spike_delta", ev): [0.1, 0.2, 0.3]})
+    p = spec.payload_for(base, 2)
+    assert base["rqs_input"]["avg_active_users"]["mean"] != 30          # the base is not touched
+    g = flatten(p)
+    assert g.pod.users_mean == 30 and g.pod.rate_per_user == 2.0
+    e = f.edge_ids.index("client-lb")
+    assert g.pod.edges[e].mean == 0.003 and g.pod.edges[e].dropout == 0.0
+    s = f.server_ids.index("srv-3")
+    assert g.pod.servers[s].cpu_cores == 4
+    assert g.pod.endpoints[f.endpoint_index[("srv-3", 0)]].total_ram == 512
+    assert g.pod.steps[f.step_index[("srv-3", 0, 0)]].duration == 0.004
+    amps = sorted(abs(g.pod.spike_marks[i].delta) for i in range(g.pod.n_spike_marks))
+    assert amps[-1] == 0.3
+    # a zero-RAM row drops the RAM step altogether
+    assert flatten(spec.payload_for(base, 1)).pod.endpoints[f.endpoint_index[("srv-3", 0)]].total_ram == 0
+    # everything the sweep did not name is unchanged
+    assert bytes(g.pod.servers[0]) == bytes(f.pod.servers[0])
+
+
+def test_sweep_runner_hands_out_payloads_without_a_device():
+    from asyncflow_b200 import SweepRunner
+    base = load_scenario("c1_my_service.yml")
+    sw = SweepRunner(base, 4, {("users_mean",): [10, 20, 30, 40]}, pinned=False)
+    assert sw.payload_for(3)["rqs_input"]["avg_active_users"]["mean"] == 40
+    r = sw.replica_runner(2)
+    assert (r.seed, r.replica) == (sw.seed, 2) and r.simulation_input["rqs_input"]["avg_active_users"]["mean"] == 30
+    with pytest.raises(IndexError):
+        sw.payload_for(4)
+    with pytest.raises(ValueError):
+        SweepRunner(flatten(base), 2, pinned=False).payload_for(0)
+
+
 @pytest.mark.reference
 @pytest.mark.skipif(not ref_harness.reference_available(), reason="/root/reference not on this box")
 @pytest.mark.parametrize("name", ["c1_my_service.yml", "c4_lb8_events.yml", "mixed_lc.yml", "ev_spikes_outages.yml"])

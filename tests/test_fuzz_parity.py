@@ -23,3 +23,25 @@ def test_twin_equals_oracle_on_random_scenarios(seed):
     assert st["flags"] == 0
     assert_matches_oracle(o, flat, stats=st, clocks=r["trace_clocks"][0, :n], sent=r["sent"][0],
                           dropped=r["dropped"][0], series=r["trace_series"][0][:, :nt], throughput=r["thr"][0])
+
+
+@pytest.mark.parametrize("seed", range(300, 330))
+def test_twin_equals_oracle_on_random_sweeps(seed):
+    """Every sweep field of the C ABI (AF_FIELD_*): replica i of a random sweep == the oracle run on
+    the scenario that SweepSpec.payload_for(i) spells out."""
+    from asyncflow_b200.flatten import SweepSpec
+
+    payload = fuzz.scenario(seed)
+    flat = flatten(payload)
+    n = 3
+    spec = SweepSpec(flat, n, fuzz.sweep_columns(seed, payload, n))
+    r = twin.run(flat, seed=SEED, replica_begin=0, n=n, sweep=spec, trace=n, clock_cap=100000,
+                 request_capacity=200000)
+    for i in range(n):
+        p = spec.payload_for(payload, i)
+        o = des_port.simulate(p, seed=SEED, replica=i)
+        st = r["stats"][i]
+        k, nt = int(st["completed"]), int(st["n_ticks"])
+        assert st["flags"] == 0
+        assert_matches_oracle(o, flatten(p), stats=st, clocks=r["trace_clocks"][i, :k], sent=r["sent"][i],
+                              dropped=r["dropped"][i], series=r["trace_series"][i][:, :nt], throughput=r["thr"][i])

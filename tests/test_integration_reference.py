@@ -57,3 +57,26 @@ def test_reference_analyzer_on_engine_results_equals_reference_run(name, horizon
     t_b, v_b = mine.get_series("ram_in_use", mine.flat.server_ids[0])
     assert v_a == v_b and np.allclose(t_a, t_b)
     assert mine.format_latency_stats() == ra.format_latency_stats()
+
+
+@pytest.mark.parametrize("seed", [301, 305, 312, 327])
+def test_sweep_row_equals_unmodified_reference_on_payload_for(seed):
+    """A sweep point handed back to the reference: SweepSpec.payload_for(i) passes the reference's
+    own SimulationPayload validation, and the UNMODIFIED reference actors run on it produce the
+    clocks the engine produced for row i of the sweep."""
+    import fuzz
+
+    from asyncflow_b200.flatten import SweepSpec
+
+    payload = fuzz.scenario(seed)
+    flat = flatten(payload)
+    n = 2
+    spec = SweepSpec(flat, n, fuzz.sweep_columns(seed, payload, n))
+    r = twin.run(flat, seed=SEED, replica_begin=0, n=n, sweep=spec, trace=n, clock_cap=100000, request_capacity=200000)
+    for i in range(n):
+        p = spec.payload_for(payload, i)
+        ref = ref_harness.run_reference(p, seed=SEED, replica=i)          # validates with the reference schema
+        k = int(r["stats"][i]["completed"])
+        got = [tuple(x) for x in r["trace_clocks"][i, :k].tolist()]
+        assert got == [tuple(w) for w in ref["clocks"]]
+        assert dict(zip(flat.edge_ids, map(int, r["dropped"][i]))) == ref["edge_dropped"]
