@@ -116,6 +116,20 @@ AF_IN uint32_t pk_ep(uint32_t p) { return (p >> 16) & 0xFFFu; }
 
 struct ReqRec { double t0; uint32_t rid; uint32_t pack; };          // 16 B
 
+#if defined(AF_PREDRAW)
+// Build variant AF_PREDRAW -- lane-parallel, memoised edge variates.
+// An edge's random numbers are a pure function of (seed, replica, request id, hop, edge parameters)
+// (oracle/afrng.py), and on every topology the reference accepts an edge is crossed at ONE hop count
+// (generator edge 1, client edge 3, LB edges 5, a server's exit = its entry + 2).  So instead of all 32
+// lanes drawing the same variate at each send, the arrival handler lets lane l draw edge (l % rows) of
+// request id (base + 1 + l / rows): one warp-wide pass fills `chunk = 32 / rows` future requests, and
+// edge_send() reads its value from a shared-memory ring.  The ring is a MEMO, not a queue: a miss (the
+// request is older than the ring, the edge has no row, or the hop differs from the planned one) simply
+// draws as before, so results are bit-identical with or without it.
+constexpr int32_t PRE_MAX_ROWS = 6;
+constexpr int32_t PRE_RING = 32;
+#endif
+
 // ---- per-warp private tables (shared memory on the device) -------------------
 struct EdgeS {            // 48 B
     double mean, sigma, dropout, spike;
@@ -154,6 +168,9 @@ struct State {
     // generator (two clocks: the sampler's virtual one and the simulation's)
     double g_vnow, g_window_end, g_lam;
     uint32_t g_pos, generated, g_done, need_arrival, arm_seq;
+#if defined(AF_PREGEN)
+    uint32_t g_lo, g_pad;      // the gap memo holds stream positions [g_lo, g_lo + 32)
+#endif
     // parameters that may be swept
     double users_mean, users_sigma, rate_per_user;
     // load balancer / timelines
@@ -162,7 +179,11 @@ struct State {
     uint32_t tick_seq, n_ticks;
     double tick_time;
     // results
+#if defined(AF_PREDRAW)
+    uint32_t completed, flags, traced, pre_hi;   // pre_hi: edge variates of request ids <= pre_hi have been drawn
+#else
     uint32_t completed, flags, traced, pad0;
+#endif
     uint64_t n_events;
     double lat_sum, lat_sumsq, lat_min, lat_max;
 };
@@ -184,6 +205,14 @@ struct Layout {
     int32_t off_ev_time, off_ev_key, off_rq_rec, off_rq_next, off_edge, off_server,
             off_endpoint, off_step, off_lb, off_spike, off_outage, off_samp_sum, off_samp_max, off_nq, off_inbox;
     int32_t warp_bytes;
+#if defined(AF_PREGEN)
+    int32_t off_gmemo;             // 32 f64: ln(1 - u) of 32 consecutive positions of the generator stream
+#endif
+#if defined(AF_PREDRAW)
+    // memoised edge variates (see pre_refill): `pre_rows` edges x `pre_ring` request ids of f64
+    int32_t off_pre, pre_rows, pre_ring, pre_chunk;
+    int32_t pre_edge[PRE_MAX_ROWS];
+#endif
 };
 
 constexpr int32_t NQ_CAP = 128;   // now-queue capacity (power of two)
@@ -207,6 +236,14 @@ inline void layout_finalize(Layout& L) {
     L.off_rq_next = o;  o += 4 * L.rq_smem;
     L.off_samp_max = o; o += 4 * L.n_series;
     L.off_lb = o;       o += 4 * L.n_lb_edges;
+#if defined(AF_PREGEN)
+    o = align_up(o, 8);
+    L.off_gmemo = o;    o += 8 * 32;
+#endif
+#if defined(AF_PREDRAW)
+    o = align_up(o, 8);
+    L.off_pre = o;      o += 8 * L.pre_rows * L.pre_ring;
+#endif
     L.warp_bytes = align_up(o, 16);
 }
 
@@ -262,6 +299,12 @@ AF_TBL(tbl_samp_sum, uint64_t, off_samp_sum)
 AF_TBL(tbl_samp_max, uint32_t, off_samp_max)
 AF_TBL(tbl_nq, uint64_t, off_nq)
 AF_TBL(tbl_inbox, InboxS, off_inbox)
+#if defined(AF_PREDRAW)
+AF_TBL(tbl_pre, double, off_pre)
+#endif
+#if defined(AF_PREGEN)
+AF_TBL(tbl_gmemo, double, off_gmemo)
+#endif
 
 // ---- warp primitives (a warp of ONE lane on the host) ------------------------
 #if AF_DEVICE_CODE
@@ -487,6 +530,28 @@ AF_FN void nq_push(State& W, uint32_t kind, uint32_t aux, uint32_t slot) {
 // generator: samplers/poisson_poisson.py:52-82 / gaussian_poisson.py:64-94.
 // Returns false when the sampler is exhausted; otherwise the next yielded gap.
 // ---------------------------------------------------------------------------------
+#if defined(AF_PREGEN)
+// Build variant AF_PREGEN -- the inter-arrival gaps' logarithms, 32 stream positions per warp pass.
+// A gap is -ln(1 - max(u_pos, 1e-15)) / lambda with u_pos the pos-th uniform of the replica's
+// generator stream (a pure function of pos, oracle/afrng.py GenStream); the user draws that share the
+// stream only move `pos`.  Lane l computes position pos + l; gen_next_gap() then reads ln(1 - u) from
+// shared memory.  Same operations on the same operands as the direct path: bit-identical results.
+AF_FN void gen_refill(State& W, uint32_t pos) {
+    AF_SHARED(&W);
+    double* memo = tbl_gmemo(W);
+#pragma unroll 1
+    for (int32_t l = lane_id(); l < 32; l += WARP) {
+        const uint32_t p = pos + (uint32_t)l;
+        afr::Src s = afr::make_gen(AF_G.seed, W.replica, p);
+        double u = s.next53();
+        if (u < 1e-15) u = 1e-15;                   // max(u, 1e-15)
+        memo[p & 31u] = afr::af_log(1.0 - u);
+    }
+    w_sync();
+    W.g_lo = pos;
+}
+#endif
+
 AF_IN bool gen_next_gap(State& W, double& gap) {
     const double T = W.horizon;
     double vnow = W.g_vnow, wend = W.g_window_end, lam = W.g_lam;
@@ -501,11 +566,17 @@ AF_IN bool gen_next_gap(State& W, double& gap) {
             lam = d.value * W.rate_per_user;
         }
         if (lam <= 0.0) { vnow = wend; continue; }
+#if defined(AF_PREGEN)
+        if (pos - W.g_lo >= 32u) gen_refill(W, pos);
+        double dt = afr::af_div(-tbl_gmemo(W)[pos & 31u], lam);
+        pos += 1u;
+#else
         afr::Src s = afr::make_gen(AF_G.seed, W.replica, pos);
         double u = s.next53();
         pos = s.pos;
         if (u < 1e-15) u = 1e-15;                   // max(u, 1e-15)
         double dt = afr::af_div(-afr::af_log(1.0 - u), lam);
+#endif
         if (vnow + dt > T) break;
         if (vnow + dt >= wend) { vnow = wend; continue; }
         vnow += dt;
@@ -528,11 +599,59 @@ AF_IN void arm_generator(State& W) {
 // edges: EdgeRuntime.transport -> Initialize (URGENT) -> _deliver up to its timeout
 // (edge.py:73-107).  Called at the END of the item that called transport().
 // ---------------------------------------------------------------------------------
+#if defined(AF_PREDRAW)
+// EdgeS.meta carries the plan: row + 1 in [16:20) (0 = this edge is not memoised), planned hop in [20:28)
+AF_IN uint32_t meta_row1(uint32_t meta) { return (meta >> 16) & 15u; }
+AF_IN uint32_t meta_hop(uint32_t meta) { return (meta >> 20) & 0xFFu; }
+AF_IN double pre_encode(const afr::EdgeDraw& d, double dropout) { return d.u < dropout ? -1.0 : d.transit; }  // transit >= 0 always
+
+#if !AF_DEVICE_CODE
+static uint64_t g_pre_lookups[2];                    // [miss, hit]
+#endif
+// Draw the edge variates of the next `pre_chunk` request ids, one (request, edge) pair per lane.
+AF_FN void pre_refill(State& W) {
+    AF_SHARED(&W);
+    const uint32_t base = W.pre_hi;
+    const int32_t rows = AF_L.pre_rows, n = rows * AF_L.pre_chunk;
+    double* pre = tbl_pre(W);
+#pragma unroll 1
+    for (int32_t l = lane_id(); l < n; l += WARP) {
+        const uint32_t row = (uint32_t)(l % rows), rid = base + 1u + (uint32_t)(l / rows);
+        const EdgeS& E = tbl_edge(W)[AF_L.pre_edge[row]];
+        const double dropout = E.dropout;
+        afr::EdgeDraw d = afr::edge_draw(AF_G.seed, W.replica, rid, meta_hop(E.meta), (int)(E.meta & 7u), E.mean, E.sigma, dropout);
+        pre[row * (uint32_t)PRE_RING + (rid & (uint32_t)(PRE_RING - 1))] = pre_encode(d, dropout);
+    }
+    w_sync();
+    W.pre_hi = base + (uint32_t)AF_L.pre_chunk;
+}
+#endif
+
 AF_FN void edge_send(State& W, uint32_t slot, uint32_t e, uint32_t rid, uint32_t hops) {
     AF_SHARED(&W);
     EdgeS& E = tbl_edge(W)[e];
     uint32_t s = W.seq++;                            // the timeout's place in SimPy's eid order
     const double dropout = E.dropout;
+#if defined(AF_PREDRAW)
+    const uint32_t meta = E.meta, row1 = meta_row1(meta), hi = W.pre_hi;
+    double v;                                        // < 0: dropped, else the transit time
+    const bool memo = AF_LIKELY(row1 != 0u && hops == meta_hop(meta) && rid <= hi && rid + (uint32_t)PRE_RING > hi);
+#if !AF_DEVICE_CODE
+    g_pre_lookups[memo ? 1 : 0] += 1;                // host twin only: lets the tests see that the memo is live
+#endif
+    if (memo)
+        v = tbl_pre(W)[(row1 - 1u) * (uint32_t)PRE_RING + (rid & (uint32_t)(PRE_RING - 1))];
+    else
+        v = pre_encode(afr::edge_draw(AF_G.seed, W.replica, rid, hops, (int)(meta & 7u), E.mean, E.sigma, dropout), dropout);
+    E.sent += 1;
+    if (v < 0.0) {                                  // the request vanishes (edge.py:79-86)
+        E.dropped += 1;
+        rq_release(W, slot);
+        return;
+    }
+    E.conn += 1;
+    double effective = v + E.spike;                // spike read at SEND time (edge.py:94-106)
+#else
     afr::EdgeDraw d = afr::edge_draw(AF_G.seed, W.replica, rid, hops, (int)(E.meta & 7u), E.mean, E.sigma, dropout);
     E.sent += 1;
     if (d.u < dropout) {                            // the request vanishes (edge.py:79-86)
@@ -542,6 +661,7 @@ AF_FN void edge_send(State& W, uint32_t slot, uint32_t e, uint32_t rid, uint32_t
     }
     E.conn += 1;
     double effective = d.transit + E.spike;        // spike read at SEND time (edge.py:94-106)
+#endif
     push_seq(W, W.now + effective, mk_payload(K_DELIVER, e, slot), s);
 }
 
@@ -819,7 +939,11 @@ AF_IN void on_deliver(State& W, uint32_t slot, uint32_t e) {
     ReqRec r = rq_load(W, slot);
     r.pack += 1;                                     // record_hop(edge)
     const uint32_t tk = (meta >> 3) & 3u;
+    #if defined(AF_PREDRAW)
+    const uint32_t node = tk == AF_TARGET_CLIENT ? NODE_CLIENT : (tk == AF_TARGET_LB ? NODE_LB : NODE_SERVER0 + ((meta >> 5) & 0xFFu));
+#else
     const uint32_t node = tk == AF_TARGET_CLIENT ? NODE_CLIENT : (tk == AF_TARGET_LB ? NODE_LB : NODE_SERVER0 + (meta >> 5));
+#endif
     if (can_fuse(W)) {                               // (implies: every inbox empty, every consumer in get())
         node_got(W, node, slot, r.t0, r.rid, r.pack);   // put -> pending get -> resume, nothing in between
         return;                                      // (the consumer stores the record's new pack itself)
@@ -842,6 +966,9 @@ AF_IN void on_arrival(State& W) {
     if (slot == NIL) return;
     ReqRec r; r.t0 = W.now; r.rid = rid; r.pack = 1;  // record_hop(generator)
     rq_store(W, slot, r);
+#if defined(AF_PREDRAW)
+    if (AF_L.pre_rows > 0 && rid > W.pre_hi) pre_refill(W);
+#endif
     edge_send(W, slot, (uint32_t)AF_L.gen_edge, rid, 1u);
 }
 
@@ -948,6 +1075,9 @@ AF_FN void load_params(State& W) {
         EdgeS e;
         e.mean = a.mean; e.sigma = a.sigma; e.dropout = a.dropout; e.spike = 0.0;
         e.meta = (uint32_t)a.dist | ((uint32_t)a.target_kind << 3) | ((uint32_t)a.target_index << 5);
+#if defined(AF_PREDRAW)
+        e.meta |= (uint32_t)a.reserved << 16;        // the host's plan (afh::predraw_plan): row + 1 | hop << 4
+#endif
         e.conn = 0; e.sent = 0; e.dropped = 0;
         tbl_edge(W)[i] = e;
     }
@@ -1063,6 +1193,12 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
     W.lb_n = AF_L.n_lb_edges;
     W.spike_cur = 0; W.outage_cur = 0;
     W.n_ticks = 0; W.completed = 0; W.flags = 0; W.n_events = 0;
+#if defined(AF_PREDRAW)
+    W.pre_hi = 0;
+#endif
+#if defined(AF_PREGEN)
+    W.g_lo = 0x80000000u;                            // nothing memoised yet
+#endif
     W.lat_sum = 0.0; W.lat_sumsq = 0.0; W.lat_min = afr::u2d(INF_BITS); W.lat_max = 0.0;
     W.traced = (int64_t)local_index < (int64_t)AF_L.trace_replicas ? 1u : 0u;
     w_sync();

@@ -35,7 +35,14 @@ extern "C" int af_twin_run(const AfScenario* sc, const AfSweep* sw, uint64_t swe
     afh::make_layout(*sc, *opt, sw ? sw->n_columns : 0, L);
     afc::Globals& G = afc::h_G;
     memset(&G, 0, sizeof G);
-    G.edges = sc->edges; G.servers = sc->servers; G.endpoints = sc->endpoints; G.steps = sc->steps;
+#if defined(AF_PREDRAW)
+    std::vector<AfEdge> planned(sc->edges, sc->edges + sc->n_edges);
+    afh::predraw_annotate(*sc, planned.data());
+    G.edges = planned.data(); G.servers = sc->servers;
+#else
+    G.edges = sc->edges; G.servers = sc->servers;
+#endif
+    G.endpoints = sc->endpoints; G.steps = sc->steps;
     G.lb_edges = sc->lb_edges; G.spikes = sc->spike_marks; G.outages = sc->outage_marks;
     if (sw) { G.sweep_cols = sw->columns; G.sweep_vals = sw->values; G.sweep_first = sweep_first; G.sweep_rows = sw->n_rows; }
     std::vector<double> sp_t((size_t)(L.ev_total - L.ev_smem) + 1);
@@ -78,4 +85,14 @@ extern "C" int af_twin_sizeof(int which) {
     case 10: return (int)sizeof(AfReplicaStats);
     default: return -1;
     }
+}
+
+// memo statistics of the AF_PREDRAW build variant (zeros in the default build): [misses, hits] since the last call
+extern "C" void af_twin_pre_lookups(uint64_t* out) {
+#if defined(AF_PREDRAW)
+    out[0] = afc::g_pre_lookups[0]; out[1] = afc::g_pre_lookups[1];
+    afc::g_pre_lookups[0] = afc::g_pre_lookups[1] = 0;
+#else
+    out[0] = out[1] = 0;
+#endif
 }

@@ -1,0 +1,56 @@
+"""Build variants of the engine core (AF_PREDRAW / AF_PREGEN, af_core.cuh) must be BIT-IDENTICAL to the
+product build: they only move where random numbers are computed (lane-parallel, memoised), never which
+numbers.  Checked here on the CPU twin, byte for byte against the default twin (which the rest of the
+suite pins to the oracle); tools/check_variant_gpu.py repeats it on the device."""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import fuzz
+import numpy as np
+import pytest
+import twin
+from helpers import PARITY_CASES, SEED, load_scenario
+
+from asyncflow_b200.flatten import SweepSpec, flatten
+
+VARIANTS = ["predraw", "pregen", "memo"]
+
+
+def same(a: dict, b: dict) -> None:
+    for k in a:
+        if k == "stats":
+            assert a[k].tobytes() == b[k].tobytes(), k
+        else:
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("name", sorted(PARITY_CASES))
+def test_variant_equals_product_build_on_parity_scenarios(variant, name):
+    flat = flatten(load_scenario(name, PARITY_CASES[name]))
+    kw = dict(seed=SEED, replica_begin=3, n=2, trace=2, clock_cap=100000, request_capacity=200000)
+    same(twin.run(flat, **kw), twin.run(flat, variant=variant, **kw))
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("seed", range(400, 430))
+def test_variant_equals_product_build_on_random_scenarios_and_sweeps(variant, seed):
+    payload = fuzz.scenario(seed)
+    flat = flatten(payload)
+    spec = SweepSpec(flat, 2, fuzz.sweep_columns(seed, payload, 2))
+    kw = dict(seed=SEED, replica_begin=0, n=2, sweep=spec, trace=2, clock_cap=100000, request_capacity=200000)
+    same(twin.run(flat, **kw), twin.run(flat, variant=variant, **kw))
+
+
+def test_the_edge_memo_is_live_and_mostly_hits():
+    L = twin.lib("predraw")
+    out = (C.c_uint64 * 2)()
+    for name, floor in (("c1_my_service.yml", 0.99), ("c3_lb_two_servers.yml", 0.99), ("c4_lb8_events.yml", 0.5)):
+        flat = flatten(load_scenario(name, 10))
+        L.af_twin_pre_lookups(out)
+        twin.run(flat, seed=SEED, n=1, variant="predraw")
+        L.af_twin_pre_lookups(out)
+        miss, hit = int(out[0]), int(out[1])
+        assert hit + miss > 1000 and hit / (hit + miss) >= floor, (name, miss, hit)

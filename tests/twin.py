@@ -21,36 +21,41 @@ _SRC = [_DIR / "af_host_twin.cpp"] + sorted((_DIR.parent.parent / "asyncflow_b20
     + [_DIR.parent.parent / "include" / "asyncflow_b200.h"]
 
 
-def build() -> Path:
+VARIANTS = {None: [], "predraw": ["-DAF_PREDRAW"], "pregen": ["-DAF_PREGEN"],
+            "memo": ["-DAF_PREDRAW", "-DAF_PREGEN"]}      # build variants of the engine core (af_core.cuh)
+
+
+def build(variant: str | None = None) -> Path:
+    so = _SO if variant is None else _SO.with_name(f"libaf_host_twin_{variant}.so")
     newest = max(p.stat().st_mtime for p in _SRC)
-    if not _SO.exists() or _SO.stat().st_mtime < newest:
-        _SO.parent.mkdir(exist_ok=True)
+    if not so.exists() or so.stat().st_mtime < newest:
+        so.parent.mkdir(exist_ok=True)
         subprocess.run(
-            ["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-x", "c++",
-             "-o", str(_SO), str(_DIR / "af_host_twin.cpp")], check=True)
-    return _SO
+            ["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", *VARIANTS[variant], "-x", "c++",
+             "-o", str(so), str(_DIR / "af_host_twin.cpp")], check=True)
+    return so
 
 
-_lib = None
+_libs: dict = {}
 
 
-def lib() -> C.CDLL:
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(str(build()))
-        _lib.af_twin_error.restype = C.c_char_p
-        _lib.af_twin_hist_percentile.restype = C.c_double
-        _lib.af_twin_hist_percentile.argtypes = [C.c_void_p, C.c_uint64, C.c_double]
-        _lib.af_twin_trace_tick_capacity.argtypes = [C.POINTER(K.AfScenario)]
-        _lib.af_twin_run.argtypes = [
+def lib(variant: str | None = None) -> C.CDLL:
+    if variant not in _libs:
+        L = C.CDLL(str(build(variant)))
+        L.af_twin_error.restype = C.c_char_p
+        L.af_twin_hist_percentile.restype = C.c_double
+        L.af_twin_hist_percentile.argtypes = [C.c_void_p, C.c_uint64, C.c_double]
+        L.af_twin_trace_tick_capacity.argtypes = [C.POINTER(K.AfScenario)]
+        L.af_twin_run.argtypes = [
             C.POINTER(K.AfScenario), C.POINTER(K.AfSweep), C.c_uint64, C.POINTER(K.AfOptions),
             C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 10
-    return _lib
+        _libs[variant] = L
+    return _libs[variant]
 
 
 def run(flat, *, seed: int, replica_begin: int = 0, n: int = 1, sweep=None, sweep_first: int = 0, trace: int = 0,
-        clock_cap: int = 0, event_capacity: int = 0, request_capacity: int = 0) -> dict:
-    L = lib()
+        clock_cap: int = 0, event_capacity: int = 0, request_capacity: int = 0, variant: str | None = None) -> dict:
+    L = lib(variant)
     opt = K.AfOptions(event_capacity, request_capacity, 0, 0, 1, 1, trace, clock_cap)
     T = flat.horizon_s
     ne, nser = flat.n_edges, flat.n_series
