@@ -15,11 +15,11 @@ There is no CPU fallback: without the CUDA library / a B200 the runners raise
 
 from ._capi import EngineUnavailable
 from .engine import Engine, EngineError
-from .flatten import FlatScenario, SweepSpec, flatten
+from .flatten import FlatScenario, SweepSpec, balanced_order, flatten
 from .results import ReplicaResults, SweepResults
 from .runner import GpuSimulationRunner, SweepRunner
 
 __all__ = [
-    "Engine", "EngineError", "EngineUnavailable", "FlatScenario", "SweepSpec", "flatten",
+    "Engine", "EngineError", "EngineUnavailable", "FlatScenario", "SweepSpec", "balanced_order", "flatten",
     "GpuSimulationRunner", "SweepRunner", "ReplicaResults", "SweepResults",
 ]

@@ -269,6 +269,26 @@ def flatten(payload: Any) -> FlatScenario:
 # --------------------------------------------------------------------------- #
 # sweeps                                                                      #
 # --------------------------------------------------------------------------- #
+def balanced_order(cost: Any, deal: int = 1) -> np.ndarray:
+    """Launch order for a skewed sweep: ``order[p]`` = the sweep row that runs at position ``p``
+    (= gets replica id ``p``).
+
+    The engine hands replicas to warps in id order through one work counter, so a sweep sorted by
+    ASCENDING load starts its most expensive replicas last and the launch ends with a few warps
+    working alone (one saturated replica costs as much as the mean warp's whole
+    share).  Heaviest-first (LPT) order removes that tail.  ``deal`` > 1 additionally deals the sorted
+    rows round-robin into ``deal`` consecutive blocks, so that the contiguous replica ranges of
+    ``deal`` GPU ranks (``distributed.shard_bounds``) each get the same mix, heaviest first
+    (SURVEY.md 8e).  Stable: equal costs keep their row order, a flat sweep comes back unchanged.
+    """
+    c = np.asarray(cost, dtype=np.float64).ravel()
+    by_cost = np.argsort(-c, kind="stable")
+    deal = max(1, int(deal))
+    if deal == 1:
+        return by_cost.astype(np.int64)
+    return np.concatenate([by_cost[b::deal] for b in range(deal)]).astype(np.int64)
+
+
 class SweepSpec:
     """Per-replica overrides of scenario fields (the Monte-Carlo sweep).
 
@@ -320,6 +340,22 @@ class SweepSpec:
                        else np.zeros((self.n_replicas, 0)))
         self._cols = (K.AfSweepColumn * max(1, len(cols)))(*[K.AfSweepColumn(f, i) for f, i in cols])
         self.columns = cols
+
+    def estimated_cost(self, flat: FlatScenario) -> np.ndarray:
+        """Expected arrivals per row (users x rate x horizon): the load proxy ``balanced_order`` sorts by."""
+        users = np.full(self.n_replicas, float(flat.pod.users_mean))
+        rate = np.full(self.n_replicas, float(flat.pod.rate_per_user))
+        for sel, arr in self.selectors:
+            if sel[0] == "users_mean":
+                users = arr
+            elif sel[0] == "rate_per_user":
+                rate = arr
+        return np.maximum(users, 0.0) * np.maximum(rate, 0.0) * float(flat.horizon_s)
+
+    def permuted(self, flat: FlatScenario, order: np.ndarray) -> "SweepSpec":
+        """The same sweep with row ``order[p]`` at position ``p``."""
+        order = np.asarray(order, dtype=np.int64)
+        return SweepSpec(flat, self.n_replicas, {sel: arr[order] for sel, arr in self.selectors})
 
     def payload_for(self, payload: Any, replica: int) -> dict:
         """The scenario of ONE replica of the sweep as a plain YAML-shaped dict.

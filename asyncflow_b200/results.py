@@ -162,6 +162,7 @@ class SweepResults:
         self.throughput = throughput
         self.histograms = histograms
         self.replica_begin = replica_begin
+        self.rows: np.ndarray | None = None      # sweep row of each result row (set by SweepRunner)
 
     def __len__(self) -> int:
         return int(self.stats.shape[0])
@@ -246,6 +247,13 @@ class SweepResults:
             "p99_mean": float(np.nanmean(self.stats["p99"][ok])) if ok.any() else float("nan"),
             "overflowed": float(self.overflowed.sum()),
         }
+
+    def take(self, index: Any) -> "SweepResults":
+        """Rows ``index`` (any numpy index) as a new SweepResults -- e.g. the inverse of a launch order."""
+        g = lambda a: None if a is None else a[index]  # noqa: E731
+        return SweepResults(self.flat, self.stats[index], self.edge_sent[index], self.edge_dropped[index],
+                            self.samp_sum[index], self.samp_max[index], g(self.throughput), g(self.histograms),
+                            self.replica_begin)
 
     @staticmethod
     def concatenate(parts: list["SweepResults"]) -> "SweepResults":

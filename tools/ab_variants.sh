@@ -14,5 +14,7 @@ for v in "" _predraw _pregen _memo; do
   timeout 200 python tools/quick_bench.py --scenario c3_lb_two_servers.yml --replicas 40000 --horizon 20 --reps 3 | tail -2
   timeout 200 python tools/quick_bench.py --scenario c1_my_service.yml --replicas 40000 --horizon 60 --reps 2 --sweep none | tail -1
   timeout 200 python tools/quick_bench.py --scenario c1_my_service.yml --replicas 10000 --horizon 60 --reps 2 --sweep users | tail -1
+  echo "--- same, heaviest rows first (host-side launch order)"
+  timeout 200 python tools/quick_bench.py --scenario c1_my_service.yml --replicas 10000 --horizon 60 --reps 2 --sweep users --balance | tail -1
   timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline | cut -c1-400
 done

@@ -16,6 +16,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--sweep", default="rtt")
 ap.add_argument("--no-metrics", action="store_true")
 ap.add_argument("--users", type=float, default=0.0)
+ap.add_argument("--balance", action="store_true", help="launch heaviest rows first (SweepRunner(balance=True))")
 a = ap.parse_args()
 d = yaml.safe_load((ROOT / "tests" / "scenarios" / a.scenario).read_text())
 d["sim_settings"]["total_simulation_time"] = a.horizon
@@ -31,7 +32,7 @@ if a.sweep == "rtt":
     sweep = {("edge_mean", e): rtt for e in flat.edge_ids}
 elif a.sweep == "users":
     sweep = {("users_mean",): np.linspace(10, 1000, n)}
-sw = SweepRunner(flat, n, sweep, warps_per_block=a.wpb, blocks_per_sm=a.bps)
+sw = SweepRunner(flat, n, sweep, warps_per_block=a.wpb, blocks_per_sm=a.bps, balance=a.balance)
 for i in range(a.reps):
     t = time.time(); res = sw.run(); wall = time.time() - t
     ms_total, ms_sim = sw.last_ms
