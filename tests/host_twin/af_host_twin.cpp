@@ -96,3 +96,13 @@ extern "C" void af_twin_pre_lookups(uint64_t* out) {
     out[0] = out[1] = 0;
 #endif
 }
+
+// pool statistics of the AF_SORTED_POOL build variant (zeros otherwise), since the last call:
+// [ring pushes, unsorted pushes, ring -> unsorted switches, unsorted -> ring switches]
+extern "C" void af_twin_pool_counts(uint64_t* out) {
+#if defined(AF_SORTED_POOL)
+    for (int i = 0; i < 4; ++i) { out[i] = afc::g_pool_counts[i]; afc::g_pool_counts[i] = 0; }
+#else
+    for (int i = 0; i < 4; ++i) out[i] = 0;
+#endif
+}

@@ -1,4 +1,4 @@
-"""Build variants of the engine core (AF_PREDRAW / AF_PREGEN, af_core.cuh) must be BIT-IDENTICAL to the
+"""Build variants of the engine core (AF_PREDRAW / AF_PREGEN / AF_SORTED_POOL, af_core.cuh) must be BIT-IDENTICAL to the
 product build: they only move where random numbers are computed (lane-parallel, memoised), never which
 numbers.  Checked here on the CPU twin, byte for byte against the default twin (which the rest of the
 suite pins to the oracle); tools/check_variant_gpu.py repeats it on the device."""
@@ -15,7 +15,7 @@ from helpers import PARITY_CASES, SEED, load_scenario
 
 from asyncflow_b200.flatten import SweepSpec, flatten
 
-VARIANTS = ["predraw", "pregen", "memo"]
+VARIANTS = ["predraw", "pregen", "memo", "sorted", "all"]
 
 
 def same(a: dict, b: dict) -> None:
@@ -54,3 +54,18 @@ def test_the_edge_memo_is_live_and_mostly_hits():
         L.af_twin_pre_lookups(out)
         miss, hit = int(out[0]), int(out[1])
         assert hit + miss > 1000 and hit / (hit + miss) >= floor, (name, miss, hit)
+
+
+def test_the_sorted_pool_exercises_both_modes_and_both_switches():
+    L = twin.lib("sorted")
+    out = (C.c_uint64 * 4)()
+    seen = np.zeros(4, dtype=np.int64)
+    for name, horizon in (("c3_lb_two_servers.yml", 10), ("c4_lb8_events.yml", 120), ("poisson_ties.yml", None)):
+        flat = flatten(load_scenario(name, horizon))
+        L.af_twin_pool_counts(out)
+        twin.run(flat, seed=SEED, n=1, variant="sorted", request_capacity=200000)
+        L.af_twin_pool_counts(out)
+        if name.startswith("c3"):
+            assert out[1] == 0 and out[0] > 5000          # nominal load never leaves the sorted ring
+        seen += np.array(list(out), dtype=np.int64)
+    assert (seen > 0).all(), seen.tolist()                # ring pushes, unsorted pushes, A->B, B->A

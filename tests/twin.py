@@ -22,7 +22,8 @@ _SRC = [_DIR / "af_host_twin.cpp"] + sorted((_DIR.parent.parent / "asyncflow_b20
 
 
 VARIANTS = {None: [], "predraw": ["-DAF_PREDRAW"], "pregen": ["-DAF_PREGEN"],
-            "memo": ["-DAF_PREDRAW", "-DAF_PREGEN"]}      # build variants of the engine core (af_core.cuh)
+            "memo": ["-DAF_PREDRAW", "-DAF_PREGEN"], "sorted": ["-DAF_SORTED_POOL"],
+            "all": ["-DAF_PREDRAW", "-DAF_PREGEN", "-DAF_SORTED_POOL"]}      # build variants of the engine core (af_core.cuh)
 
 
 def build(variant: str | None = None) -> Path:

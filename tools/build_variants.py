@@ -21,6 +21,8 @@ VARIANTS = {
     "predraw": ["-DAF_PREDRAW"],                 # lane-parallel memoised edge variates
     "pregen": ["-DAF_PREGEN"],                   # lane-parallel memoised inter-arrival logs
     "memo": ["-DAF_PREDRAW", "-DAF_PREGEN"],     # both
+    "sorted": ["-DAF_SORTED_POOL"],              # sorted 32-entry front ring of the pending-event pool
+    "all": ["-DAF_PREDRAW", "-DAF_PREGEN", "-DAF_SORTED_POOL"],
 }
 
 
