@@ -134,3 +134,55 @@ def sweep_columns(seed: int, payload: dict, n: int) -> dict:
     if not cols:
         cols[("users_mean",)] = [rng.choice([30, 80, 200]) for _ in range(n)]
     return cols
+
+
+def big_scenario(seed: int) -> dict:
+    """C5-shaped random topologies: an LB over 5-12 front ends, some of which chain to a back end
+    (several front ends may share one) before the reply returns to the client.  More edges than the
+    variants' memo rows, more pending events than the sorted ring: the fallback paths get exercised."""
+    rng = random.Random(seed * 104729 + 7)
+    n_fe = rng.randint(5, 12)
+    n_be = rng.randint(1, 4)
+    servers, edges = [], []
+
+    def server(sid: str) -> dict:
+        return {"id": sid, "server_resources": {"cpu_cores": rng.choice([1, 2, 4]), "ram_mb": rng.choice([256, 512, 2048])},
+                "endpoints": [_endpoint(rng, f"/e{j}") for j in range(rng.randint(1, 2))]}
+    fes = [f"fe{i}" for i in range(n_fe)]
+    bes = [f"be{i}" for i in range(n_be)]
+    servers += [server(s) for s in fes + bes]
+    edges.append({"id": "g-c", "source": "gen", "target": "cl", "latency": _latency(rng)})
+    edges.append({"id": "c-lb", "source": "cl", "target": "lb", "latency": _latency(rng)})
+    used_be = set()
+    for f in fes:
+        edges.append({"id": f"lb-{f}", "source": "lb", "target": f, "latency": _latency(rng),
+                      "dropout_rate": rng.choice([0.0, 0.01])})
+        if rng.random() < 0.5:
+            b = rng.choice(bes)
+            used_be.add(b)
+            edges.append({"id": f"{f}-{b}", "source": f, "target": b, "latency": _latency(rng)})
+        else:
+            edges.append({"id": f"{f}-c", "source": f, "target": "cl", "latency": _latency(rng)})
+    for b in bes:                                       # every server needs an exit, used or not
+        edges.append({"id": f"{b}-c", "source": b, "target": "cl", "latency": _latency(rng)})
+    events = []
+    if rng.random() < 0.5:
+        events.append({"event_id": "out1", "target_id": rng.choice(fes), "start": {"kind": "server_down", "t_start": 1.5},
+                       "end": {"kind": "server_up", "t_end": 3.0}})
+    if rng.random() < 0.5:
+        events.append({"event_id": "sp1", "target_id": rng.choice(edges)["id"],
+                       "start": {"kind": "network_spike_start", "t_start": 1.0, "spike_s": rng.choice([0.004, 0.05])},
+                       "end": {"kind": "network_spike_end", "t_end": 2.5}})
+    doc = {
+        "rqs_input": {"id": "gen", "avg_active_users": {"mean": rng.choice([200, 600, 1500])},
+                      "avg_request_per_minute_per_user": {"mean": rng.choice([60, 120])},
+                      "user_sampling_window": rng.choice([1, 60])},
+        "topology_graph": {"nodes": {"client": {"id": "cl"}, "servers": servers,
+                                     "load_balancer": {"id": "lb", "algorithms": rng.choice(["round_robin", "least_connection"]),
+                                                       "server_covered": fes}},
+                           "edges": edges},
+        "sim_settings": {"total_simulation_time": rng.choice([5, 6]), "sample_period_s": 0.05},
+    }
+    if events:
+        doc["events"] = events
+    return doc

@@ -45,3 +45,19 @@ def test_twin_equals_oracle_on_random_sweeps(seed):
         assert st["flags"] == 0
         assert_matches_oracle(o, flatten(p), stats=st, clocks=r["trace_clocks"][i, :k], sent=r["sent"][i],
                               dropped=r["dropped"][i], series=r["trace_series"][i][:, :nt], throughput=r["thr"][i])
+
+
+@pytest.mark.parametrize("seed", range(0, 16))
+def test_twin_equals_oracle_on_big_topologies(seed):
+    """C5-shaped: LB over 5-12 front ends chaining into shared back ends, overloaded -- hundreds to
+    thousands of pending events and queued requests (the HBM tiers of both pools)."""
+    payload = fuzz.big_scenario(seed)
+    flat = flatten(payload)
+    o = des_port.simulate(payload, seed=SEED, replica=seed)
+    r = twin.run(flat, seed=SEED, replica_begin=seed, n=1, trace=1, clock_cap=200000, request_capacity=400000,
+                 event_capacity=8192)
+    st = r["stats"][0]
+    n, nt = int(st["completed"]), int(st["n_ticks"])
+    assert st["flags"] == 0
+    assert_matches_oracle(o, flat, stats=st, clocks=r["trace_clocks"][0, :n], sent=r["sent"][0],
+                          dropped=r["dropped"][0], series=r["trace_series"][0][:, :nt], throughput=r["thr"][0])

@@ -79,7 +79,10 @@ def test_port_equals_reference_on_random_tie_prone_scenarios(seed):
     must reproduce the unmodified reference actors bit for bit -- the fuzz tests then compare the
     engine with the port."""
     import fuzz
-    payload = fuzz.scenario(seed)
+    _port_equals_reference(fuzz.scenario(seed), seed)
+
+
+def _port_equals_reference(payload, seed):
     r = ref_harness.run_reference(payload, seed=SEED, replica=seed)
     o = des_port.simulate(payload, seed=SEED, replica=seed)
     for k in ("generated", "completed", "clocks", "edge_sent", "edge_dropped"):
@@ -90,3 +93,12 @@ def test_port_equals_reference_on_random_tie_prone_scenarios(seed):
     for eid, ser in r["edge_series"].items():
         for k, v in ser.items():
             assert list(v) == list(o["edge_series"][eid][k]), (eid, k)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="/root/reference not on this box")
+@pytest.mark.parametrize("seed", range(0, 8))
+def test_port_equals_reference_on_big_topologies(seed):
+    """C5-shaped random topologies (fuzz.big_scenario): LB over many front ends, shared back ends."""
+    import fuzz
+    _port_equals_reference(fuzz.big_scenario(seed), seed)

@@ -44,6 +44,14 @@ def test_variant_equals_product_build_on_random_scenarios_and_sweeps(variant, se
     same(twin.run(flat, **kw), twin.run(flat, variant=variant, **kw))
 
 
+@pytest.mark.parametrize("variant", ["memo", "sorted", "all"])
+@pytest.mark.parametrize("seed", range(16, 28))
+def test_variant_equals_product_build_on_big_topologies(variant, seed):
+    flat = flatten(fuzz.big_scenario(seed))
+    kw = dict(seed=SEED, replica_begin=seed, n=1, trace=1, clock_cap=200000, request_capacity=400000, event_capacity=8192)
+    same(twin.run(flat, **kw), twin.run(flat, variant=variant, **kw))
+
+
 def test_the_edge_memo_is_live_and_mostly_hits():
     L = twin.lib("predraw")
     out = (C.c_uint64 * 2)()

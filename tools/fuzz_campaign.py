@@ -1,6 +1,6 @@
 """Offline fuzz campaign: engine state machine (CPU twin) vs the oracle on many random scenarios.
 
-    python tools/fuzz_campaign.py --first 1000 --count 2000 --jobs 8
+    python tools/fuzz_campaign.py --first 1000 --count 2000 --jobs 8 [--variant all]
 
 Test tooling (uses oracle/ and tests/host_twin); prints the failing seeds, exits non-zero on any.
 """
@@ -17,6 +17,10 @@ for p in (ROOT, ROOT / "tests", ROOT / "oracle", ROOT / "oracle" / "simpy_shim")
     sys.path.insert(0, str(p))
 
 
+VARIANT = None
+BIG = False
+
+
 def one(seed: int):
     import des_port
     import fuzz
@@ -25,10 +29,11 @@ def one(seed: int):
 
     from asyncflow_b200.flatten import flatten
     try:
-        payload = fuzz.scenario(seed)
+        payload = fuzz.big_scenario(seed) if BIG else fuzz.scenario(seed)
         flat = flatten(payload)
         o = des_port.simulate(payload, seed=SEED, replica=seed)
-        r = twin.run(flat, seed=SEED, replica_begin=seed, n=1, trace=1, clock_cap=100000, request_capacity=200000)
+        r = twin.run(flat, seed=SEED, replica_begin=seed, n=1, trace=1, clock_cap=200000, request_capacity=400000,
+                     event_capacity=8192, variant=VARIANT)
         st = r["stats"][0]
         n, nt = int(st["completed"]), int(st["n_ticks"])
         assert st["flags"] == 0, f"flags {int(st['flags'])}"
@@ -44,9 +49,13 @@ def main() -> None:
     ap.add_argument("--first", type=int, default=1000)
     ap.add_argument("--count", type=int, default=500)
     ap.add_argument("--jobs", type=int, default=8)
+    ap.add_argument("--variant", default=None, help="engine build variant of tests/twin.py (predraw, pregen, memo, sorted, all)")
+    ap.add_argument("--big", action="store_true", help="C5-shaped topologies (fuzz.big_scenario)")
     a = ap.parse_args()
+    global VARIANT, BIG
+    VARIANT, BIG = a.variant, a.big
     import twin
-    twin.build()
+    twin.build(a.variant)
     bad = []
     total = 0
     with mp.get_context("fork").Pool(a.jobs) as pool:
