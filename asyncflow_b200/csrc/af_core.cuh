@@ -213,7 +213,7 @@ struct Layout {
             off_endpoint, off_step, off_lb, off_spike, off_outage, off_samp_sum, off_samp_max, off_nq, off_inbox;
     int32_t warp_bytes;
 #if defined(AF_SORTED_POOL)
-    int32_t off_sort;              // 8 x (time, key): staging for the unsorted -> sorted conversion
+    int32_t off_sort;              // SORT_BACK_AT x (time, key): staging for the unsorted -> sorted conversion
 #endif
 #if defined(AF_PREGEN)
     int32_t off_gmemo;             // 32 f64: ln(1 - u) of 32 consecutive positions of the generator stream
@@ -248,7 +248,7 @@ inline void layout_finalize(Layout& L) {
     L.off_lb = o;       o += 4 * L.n_lb_edges;
 #if defined(AF_SORTED_POOL)
     o = align_up(o, 8);
-    L.off_sort = o;     o += 16 * 8;
+    L.off_sort = o;     o += 16 * 16;
 #endif
 #if defined(AF_PREGEN)
     o = align_up(o, 8);
@@ -443,16 +443,17 @@ AF_FN int32_t pool_find_hole(State& W) {
 }
 
 #if defined(AF_SORTED_POOL)
-// Build variant AF_SORTED_POOL -- while at most 32 events are pending (every nominal-load scenario) the
-// pool is a SORTED ring of one element per lane in the first 32 shared-memory slots: push inserts in
-// (time, seq) order with one ballot (each lane compares its element and moves it up one slot), pop
-// reads the head.  No scan, no reductions: ~35 instructions per event instead of ~160 (ncu r1i: scan +
-// remove + push = 29 % of the executed instructions).  When a 33rd event arrives the 32 slots are
-// re-interpreted as the unsorted pool below (pmode 1, the round-1 code, unchanged); when that pool
-// drains to 8 events it is sorted back into the ring (pool_sort_back).  Order of pops is the same total
-// order (time, seq) in both modes, so results are bit-identical.
-constexpr uint32_t RING = 32u;
-constexpr int32_t SORT_BACK_AT = 8;
+// Build variant AF_SORTED_POOL -- while at most 64 events are pending (every nominal-load scenario: peak
+// 12-17 on C1/C2/C3, 56 on C4) the pool is a SORTED ring in the 64 shared-memory slots, lane l holding
+// logical elements l and l + 32: push inserts in (time, seq) order with one ballot per 32 elements (each
+// lane compares its element and moves it up one slot), pop reads the head.  No scan, no reductions:
+// ~90 instructions per event instead of ~160 (ncu r1i: scan + remove + push = 29 % of the executed
+// instructions).  When a 65th event arrives the 64 slots are re-interpreted as the unsorted pool below
+// (pmode 1, the round-1 code, unchanged); when that pool drains to 16 events it is sorted back into the
+// ring (pool_remove_b).  Order of pops is the same total order (time, seq) in both modes, so results are
+// bit-identical.
+constexpr uint32_t RING = 64u;                      // = the shared-memory tier of the pool (two elements per lane)
+constexpr int32_t SORT_BACK_AT = 16;
 #if !AF_DEVICE_CODE
 static uint64_t g_pool_counts[4];                    // host twin only: [ring pushes, unsorted pushes, ring -> unsorted, unsorted -> ring]
 #define AF_POOL_COUNT(i) (g_pool_counts[i] += 1)
@@ -471,13 +472,21 @@ AF_FN void push_seq(State& W, double t, uint32_t payload, uint32_t s) {
             const uint64_t tb = afr::d2u(t), key = ((uint64_t)s << 32) | payload;
             double* const T = tbl_ev_time(W); uint64_t* const Kk = tbl_ev_key(W);
 #if AF_DEVICE_CODE
-            const uint32_t l = (uint32_t)lane_id(), ph = (rh + l) & (RING - 1u);
-            const bool mine = l < n;
+            // lane l holds logical elements l and l + 32 (the second only when more than 32 are pending)
+            const uint32_t l = (uint32_t)lane_id(), ph = (rh + l) & (RING - 1u), ph2 = (ph + 32u) & (RING - 1u);
+            const bool mine = l < n, mine2 = l + 32u < n;
             const uint64_t tl = mine ? afr::d2u(T[ph]) : 0ull, kl = mine ? Kk[ph] : 0ull;
             const bool before = mine && (tl < tb || (tl == tb && (uint32_t)(kl >> 32) < s));
-            const uint32_t pos = (uint32_t)__popc(w_ballot(before));   // sorted, so `before` is a prefix
-            w_sync();                                // every lane holds its element before any slot is rewritten
+            uint32_t pos = (uint32_t)__popc(w_ballot(before));         // sorted, so `before` is a prefix
+            uint64_t tl2 = 0ull, kl2 = 0ull;
+            if (n > 32u) {                           // (uniform)
+                if (mine2) { tl2 = afr::d2u(T[ph2]); kl2 = Kk[ph2]; }
+                const bool before2 = mine2 && (tl2 < tb || (tl2 == tb && (uint32_t)(kl2 >> 32) < s));
+                pos += (uint32_t)__popc(w_ballot(before2));
+            }
+            w_sync();                                // every lane holds its elements before any slot is rewritten
             if (mine && l >= pos) { const uint32_t q = (ph + 1u) & (RING - 1u); T[q] = afr::u2d(tl); Kk[q] = kl; }
+            if (mine2 && l + 32u >= pos) { const uint32_t q = (ph2 + 1u) & (RING - 1u); T[q] = afr::u2d(tl2); Kk[q] = kl2; }
 #else
             uint32_t pos = 0;
             for (uint32_t l = 0; l < n; ++l) {
@@ -499,7 +508,7 @@ AF_FN void push_seq(State& W, double t, uint32_t payload, uint32_t s) {
             AF_POOL_COUNT(0);
             return;
         }
-        // the ring is full: its 32 slots ARE a valid unsorted pool without holes; carry on below
+        // the ring is full: its 64 slots ARE a valid unsorted pool without holes; carry on below
         W.pmode = 1u; W.ev_hw = (int32_t)RING; W.ev_last_free = -1; W.ev_hole = -1;
         AF_POOL_COUNT(2);
     }
