@@ -55,3 +55,27 @@ def test_engine_create_fails_loudly_without_a_gpu():
                                              {"id": "b", "source": "c", "target": "s", "latency": {"mean": 0.1}},
                                              {"id": "d", "source": "s", "target": "c", "latency": {"mean": 0.1}}]},
                                "sim_settings": {"total_simulation_time": 5}}).run()
+
+
+def test_missing_library_is_an_error_not_a_fallback():
+    """No CPU path behind the product API: without the CUDA library the first use raises."""
+    import subprocess
+    import sys
+    code = ("import os; os.environ['ASYNCFLOW_B200_LIB'] = '/nonexistent/libasyncflow_b200.so'\n"
+            "from asyncflow_b200 import Engine, EngineUnavailable\n"
+            "try:\n    Engine(0)\nexcept EngineUnavailable as e:\n    print('raised', 'no CPU fallback' in str(e))\n")
+    p = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert p.stdout.strip() == "raised True", p.stdout + p.stderr
+
+
+def test_product_package_never_reaches_into_the_oracle_or_the_tests():
+    """oracle/ and tests/ are checkers: nothing under asyncflow_b200/ may import or locate them."""
+    import re
+    bad = re.compile(r"^\s*(from|import)\s+(des_port|afrng|afrng_c|ref_harness|simpy|twin|fuzz|helpers)\b|sys\.path|oracle[/\\]|host_twin")
+    for path in sorted((ROOT / "asyncflow_b200").rglob("*.py")):
+        for i, line in enumerate(path.read_text().splitlines(), 1):
+            code = line.split("#", 1)[0]
+            assert not bad.search(code) or "``" in line or '"""' in line or "oracle/afrng.py" in line, f"{path}:{i}: {line.strip()}"
+    for path in sorted((ROOT / "asyncflow_b200" / "csrc").glob("*")):
+        text = path.read_text()
+        assert "#include \"../../oracle" not in text and "#include \"../../tests" not in text, path
