@@ -16,10 +16,10 @@ There is no CPU fallback: without the CUDA library / a B200 the runners raise
 from ._capi import EngineUnavailable
 from .engine import Engine, EngineError
 from .flatten import FlatScenario, SweepSpec, balanced_order, flatten
-from .results import ReplicaResults, SweepResults
+from .results import ReplicaResults, SweepResults, series_bands
 from .runner import GpuSimulationRunner, SweepRunner
 
 __all__ = [
     "Engine", "EngineError", "EngineUnavailable", "FlatScenario", "SweepSpec", "balanced_order", "flatten",
-    "GpuSimulationRunner", "SweepRunner", "ReplicaResults", "SweepResults",
+    "GpuSimulationRunner", "SweepRunner", "ReplicaResults", "SweepResults", "series_bands",
 ]

@@ -146,6 +146,23 @@ class ReplicaResults:
         return ResultsAnalyzer(**self.holders())
 
 
+def series_bands(replicas: list[ReplicaResults], key: Any, entity_id: str) -> dict[str, np.ndarray]:
+    """Per-tick mean / min / max of one sampled series across fully traced replicas.
+
+    ``key`` / ``entity_id`` are what ``ResultsAnalyzer.get_series`` takes (``metrics/analyzer.py:239-262``);
+    returns ``{"t", "mean", "min", "max", "n"}`` -- the band a dashboard draws around one replica's curve.
+    """
+    cols = [np.asarray(r.get_series(key, entity_id)[1], dtype=np.float64) for r in replicas]
+    cols = [c for c in cols if c.size]
+    if not cols:
+        z = np.zeros(0)
+        return {"t": z, "mean": z, "min": z, "max": z, "n": 0}
+    m = min(c.size for c in cols)
+    a = np.stack([c[:m] for c in cols])
+    return {"t": np.arange(m) * replicas[0].flat.sample_period, "mean": a.mean(axis=0), "min": a.min(axis=0),
+            "max": a.max(axis=0), "n": len(cols)}
+
+
 class SweepResults:
     """Per-replica summaries of a sweep (all arrays have one row per replica)."""
 
@@ -163,6 +180,7 @@ class SweepResults:
         self.histograms = histograms
         self.replica_begin = replica_begin
         self.rows: np.ndarray | None = None      # sweep row of each result row (set by SweepRunner)
+        self.traced: list[ReplicaResults] = []    # full clocks + sampled series of the first `trace_replicas` replica ids
 
     def __len__(self) -> int:
         return int(self.stats.shape[0])
@@ -251,9 +269,15 @@ class SweepResults:
     def take(self, index: Any) -> "SweepResults":
         """Rows ``index`` (any numpy index) as a new SweepResults -- e.g. the inverse of a launch order."""
         g = lambda a: None if a is None else a[index]  # noqa: E731
-        return SweepResults(self.flat, self.stats[index], self.edge_sent[index], self.edge_dropped[index],
-                            self.samp_sum[index], self.samp_max[index], g(self.throughput), g(self.histograms),
-                            self.replica_begin)
+        out = SweepResults(self.flat, self.stats[index], self.edge_sent[index], self.edge_dropped[index],
+                           self.samp_sum[index], self.samp_max[index], g(self.throughput), g(self.histograms),
+                           self.replica_begin)
+        out.traced = self.traced
+        return out
+
+    def bands(self, key: Any, entity_id: str) -> dict[str, np.ndarray]:
+        """``series_bands`` over this sweep's traced replicas (``SweepRunner(trace_replicas=k)``)."""
+        return series_bands(self.traced, key, entity_id)
 
     @staticmethod
     def concatenate(parts: list["SweepResults"]) -> "SweepResults":

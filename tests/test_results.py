@@ -2,6 +2,8 @@
 
 from __future__ import annotations
 
+from types import SimpleNamespace
+
 import numpy as np
 import pytest
 import twin
@@ -83,3 +85,38 @@ def test_arrivals_bound_is_generous():
     b = arrivals_bound(flat)
     assert b > 100 * (100 / 60) * 60 * 1.5          # mean arrivals ~10 000: the bound leaves > 50 % head-room
     assert arrivals_bound(flat, users_mean=1000.0) > 1000 * (100 / 60) * 60
+
+
+def test_series_bands_across_traced_replicas_match_numpy():
+    """per-tick mean/min/max of a sampled series over the traced replicas of a sweep."""
+    from asyncflow_b200 import series_bands
+    from asyncflow_b200.flatten import SweepSpec
+
+    payload = load_scenario("c3_lb_two_servers.yml", 12)
+    flat = flatten(payload)
+    k = 6
+    spec = SweepSpec(flat, k, {("users_mean",): np.linspace(100, 600, k)})
+    r = twin.run(flat, seed=SEED, replica_begin=0, n=k, sweep=spec, trace=k, clock_cap=100000)
+    reps = []
+    for i in range(k):
+        st = r["stats"][i]
+        n, nt = int(st["completed"]), int(st["n_ticks"])
+        reps.append(ReplicaResults(flat=flat, clocks=r["trace_clocks"][i, :n].copy(), series=r["trace_series"][i][:, :nt].copy(),
+                                   generated=int(st["generated"]), edge_sent={}, edge_dropped={}, n_events=int(st["n_events"]),
+                                   flags=int(st["flags"])))
+    b = series_bands(reps, "ram_in_use", "srv-1")
+    raw = np.stack([r["trace_series"][i][3 * flat.server_ids.index("srv-1") + 2, :len(b["t"])] for i in range(k)]).astype(np.float64)
+    assert b["n"] == k and len(b["t"]) == int(r["stats"][0]["n_ticks"])
+    np.testing.assert_array_equal(b["mean"], raw.mean(axis=0))
+    np.testing.assert_array_equal(b["min"], raw.min(axis=0))
+    np.testing.assert_array_equal(b["max"], raw.max(axis=0))
+    assert b["max"].max() > b["min"].max()                         # the sweep does spread the curves
+    np.testing.assert_allclose(b["t"][:3], [0.0, flat.sample_period, 2 * flat.sample_period])
+    # edge series, enum-like keys and unknown entities behave like ResultsAnalyzer.get_series
+    e = series_bands(reps, SimpleNamespace(value="edge_concurrent_connection"), flat.edge_ids[0])
+    assert e["n"] == k and e["max"].max() >= 1
+    assert series_bands(reps, "ram_in_use", "nope")["n"] == 0
+    # a SweepResults carries them along
+    sw = SweepResults(flat, r["stats"], r["sent"], r["dropped"], r["samp_sum"], r["samp_max"])
+    sw.traced = reps
+    np.testing.assert_array_equal(sw.take(np.arange(k)[::-1]).bands("ram_in_use", "srv-1")["mean"], b["mean"])

@@ -1,0 +1,124 @@
+"""SweepRunner's host-side orchestration, end to end on the CPU twin (tests/twin_engine.py stands in for
+the ctypes engine): plain runs, shard ranges, heaviest-first launch order, traced replicas, drill-down."""
+
+from __future__ import annotations
+
+import des_port
+import numpy as np
+from helpers import SEED, load_scenario
+from twin_engine import TwinEngine
+
+from asyncflow_b200 import SweepRunner
+from asyncflow_b200.distributed import shard_bounds
+
+USERS = [40.0, 250.0, 15.0, 120.0, 70.0, 180.0, 30.0]
+RTT = [0.001, 0.002, 0.003, 0.004, 0.005, 0.006, 0.007]
+
+
+def runner(**kw) -> SweepRunner:
+    base = load_scenario("c1_my_service.yml", 6)
+    sw = SweepRunner(base, len(USERS), {("users_mean",): USERS, ("edge_mean", "client-app"): RTT}, seed=SEED,
+                     pinned=False, throughput=True, **kw)
+    sw._engine = TwinEngine()
+    sw._engine.upload(sw.flat)
+    return sw
+
+
+def oracle_row(sw: SweepRunner, row: int) -> dict:
+    return des_port.simulate(sw.payload_for(row), seed=SEED, replica=int(sw.replica_ids[row]))
+
+
+def test_plain_run_returns_one_row_per_sweep_row():
+    sw = runner()
+    res = sw.run()
+    assert len(res) == len(USERS) and res.rows.tolist() == list(range(len(USERS)))
+    for row in range(len(USERS)):
+        o = oracle_row(sw, row)
+        assert int(res.generated[row]) == o["generated"] and int(res.completed[row]) == o["completed"]
+        assert dict(zip(sw.flat.edge_ids, map(int, res.edge_dropped[row]))) == o["edge_dropped"]
+    assert sw.h2d_bytes == len(USERS) * 2 * 8 and sw.d2h_bytes > 0
+
+
+def test_balanced_run_comes_back_in_row_order_with_the_ids_it_names():
+    sw = runner(balance=True)
+    assert sw.order.tolist() == [1, 5, 3, 4, 0, 6, 2]
+    res = sw.run()
+    assert res.rows.tolist() == list(range(len(USERS)))
+    gen = res.generated.astype(np.int64)
+    assert np.argmax(gen) == 1 and np.argmin(gen) == 2           # users 250 / users 15: rows, not launch positions
+    for row in range(len(USERS)):
+        o = oracle_row(sw, row)                                   # replica id = replica_ids[row]
+        assert int(res.generated[row]) == o["generated"] and int(res.completed[row]) == o["completed"]
+        assert abs(float(res.stats["lat_sum"][row]) - sum(b - a for a, b in o["clocks"])) < 1e-9
+    # the per-second throughput rows were un-permuted with everything else
+    assert int(res.throughput[1].sum()) == int(res.completed[1])
+
+
+def test_shards_of_a_dealt_sweep_cover_every_row_once():
+    world = 2
+    sw_all = runner(balance=True, deal=world)
+    full = sw_all.run()
+    seen = []
+    for rank in range(world):
+        sw = runner(balance=True, deal=world)
+        b, e = shard_bounds(len(USERS), rank, world)
+        part = sw.run(b, e)                                       # a shard: id order, .rows names the sweep rows
+        assert part.rows.tolist() == sw.order[b:e].tolist()
+        for j, row in enumerate(part.rows):
+            assert int(part.generated[j]) == int(full.generated[row])     # independent of the world size
+            assert float(part.stats["lat_sum"][j]) == float(full.stats["lat_sum"][row])
+        seen += part.rows.tolist()
+        cost = np.array(USERS)[part.rows]
+        assert (np.diff(cost) <= 0).all()                         # heaviest first inside the shard
+    assert sorted(seen) == list(range(len(USERS)))
+    calls = [c for c in sw._engine.calls if c[0] == "upload_sweep"]
+    assert calls[-1][1:] == (b, b, e - b)
+
+
+def test_traced_replicas_and_bands():
+    sw = runner(trace_replicas=3)
+    res = sw.run()
+    cfg = [c for c in sw._engine.calls if c[0] == "configure"][-1][1]
+    assert cfg["trace_replicas"] == 3 and cfg["trace_clock_capacity"] == sw.request_capacity
+    assert len(res.traced) == 3
+    for j, rep in enumerate(res.traced):
+        o = oracle_row(sw, j)
+        assert rep.clocks.shape == (o["completed"], 2)
+        assert [tuple(x) for x in rep.clocks.tolist()] == [tuple(c) for c in o["clocks"]]
+        assert rep.get_latency_stats()["total_requests"] == o["completed"]
+    band = res.bands("ram_in_use", "app-1")
+    assert band["n"] == 3 and (band["min"] <= band["mean"]).all() and (band["mean"] <= band["max"]).all()
+    # drill-down replays the same replica
+    rr = sw.replica_runner(1)
+    assert (rr.seed, rr.replica) == (SEED, 1) and rr.simulation_input["rqs_input"]["avg_active_users"]["mean"] == USERS[1]
+    # an untraced sweep configures no tracing at all (the bench path)
+    plain = runner()
+    plain.run()
+    cfg = [c for c in plain._engine.calls if c[0] == "configure"][-1][1]
+    assert cfg["trace_replicas"] == 0 and cfg["trace_clock_capacity"] == 0
+
+
+def test_single_replica_runner_on_the_twin_engine(monkeypatch):
+    """GpuSimulationRunner.run(): capacity retry loop and the ReplicaResults it assembles."""
+    import asyncflow_b200.runner as R
+    engines = []
+
+    def make(device=0):
+        e = TwinEngine(device)
+        engines.append(e)
+        return e
+    monkeypatch.setattr(R, "Engine", make)
+    payload = load_scenario("overload_single.yml")
+    monkeypatch.setattr(R, "arrivals_bound", lambda flat, *a: 300)      # far too small: forces the x4 retries
+    res = R.GpuSimulationRunner(simulation_input=payload, seed=SEED, replica=5).run()
+    o = des_port.simulate(payload, seed=SEED, replica=5)
+    assert [tuple(x) for x in res.clocks.tolist()] == [tuple(c) for c in o["clocks"]]
+    assert res.generated == o["generated"] and res.edge_dropped == o["edge_dropped"] and res.flags == 0
+    runs = [c for c in engines[0].calls if c[0] == "run"]
+    caps = [c[1]["request_capacity"] for c in engines[0].calls if c[0] == "configure"]
+    assert len(runs) >= 2 and caps == sorted(caps) and caps[-1] >= 4 * caps[0]
+    import pytest
+    with pytest.raises(RuntimeError):
+        r = R.GpuSimulationRunner(simulation_input=payload, seed=SEED)
+        r._ran = True
+        r.run()
