@@ -102,3 +102,57 @@ def test_merged_histogram_percentile_matches_numpy():
     g = all_gather_summary(*summary_block(stats, hist))
     for q in (50, 95, 99):
         assert abs(g.percentile(q) - np.percentile(lat, q)) < 0.01 * np.percentile(lat, q)
+
+
+def _sharded_worker(rank, world, port, q):
+    """The product's run_sharded() itself, on a runner whose engine is the CPU twin."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from twin_engine import TwinEngine
+
+    from asyncflow_b200 import SweepRunner
+    from asyncflow_b200.distributed import run_sharded
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    base = load_scenario("c1_my_service.yml", 6)
+    sw = SweepRunner(base, N, {("users_mean",): np.linspace(20, 400, N)}, seed=SEED, pinned=False, balance=True, deal=world)
+    sw._engine = TwinEngine()
+    sw._engine.upload(sw.flat)
+    res, g = run_sharded(sw)
+    q.put((rank, res.rows.tolist(), res.completed.tolist(), g.completed, g.generated, g.replicas, g.per_rank_completed,
+           int(np.asarray(g.histogram).sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_run_sharded_on_a_dealt_sweep_two_ranks():
+    from twin_engine import TwinEngine
+
+    from asyncflow_b200 import SweepRunner
+    base = load_scenario("c1_my_service.yml", 6)
+    one = SweepRunner(base, N, {("users_mean",): np.linspace(20, 400, N)}, seed=SEED, pinned=False, balance=True, deal=2)
+    one._engine = TwinEngine()
+    one._engine.upload(one.flat)
+    full = one.run()
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (_, rows0, c0, *g0), (_, rows1, c1, *g1) = got
+    assert sorted(rows0 + rows1) == list(range(N))
+    for rows, comp in ((rows0, c0), (rows1, c1)):
+        assert comp == [int(full.completed[r]) for r in rows]          # same result per row as the one-process run
+    assert g0 == g1
+    completed, generated, replicas, per_rank, hist_total = g0
+    assert completed == int(full.completed.sum()) and generated == int(full.generated.sum()) and replicas == N
+    assert per_rank == [sum(c0), sum(c1)] and hist_total == completed
+    # dealing balanced the two ranks' work (the undealt contiguous split would be ~1:3)
+    assert max(per_rank) / min(per_rank) < 1.35
