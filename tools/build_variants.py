@@ -23,6 +23,7 @@ VARIANTS = {
     "memo": ["-DAF_PREDRAW", "-DAF_PREGEN"],     # both
     "sorted": ["-DAF_SORTED_POOL"],              # sorted 32-entry front ring of the pending-event pool
     "all": ["-DAF_PREDRAW", "-DAF_PREGEN", "-DAF_SORTED_POOL"],
+    "all_mb6": ["-DAF_PREDRAW", "-DAF_PREGEN", "-DAF_SORTED_POOL", "-DAF_MIN_BLOCKS=6"],   # 80 registers, 24 warps/SM
 }
 
 
