@@ -5,7 +5,8 @@
 # (C3 as written; the bench workload's shape; saturated C2).  Build the variants beforehand on the
 # build box (python tools/build_variants.py) -- the .so files travel with the snapshot.
 cd "$(dirname "$0")/.." || exit 1
-for v in "" _predraw _pregen _memo _sorted _all _all_mb6; do
+# VARIANTS="_all _sorted" bash tools/ab_variants.sh   picks a subset ("" = the product build, always first)
+for v in "" ${VARIANTS:-_predraw _pregen _memo _sorted _all _all_mb6}; do
   lib="asyncflow_b200/_lib/libasyncflow_b200${v}.so"
   [ -f "$lib" ] || { echo "missing $lib"; continue; }
   echo "=== $lib"
