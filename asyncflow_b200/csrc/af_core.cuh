@@ -126,8 +126,15 @@ struct ReqRec { double t0; uint32_t rid; uint32_t pack; };          // 16 B
 // edge_send() reads its value from a shared-memory ring.  The ring is a MEMO, not a queue: a miss (the
 // request is older than the ring, the edge has no row, or the hop differs from the planned one) simply
 // draws as before, so results are bit-identical with or without it.
-constexpr int32_t PRE_MAX_ROWS = 6;
-constexpr int32_t PRE_RING = 32;
+#ifndef AF_PRE_MAX_ROWS
+#define AF_PRE_MAX_ROWS 6          /* edges that get a memo row (<= 15); rows x ring x 8 B of shared memory per warp */
+#endif
+#ifndef AF_PRE_RING
+#define AF_PRE_RING 32             /* request ids per row, a power of two */
+#endif
+constexpr int32_t PRE_MAX_ROWS = AF_PRE_MAX_ROWS;
+constexpr int32_t PRE_RING = AF_PRE_RING;
+static_assert(PRE_MAX_ROWS >= 1 && PRE_MAX_ROWS <= 15 && (PRE_RING & (PRE_RING - 1)) == 0 && PRE_RING >= 2, "memo geometry");
 #endif
 
 // ---- per-warp private tables (shared memory on the device) -------------------

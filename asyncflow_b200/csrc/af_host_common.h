@@ -119,6 +119,7 @@ inline void make_layout(const AfScenario& s, const AfOptions& o, int32_t n_sweep
     {
         PredrawPlan p = predraw_plan(s);
         L.pre_rows = p.rows; L.pre_ring = afc::PRE_RING; L.pre_chunk = p.rows ? 32 / p.rows : 0;
+        if (L.pre_chunk > afc::PRE_RING) L.pre_chunk = afc::PRE_RING;   // one pass must not lap the ring
         for (int r = 0; r < afc::PRE_MAX_ROWS; ++r) L.pre_edge[r] = r < p.rows ? p.edge_of_row[r] : 0;
     }
 #endif
