@@ -127,14 +127,14 @@ struct ReqRec { double t0; uint32_t rid; uint32_t pack; };          // 16 B
 // request is older than the ring, the edge has no row, or the hop differs from the planned one) simply
 // draws as before, so results are bit-identical with or without it.
 #ifndef AF_PRE_MAX_ROWS
-#define AF_PRE_MAX_ROWS 6          /* edges that get a memo row (<= 15); rows x ring x 8 B of shared memory per warp */
+#define AF_PRE_MAX_ROWS 15         /* edges that get a memo row (<= 15: 4 bits of EdgeS.meta) */
 #endif
-#ifndef AF_PRE_RING
-#define AF_PRE_RING 32             /* request ids per row, a power of two */
+#ifndef AF_PRE_BUDGET
+#define AF_PRE_BUDGET 2048         /* bytes of shared memory per warp the memo may take: ring = 32, 16 or 8 ids per row */
 #endif
 constexpr int32_t PRE_MAX_ROWS = AF_PRE_MAX_ROWS;
-constexpr int32_t PRE_RING = AF_PRE_RING;
-static_assert(PRE_MAX_ROWS >= 1 && PRE_MAX_ROWS <= 15 && (PRE_RING & (PRE_RING - 1)) == 0 && PRE_RING >= 2, "memo geometry");
+constexpr int32_t PRE_BUDGET = AF_PRE_BUDGET;
+static_assert(PRE_MAX_ROWS >= 1 && PRE_MAX_ROWS <= 15 && PRE_BUDGET >= 64, "memo geometry");
 #endif
 
 // ---- per-warp private tables (shared memory on the device) -------------------
@@ -750,6 +750,7 @@ AF_FN void pre_refill(State& W) {
     AF_SHARED(&W);
     const uint32_t base = W.pre_hi;
     const int32_t rows = AF_L.pre_rows, n = rows * AF_L.pre_chunk;
+    const uint32_t ring = (uint32_t)AF_L.pre_ring;
     double* pre = tbl_pre(W);
 #pragma unroll 1
     for (int32_t l = lane_id(); l < n; l += WARP) {
@@ -757,7 +758,7 @@ AF_FN void pre_refill(State& W) {
         const EdgeS& E = tbl_edge(W)[AF_L.pre_edge[row]];
         const double dropout = E.dropout;
         afr::EdgeDraw d = afr::edge_draw(AF_G.seed, W.replica, rid, meta_hop(E.meta), (int)(E.meta & 7u), E.mean, E.sigma, dropout);
-        pre[row * (uint32_t)PRE_RING + (rid & (uint32_t)(PRE_RING - 1))] = pre_encode(d, dropout);
+        pre[row * ring + (rid & (ring - 1u))] = pre_encode(d, dropout);
     }
     w_sync();
     W.pre_hi = base + (uint32_t)AF_L.pre_chunk;
@@ -770,14 +771,14 @@ AF_FN void edge_send(State& W, uint32_t slot, uint32_t e, uint32_t rid, uint32_t
     uint32_t s = W.seq++;                            // the timeout's place in SimPy's eid order
     const double dropout = E.dropout;
 #if defined(AF_PREDRAW)
-    const uint32_t meta = E.meta, row1 = meta_row1(meta), hi = W.pre_hi;
+    const uint32_t meta = E.meta, row1 = meta_row1(meta), hi = W.pre_hi, ring = (uint32_t)AF_L.pre_ring;
     double v;                                        // < 0: dropped, else the transit time
-    const bool memo = AF_LIKELY(row1 != 0u && hops == meta_hop(meta) && rid <= hi && rid + (uint32_t)PRE_RING > hi);
+    const bool memo = AF_LIKELY(row1 != 0u && hops == meta_hop(meta) && rid <= hi && rid + ring > hi);
 #if !AF_DEVICE_CODE
     g_pre_lookups[memo ? 1 : 0] += 1;                // host twin only: lets the tests see that the memo is live
 #endif
     if (memo)
-        v = tbl_pre(W)[(row1 - 1u) * (uint32_t)PRE_RING + (rid & (uint32_t)(PRE_RING - 1))];
+        v = tbl_pre(W)[(row1 - 1u) * ring + (rid & (ring - 1u))];
     else
         v = pre_encode(afr::edge_draw(AF_G.seed, W.replica, rid, hops, (int)(meta & 7u), E.mean, E.sigma, dropout), dropout);
     E.sent += 1;

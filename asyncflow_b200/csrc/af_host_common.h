@@ -86,7 +86,7 @@ inline int32_t trace_tick_capacity(const AfScenario& s) {
 // generator 1 (rqs_generator.py:113), client 3 (client.py:55-60), then +2 per node (the edge's and
 // the node's record_hop).  First assignment wins; the kernel compares the planned hop with the actual
 // one at every send, so an edge reachable at two depths only loses memo hits, never correctness.
-struct PredrawPlan { std::vector<int32_t> hop, row; int32_t rows = 0; int32_t edge_of_row[afc::PRE_MAX_ROWS]; };
+struct PredrawPlan { std::vector<int32_t> hop, row; int32_t rows = 0, ring = 0, chunk = 0; int32_t edge_of_row[afc::PRE_MAX_ROWS]; };
 inline PredrawPlan predraw_plan(const AfScenario& s) {
     PredrawPlan p;
     p.hop.assign((size_t)s.n_edges, -1); p.row.assign((size_t)s.n_edges, -1);
@@ -100,10 +100,15 @@ inline PredrawPlan predraw_plan(const AfScenario& s) {
         if (E.target_kind == AF_TARGET_LB) { for (int k = 0; k < s.n_lb_edges; ++k) set(s.lb_edges[k], h + 2); }
         else if (E.target_kind == AF_TARGET_SERVER) set(s.servers[E.target_index].out_edge, h + 2);
     }
-    for (int32_t e : order) {
-        if (p.rows >= afc::PRE_MAX_ROWS) break;
-        p.row[(size_t)e] = p.rows; p.edge_of_row[p.rows++] = e;
-    }
+    // geometry: as many rows as edges (<= PRE_MAX_ROWS), as deep a ring as the byte budget allows (32, 16, 8
+    // request ids per row), then fewer rows if even 8 do not fit
+    int32_t rows = (int32_t)order.size() < afc::PRE_MAX_ROWS ? (int32_t)order.size() : afc::PRE_MAX_ROWS;
+    int32_t ring = 32;
+    while (ring > 8 && 8 * rows * ring > afc::PRE_BUDGET) ring /= 2;
+    while (rows > 0 && 8 * rows * ring > afc::PRE_BUDGET) --rows;
+    p.rows = rows; p.ring = ring;
+    p.chunk = rows ? (32 / rows < ring ? 32 / rows : ring) : 0;          // one pass must not lap the ring
+    for (int32_t r = 0; r < rows; ++r) { p.row[(size_t)order[(size_t)r]] = r; p.edge_of_row[r] = order[(size_t)r]; }
     return p;
 }
 // what af_scenario_upload writes into AfEdge.reserved (bits [16:28) of the kernel's EdgeS.meta)
@@ -118,8 +123,7 @@ inline void make_layout(const AfScenario& s, const AfOptions& o, int32_t n_sweep
 #if defined(AF_PREDRAW)
     {
         PredrawPlan p = predraw_plan(s);
-        L.pre_rows = p.rows; L.pre_ring = afc::PRE_RING; L.pre_chunk = p.rows ? 32 / p.rows : 0;
-        if (L.pre_chunk > afc::PRE_RING) L.pre_chunk = afc::PRE_RING;   // one pass must not lap the ring
+        L.pre_rows = p.rows; L.pre_ring = p.ring; L.pre_chunk = p.chunk;
         for (int r = 0; r < afc::PRE_MAX_ROWS; ++r) L.pre_edge[r] = r < p.rows ? p.edge_of_row[r] : 0;
     }
 #endif

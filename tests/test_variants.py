@@ -15,7 +15,7 @@ from helpers import PARITY_CASES, SEED, load_scenario
 
 from asyncflow_b200.flatten import SweepSpec, flatten
 
-VARIANTS = ["predraw", "pregen", "memo", "sorted", "all", "wide", "tiny"]
+VARIANTS = ["predraw", "pregen", "memo", "sorted", "all", "narrow", "tiny"]
 
 
 def same(a: dict, b: dict) -> None:

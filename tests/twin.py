@@ -24,8 +24,8 @@ _SRC = [_DIR / "af_host_twin.cpp"] + sorted((_DIR.parent.parent / "asyncflow_b20
 VARIANTS = {None: [], "predraw": ["-DAF_PREDRAW"], "pregen": ["-DAF_PREGEN"],
             "memo": ["-DAF_PREDRAW", "-DAF_PREGEN"], "sorted": ["-DAF_SORTED_POOL"],
             "all": ["-DAF_PREDRAW", "-DAF_PREGEN", "-DAF_SORTED_POOL"],
-            "wide": ["-DAF_PREDRAW", "-DAF_PRE_MAX_ROWS=15", "-DAF_PRE_RING=8"],      # other memo geometries
-            "tiny": ["-DAF_PREDRAW", "-DAF_PRE_MAX_ROWS=1", "-DAF_PRE_RING=4"]}      # build variants of the engine core (af_core.cuh)
+            "narrow": ["-DAF_PREDRAW", "-DAF_PRE_MAX_ROWS=6", "-DAF_PRE_BUDGET=1536"],   # other memo geometries
+            "tiny": ["-DAF_PREDRAW", "-DAF_PRE_MAX_ROWS=3", "-DAF_PRE_BUDGET=64"]}      # build variants of the engine core (af_core.cuh)
 
 
 def build(variant: str | None = None) -> Path:
