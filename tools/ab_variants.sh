@@ -2,7 +2,7 @@
 # A/B the engine's build variants against the product build in ONE GPU session:
 #   gpurun --timeout 1800 -- 'bash tools/ab_variants.sh > gpurun_out/ab.log 2>&1'      (~3 GPU-min per library)
 # For every library: device parity vs the oracle first, then the same three timings
-# (C3 as written; the bench workload's shape; saturated C2).  Build the variants beforehand on the
+# (C3 as written; C1; saturated C2; C4; bench.py).  Build the variants beforehand on the
 # build box (python tools/build_variants.py) -- the .so files travel with the snapshot.
 cd "$(dirname "$0")/.." || exit 1
 # VARIANTS="_all _sorted" bash tools/ab_variants.sh   picks a subset ("" = the product build, always first)
@@ -15,7 +15,8 @@ for v in "" ${VARIANTS:-_predraw _pregen _memo _sorted _all _all_mb6}; do
   timeout 200 python tools/quick_bench.py --scenario c3_lb_two_servers.yml --replicas 40000 --horizon 20 --reps 3 | tail -2
   timeout 200 python tools/quick_bench.py --scenario c1_my_service.yml --replicas 40000 --horizon 60 --reps 2 --sweep none | tail -1
   timeout 200 python tools/quick_bench.py --scenario c1_my_service.yml --replicas 10000 --horizon 60 --reps 2 --sweep users | tail -1
-  echo "--- same, heaviest rows first (host-side launch order)"
+  timeout 200 python tools/quick_bench.py --scenario c4_lb8_events.yml --replicas 20000 --horizon 120 --reps 2 --sweep none | tail -1
+  echo "--- saturated C2 again, heaviest rows first (host-side launch order)"
   timeout 200 python tools/quick_bench.py --scenario c1_my_service.yml --replicas 10000 --horizon 60 --reps 2 --sweep users --balance | tail -1
   timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline | cut -c1-400
 done
