@@ -58,6 +58,14 @@
 // The same source compiles for the host with a warp of ONE lane
 // (tests/host_twin -- a debugging twin used by the CPU-only tests; it is NOT
 // reachable from the product API).
+//
+// Build variants (all off in the product build, whose SASS they do not change; each is
+// bit-identical to it by construction and checked so on the twin, tests/test_variants.py;
+// tools/build_variants.py + tools/ab_variants.sh build and time them on the GPU):
+//   -DAF_PREDRAW      lane-parallel, memoised edge variates            (search "AF_PREDRAW")
+//   -DAF_PREGEN       lane-parallel, memoised inter-arrival logarithms (search "AF_PREGEN")
+//   -DAF_SORTED_POOL  sorted 64-entry front ring for the event pool    (search "AF_SORTED_POOL")
+//   -DAF_MIN_BLOCKS=n register budget (af_engine.cu), -DAF_PRE_MAX_ROWS / -DAF_PRE_BUDGET memo geometry
 #pragma once
 #include "af_rng.cuh"
 #include "../../include/asyncflow_b200.h"
