@@ -24,7 +24,7 @@ from asyncflow_b200 import Engine, flatten  # noqa: E402
 def check(eng: Engine, payload: dict, replica: int) -> int:
     flat = flatten(payload)
     eng.upload(flat)
-    eng.configure(trace_replicas=1, trace_clock_capacity=100000, request_capacity=200000, throughput=True)
+    eng.configure(trace_replicas=1, trace_clock_capacity=400000, request_capacity=400000, throughput=True)
     eng.run(SEED, replica, replica + 1)
     st = eng.stats()
     sent, dropped = eng.edge_counts()
