@@ -65,6 +65,7 @@
 //   -DAF_PREDRAW      lane-parallel, memoised edge variates            (search "AF_PREDRAW")
 //   -DAF_PREGEN       lane-parallel, memoised inter-arrival logarithms (search "AF_PREGEN")
 //   -DAF_SORTED_POOL  sorted 64-entry front ring for the event pool    (search "AF_SORTED_POOL")
+//   -DAF_PIN_ACTIVE   served requests stay in the shared-memory tier   (search "AF_PIN_ACTIVE")
 //   -DAF_MIN_BLOCKS=n register budget (af_engine.cu), -DAF_PRE_MAX_ROWS / -DAF_PRE_BUDGET memo geometry
 #pragma once
 #include "af_rng.cuh"
@@ -180,6 +181,9 @@ struct State {
     uint32_t nq_head, nq_tail, busy;   // busy = 2 * (items in the now-queue) + (pool may hold an event of this instant)
     // request table
     uint32_t rq_free, rq_hw, rq_live, peak_rq;
+#if defined(AF_PIN_ACTIVE)
+    uint32_t rq_free_hi, rq_hw_hi;   // the HBM tier's own free list and bump pointer (rq_free / rq_hw: shared-memory tier)
+#endif
     // generator (two clocks: the sampler's virtual one and the simulation's)
     double g_vnow, g_window_end, g_lam;
     uint32_t g_pos, generated, g_done, need_arrival, arm_seq;
@@ -370,13 +374,23 @@ static inline void red_add_u32(uint32_t* p, uint32_t v) { *p += v; }
 #else
 #define AF_IN_SMEM(idx, cap) AF_LIKELY((int32_t)(idx) < (cap))
 #endif
+// (host twin, -DAF_COUNT_TIERS: how many request-record accesses each tier serves -- a measurement aid)
+#if defined(AF_COUNT_TIERS) && !AF_DEVICE_CODE
+static uint64_t g_rq_tier[2];                        // [shared-memory tier, HBM tier]
+#define AF_TIER_COUNT(s) (g_rq_tier[(int32_t)(s) < AF_L.rq_smem ? 0 : 1] += 1)
+#else
+#define AF_TIER_COUNT(s) ((void)0)
+#endif
 AF_IN ReqRec rq_load(const State& W, uint32_t s) {
+    AF_TIER_COUNT(s);
     return AF_IN_SMEM(s, AF_L.rq_smem) ? tbl_rq_rec(W)[s] : W.sp_rq_rec[s - AF_L.rq_smem];
 }
 AF_IN void rq_store(State& W, uint32_t s, const ReqRec& r) {
+    AF_TIER_COUNT(s);
     if (AF_IN_SMEM(s, AF_L.rq_smem)) tbl_rq_rec(W)[s] = r; else W.sp_rq_rec[s - AF_L.rq_smem] = r;
 }
 AF_IN void rq_set_pack(State& W, uint32_t s, uint32_t pack) {
+    AF_TIER_COUNT(s);
     if (AF_IN_SMEM(s, AF_L.rq_smem)) tbl_rq_rec(W)[s].pack = pack; else W.sp_rq_rec[s - AF_L.rq_smem].pack = pack;
 }
 AF_IN uint32_t nx_load(const State& W, uint32_t s) {
@@ -393,6 +407,50 @@ AF_IN uint64_t evk_load(const State& W, int32_t k) {
 }
 
 // ---- request slots (free list threaded through rq_next) ------------------------
+#if defined(AF_PIN_ACTIVE)
+// Build variant AF_PIN_ACTIVE -- requests that are being SERVED stay in the shared-memory tier.
+// A saturated replica holds thousands of requests, almost all of them parked in a server's RAM queue
+// (17 admitted, 7x10^4 waiting); with one free list the ~20 requests that generate
+// every event end up in arbitrary slots, i.e. in the HBM tier, and each handler pays L2 round trips for
+// its record.  Here the two tiers have their own free lists: a request is moved OUT to an HBM slot when
+// it joins a RAM queue (ram_enqueue) and back IN to a shared-memory slot when it is admitted (I_RAM_OK).
+// While it waits, nothing but the queue's links refers to its slot, so renaming it is invisible: same
+// events, same order, same results; live/peak counters are not touched by a move.
+AF_IN uint32_t rq_take_lo(State& W) {
+    uint32_t s = W.rq_free;
+    if (s != NIL) { W.rq_free = nx_load(W, s); return s; }
+    if ((int32_t)W.rq_hw < AF_L.rq_smem) return W.rq_hw++;
+    return NIL;
+}
+AF_IN uint32_t rq_take_hi(State& W) {
+    uint32_t s = W.rq_free_hi;
+    if (s != NIL) { W.rq_free_hi = nx_load(W, s); return s; }
+    if ((int32_t)W.rq_hw_hi < AF_L.rq_total) return W.rq_hw_hi++;
+    return NIL;
+}
+AF_IN void rq_give(State& W, uint32_t s) {
+    if ((int32_t)s < AF_L.rq_smem) { nx_store(W, s, W.rq_free); W.rq_free = s; }
+    else { nx_store(W, s, W.rq_free_hi); W.rq_free_hi = s; }
+}
+AF_IN uint32_t rq_alloc(State& W) {
+    uint32_t s = rq_take_lo(W);
+    if (s == NIL) s = rq_take_hi(W);
+    if (s == NIL) { W.flags |= AF_FLAG_REQUEST_OVERFLOW; return NIL; }
+    uint32_t live = ++W.rq_live;
+    if (live > W.peak_rq) W.peak_rq = live;
+    return s;
+}
+AF_IN void rq_release(State& W, uint32_t s) { rq_give(W, s); --W.rq_live; }
+// rename `slot` into the other tier if that tier has room; returns the slot to use from now on
+AF_FN uint32_t rq_move(State& W, uint32_t slot, uint32_t to_lo) {
+    AF_SHARED(&W);
+    const uint32_t s2 = to_lo ? rq_take_lo(W) : rq_take_hi(W);
+    if (s2 == NIL) return slot;
+    rq_store(W, s2, rq_load(W, slot));
+    rq_give(W, slot);
+    return s2;
+}
+#else
 AF_IN uint32_t rq_alloc(State& W) {
     uint32_t s;
     if (W.rq_free != NIL) { s = W.rq_free; W.rq_free = nx_load(W, s); }
@@ -403,6 +461,8 @@ AF_IN uint32_t rq_alloc(State& W) {
     return s;
 }
 AF_IN void rq_release(State& W, uint32_t s) { nx_store(W, s, W.rq_free); W.rq_free = s; --W.rq_live; }
+
+#endif
 
 // intrusive FIFOs (RAM waiters, CPU waiters) through the same `next` links
 AF_FN void fifo_push(State& W, uint32_t& head, uint32_t& tail, uint32_t s) {
@@ -861,6 +921,10 @@ AF_FN void ram_walk(State& W, ServerS& S, uint32_t sidx) {
 }
 // RAM.get(total_ram) of a request that cannot be served at once: join the queue, walk it
 AF_IN void ram_enqueue(State& W, ServerS& S, uint32_t sidx, uint32_t slot, uint32_t total_ram) {
+#if defined(AF_PIN_ACTIVE)
+    // it will wait unless the walk below admits it at once (queue empty and it fits): park it in the HBM tier
+    if ((int32_t)slot < AF_L.rq_smem && !(S.ramq_head == NIL && (int32_t)total_ram <= S.ram_free)) slot = rq_move(W, slot, 0u);
+#endif
     if (S.ramq_head == NIL) S.ramq_head_need = total_ram;
     fifo_push(W, S.ramq_head, S.ramq_tail, slot);
     ram_walk(W, S, sidx);
@@ -1045,7 +1109,8 @@ AF_FN void node_got(State& W, uint32_t node, uint32_t slot, double t0, uint32_t 
 // one zero-delay item (single call site in run_replica)
 // ---------------------------------------------------------------------------------
 AF_IN void run_item(State& W, uint32_t item) {
-    const uint32_t kind = item >> 29, aux = (item >> SLOT_BITS) & AUX_MASK, slot = item & SLOT_MASK;
+    const uint32_t kind = item >> 29, aux = (item >> SLOT_BITS) & AUX_MASK;
+    uint32_t slot = item & SLOT_MASK;
     AF_TRACE("it t=%.17g kind=%u aux=%u slot=%u\n", W.now, kind, aux, slot);
     if (kind == I_PUT) {                             // a StorePut event is processed
         InboxS& b = tbl_inbox(W)[aux];
@@ -1056,6 +1121,9 @@ AF_IN void run_item(State& W, uint32_t item) {
         consumer_get(W, NODE_CLIENT);
     } else if (kind == I_RAM_OK) {                   // the RAM get event is processed: the handler resumes
         ServerS& S = tbl_server(W)[aux];
+#if defined(AF_PIN_ACTIVE)
+        if ((int32_t)slot >= AF_L.rq_smem) slot = rq_move(W, slot, 1u);   // admitted: back into the fast tier
+#endif
         ReqRec r = rq_load(W, slot);
         S.ram_in_use += (int32_t)tbl_endpoint(W)[pk_ep(r.pack)].total_ram;
         run_steps(W, slot, aux, r.rid, r.pack);
@@ -1335,6 +1403,9 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
     W.ev_hw = 0; W.ev_live = 0; W.ev_last_free = -1; W.ev_hole = -1; W.peak_ev = 0;
     W.nq_head = 0; W.nq_tail = 0; W.busy = 0;
     W.rq_free = NIL; W.rq_hw = 0; W.rq_live = 0; W.peak_rq = 0;
+#if defined(AF_PIN_ACTIVE)
+    W.rq_free_hi = NIL; W.rq_hw_hi = (uint32_t)AF_L.rq_smem;
+#endif
     W.g_vnow = 0.0; W.g_window_end = 0.0; W.g_lam = 0.0; W.g_pos = 0; W.generated = 0; W.g_done = 0;
     W.lb_n = AF_L.n_lb_edges;
     W.spike_cur = 0; W.outage_cur = 0;

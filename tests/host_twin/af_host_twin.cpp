@@ -106,3 +106,13 @@ extern "C" void af_twin_pool_counts(uint64_t* out) {
     for (int i = 0; i < 4; ++i) out[i] = 0;
 #endif
 }
+
+// request-record accesses per tier since the last call (twin built with -DAF_COUNT_TIERS; zeros otherwise)
+extern "C" void af_twin_tier_counts(uint64_t* out) {
+#if defined(AF_COUNT_TIERS)
+    out[0] = afc::g_rq_tier[0]; out[1] = afc::g_rq_tier[1];
+    afc::g_rq_tier[0] = afc::g_rq_tier[1] = 0;
+#else
+    out[0] = out[1] = 0;
+#endif
+}

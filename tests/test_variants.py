@@ -1,4 +1,4 @@
-"""Build variants of the engine core (AF_PREDRAW / AF_PREGEN / AF_SORTED_POOL, af_core.cuh) must be BIT-IDENTICAL to the
+"""Build variants of the engine core (AF_PREDRAW / AF_PREGEN / AF_SORTED_POOL / AF_PIN_ACTIVE, af_core.cuh) must be BIT-IDENTICAL to the
 product build: they only move where random numbers are computed (lane-parallel, memoised), never which
 numbers.  Checked here on the CPU twin, byte for byte against the default twin (which the rest of the
 suite pins to the oracle); tools/check_variant_gpu.py repeats it on the device."""
@@ -15,7 +15,7 @@ from helpers import PARITY_CASES, SEED, load_scenario
 
 from asyncflow_b200.flatten import SweepSpec, flatten
 
-VARIANTS = ["predraw", "pregen", "memo", "sorted", "all", "narrow", "tiny"]
+VARIANTS = ["predraw", "pregen", "memo", "sorted", "pin", "all", "all4", "narrow", "tiny"]
 
 
 def same(a: dict, b: dict) -> None:
@@ -44,7 +44,7 @@ def test_variant_equals_product_build_on_random_scenarios_and_sweeps(variant, se
     same(twin.run(flat, **kw), twin.run(flat, variant=variant, **kw))
 
 
-@pytest.mark.parametrize("variant", ["memo", "sorted", "all"])
+@pytest.mark.parametrize("variant", ["memo", "sorted", "pin", "all4"])
 @pytest.mark.parametrize("seed", range(16, 28))
 def test_variant_equals_product_build_on_big_topologies(variant, seed):
     flat = flatten(fuzz.big_scenario(seed))
@@ -77,3 +77,18 @@ def test_the_sorted_pool_exercises_both_modes_and_both_switches():
             assert out[1] == 0 and out[0] > 5000          # nominal load never leaves the sorted ring
         seen += np.array(list(out), dtype=np.int64)
     assert (seen > 0).all(), seen.tolist()                # ring pushes, unsorted pushes, A->B, B->A
+
+
+def test_pinning_keeps_served_requests_in_the_fast_tier():
+    """Saturated single server (thousands queued): share of request-record accesses that go to the HBM tier."""
+    out = (C.c_uint64 * 2)()
+    share = {}
+    flat = flatten(load_scenario("overload_single.yml"))
+    for variant in ("count", "pin_count"):
+        L = twin.lib(variant)
+        L.af_twin_tier_counts(out)
+        r = twin.run(flat, seed=SEED, n=1, variant=variant, request_capacity=400000)
+        L.af_twin_tier_counts(out)
+        assert r["stats"][0]["peak_requests"] > 1000
+        share[variant] = out[1] / (out[0] + out[1])
+    assert share["count"] > 0.85 and share["pin_count"] < 0.25, share

@@ -24,6 +24,9 @@ _SRC = [_DIR / "af_host_twin.cpp"] + sorted((_DIR.parent.parent / "asyncflow_b20
 VARIANTS = {None: [], "predraw": ["-DAF_PREDRAW"], "pregen": ["-DAF_PREGEN"],
             "memo": ["-DAF_PREDRAW", "-DAF_PREGEN"], "sorted": ["-DAF_SORTED_POOL"],
             "all": ["-DAF_PREDRAW", "-DAF_PREGEN", "-DAF_SORTED_POOL"],
+            "pin": ["-DAF_PIN_ACTIVE"],
+            "count": ["-DAF_COUNT_TIERS"], "pin_count": ["-DAF_PIN_ACTIVE", "-DAF_COUNT_TIERS"],
+            "all4": ["-DAF_PREDRAW", "-DAF_PREGEN", "-DAF_SORTED_POOL", "-DAF_PIN_ACTIVE"],
             "narrow": ["-DAF_PREDRAW", "-DAF_PRE_MAX_ROWS=6", "-DAF_PRE_BUDGET=1536"],   # other memo geometries
             "tiny": ["-DAF_PREDRAW", "-DAF_PRE_MAX_ROWS=3", "-DAF_PRE_BUDGET=64"]}      # build variants of the engine core (af_core.cuh)
 

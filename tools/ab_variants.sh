@@ -6,7 +6,7 @@
 # build box (python tools/build_variants.py) -- the .so files travel with the snapshot.
 cd "$(dirname "$0")/.." || exit 1
 # VARIANTS="_all _sorted" bash tools/ab_variants.sh   picks a subset ("" = the product build, always first)
-for v in "" ${VARIANTS:-_predraw _pregen _memo _sorted _all _all_mb6}; do
+for v in "" ${VARIANTS:-_predraw _pregen _memo _sorted _pin _all _all4 _all_mb6}; do
   lib="asyncflow_b200/_lib/libasyncflow_b200${v}.so"
   [ -f "$lib" ] || { echo "missing $lib"; continue; }
   echo "=== $lib"

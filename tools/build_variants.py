@@ -22,7 +22,9 @@ VARIANTS = {
     "pregen": ["-DAF_PREGEN"],                   # lane-parallel memoised inter-arrival logs
     "memo": ["-DAF_PREDRAW", "-DAF_PREGEN"],     # both
     "sorted": ["-DAF_SORTED_POOL"],              # sorted 32-entry front ring of the pending-event pool
+    "pin": ["-DAF_PIN_ACTIVE"],                  # requests being served stay in the shared-memory tier
     "all": ["-DAF_PREDRAW", "-DAF_PREGEN", "-DAF_SORTED_POOL"],
+    "all4": ["-DAF_PREDRAW", "-DAF_PREGEN", "-DAF_SORTED_POOL", "-DAF_PIN_ACTIVE"],
     "all_mb6": ["-DAF_PREDRAW", "-DAF_PREGEN", "-DAF_SORTED_POOL", "-DAF_MIN_BLOCKS=6"],   # 80 registers, 24 warps/SM
 }
 
