@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B the engine's build variants against the product build in ONE GPU session:
-#   gpurun --timeout 1800 -- 'bash tools/ab_variants.sh > gpurun_out/ab.log 2>&1'      (~3 GPU-min per library)
+#   gpurun --timeout 2400 -- 'bash tools/ab_variants.sh > gpurun_out/ab.log 2>&1'      (~3 GPU-min per library)
 # For every library: device parity vs the oracle first, then the same three timings
 # (C3 as written; C1; saturated C2; C4; bench.py).  Build the variants beforehand on the
 # build box (python tools/build_variants.py) -- the .so files travel with the snapshot.
