@@ -21,10 +21,11 @@ from helpers import PARITY_CASES, SEED, assert_matches_oracle, load_scenario  # 
 from asyncflow_b200 import Engine, flatten  # noqa: E402
 
 
-def check(eng: Engine, payload: dict, replica: int) -> int:
+def check(eng: Engine, payload: dict, replica: int, event_capacity: int = 0) -> int:
     flat = flatten(payload)
     eng.upload(flat)
-    eng.configure(trace_replicas=1, trace_clock_capacity=400000, request_capacity=400000, throughput=True)
+    eng.configure(trace_replicas=1, trace_clock_capacity=400000, request_capacity=400000, throughput=True,
+                  event_capacity=event_capacity)
     eng.run(SEED, replica, replica + 1)
     st = eng.stats()
     sent, dropped = eng.edge_counts()
@@ -43,7 +44,9 @@ def main() -> None:
             total += check(eng, load_scenario(name, horizon), 7)
         for seed in range(500, 540):
             total += check(eng, fuzz.scenario(seed), seed)
-    print(f"OK: {len(PARITY_CASES)} scenarios + 40 random scenarios, {total} completions bit-exact vs the oracle")
+        for seed in range(40, 48):                       # C5-shaped, overloaded: both HBM tiers, unsorted pool
+            total += check(eng, fuzz.big_scenario(seed), seed, event_capacity=8192)
+    print(f"OK: {len(PARITY_CASES)} scenarios + 40 random + 8 big random scenarios, {total} completions bit-exact vs the oracle")
 
 
 if __name__ == "__main__":
