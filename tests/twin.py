@@ -18,7 +18,7 @@ from asyncflow_b200 import _capi as K
 _DIR = Path(__file__).resolve().parent / "host_twin"
 _SO = _DIR / "_build" / "libaf_host_twin.so"
 _SRC = [_DIR / "af_host_twin.cpp"] + sorted((_DIR.parent.parent / "asyncflow_b200" / "csrc").glob("*.*h")) \
-    + [_DIR.parent.parent / "include" / "asyncflow_b200.h"]
+    + [_DIR.parent.parent / "include" / "asyncflow_b200.h", _DIR.parent.parent / "asyncflow_b200" / "csrc" / "ENGINE_DEFINES"]
 
 
 VARIANTS = {None: [], "predraw": ["-DAF_PREDRAW"], "pregen": ["-DAF_PREGEN"],
@@ -31,13 +31,18 @@ VARIANTS = {None: [], "predraw": ["-DAF_PREDRAW"], "pregen": ["-DAF_PREGEN"],
             "tiny": ["-DAF_PREDRAW", "-DAF_PRE_MAX_ROWS=3", "-DAF_PRE_BUDGET=64"]}      # build variants of the engine core (af_core.cuh)
 
 
+def product_defines() -> list[str]:
+    f = _DIR.parent.parent / "asyncflow_b200" / "csrc" / "ENGINE_DEFINES"
+    return [ln.strip() for ln in f.read_text().splitlines() if ln.strip() and not ln.startswith("#")] if f.exists() else []
+
+
 def build(variant: str | None = None) -> Path:
     so = _SO if variant is None else _SO.with_name(f"libaf_host_twin_{variant}.so")
     newest = max(p.stat().st_mtime for p in _SRC)
     if not so.exists() or so.stat().st_mtime < newest:
         so.parent.mkdir(exist_ok=True)
         subprocess.run(
-            ["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", *VARIANTS[variant], "-x", "c++",
+            ["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", *(product_defines() if variant is None else VARIANTS[variant]), "-x", "c++",
              "-o", str(so), str(_DIR / "af_host_twin.cpp")], check=True)
     return so
 
