@@ -122,3 +122,34 @@ def test_single_replica_runner_on_the_twin_engine(monkeypatch):
         r = R.GpuSimulationRunner(simulation_input=payload, seed=SEED)
         r._ran = True
         r.run()
+
+
+def test_overflowed_replicas_are_rerun_with_larger_pools():
+    """Tiny pools: the saturated rows overflow (flagged); retry_overflow re-runs just them, exactly."""
+    base = load_scenario("c1_my_service.yml", 6)
+    users = [30.0, 900.0, 40.0, 800.0, 850.0, 20.0]
+
+    def make(**kw):
+        sw = SweepRunner(base, len(users), {("users_mean",): users}, seed=SEED, pinned=False, throughput=True,
+                         request_capacity=300, event_capacity=64, **kw)
+        sw._engine = TwinEngine()
+        sw._engine.upload(sw.flat)
+        return sw
+    plain = make().run()
+    assert plain.overflowed.tolist() == [False, True, False, True, True, False]
+    sw = make()
+    res = sw.run(retry_overflow=True)
+    assert not res.overflowed.any()
+    ranges = [(c[2], c[3]) for c in sw._engine.calls if c[0] == "run"]
+    assert ranges[0] == (0, 6) and set(ranges[1:]) >= {(1, 2), (3, 5)}      # only the flagged ids, grouped
+    for row in range(len(users)):
+        o = oracle_row(sw, row)
+        assert int(res.generated[row]) == o["generated"] and int(res.completed[row]) == o["completed"]
+        assert int(res.throughput[row].sum()) == o["completed"]
+    # the rows that never overflowed were not touched
+    for row in (0, 2, 5):
+        assert plain.stats[row].tobytes() == res.stats[row].tobytes()
+    # with a balanced launch order the patched rows still come back in row order
+    bal = make(balance=True)
+    rb = bal.run(retry_overflow=True)
+    assert not rb.overflowed.any() and np.argmax(rb.generated) == 1
