@@ -153,3 +153,19 @@ def test_overflowed_replicas_are_rerun_with_larger_pools():
     bal = make(balance=True)
     rb = bal.run(retry_overflow=True)
     assert not rb.overflowed.any() and np.argmax(rb.generated) == 1
+
+
+def test_frame_lists_parameters_next_to_statistics():
+    pd = __import__("pytest").importorskip("pandas")
+    sw = runner(balance=True)
+    res = sw.run()
+    df = sw.frame(res)
+    assert list(df["row"]) == list(range(len(USERS)))
+    assert list(df["users_mean"]) == USERS and list(df["edge_mean:client-app"]) == RTT
+    assert list(df["replica_id"]) == sw.replica_ids.tolist()
+    assert (df["completed"] <= df["generated"]).all() and df["p95_s"].notna().all()
+    part = sw.run(2, 5)                                   # a shard: rows are named, parameters follow them
+    dfp = sw.frame(part)
+    assert list(dfp["row"]) == sw.order[2:5].tolist()
+    assert list(dfp["users_mean"]) == [USERS[r] for r in sw.order[2:5]]
+    assert isinstance(df, pd.DataFrame)
