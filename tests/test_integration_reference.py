@@ -80,3 +80,32 @@ def test_sweep_row_equals_unmodified_reference_on_payload_for(seed):
         got = [tuple(x) for x in r["trace_clocks"][i, :k].tolist()]
         assert got == [tuple(w) for w in ref["clocks"]]
         assert dict(zip(flat.edge_ids, map(int, r["dropped"][i]))) == ref["edge_dropped"]
+
+
+REFERENCE_YAMLS = ["examples/yaml_input/data/two_servers_lb.yml", "examples/yaml_input/data/event_inj_single_server.yml",
+                   "examples/yaml_input/data/heavy_inj_single_server.yml", "examples/yaml_input/data/single_server.yml",
+                   "examples/yaml_input/data/event_inj_lb.yml", "tests/integration/single_server/data/single_server.yml"]
+
+
+@pytest.mark.parametrize("rel", REFERENCE_YAMLS)
+def test_every_scenario_file_the_reference_ships_runs_identically(rel):
+    """The reference's own example / test YAMLs, as they lie in /root/reference (read at test time, not
+    copied): unmodified reference actors == engine state machine, clock for clock and series for series."""
+    import yaml
+    from pathlib import Path
+
+    payload = yaml.safe_load((Path(ref_harness.REFERENCE_SRC).parent / rel).read_text())
+    full = int(payload["sim_settings"].get("total_simulation_time", 3600))
+    horizon = min(full, 40)
+    payload["sim_settings"]["total_simulation_time"] = horizon
+    for ev in payload.get("events") or []:                 # same timeline, compressed into the shortened horizon
+        ev["start"]["t_start"] = float(ev["start"]["t_start"]) * horizon / full
+        ev["end"]["t_end"] = float(ev["end"]["t_end"]) * horizon / full
+    ref = ref_harness.run_reference(payload, seed=SEED, replica=2)
+    mine = twin_results(payload, 2)
+    assert [tuple(x) for x in mine.clocks.tolist()] == [tuple(c) for c in ref["clocks"]]
+    assert mine.generated == ref["generated"] and mine.edge_dropped == ref["edge_dropped"]
+    ma, mb = ref["analyzer"].get_sampled_metrics(), mine.get_sampled_metrics()
+    for metric in ma:
+        for ent in ma[metric]:
+            assert list(ma[metric][ent]) == list(mb[metric][ent]), (metric, ent)
