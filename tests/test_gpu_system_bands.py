@@ -1,4 +1,4 @@
-"""The reference's own end-to-end acceptance bands, applied to the CUDA engine.
+"""The reference's own end-to-end acceptance bands, applied to the CUDA engine (and to its CPU twin).
 
 The reference's system tests (tests/system/*.py, enabled with ASYNCFLOW_RUN_SYSTEM_TESTS=1) are the
 only end-to-end pins upstream has: loose statistical bands on one unseeded run.  Here the same
@@ -16,8 +16,19 @@ from helpers import SEED
 
 from asyncflow_b200 import GpuSimulationRunner, SweepRunner, flatten
 
-pytestmark = pytest.mark.gpu
 N = 512
+
+
+@pytest.fixture(autouse=True, params=[pytest.param("twin"), pytest.param("gpu", marks=pytest.mark.gpu)])
+def engine_kind(request, monkeypatch):
+    """Every band is checked twice: on the CUDA engine (GPU box) and, with the identical runner code, on
+    the CPU twin standing in for it (tests/twin_engine.py) -- the same state machine, so the statistics the
+    bands test are available without a GPU too."""
+    if request.param == "twin":
+        import asyncflow_b200.runner as R
+        from twin_engine import TwinEngine
+        monkeypatch.setattr(R, "Engine", TwinEngine)
+    return request.param
 
 
 def _server(sid: str) -> dict:
