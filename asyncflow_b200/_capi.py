@@ -27,7 +27,10 @@ FIELDS = {
     "edge_dropout": 5, "server_cpu_cores": 6, "server_ram_mb": 7, "step_duration": 8,
     "endpoint_ram": 9, "spike_delta": 10,
 }
-FLAG_EVENT_OVERFLOW, FLAG_REQUEST_OVERFLOW, FLAG_TRACE_TRUNCATED, FLAG_NOWQ_OVERFLOW = 1, 2, 4, 8
+FLAG_EVENT_OVERFLOW, FLAG_REQUEST_OVERFLOW, FLAG_TRACE_TRUNCATED, FLAG_NOWQ_OVERFLOW, FLAG_LB_EMPTY = 1, 2, 4, 8, 16
+MODE_AUTO, MODE_WARP, MODE_LANE = 0, 1, 2
+SELFTEST_EDGE, SELFTEST_GEN_UNIFORM, SELFTEST_GEN_USERS, SELFTEST_ENDPOINT = 0, 1, 2, 3
+MODES = {"auto": MODE_AUTO, "warp": MODE_WARP, "lane": MODE_LANE}
 
 
 class AfEdge(C.Structure):
@@ -110,6 +113,12 @@ STATS_DTYPE = np.dtype([
 assert STATS_DTYPE.itemsize == C.sizeof(AfReplicaStats)
 
 
+class AfRunPasses(C.Structure):
+    _fields_ = [("lane_pass", C.c_int32), ("warp_pass", C.c_int32), ("lane_warps_per_sm", C.c_int32),
+                ("lane_bytes", C.c_int32), ("lane_events_smem", C.c_int32), ("lane_requests_smem", C.c_int32),
+                ("lane_replicas", C.c_uint64), ("warp_replicas", C.c_uint64)]
+
+
 class EngineUnavailable(RuntimeError):
     """The CUDA engine cannot run here (library not built or no usable GPU)."""
 
@@ -121,7 +130,8 @@ EXPORTS = [
     "af_engine_configure", "af_scenario_upload", "af_sweep_upload", "af_run", "af_sync",
     "af_last_run_ms", "af_launch_count", "af_fetch_stats", "af_fetch_edge_counts",
     "af_fetch_histograms", "af_fetch_throughput", "af_fetch_sampled", "af_fetch_trace_clocks",
-    "af_fetch_trace_series", "af_reduce_histograms",
+    "af_fetch_trace_series", "af_reduce_histograms", "af_engine_set_mode", "af_last_run_passes",
+    "af_selftest_rng",
 ]
 
 _lib = None
@@ -162,6 +172,9 @@ def load() -> C.CDLL:
     lib.af_fetch_trace_clocks.argtypes = [vp, u64, vp, u64, C.POINTER(u64)]
     lib.af_fetch_trace_series.argtypes = [vp, u64, vp, u64, C.POINTER(u64)]
     lib.af_reduce_histograms.argtypes = [vp, vp]
+    lib.af_engine_set_mode.argtypes = [vp, i32]
+    lib.af_last_run_passes.argtypes = [vp, C.POINTER(AfRunPasses)]
+    lib.af_selftest_rng.argtypes = [vp, u64, u64, i32, i32, C.c_double, C.c_double, C.c_uint32, u64, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("af_abi_version",):

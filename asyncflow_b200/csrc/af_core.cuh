@@ -106,6 +106,8 @@
 
 namespace afc {
 
+// flags that end a replica early (its partial results are written back with the flag set)
+constexpr uint32_t STOP_FLAGS = AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW | AF_FLAG_NOWQ_OVERFLOW | AF_FLAG_LB_EMPTY;
 constexpr uint32_t NIL = 0xFFFFFFFFu;
 constexpr uint64_t INF_BITS = 0x7FF0000000000000ull;
 
@@ -293,6 +295,8 @@ struct Globals {
     uint32_t* hist; uint32_t* thr; uint64_t* samp_sum; uint32_t* samp_max;
     double* trace_clocks; uint32_t* trace_series; uint32_t* trace_counts;
     unsigned long long* work_counter;
+    // second pass (af_engine.cu): the replicas the thread-per-replica pass flagged; NULL = every replica of the launch
+    const uint32_t* redo_list; const uint32_t* redo_count;
     uint64_t seed, replica_begin, n_replicas;
 };
 
@@ -1088,6 +1092,9 @@ AF_FN void node_got(State& W, uint32_t node, uint32_t slot, double t0, uint32_t 
     rq_set_pack(W, slot, r.pack);
     uint32_t* lb = tbl_lb(W);
     const int32_t n = W.lb_n;
+    // every covered server is down: the reference dies here (StopIteration inside round_robin); the replica
+    // stops and says so (flatten() rejects timelines that can reach this state)
+    if (AF_UNLIKELY(n <= 0)) { W.flags |= AF_FLAG_LB_EMPTY; return; }
     uint32_t pick = lb[0];
     if (AF_L.lb_algo == AF_LB_ROUND_ROBIN) {         // lb_algorithms.py:22-36
 #pragma unroll 1
@@ -1364,6 +1371,11 @@ AF_FN void load_params(State& W) {
         }
         w_sync();
     }
+    if (AF_G.redo_list) {                            // a re-run: the first pass left partial counts in the accumulating outputs
+        if (AF_L.collect_hist) for (int32_t b = lane; b < AF_HIST_BINS; b += WARP) AF_G.hist[W.local * AF_HIST_BINS + (uint32_t)b] = 0;
+        if (AF_L.collect_thr) for (int32_t b = lane; b < AF_L.horizon_s; b += WARP) AF_G.thr[W.local * (uint64_t)AF_L.horizon_s + (uint32_t)b] = 0;
+        w_sync();
+    }
 }
 
 AF_FN void write_back(State& W) {
@@ -1446,7 +1458,7 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
             W.nq_head += 1;
             W.busy = busy - 2u;
             run_item(W, item);
-            if (W.flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW | AF_FLAG_NOWQ_OVERFLOW)) break;
+            if (W.flags & STOP_FLAGS) break;
             continue;
         }
         PoolMin m;
@@ -1467,7 +1479,7 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
                 W.busy = (same_t ? busy : (busy & ~1u)) - 2u;
                 W.nq_head += 1;
                 run_item(W, (uint32_t)front);
-                if (W.flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW | AF_FLAG_NOWQ_OVERFLOW)) break;
+                if (W.flags & STOP_FLAGS) break;
                 continue;
             }
         } else if (!have_ev) break;
@@ -1496,7 +1508,7 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
         else if (kind == K_ARRIVAL) on_arrival(W);
         else if (kind == K_SPIKE) on_spike(W);
         else on_outage(W);
-        if (W.flags & (AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW | AF_FLAG_NOWQ_OVERFLOW)) break;
+        if (W.flags & STOP_FLAGS) break;
     }
     W.n_events = n_events;
     take_samples(W, W.horizon, 0u);                   // ticks strictly before the horizon

@@ -1,7 +1,14 @@
 // af_engine.cu -- sm_100a kernels and the C ABI of include/asyncflow_b200.h.
 //
 // Kernels:
-//   af_sim_kernel         one replica per warp, persistent CTAs pulling replica
+//   af_lane_kernel        one replica per THREAD (af_lane.cuh): the first pass of every run.  One
+//                         persistent CTA per SM; a lane's mutable state is word-interleaved in shared
+//                         memory (conflict-free at any divergence), deep tiers in global memory; lanes
+//                         pull replica indices from a global counter.
+//   af_flagged_kernel     compacts the replicas whose pools overflowed in the first pass (its tiers are
+//                         sized for nominal load) into a list ...
+//   af_sim_kernel         ... which the warp-per-replica engine (af_core.cuh, large HBM tiers) re-runs.
+//                         One replica per warp, persistent CTAs pulling replica
 //                         indices from a global counter (skewed sweeps balance
 //                         themselves); per-warp workspace in shared memory with
 //                         spill tiers in HBM; the replica state machine is
@@ -14,6 +21,7 @@
 // (-fmad=false is part of the parity contract: see af_rng.cuh).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <new>
@@ -21,6 +29,12 @@
 #include <vector>
 
 #include "af_host_common.h"
+#include "af_lane_host.h"
+
+// thread-per-replica pass: warps per SM when the caller does not say (AfOptions.warps_per_block)
+#ifndef AF_LANE_DEFAULT_WARPS
+#define AF_LANE_DEFAULT_WARPS 8
+#endif
 
 // occupancy knob: registers are capped (64/thread) so that 8 128-thread CTAs fit per SM.
 // Measured on B200, C3 x 40k replicas: uncapped (94 regs, 20 warps/SM) 2.04e8 completions/s,
@@ -50,9 +64,66 @@ __global__ void AF_LAUNCH_BOUNDS af_sim_kernel() {
         unsigned long long r = 0;
         if (lane == 0) r = atomicAdd(afc::c_G.work_counter, 1ull);
         r = __shfl_sync(0xFFFFFFFFu, r, 0);
-        if (r >= afc::c_G.n_replicas) break;
+        if (afc::c_G.redo_list) {                      // second pass: only the replicas the first pass flagged
+            if (r >= (unsigned long long)*afc::c_G.redo_count) break;
+            r = afc::c_G.redo_list[r];
+        } else if (r >= afc::c_G.n_replicas) break;
         afc::run_replica(W, (uint64_t)r);
         __syncwarp();
+    }
+}
+
+// One replica per thread.  Compiled for one CTA of up to 512 threads per SM (the shared-memory budget of a
+// lane decides the CTA size at launch; registers: 128 per thread at 512 threads).
+#ifndef AF_LANE_MAX_THREADS
+#define AF_LANE_MAX_THREADS 512
+#endif
+__global__ void __launch_bounds__(AF_LANE_MAX_THREADS, 1) af_lane_kernel() {
+    extern __shared__ __align__(16) unsigned char af_smem[];
+    const afl::Cfg& C = afl::c_cfg;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    unsigned char* ws = af_smem + (size_t)warp * (size_t)C.warp_bytes;
+    unsigned char* gs = C.gtier + ((uint64_t)blockIdx.x * (blockDim.x >> 5) + warp) * C.gwarp_bytes;
+    afl::Mem m;
+    m.s64 = ws + lane * 8u; m.s32 = ws + (size_t)C.n64 * afl::STRIDE64 + lane * 4u;
+    m.g64 = gs + lane * 8u; m.g32 = gs + (size_t)C.gn64 * afl::STRIDE64 + lane * 4u;
+    afl::run_lane(m,
+        [&]() -> uint64_t {
+            const unsigned long long k = atomicAdd(C.work_counter, 1ull);
+            return k < C.n_replicas ? (uint64_t)k : ~0ull;
+        },
+        [](bool alive) -> bool { return __any_sync(0xFFFFFFFFu, alive) != 0; });
+}
+
+// replicas whose pools overflowed in the thread-per-replica pass -> list for the warp-per-replica pass
+__global__ void af_flagged_kernel(const AfReplicaStats* __restrict__ stats, uint64_t n, uint32_t mask,
+                                  uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (stats[i].flags & mask)) list[atomicAdd(count, 1u)] = (uint32_t)i;
+}
+
+// AF-RNG on the device, outside the state machine: what tests/test_gpu_rng.py compares with oracle/afrng_c
+// (kind: see af_selftest_rng in the header)
+__global__ void af_selftest_rng_kernel(uint64_t seed, uint64_t replica, int kind, int dist, double mean, double sigma,
+                                       uint32_t hop, uint64_t n, double* __restrict__ a, double* __restrict__ b) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (kind == AF_SELFTEST_EDGE) {
+        const afr::EdgeDraw d = afr::edge_draw(seed, replica, (uint32_t)i + 1u, hop, dist, mean, sigma, 0.0);
+        a[i] = d.u; b[i] = d.transit;
+    } else if (kind == AF_SELFTEST_GEN_UNIFORM) {
+        afr::Src s = afr::make_gen(seed, replica, (uint32_t)i);
+        double u = s.next53();
+        a[i] = u;
+        if (u < 1e-15) u = 1e-15;
+        b[i] = -afr::af_log(1.0 - u);
+    } else if (kind == AF_SELFTEST_GEN_USERS) {
+        const afr::GenDraw g = afr::gen_users(seed, replica + i, 0u, dist, mean, sigma);
+        a[i] = g.value; b[i] = (double)g.pos;
+    } else {
+        afr::Src src = afr::make_request(seed, replica, afr::P_SERVER, (uint32_t)i + 1u, hop);
+        src.load(0);
+        a[i] = (double)(uint32_t)(((uint64_t)src.w.x * (uint32_t)dist) >> 32); b[i] = 0.0;
     }
 }
 
@@ -184,7 +255,14 @@ struct af_engine {
     DevBuf d_edges, d_servers, d_eps, d_steps, d_lb, d_spikes, d_outages;
     // sweep
     int32_t sweep_cols = 0; uint64_t sweep_rows = 0, sweep_first = 0;
+    std::vector<AfSweepColumn> h_sweep_cols;
     DevBuf d_sweep_cols, d_sweep_vals;
+    // thread-per-replica pass: read-only tables (af_lane_host.h), global tiers, the list of flagged replicas
+    int mode = AF_MODE_AUTO;
+    aflh::Tables lt;
+    DevBuf d_l_edges, d_l_servers, d_l_eps, d_l_steps, d_l_spikes, d_l_outages, d_l_lb, d_l_cols, d_gtier, d_redo_list, d_redo_count, d_counter2;
+    afl::Cfg C_host{};
+    bool last_lane = false, last_warp = false; int last_lane_warps = 0;
     // spill + outputs
     DevBuf d_sp_evt, d_sp_evk, d_sp_rq, d_sp_nx;
     DevBuf d_stats, d_sent, d_dropped, d_hist, d_thr, d_ssum, d_smax, d_tclk, d_tser, d_tcnt, d_counter, d_htot;
@@ -243,6 +321,9 @@ int af_engine_create(int device, af_engine** out) {
         g_create_error = cudaGetErrorString(ce); delete e; return AF_ERR_CUDA;
     }
     e->opt.collect_histogram = 1; e->opt.collect_throughput = 1;
+    if (const char* m = getenv("ASYNCFLOW_B200_ENGINE")) {      // kernel experiments: pin the pass structure
+        if (!strcmp(m, "warp")) e->mode = AF_MODE_WARP; else if (!strcmp(m, "lane")) e->mode = AF_MODE_LANE;
+    }
     *out = e;
     return AF_OK;
 }
@@ -255,7 +336,9 @@ void af_engine_destroy(af_engine* e) {
         std::lock_guard<std::mutex> lock(g_const_mutex);
         if (g_const_owner[e->device % kMaxDevices] == e) g_const_owner[e->device % kMaxDevices] = nullptr;
     }
-    DevBuf* bufs[] = {&e->d_edges, &e->d_servers, &e->d_eps, &e->d_steps, &e->d_lb, &e->d_spikes, &e->d_outages,
+    DevBuf* bufs[] = {&e->d_l_edges, &e->d_l_servers, &e->d_l_eps, &e->d_l_steps, &e->d_l_spikes, &e->d_l_outages, &e->d_l_lb, &e->d_l_cols,
+                      &e->d_gtier, &e->d_redo_list, &e->d_redo_count, &e->d_counter2,
+                      &e->d_edges, &e->d_servers, &e->d_eps, &e->d_steps, &e->d_lb, &e->d_spikes, &e->d_outages,
                       &e->d_sweep_cols, &e->d_sweep_vals, &e->d_sp_evt, &e->d_sp_evk, &e->d_sp_rq, &e->d_sp_nx,
                       &e->d_stats, &e->d_sent, &e->d_dropped, &e->d_hist, &e->d_thr, &e->d_ssum, &e->d_smax,
                       &e->d_tclk, &e->d_tser, &e->d_tcnt, &e->d_counter, &e->d_htot};
@@ -267,7 +350,7 @@ void af_engine_destroy(af_engine* e) {
 
 int af_engine_configure(af_engine* e, const AfOptions* opt) {
     if (!e || !opt) return AF_ERR_INVALID;
-    if (opt->event_capacity < 0 || opt->request_capacity < 0 || opt->warps_per_block < 0 || opt->warps_per_block > 32
+    if (opt->event_capacity < 0 || opt->request_capacity < 0 || opt->warps_per_block < 0 || opt->warps_per_block > 32 || opt->blocks_per_sm < 0
         || opt->trace_replicas < 0 || opt->trace_clock_capacity < 0)
         return e->fail(AF_ERR_INVALID, "AfOptions: negative or out-of-range field");
     e->opt = *opt;
@@ -305,7 +388,7 @@ int af_scenario_upload(af_engine* e, const AfScenario* s) {
     e->sc.steps = e->h_steps.data(); e->sc.lb_edges = e->h_lb.data(); e->sc.spike_marks = e->h_spikes.data();
     e->sc.outage_marks = e->h_outages.data();
     e->have_scenario = true;
-    e->sweep_cols = 0; e->sweep_rows = 0;     // a sweep belongs to the scenario it was built for
+    e->sweep_cols = 0; e->sweep_rows = 0; e->h_sweep_cols.clear();     // a sweep belongs to the scenario it was built for
     e->ran = false;
     return AF_OK;
 }
@@ -315,7 +398,7 @@ int af_sweep_upload(af_engine* e, const AfSweep* sw, uint64_t first_replica) {
     if (!e->have_scenario) return e->fail(AF_ERR_STATE, "af_sweep_upload before af_scenario_upload");
     AF_CUDA(e, cudaSetDevice(e->device), "cudaSetDevice");
     AF_CUDA(e, cudaStreamSynchronize(e->stream), "sync before sweep upload");
-    if (!sw || sw->n_columns == 0 || sw->n_rows == 0) { e->sweep_cols = 0; e->sweep_rows = 0; return AF_OK; }
+    if (!sw || sw->n_columns == 0 || sw->n_rows == 0) { e->sweep_cols = 0; e->sweep_rows = 0; e->h_sweep_cols.clear(); return AF_OK; }
     if (!sw->columns || !sw->values) return e->fail(AF_ERR_INVALID, "sweep: null columns/values");
     const AfScenario& s = e->sc;
     for (int c = 0; c < sw->n_columns; ++c) {
@@ -331,6 +414,26 @@ int af_sweep_upload(af_engine* e, const AfSweep* sw, uint64_t first_replica) {
         }
         if (i < 0 || i >= lim) return e->fail(AF_ERR_INVALID, "sweep: column index out of range");
     }
+    // the values get the checks afh::validate applies to the base scenario (a swept cpu_cores of 0 would queue forever)
+    for (uint64_t r = 0; r < sw->n_rows; ++r)
+        for (int c = 0; c < sw->n_columns; ++c) {
+            const double v = sw->values[r * (uint64_t)sw->n_columns + (uint64_t)c];
+            bool ok = v == v && v - v == 0.0;                     // finite
+            switch (sw->columns[c].field) {
+            case AF_FIELD_EDGE_DROPOUT: ok = ok && v >= 0.0 && v <= 1.0; break;
+            case AF_FIELD_SERVER_CPU_CORES: case AF_FIELD_SERVER_RAM_MB: ok = ok && v >= 1.0 && v <= 2147483647.0; break;
+            case AF_FIELD_ENDPOINT_RAM: ok = ok && v >= 0.0 && v <= 2147483647.0; break;
+            case AF_FIELD_EDGE_MEAN: ok = ok && (v >= 0.0 || s.edges[sw->columns[c].index].dist == AF_DIST_LOG_NORMAL || s.edges[sw->columns[c].index].dist == AF_DIST_NORMAL); break;
+            case AF_FIELD_USERS_SIGMA: ok = ok && v >= 0.0 && s.users_dist == AF_DIST_NORMAL; break;
+            default: ok = ok && v >= 0.0; break;            // users, rates, sigmas, durations, spike amplitudes
+            }
+            if (!ok) {
+                char b[200]; snprintf(b, sizeof b, "sweep: row %llu column %d (field %d, index %d): value %g out of range",
+                                      (unsigned long long)r, c, sw->columns[c].field, sw->columns[c].index, v);
+                return e->fail(AF_ERR_INVALID, b);
+            }
+        }
+    e->h_sweep_cols.assign(sw->columns, sw->columns + sw->n_columns);
     size_t cb = (size_t)sw->n_columns * sizeof(AfSweepColumn), vb = (size_t)sw->n_columns * sw->n_rows * sizeof(double);
     AF_CUDA(e, e->d_sweep_cols.ensure(cb), "sweep columns");
     AF_CUDA(e, e->d_sweep_vals.ensure(vb), "sweep values");
@@ -341,42 +444,107 @@ int af_sweep_upload(af_engine* e, const AfSweep* sw, uint64_t first_replica) {
     return AF_OK;
 }
 
+// shared-memory budget of one lane when the CTA has `warps` warps (one CTA per SM)
+static int32_t lane_budget(const af_engine* e, int warps) { return (int32_t)((e->max_smem_optin / (warps * 32)) & ~3); }
+
 int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     if (!e) return AF_ERR_INVALID;
     if (!e->have_scenario) return e->fail(AF_ERR_STATE, "af_run before af_scenario_upload");
     if (end <= begin) return e->fail(AF_ERR_INVALID, "af_run: empty replica range");
+    if (end - begin > 0xFFFFFFFFull) return e->fail(AF_ERR_INVALID, "af_run: more than 2^32 replicas in one call");
     AF_CUDA(e, cudaSetDevice(e->device), "cudaSetDevice");
     const uint64_t n = end - begin;
+    int rc;
+
+    // ---- pass structure ---------------------------------------------------------------------------------
+    // AUTO: every replica runs on the thread-per-replica engine with tiers sized for nominal load; the ones
+    // it flags (pool overflow) are re-run by the warp-per-replica engine with the caller's capacities.
+    bool lane = e->mode != AF_MODE_WARP;
+    afl::Cfg& C = e->C_host;
+    int lane_warps = 0;
+    if (lane) {
+        std::string why;
+        if (!aflh::build_tables(e->sc, e->h_sweep_cols.data(), e->sweep_cols, e->lt, why)) {
+            if (e->mode == AF_MODE_LANE) return e->fail(AF_ERR_INVALID, why);
+            lane = false;
+        }
+    }
+    if (lane) {
+        AfOptions o = e->opt;
+        if (e->mode == AF_MODE_AUTO) {                 // nominal-load tiers; anything larger escalates
+            if (o.event_capacity <= 0 || o.event_capacity > aflh::LANE_EVENT_CAPACITY) o.event_capacity = aflh::LANE_EVENT_CAPACITY;
+            if (o.request_capacity <= 0 || o.request_capacity > aflh::LANE_REQUEST_CAPACITY) o.request_capacity = aflh::LANE_REQUEST_CAPACITY;
+        }
+        lane_warps = e->opt.warps_per_block > 0 ? e->opt.warps_per_block : AF_LANE_DEFAULT_WARPS;
+        if (lane_warps > AF_LANE_MAX_THREADS / 32) lane_warps = AF_LANE_MAX_THREADS / 32;
+        // fewer warps per SM when the topology's fixed tables need a larger share of shared memory
+        while (lane_warps > 1 && lane_budget(e, lane_warps) < aflh::min_lane_bytes(e->sc, e->lt) + 256) lane_warps /= 2;
+        memset(&C, 0, sizeof C);
+        if (!aflh::make_cfg(e->sc, o, e->lt, lane_budget(e, lane_warps), afh::trace_tick_capacity(e->sc), C)) {
+            if (e->mode == AF_MODE_LANE) return e->fail(AF_ERR_INVALID, "scenario tables do not fit a lane's shared memory (thread-per-replica engine)");
+            lane = false;
+        }
+    }
+    const bool warp = e->mode == AF_MODE_WARP || e->mode == AF_MODE_AUTO;
+    const bool redo = lane && warp;
+
     afc::Layout& L = e->L;
     memset(&L, 0, sizeof L);
     afh::make_layout(e->sc, e->opt, e->sweep_cols, L);
 
-    // launch shape: persistent CTAs, as many warps per SM as shared memory allows
-    // the kernel is compiled for CTAs of at most 4 warps (__launch_bounds__(128, AF_MIN_BLOCKS))
-    int wpb = e->opt.warps_per_block > 0 ? e->opt.warps_per_block : 4;
-    if (wpb > 4) wpb = 4;
-    size_t smem = (size_t)wpb * (size_t)L.warp_bytes;
-    while (wpb > 1 && smem > (size_t)e->max_smem_optin) { --wpb; smem = (size_t)wpb * (size_t)L.warp_bytes; }
-    if (smem > (size_t)e->max_smem_optin)
-        return e->fail(AF_ERR_INVALID, "scenario tables do not fit in shared memory (one warp needs more than the 227 KB opt-in limit)");
-    AF_CUDA(e, cudaFuncSetAttribute(af_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute");
-    int bps = 0;
-    AF_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, af_sim_kernel, wpb * 32, smem), "occupancy");
-    if (bps < 1) return e->fail(AF_ERR_CUDA, "kernel cannot be resident (occupancy 0)");
-    if (e->opt.blocks_per_sm > 0 && e->opt.blocks_per_sm < bps) bps = e->opt.blocks_per_sm;
-    uint64_t grid = (uint64_t)e->sm_count * (uint64_t)bps;
-    uint64_t need_blocks = (n + wpb - 1) / wpb;
-    if (grid > need_blocks) grid = need_blocks;
-    const uint64_t warp_slots = grid * wpb;
+    // ---- launch shapes -------------------------------------------------------------------------------------
+    // warp-per-replica: persistent CTAs of <= 4 warps (__launch_bounds__(128, AF_MIN_BLOCKS)), as many per SM as fit
+    int wpb = 4; size_t smem = 0; uint64_t grid = 0, warp_slots = 0;
+    if (warp) {
+        if (!lane && e->opt.warps_per_block > 0 && e->opt.warps_per_block < 4) wpb = e->opt.warps_per_block;
+        smem = (size_t)wpb * (size_t)L.warp_bytes;
+        while (wpb > 1 && smem > (size_t)e->max_smem_optin) { --wpb; smem = (size_t)wpb * (size_t)L.warp_bytes; }
+        if (smem > (size_t)e->max_smem_optin)
+            return e->fail(AF_ERR_INVALID, "scenario tables do not fit in shared memory (one warp needs more than the 227 KB opt-in limit)");
+        AF_CUDA(e, cudaFuncSetAttribute(af_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute");
+        int bps = 0;
+        AF_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, af_sim_kernel, wpb * 32, smem), "occupancy");
+        if (bps < 1) return e->fail(AF_ERR_CUDA, "kernel cannot be resident (occupancy 0)");
+        if (e->opt.blocks_per_sm > 0 && e->opt.blocks_per_sm < bps) bps = e->opt.blocks_per_sm;
+        grid = (uint64_t)e->sm_count * (uint64_t)bps;
+        const uint64_t need_blocks = (n + wpb - 1) / wpb;
+        if (grid > need_blocks) grid = need_blocks;
+        warp_slots = grid * wpb;
+    }
+    // thread-per-replica: one persistent CTA per SM
+    uint64_t lgrid = 0; size_t lsmem = 0;
+    if (lane) {
+        lsmem = (size_t)lane_warps * (size_t)C.warp_bytes;
+        AF_CUDA(e, cudaFuncSetAttribute(af_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem), "smem attribute");
+        lgrid = (uint64_t)e->sm_count;
+        const uint64_t need = (n + (uint64_t)lane_warps * 32 - 1) / ((uint64_t)lane_warps * 32);
+        if (lgrid > need) lgrid = need;
+    }
 
-    // spill tiers and outputs (grow-only)
-    const uint64_t ev_sp = (uint64_t)(L.ev_total - L.ev_smem), rq_sp = (uint64_t)(L.rq_total - L.rq_smem);
-    AF_CUDA(e, e->d_sp_evt.ensure(warp_slots * ev_sp * 8 + 8), "spill events");
-    AF_CUDA(e, e->d_sp_evk.ensure(warp_slots * ev_sp * 8 + 8), "spill events");
-    AF_CUDA(e, e->d_sp_rq.ensure(warp_slots * rq_sp * 16 + 16), "spill requests");
-    AF_CUDA(e, e->d_sp_nx.ensure(warp_slots * rq_sp * 4 + 4), "spill requests");
+    // ---- device memory (grow-only) -----------------------------------------------------------------------------
+    if (warp) {
+        const uint64_t ev_sp = (uint64_t)(L.ev_total - L.ev_smem), rq_sp = (uint64_t)(L.rq_total - L.rq_smem);
+        AF_CUDA(e, e->d_sp_evt.ensure(warp_slots * ev_sp * 8 + 8), "spill events");
+        AF_CUDA(e, e->d_sp_evk.ensure(warp_slots * ev_sp * 8 + 8), "spill events");
+        AF_CUDA(e, e->d_sp_rq.ensure(warp_slots * rq_sp * 16 + 16), "spill requests");
+        AF_CUDA(e, e->d_sp_nx.ensure(warp_slots * rq_sp * 4 + 4), "spill requests");
+    }
+    if (lane) {
+        AF_CUDA(e, e->d_gtier.ensure(lgrid * (uint64_t)lane_warps * C.gwarp_bytes + 256), "lane global tiers");
+        if ((rc = upload_vec(e, e->d_l_edges, e->lt.edges, "lane tables"))) return rc;
+        if ((rc = upload_vec(e, e->d_l_servers, e->lt.servers, "lane tables"))) return rc;
+        if ((rc = upload_vec(e, e->d_l_eps, e->lt.endpoints, "lane tables"))) return rc;
+        if ((rc = upload_vec(e, e->d_l_steps, e->lt.steps, "lane tables"))) return rc;
+        if ((rc = upload_vec(e, e->d_l_spikes, e->lt.spikes, "lane tables"))) return rc;
+        if ((rc = upload_vec(e, e->d_l_outages, e->lt.outages, "lane tables"))) return rc;
+        if ((rc = upload_vec(e, e->d_l_lb, e->lt.lb, "lane tables"))) return rc;
+        if ((rc = upload_vec(e, e->d_l_cols, e->lt.cols, "lane tables"))) return rc;
+        AF_CUDA(e, e->d_counter2.ensure(8), "work counter");
+        AF_CUDA(e, e->d_redo_list.ensure(n * 4), "flagged-replica list");
+        AF_CUDA(e, e->d_redo_count.ensure(4), "flagged-replica count");
+    }
     const uint64_t ntr = (uint64_t)(L.trace_replicas < 0 ? 0 : L.trace_replicas) < n ? (uint64_t)L.trace_replicas : n;
-    L.trace_replicas = (int32_t)ntr;
+    L.trace_replicas = (int32_t)ntr; C.trace_replicas = (int32_t)ntr;
     AF_CUDA(e, e->d_stats.ensure(n * sizeof(AfReplicaStats)), "stats");
     AF_CUDA(e, e->d_sent.ensure(n * L.n_edges * 4), "edge counts");
     AF_CUDA(e, e->d_dropped.ensure(n * L.n_edges * 4), "edge counts");
@@ -406,24 +574,58 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     G.samp_sum = (uint64_t*)e->d_ssum.p; G.samp_max = (uint32_t*)e->d_smax.p;
     G.trace_clocks = (double*)e->d_tclk.p; G.trace_series = (uint32_t*)e->d_tser.p; G.trace_counts = (uint32_t*)e->d_tcnt.p;
     G.work_counter = (unsigned long long*)e->d_counter.p;
+    G.redo_list = redo ? (const uint32_t*)e->d_redo_list.p : nullptr;
+    G.redo_count = redo ? (const uint32_t*)e->d_redo_count.p : nullptr;
     G.seed = seed; G.replica_begin = begin; G.n_replicas = n;
+    if (lane) {
+        C.edges = (const afl::EdgeP*)e->d_l_edges.p; C.servers = (const afl::ServerP*)e->d_l_servers.p;
+        C.endpoints = (const afl::EndpointP*)e->d_l_eps.p; C.steps = (const afl::StepP*)e->d_l_steps.p;
+        C.spikes = (const afl::SpikeP*)e->d_l_spikes.p; C.outages = (const afl::OutageP*)e->d_l_outages.p;
+        C.lb_edges = (const int32_t*)e->d_l_lb.p; C.cols = (const afl::ColP*)e->d_l_cols.p;
+        C.sweep_vals = G.sweep_vals; C.sweep_first = G.sweep_first; C.sweep_rows = G.sweep_rows;
+        C.gtier = (unsigned char*)e->d_gtier.p;
+        C.stats = G.stats; C.edge_sent = G.edge_sent; C.edge_dropped = G.edge_dropped; C.hist = G.hist; C.thr = G.thr;
+        C.samp_sum = G.samp_sum; C.samp_max = G.samp_max; C.trace_clocks = G.trace_clocks; C.trace_series = G.trace_series;
+        C.trace_counts = G.trace_counts;
+        C.work_counter = (unsigned long long*)e->d_counter2.p;
+        C.seed = seed; C.replica_begin = begin; C.n_replicas = n;
+    }
 
-    AF_CUDA(e, cudaEventRecord(e->ev_begin, e->stream), "event");
-    AF_CUDA(e, cudaMemsetAsync(e->d_counter.p, 0, 8, e->stream), "memset");
-    if (L.collect_hist) AF_CUDA(e, cudaMemsetAsync(e->d_hist.p, 0, n * AF_HIST_BINS * 4, e->stream), "memset hist");
-    if (L.collect_thr) AF_CUDA(e, cudaMemsetAsync(e->d_thr.p, 0, n * (uint64_t)L.horizon_s * 4, e->stream), "memset thr");
-    {   // serialise against another engine that may still be running on this device
-        std::lock_guard<std::mutex> lock(g_const_mutex);
+    // ---- enqueue ---------------------------------------------------------------------------------------------------
+    // The launch parameters live in __constant__ memory, which is per device: hold the lock until this engine's
+    // copies and launches are in its stream, and wait for the device's previous engine before overwriting them.
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    {
         af_engine*& owner = g_const_owner[e->device % kMaxDevices];
         if (owner && owner != e) AF_CUDA(e, cudaStreamSynchronize(owner->stream), "waiting for the device's previous engine");
         owner = e;
     }
-    AF_CUDA(e, cudaMemcpyToSymbolAsync(afc::c_L, &L, sizeof L, 0, cudaMemcpyHostToDevice, e->stream), "layout -> constant memory");
-    e->G_host = G;   // keep the source alive until the async copy has been issued from pageable memory
-    AF_CUDA(e, cudaMemcpyToSymbolAsync(afc::c_G, &e->G_host, sizeof G, 0, cudaMemcpyHostToDevice, e->stream), "globals -> constant memory");
-    af_sim_kernel<<<(unsigned)grid, wpb * 32, smem, e->stream>>>();
-    AF_CUDA(e, cudaGetLastError(), "af_sim_kernel launch");
-    e->launches += 1;
+    AF_CUDA(e, cudaEventRecord(e->ev_begin, e->stream), "event");
+    AF_CUDA(e, cudaMemsetAsync(e->d_counter.p, 0, 8, e->stream), "memset");
+    if (L.collect_hist) AF_CUDA(e, cudaMemsetAsync(e->d_hist.p, 0, n * AF_HIST_BINS * 4, e->stream), "memset hist");
+    if (L.collect_thr) AF_CUDA(e, cudaMemsetAsync(e->d_thr.p, 0, n * (uint64_t)L.horizon_s * 4, e->stream), "memset thr");
+    if (lane) {
+        AF_CUDA(e, cudaMemsetAsync(e->d_counter2.p, 0, 8, e->stream), "memset");
+        AF_CUDA(e, cudaMemsetAsync(e->d_redo_count.p, 0, 4, e->stream), "memset");
+        AF_CUDA(e, cudaMemcpyToSymbolAsync(afl::c_cfg, &C, sizeof C, 0, cudaMemcpyHostToDevice, e->stream), "lane config -> constant memory");
+        af_lane_kernel<<<(unsigned)lgrid, lane_warps * 32, lsmem, e->stream>>>();
+        AF_CUDA(e, cudaGetLastError(), "af_lane_kernel launch");
+        e->launches += 1;
+        if (redo) {
+            af_flagged_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>((const AfReplicaStats*)e->d_stats.p, n,
+                AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW | AF_FLAG_NOWQ_OVERFLOW, (uint32_t*)e->d_redo_list.p, (uint32_t*)e->d_redo_count.p);
+            AF_CUDA(e, cudaGetLastError(), "af_flagged_kernel launch");
+            e->launches += 1;
+        }
+    }
+    if (warp) {
+        AF_CUDA(e, cudaMemcpyToSymbolAsync(afc::c_L, &L, sizeof L, 0, cudaMemcpyHostToDevice, e->stream), "layout -> constant memory");
+        e->G_host = G;   // keep the source alive until the async copy has been issued from pageable memory
+        AF_CUDA(e, cudaMemcpyToSymbolAsync(afc::c_G, &e->G_host, sizeof G, 0, cudaMemcpyHostToDevice, e->stream), "globals -> constant memory");
+        af_sim_kernel<<<(unsigned)grid, wpb * 32, smem, e->stream>>>();
+        AF_CUDA(e, cudaGetLastError(), "af_sim_kernel launch");
+        e->launches += 1;
+    }
     AF_CUDA(e, cudaEventRecord(e->ev_sim, e->stream), "event");
     if (L.collect_hist) {
         unsigned blocks = (unsigned)((n * 32 + 255) / 256);
@@ -433,6 +635,54 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     }
     AF_CUDA(e, cudaEventRecord(e->ev_end, e->stream), "event");
     e->last_n = n; e->ran = true; e->timing_valid = false;
+    e->last_lane = lane; e->last_warp = warp; e->last_lane_warps = lane_warps;
+    return AF_OK;
+}
+
+int af_selftest_rng(af_engine* e, uint64_t seed, uint64_t replica, int kind, int dist, double mean, double sigma,
+                    uint32_t hop, uint64_t n, double* out_a, double* out_b) {
+    if (!e || !out_a || !out_b || n == 0) return AF_ERR_INVALID;
+    if (kind < AF_SELFTEST_EDGE || kind > AF_SELFTEST_ENDPOINT) return e->fail(AF_ERR_INVALID, "af_selftest_rng: unknown kind");
+    AF_CUDA(e, cudaSetDevice(e->device), "cudaSetDevice");
+    DevBuf da, db;
+    cudaError_t ce;
+    if ((ce = da.ensure(n * 8)) != cudaSuccess || (ce = db.ensure(n * 8)) != cudaSuccess) { da.release(); db.release(); return e->cuda_fail(ce, "selftest buffers"); }
+    af_selftest_rng_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(seed, replica, kind, dist, mean, sigma, hop, n, (double*)da.p, (double*)db.p);
+    e->launches += 1;
+    ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(out_a, da.p, n * 8, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(out_b, db.p, n * 8, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    da.release(); db.release();
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "af_selftest_rng");
+    return AF_OK;
+}
+
+int af_engine_set_mode(af_engine* e, int mode) {
+    if (!e) return AF_ERR_INVALID;
+    if (mode != AF_MODE_AUTO && mode != AF_MODE_WARP && mode != AF_MODE_LANE) return e->fail(AF_ERR_INVALID, "af_engine_set_mode: unknown mode");
+    e->mode = mode;
+    return AF_OK;
+}
+
+int af_last_run_passes(af_engine* e, AfRunPasses* out) {
+    if (!e || !out) return AF_ERR_INVALID;
+    if (!e->ran) return e->fail(AF_ERR_STATE, "no run yet");
+    int rc = af_sync(e);
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    out->lane_pass = e->last_lane ? 1 : 0; out->warp_pass = e->last_warp ? 1 : 0;
+    out->lane_warps_per_sm = e->last_lane_warps;
+    out->lane_bytes = e->last_lane ? e->C_host.warp_bytes / 32 : 0;
+    out->lane_events_smem = e->last_lane ? e->C_host.ev_s : 0; out->lane_requests_smem = e->last_lane ? e->C_host.rq_s : 0;
+    out->lane_replicas = e->last_lane ? e->last_n : 0;
+    out->warp_replicas = e->last_warp ? e->last_n : 0;
+    if (e->last_lane && e->last_warp) {
+        uint32_t c = 0;
+        AF_CUDA(e, cudaMemcpyAsync(&c, e->d_redo_count.p, 4, cudaMemcpyDeviceToHost, e->stream), "flagged count D2H");
+        AF_CUDA(e, cudaStreamSynchronize(e->stream), "flagged count D2H");
+        out->warp_replicas = c;
+    }
     return AF_OK;
 }
 

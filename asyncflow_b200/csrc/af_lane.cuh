@@ -1,0 +1,942 @@
+// af_lane.cuh -- the per-replica next-event engine, ONE REPLICA PER THREAD (round 2).
+//
+// Same path as af_core.cuh (SimPy's Environment.step() loop, reference
+// src/asyncflow/runtime/simulation_runner.py:369, driving the AsyncFlow actors), same event
+// semantics, same results bit for bit -- a different mapping onto the SM:
+//
+//   af_core.cuh (round 1)  one replica per WARP: all 32 lanes run the replica's scalar state machine
+//                          redundantly; ncu (profiles/r01i_*): ~560 warp-instructions per timed event,
+//                          issue-slot bound, 31 % of them 32-way-redundant random-number code.
+//   this file              one replica per LANE: every warp instruction advances up to 32 replicas.
+//                          The loop body is written as a fixed sequence of PHASES (pick -> sample ->
+//                          decode -> node -> steps -> send -> timer); a lane skips the phases its
+//                          event does not need, so the warp pays each phase at most once per 32
+//                          events (the expensive ones -- the edge's variates, the heap sift -- exist
+//                          at ONE place in the code and are shared by every event kind that needs them).
+//
+// Data layout.  A lane's mutable replica state lives in shared memory, WORD-INTERLEAVED across the
+// warp: 64-bit element e of lane l at  base64 + (e * 32 + l) * 8,  32-bit word w at
+// base32 + (w * 32 + l) * 4.  Whatever index each lane uses, the 32 lanes always hit 32 different
+// banks: every access is one conflict-free wavefront (two for 64-bit), no matter how far the
+// replicas have drifted apart.  Tables whose size depends on load (pending events, request
+// records, the now-queue) are TIERED: the first `*_s` entries in shared memory, the rest in a
+// per-lane region of global memory with the same interleave (L2-resident; one select per access,
+// no branch).  Read-only scenario tables are NOT replicated per replica: they are read through
+// the read-only data path (128-bit __ldg) and a swept field is an index into the lane's copy of its
+// sweep row.
+//
+//   code here           reference being replaced
+//   ------------------  ---------------------------------------------------------
+//   gen_next_gap        samplers/poisson_poisson.py:52-82, gaussian_poisson.py:64-94
+//   phase ARRIVAL       runtime/actors/rqs_generator.py:97-119
+//   phase SEND          runtime/actors/edge.py:73-107 (dropout, latency, spike)
+//   phase DELIVER       edge.py:110-116 (timeout fired: connection closes, Store.put)
+//   phase NODE          client.py:43-71, load_balancer.py:60-72 + routing/lb_algorithms.py:10-36,
+//                       server.py:303-313 and 88-149 (endpoint pick, RAM first)
+//   phase STEPS         server.py:197-276 (lazy CPU lock, IO queue, release, forward)
+//   cpu_walk, ram_walk  simpy Container._trigger_get (FIFO, head-of-line blocking)
+//   on_spike/on_outage  runtime/events/injection.py:167-226
+//   take_samples        metrics/collector.py:50-66
+//   complete            client.py:62-69 + metrics/analyzer.py:83-125
+//
+// Ordering rule: identical to af_core.cuh (DESIGN.md "tie rule"): timed events pop by (time, seq)
+// from a 4-ary min-heap; SimPy's zero-delay events are items of the now-queue, each with its own
+// seq; the loop runs the smallest seq among {now-queue front, heap events of the current instant};
+// an item pushed as the last action of the running item is applied at once when nothing else
+// lives at the instant (can_fuse).
+//
+// The same source compiles for the host with a "warp" of ONE lane (tests/host_twin: the CPU-only
+// tests pin this state machine to the oracle bit for bit; not reachable from the product API).
+#pragma once
+#include "af_rng.cuh"
+#include "../../include/asyncflow_b200.h"
+
+#if defined(__CUDA_ARCH__)
+#define AFL_DEVICE 1
+#else
+#define AFL_DEVICE 0
+#endif
+
+#if defined(__CUDACC__)
+#define AFL_IN __host__ __device__ __forceinline__
+#else
+#define AFL_IN static inline
+#endif
+
+#define AFL_LIKELY(x) __builtin_expect(!!(x), 1)
+#define AFL_UNLIKELY(x) __builtin_expect(!!(x), 0)
+
+#if defined(AF_TRACE_HOST) && !AFL_DEVICE
+#include <stdio.h>
+#define AFL_TRACE(...) fprintf(stderr, __VA_ARGS__)
+#else
+#define AFL_TRACE(...) ((void)0)
+#endif
+
+namespace afl {
+
+#if AFL_DEVICE
+constexpr int LANES = 32;
+#else
+constexpr int LANES = 1;
+#endif
+constexpr int STRIDE64 = LANES * 8, STRIDE32 = LANES * 4;
+
+constexpr uint32_t NIL = 0xFFFFFFFFu;
+constexpr uint64_t INF_BITS = 0x7FF0000000000000ull;
+
+// ---- event payload: kind[29:32) | aux[20:29) | slot[0:20)  (as af_core.cuh) ------------------
+enum : uint32_t { K_ARRIVAL = 0, K_DELIVER = 1, K_STEP_END = 2, K_SPIKE = 3, K_OUTAGE = 4 };
+constexpr uint32_t SLOT_BITS = 20, AUX_BITS = 9;
+constexpr uint32_t SLOT_MASK = (1u << SLOT_BITS) - 1, AUX_MASK = (1u << AUX_BITS) - 1;
+AFL_IN uint32_t mk_payload(uint32_t kind, uint32_t aux, uint32_t slot) { return (kind << 29) | (aux << SLOT_BITS) | slot; }
+
+// ---- request record pack: hops[0:8) step[8:16) ep[16:28) core[28] io[29] wait[30] -------------
+constexpr uint32_t PK_CORE = 1u << 28, PK_IO = 1u << 29, PK_WAIT = 1u << 30;
+AFL_IN uint32_t pk_hops(uint32_t p) { return p & 0xFFu; }
+AFL_IN uint32_t pk_step(uint32_t p) { return (p >> 8) & 0xFFu; }
+AFL_IN uint32_t pk_ep(uint32_t p) { return (p >> 16) & 0xFFFu; }
+
+// ---- now-queue items (as af_core.cuh) -------------------------------------------------------
+enum : uint32_t { I_PUT = 0, I_GOT = 1, I_CLIENT_LOOP = 2, I_RAM_OK = 3, I_CPU_OK = 4, I_CPU_PUT = 5, I_RAM_PUT = 6 };
+constexpr uint32_t NODE_CLIENT = 0, NODE_LB = 1, NODE_SERVER0 = 2;
+constexpr int32_t NQ_TOTAL = 128;          // pending zero-delay items per replica (power of two)
+
+// ---- read-only scenario tables (global memory, shared by all replicas; 16-byte multiples so that
+//      a record is one or a few 128-bit loads).  `c_*` = index into the lane's sweep-row copy, -1 = not swept.
+struct alignas(16) EdgeP { double mean, sigma, dropout; uint32_t meta; int16_t c_mean, c_sigma, c_drop, pad; uint32_t pad2[2]; };   // 48 B; meta: dist[0:3) | target_kind[3:5) | target_index[5:)
+struct alignas(16) ServerP { int32_t cpu_cores, ram_mb; uint32_t out_edge, ep_begin, n_ep; int32_t c_cores, c_ram, pad; };           // 32 B
+struct alignas(16) EndpointP { uint32_t step_begin, n_steps, total_ram; int32_t c_ram; };                                            // 16 B
+struct alignas(16) StepP { double dur; uint32_t kind; int32_t c_dur; };                                                              // 16 B
+struct alignas(16) SpikeP { double fire, delta; uint32_t edge; int32_t c_delta; uint32_t pad[2]; };                                  // 32 B
+struct alignas(16) OutageP { double fire; int32_t lb_edge, down; };                                                                  // 16 B
+struct ColP { int32_t field, index, slot, pad; double base; };     // one sweep column: slot = index into the lane's row copy (-1: consumed at start)
+
+// words of a server's mutable record (32-bit region)
+enum : int32_t { SV_CPU_FREE = 0, SV_RAM_FREE, SV_READY_Q, SV_IO_Q, SV_RAM_IN_USE, SV_RAMQ_HEAD, SV_RAMQ_TAIL,
+                 SV_CPUQ_HEAD, SV_CPUQ_TAIL, SV_RAMQ_NEED, SV_WORDS };
+enum : int32_t { IB_HEAD = 0, IB_TAIL, IB_PENDING, IB_WORDS };
+
+// Everything the kernel needs to know about one launch; built on the host (af_lane_host.h).
+struct Cfg {
+    int32_t n_edges, n_servers, n_endpoints, n_steps, n_lb_edges, lb_algo;
+    int32_t gen_edge, client_edge, n_spike, n_outage;
+    int32_t users_dist, window_s, horizon_s;
+    uint32_t metrics_mask;
+    double users_mean, users_sigma, rate_per_user, sample_period;
+    int32_t n_series, n_sweep_cols, n_row;          // n_row: sweep columns kept per lane (looked up during the run)
+    int32_t collect_hist, collect_thr, trace_replicas, trace_clock_cap, trace_tick_cap;
+    int32_t redo;                                   // 1: replica indices come from redo_list (re-run of flagged replicas)
+    // tiered tables: entries in shared memory / in total
+    int32_t ev_s, ev_total, rq_s, rq_total, nq_s;
+    // shared-memory layout of a warp: 64-bit region (element offsets), then 32-bit region (word offsets)
+    int32_t o64_evt, o64_evk, o64_t0, o64_nq, o64_spike, o64_ssum, o64_row, n64;
+    int32_t o32_rid, o32_pack, o32_next, o32_conn, o32_sent, o32_drop, o32_srv, o32_inbox, o32_lb, o32_smax, n32;
+    int32_t warp_bytes;                             // n64 * 256 + n32 * 128
+    // global tier of a warp (same interleave): element / word offsets, sizes
+    int32_t g64_evt, g64_evk, g64_t0, g64_nq, gn64;
+    int32_t g32_rid, g32_pack, g32_next, gn32;
+    uint64_t gwarp_bytes;                           // gn64 * 256 + gn32 * 128
+    // device pointers
+    const EdgeP* edges; const ServerP* servers; const EndpointP* endpoints; const StepP* steps;
+    const SpikeP* spikes; const OutageP* outages; const int32_t* lb_edges; const ColP* cols;
+    const double* sweep_vals; uint64_t sweep_first, sweep_rows;
+    unsigned char* gtier;                           // global tiers, one region per resident warp
+    AfReplicaStats* stats; uint32_t* edge_sent; uint32_t* edge_dropped;
+    uint32_t* hist; uint32_t* thr; uint64_t* samp_sum; uint32_t* samp_max;
+    double* trace_clocks; uint32_t* trace_series; uint32_t* trace_counts;
+    unsigned long long* work_counter;
+    const uint32_t* redo_list; const uint32_t* redo_count;
+    uint64_t seed, replica_begin, n_replicas;
+};
+
+#if defined(__CUDACC__)
+__constant__ Cfg c_cfg;
+#endif
+#if AFL_DEVICE
+#define AFL_C c_cfg
+#else
+static Cfg h_cfg;
+#define AFL_C h_cfg
+#endif
+
+// ---- read-only loads ----------------------------------------------------------------------------
+template <class T> AFL_IN T ro(const T* p) {
+#if AFL_DEVICE
+    static_assert(sizeof(T) % 16 == 0, "16-byte records");
+    T v;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&v);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i) d[i] = __ldg(s + i);
+    return v;
+#else
+    return *p;
+#endif
+}
+
+// ---- the lane's memory ------------------------------------------------------------------------------
+struct Mem {
+    unsigned char* s64; unsigned char* s32;     // shared-memory regions of the warp, already offset by the lane
+    unsigned char* g64; unsigned char* g32;     // global tier of the warp, already offset by the lane
+};
+AFL_IN uint64_t* e64(const Mem& m, int32_t elem) { return reinterpret_cast<uint64_t*>(m.s64 + (size_t)elem * STRIDE64); }
+AFL_IN double* f64(const Mem& m, int32_t elem) { return reinterpret_cast<double*>(m.s64 + (size_t)elem * STRIDE64); }
+AFL_IN uint32_t* w32(const Mem& m, int32_t word) { return reinterpret_cast<uint32_t*>(m.s32 + (size_t)word * STRIDE32); }
+AFL_IN int32_t* i32(const Mem& m, int32_t word) { return reinterpret_cast<int32_t*>(m.s32 + (size_t)word * STRIDE32); }
+// tiered: entry idx of a table whose first `split` entries are in shared memory
+AFL_IN uint64_t* t64(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split) {
+    return reinterpret_cast<uint64_t*>(AFL_LIKELY(idx < split) ? m.s64 + (size_t)(os + idx) * STRIDE64
+                                                               : m.g64 + (size_t)(og + idx - split) * STRIDE64);
+}
+AFL_IN uint32_t* t32(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split) {
+    return reinterpret_cast<uint32_t*>(AFL_LIKELY(idx < split) ? m.s32 + (size_t)(os + idx) * STRIDE32
+                                                               : m.g32 + (size_t)(og + idx - split) * STRIDE32);
+}
+
+// the replica's scalar state: registers (nothing here is indexed dynamically)
+struct St {
+    uint64_t replica, local;
+    double now, horizon;
+    uint32_t seq; int32_t ev_n; uint32_t peak_ev;
+    uint32_t nq_head, nq_tail, busy;            // busy = 2 * (items in the now-queue) + (the heap may hold an event of this instant)
+    uint32_t rq_free, rq_hw, rq_live, peak_rq;
+    double g_vnow, g_wend, g_lam;               // generator: the sampler's virtual clock (the simulation's is `now`)
+    uint32_t g_pos, generated, g_done, need_arrival, arm_seq;
+    double users_mean, users_sigma, rate_per_user;
+    int32_t lb_n, spike_cur, outage_cur;
+    uint32_t tick_seq, n_ticks; double tick_time;
+    uint32_t completed, flags, traced;
+    uint64_t n_events;
+    double lat_sum, lat_sumsq, lat_min, lat_max;
+};
+
+// flags that end a replica early (its partial results are written back with the flag set)
+constexpr uint32_t STOP_FLAGS = AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW | AF_FLAG_NOWQ_OVERFLOW | AF_FLAG_LB_EMPTY;
+
+// ---- swept parameters ----------------------------------------------------------------------------
+AFL_IN double row_val(const Mem& m, int32_t c) { return *f64(m, AFL_C.o64_row + c); }
+AFL_IN uint32_t ep_total_ram(const Mem& m, uint32_t ep) {
+    const EndpointP p = ro(AFL_C.endpoints + ep);
+    return p.c_ram >= 0 ? (uint32_t)row_val(m, p.c_ram) : p.total_ram;
+}
+
+// ---- request records (tiered): t0 | rid, pack, next ----------------------------------------------
+AFL_IN double* rq_t0(const Mem& m, uint32_t s) { return reinterpret_cast<double*>(t64(m, AFL_C.o64_t0, AFL_C.g64_t0, (int32_t)s, AFL_C.rq_s)); }
+AFL_IN uint32_t* rq_rid(const Mem& m, uint32_t s) { return t32(m, AFL_C.o32_rid, AFL_C.g32_rid, (int32_t)s, AFL_C.rq_s); }
+AFL_IN uint32_t* rq_pack(const Mem& m, uint32_t s) { return t32(m, AFL_C.o32_pack, AFL_C.g32_pack, (int32_t)s, AFL_C.rq_s); }
+AFL_IN uint32_t* rq_next(const Mem& m, uint32_t s) { return t32(m, AFL_C.o32_next, AFL_C.g32_next, (int32_t)s, AFL_C.rq_s); }
+
+AFL_IN uint32_t rq_alloc(St& W, const Mem& m) {
+    uint32_t s;
+    if (W.rq_free != NIL) { s = W.rq_free; W.rq_free = *rq_next(m, s); }
+    else if ((int32_t)W.rq_hw < AFL_C.rq_total) { s = W.rq_hw++; }
+    else { W.flags |= AF_FLAG_REQUEST_OVERFLOW; return NIL; }
+    const uint32_t live = ++W.rq_live;
+    if (live > W.peak_rq) W.peak_rq = live;
+    return s;
+}
+AFL_IN void rq_release(St& W, const Mem& m, uint32_t s) { *rq_next(m, s) = W.rq_free; W.rq_free = s; --W.rq_live; }
+
+// intrusive FIFOs through the `next` links; head / tail are words of the 32-bit region
+AFL_IN void fifo_push(const Mem& m, int32_t w_head, int32_t w_tail, uint32_t s) {
+    *rq_next(m, s) = NIL;
+    const uint32_t tail = *w32(m, w_tail);
+    if (tail == NIL) *w32(m, w_head) = s; else *rq_next(m, tail) = s;
+    *w32(m, w_tail) = s;
+}
+AFL_IN uint32_t fifo_pop(const Mem& m, int32_t w_head, int32_t w_tail) {
+    const uint32_t s = *w32(m, w_head);
+    const uint32_t h = *rq_next(m, s);
+    *w32(m, w_head) = h;
+    if (h == NIL) *w32(m, w_tail) = NIL;
+    return s;
+}
+
+// ---- pending timed events: 4-ary min-heap on (time bits, seq), tiered ---------------------------------
+AFL_IN uint64_t* ev_t(const Mem& m, int32_t i) { return t64(m, AFL_C.o64_evt, AFL_C.g64_evt, i, AFL_C.ev_s); }
+AFL_IN uint64_t* ev_k(const Mem& m, int32_t i) { return t64(m, AFL_C.o64_evk, AFL_C.g64_evk, i, AFL_C.ev_s); }
+AFL_IN bool ev_less(uint64_t ta, uint64_t ka, uint64_t tb, uint64_t kb) {       // times are non-negative doubles: bit order = value order
+    return ta < tb || (ta == tb && (uint32_t)(ka >> 32) < (uint32_t)(kb >> 32));
+}
+AFL_IN void heap_push(St& W, const Mem& m, uint64_t tb, uint64_t key) {
+    int32_t i = W.ev_n;
+    if (AFL_UNLIKELY(i >= AFL_C.ev_total)) { W.flags |= AF_FLAG_EVENT_OVERFLOW; return; }
+    W.ev_n = i + 1;
+    if ((uint32_t)(i + 1) > W.peak_ev) W.peak_ev = (uint32_t)(i + 1);
+#pragma unroll 1
+    while (i > 0) {
+        const int32_t p = (i - 1) >> 2;
+        const uint64_t tp = *ev_t(m, p), kp = *ev_k(m, p);
+        if (!ev_less(tb, key, tp, kp)) break;
+        *ev_t(m, i) = tp; *ev_k(m, i) = kp;
+        i = p;
+    }
+    *ev_t(m, i) = tb; *ev_k(m, i) = key;
+}
+// remove the root (the caller has read it)
+AFL_IN void heap_pop(St& W, const Mem& m) {
+    const int32_t n = --W.ev_n;
+    if (n == 0) return;
+    const uint64_t tl = *ev_t(m, n), kl = *ev_k(m, n);
+    int32_t i = 0;
+#pragma unroll 1
+    for (;;) {
+        const int32_t c = 4 * i + 1;
+        if (c >= n) break;
+        int32_t b = c;
+        uint64_t tbst = *ev_t(m, c), kbst = *ev_k(m, c);
+#pragma unroll
+        for (int32_t j = 1; j < 4; ++j) {
+            if (c + j < n) {
+                const uint64_t tj = *ev_t(m, c + j), kj = *ev_k(m, c + j);
+                if (ev_less(tj, kj, tbst, kbst)) { tbst = tj; kbst = kj; b = c + j; }
+            }
+        }
+        if (!ev_less(tbst, kbst, tl, kl)) break;
+        *ev_t(m, i) = tbst; *ev_k(m, i) = kbst;
+        i = b;
+    }
+    *ev_t(m, i) = tl; *ev_k(m, i) = kl;
+}
+
+// ---- now-queue (tiered ring of NQ_TOTAL items: seq << 32 | kind:3 aux:9 slot:20) ---------------------
+AFL_IN uint64_t* nq_at(const Mem& m, uint32_t pos) {
+    return t64(m, AFL_C.o64_nq, AFL_C.g64_nq, (int32_t)(pos & (uint32_t)(NQ_TOTAL - 1)), AFL_C.nq_s);
+}
+AFL_IN bool can_fuse(const St& W) { return AFL_LIKELY(W.busy == 0); }
+AFL_IN void nq_push(St& W, const Mem& m, uint32_t kind, uint32_t aux, uint32_t slot) {
+    const uint32_t tail = W.nq_tail;
+    if (tail - W.nq_head >= (uint32_t)NQ_TOTAL) { W.flags |= AF_FLAG_NOWQ_OVERFLOW; return; }
+    *nq_at(m, tail) = ((uint64_t)(W.seq++) << 32) | mk_payload(kind, aux, slot);
+    W.nq_tail = tail + 1;
+    W.busy += 2u;
+}
+AFL_IN uint32_t nq_take(St& W, const Mem& m) {      // (the caller has adjusted `busy`)
+    const uint32_t item = (uint32_t)*nq_at(m, W.nq_head);
+    W.nq_head += 1;
+    if (W.nq_head == W.nq_tail) { W.nq_head = 0; W.nq_tail = 0; }   // empty: restart at the shared-memory end of the ring
+    return item;
+}
+
+// ---- generator: samplers/poisson_poisson.py:52-82 / gaussian_poisson.py:64-94 -------------------------------
+AFL_IN bool gen_next_gap(St& W, double& gap) {
+    const double T = W.horizon;
+    double vnow = W.g_vnow, wend = W.g_wend, lam = W.g_lam;
+    uint32_t pos = W.g_pos;
+    bool ok = false;
+#pragma unroll 1
+    for (;;) {
+        if (!(vnow < T)) break;
+        if (vnow >= wend) {
+            wend = vnow + (double)AFL_C.window_s;
+            afr::GenDraw d = afr::gen_users(AFL_C.seed, W.replica, pos, AFL_C.users_dist, W.users_mean, W.users_sigma);
+            pos = d.pos;
+            lam = d.value * W.rate_per_user;
+        }
+        if (lam <= 0.0) { vnow = wend; continue; }
+        afr::Src s = afr::make_gen(AFL_C.seed, W.replica, pos);
+        double u = s.next53();
+        pos = s.pos;
+        if (u < 1e-15) u = 1e-15;                   // max(u, 1e-15)
+        const double dt = afr::af_div(-afr::af_log(1.0 - u), lam);
+        if (vnow + dt > T) break;
+        if (vnow + dt >= wend) { vnow = wend; continue; }
+        vnow += dt;
+        gap = dt;
+        ok = true;
+        break;
+    }
+    W.g_vnow = vnow; W.g_wend = wend; W.g_lam = lam; W.g_pos = pos;
+    return ok;
+}
+
+// ---- Stores (mailboxes), Containers: as af_core.cuh ----------------------------------------------------
+AFL_IN int32_t ib_word(uint32_t node, int32_t f) { return AFL_C.o32_inbox + (int32_t)node * IB_WORDS + f; }
+AFL_IN int32_t sv_word(uint32_t sidx, int32_t f) { return AFL_C.o32_srv + (int32_t)sidx * SV_WORDS + f; }
+
+// `yield box.get()` of the node's consumer process
+AFL_IN void consumer_get(St& W, const Mem& m, uint32_t node) {
+    if (AFL_UNLIKELY(*w32(m, ib_word(node, IB_HEAD)) != NIL)) {
+        const uint32_t it = fifo_pop(m, ib_word(node, IB_HEAD), ib_word(node, IB_TAIL));
+        nq_push(W, m, I_GOT, node, it);
+    } else *w32(m, ib_word(node, IB_PENDING)) = 1;
+}
+// Container._trigger_get over the CPU queue: grant heads while a core is free
+// (returns true when `watch` was among the granted: its get is "triggered" at the call)
+AFL_IN bool cpu_walk(St& W, const Mem& m, uint32_t sidx, uint32_t watch) {
+    bool hit = false;
+#pragma unroll 1
+    while (*w32(m, sv_word(sidx, SV_CPUQ_HEAD)) != NIL && *i32(m, sv_word(sidx, SV_CPU_FREE)) > 0) {
+        const uint32_t w = fifo_pop(m, sv_word(sidx, SV_CPUQ_HEAD), sv_word(sidx, SV_CPUQ_TAIL));
+        *i32(m, sv_word(sidx, SV_CPU_FREE)) -= 1;
+        hit = hit || w == watch;
+        nq_push(W, m, I_CPU_OK, sidx, w);
+    }
+    return hit;
+}
+// ... over the RAM queue: grant heads while they fit, stop at the first that does not
+AFL_IN void ram_walk(St& W, const Mem& m, uint32_t sidx) {
+#pragma unroll 1
+    while (*w32(m, sv_word(sidx, SV_RAMQ_HEAD)) != NIL) {
+        const uint32_t need = *w32(m, sv_word(sidx, SV_RAMQ_NEED));
+        if ((int32_t)need > *i32(m, sv_word(sidx, SV_RAM_FREE))) break;
+        const uint32_t w = fifo_pop(m, sv_word(sidx, SV_RAMQ_HEAD), sv_word(sidx, SV_RAMQ_TAIL));
+        const uint32_t h = *w32(m, sv_word(sidx, SV_RAMQ_HEAD));
+        if (h != NIL) *w32(m, sv_word(sidx, SV_RAMQ_NEED)) = ep_total_ram(m, pk_ep(*rq_pack(m, h)));
+        *i32(m, sv_word(sidx, SV_RAM_FREE)) -= (int32_t)need;
+        nq_push(W, m, I_RAM_OK, sidx, w);
+    }
+}
+
+// ---- event injection (injection.py:167-226): all marks of this instant; returns true when the timeline re-arms
+AFL_IN bool on_spike(St& W, const Mem& m, double& next_fire) {
+    int32_t cur = W.spike_cur;
+    const double t = ro(AFL_C.spikes + cur).fire;
+#pragma unroll 1
+    while (cur < AFL_C.n_spike) {
+        const SpikeP p = ro(AFL_C.spikes + cur);
+        if (p.fire != t) break;
+        double delta = p.delta;
+        if (p.c_delta >= 0) { const double v = row_val(m, p.c_delta); delta = delta < 0.0 ? -v : v; }
+        double* sp = f64(m, AFL_C.o64_spike + (int32_t)p.edge);
+        *sp = *sp + delta;
+        ++cur;
+    }
+    W.spike_cur = cur;
+    if (cur < AFL_C.n_spike) { next_fire = ro(AFL_C.spikes + cur).fire; return true; }
+    return false;
+}
+AFL_IN bool on_outage(St& W, const Mem& m, double& next_fire) {
+    int32_t cur = W.outage_cur;
+    const double t = ro(AFL_C.outages + cur).fire;
+    int32_t n = W.lb_n;
+    const int32_t lb = AFL_C.o32_lb;
+#pragma unroll 1
+    while (cur < AFL_C.n_outage) {
+        const OutageP p = ro(AFL_C.outages + cur);
+        if (p.fire != t) break;
+        ++cur;
+        if (p.lb_edge < 0) continue;
+        int32_t at = -1;
+#pragma unroll 1
+        for (int32_t i = 0; i < n; ++i) if (*w32(m, lb + i) == (uint32_t)p.lb_edge) { at = i; break; }
+        if (at >= 0) {                               // pop (DOWN) or move_to_end (UP)
+#pragma unroll 1
+            for (int32_t i = at + 1; i < n; ++i) *w32(m, lb + i - 1) = *w32(m, lb + i);
+            --n;
+        }
+        if (!p.down) { *w32(m, lb + n) = (uint32_t)p.lb_edge; ++n; }
+    }
+    W.lb_n = n;
+    W.outage_cur = cur;
+    if (cur < AFL_C.n_outage) { next_fire = ro(AFL_C.outages + cur).fire; return true; }
+    return false;
+}
+
+// ---- sampled metrics: every collector tick ordered before (t, ev_seq) (collector.py:50-66) ----------------
+AFL_IN void take_samples(St& W, const Mem& m, double t, uint32_t ev_seq) {
+    const int32_t n_series = AFL_C.n_series, ns3 = 3 * AFL_C.n_servers;
+    const bool srv_on = (AFL_C.metrics_mask & 7u) == 7u;          // collector.py:60-63
+    const bool edge_on = (AFL_C.metrics_mask & AF_METRIC_EDGE_CONN) != 0;
+    double tick = W.tick_time;
+    uint32_t tseq = W.tick_seq, nt = W.n_ticks, seq = W.seq;
+    const double horizon = W.horizon;
+    const bool traced = W.traced != 0;
+#pragma unroll 1
+    while ((tick < t || (tick == t && tseq < ev_seq)) && tick < horizon) {
+#pragma unroll 1
+        for (int32_t j = 0; j < n_series; ++j) {
+            uint32_t v;
+            if (j < ns3) {
+                if (!srv_on) continue;
+                const int32_t mt = j % 3;
+                v = *w32(m, sv_word((uint32_t)(j / 3), mt == 0 ? SV_READY_Q : (mt == 1 ? SV_IO_Q : SV_RAM_IN_USE)));
+            } else {
+                if (!edge_on) continue;
+                v = *w32(m, AFL_C.o32_conn + (j - ns3));
+            }
+            *e64(m, AFL_C.o64_ssum + j) += v;
+            if (v > *w32(m, AFL_C.o32_smax + j)) *w32(m, AFL_C.o32_smax + j) = v;
+            if (traced && (int32_t)nt < AFL_C.trace_tick_cap)
+                AFL_C.trace_series[(W.local * (uint64_t)n_series + (uint32_t)j) * (uint64_t)AFL_C.trace_tick_cap + nt] = v;
+        }
+        nt += 1;
+        tseq = seq++;                                 // the collector re-arms its timeout here
+        tick = tick + AFL_C.sample_period;
+    }
+    W.tick_time = tick; W.tick_seq = tseq; W.n_ticks = nt; W.seq = seq;
+}
+
+#if AFL_DEVICE
+__device__ __forceinline__ void red_add(uint32_t* p, uint32_t v) { atomicAdd(p, v); }
+#else
+static inline void red_add(uint32_t* p, uint32_t v) { *p += v; }
+#endif
+
+// client: completion (client.py:62-69 + analyzer.py:83-125)
+AFL_IN void complete(St& W, const Mem& m, uint32_t slot, double t0) {
+    const double now = W.now;
+    const double lat = now - t0;                     // finish - start (analyzer.py:86-89)
+    const uint32_t done = ++W.completed;
+    W.lat_sum += lat;
+    W.lat_sumsq += lat * lat;
+    if (lat < W.lat_min) W.lat_min = lat;
+    if (lat > W.lat_max) W.lat_max = lat;
+    const uint64_t local = W.local;
+    if (AFL_C.collect_hist) {
+        int32_t idx = (int32_t)(afr::d2u(lat) >> (52 - AF_HIST_SUB_BITS)) - ((1023 + AF_HIST_MIN_EXP) << AF_HIST_SUB_BITS);
+        idx = idx < 0 ? 0 : (idx >= AF_HIST_BINS ? AF_HIST_BINS - 1 : idx);
+        red_add(&AFL_C.hist[local * AF_HIST_BINS + (uint32_t)idx], 1u);
+    }
+    if (AFL_C.collect_thr) {                          // bucket k counts (k, k+1] (analyzer.py:108-125)
+        int32_t b = (int32_t)ceil(now) - 1;
+        b = b < 0 ? 0 : b;
+        if (b < AFL_C.horizon_s) red_add(&AFL_C.thr[local * (uint64_t)AFL_C.horizon_s + (uint32_t)b], 1u);
+    }
+    if (AFL_UNLIKELY(W.traced != 0)) {
+        if ((int32_t)(done - 1) < AFL_C.trace_clock_cap) {
+            double* p = AFL_C.trace_clocks + (local * (uint64_t)AFL_C.trace_clock_cap + (done - 1)) * 2;
+            p[0] = t0; p[1] = now;
+        } else W.flags |= AF_FLAG_TRACE_TRUNCATED;
+    }
+    rq_release(W, m, slot);
+}
+
+// ---- set-up / write-back (once per replica) -----------------------------------------------------------------
+AFL_IN void start_replica(St& W, const Mem& m, uint64_t local_index) {
+    const Cfg& C = AFL_C;
+    W.local = local_index;
+    W.replica = C.replica_begin + local_index;
+    W.now = 0.0; W.horizon = (double)C.horizon_s; W.seq = 0;
+    W.ev_n = 0; W.peak_ev = 0;
+    W.nq_head = 0; W.nq_tail = 0; W.busy = 0;
+    W.rq_free = NIL; W.rq_hw = 0; W.rq_live = 0; W.peak_rq = 0;
+    W.g_vnow = 0.0; W.g_wend = 0.0; W.g_lam = 0.0; W.g_pos = 0; W.generated = 0; W.g_done = 0;
+    W.lb_n = C.n_lb_edges; W.spike_cur = 0; W.outage_cur = 0;
+    W.n_ticks = 0; W.completed = 0; W.flags = 0; W.n_events = 0;
+    W.lat_sum = 0.0; W.lat_sumsq = 0.0; W.lat_min = afr::u2d(INF_BITS); W.lat_max = 0.0;
+    W.traced = (int64_t)local_index < (int64_t)C.trace_replicas ? 1u : 0u;
+    W.users_mean = C.users_mean; W.users_sigma = C.users_sigma; W.rate_per_user = C.rate_per_user;
+#pragma unroll 1
+    for (int32_t i = 0; i < C.n_edges; ++i) {
+        *w32(m, C.o32_conn + i) = 0; *w32(m, C.o32_sent + i) = 0; *w32(m, C.o32_drop + i) = 0;
+        if (C.n_spike > 0) *f64(m, C.o64_spike + i) = 0.0;
+    }
+#pragma unroll 1
+    for (int32_t i = 0; i < C.n_servers; ++i) {
+        const ServerP p = ro(C.servers + i);
+        *i32(m, sv_word((uint32_t)i, SV_CPU_FREE)) = p.cpu_cores; *i32(m, sv_word((uint32_t)i, SV_RAM_FREE)) = p.ram_mb;
+        *i32(m, sv_word((uint32_t)i, SV_READY_Q)) = 0; *i32(m, sv_word((uint32_t)i, SV_IO_Q)) = 0; *i32(m, sv_word((uint32_t)i, SV_RAM_IN_USE)) = 0;
+        *w32(m, sv_word((uint32_t)i, SV_RAMQ_HEAD)) = NIL; *w32(m, sv_word((uint32_t)i, SV_RAMQ_TAIL)) = NIL;
+        *w32(m, sv_word((uint32_t)i, SV_CPUQ_HEAD)) = NIL; *w32(m, sv_word((uint32_t)i, SV_CPUQ_TAIL)) = NIL;
+        *w32(m, sv_word((uint32_t)i, SV_RAMQ_NEED)) = 0;
+    }
+#pragma unroll 1
+    for (int32_t i = 0; i < C.n_servers + 2; ++i) {
+        *w32(m, ib_word((uint32_t)i, IB_HEAD)) = NIL; *w32(m, ib_word((uint32_t)i, IB_TAIL)) = NIL; *w32(m, ib_word((uint32_t)i, IB_PENDING)) = 1;
+    }
+#pragma unroll 1
+    for (int32_t i = 0; i < C.n_lb_edges; ++i) *w32(m, C.o32_lb + i) = (uint32_t)C.lb_edges[i];
+#pragma unroll 1
+    for (int32_t j = 0; j < C.n_series; ++j) { *e64(m, C.o64_ssum + j) = 0; *w32(m, C.o32_smax + j) = 0; }
+    // sweep overrides of this replica: fields consumed here, fields looked up during the run (row copy)
+    const bool has_row = C.n_sweep_cols > 0 && W.replica >= C.sweep_first && W.replica - C.sweep_first < C.sweep_rows;
+    const double* row = C.sweep_vals + (has_row ? (W.replica - C.sweep_first) * (uint64_t)C.n_sweep_cols : 0);
+#pragma unroll 1
+    for (int32_t c = 0; c < C.n_sweep_cols; ++c) {
+        const ColP col = C.cols[c];
+        const double v = has_row ? row[c] : col.base;
+        if (col.slot >= 0) { *f64(m, C.o64_row + col.slot) = v; continue; }
+        if (!has_row) continue;
+        switch (col.field) {
+        case AF_FIELD_USERS_MEAN: W.users_mean = v; break;
+        case AF_FIELD_USERS_SIGMA: W.users_sigma = v; break;
+        case AF_FIELD_RATE_PER_USER: W.rate_per_user = v; break;
+        case AF_FIELD_SERVER_CPU_CORES: *i32(m, sv_word((uint32_t)col.index, SV_CPU_FREE)) = (int32_t)v; break;
+        case AF_FIELD_SERVER_RAM_MB: *i32(m, sv_word((uint32_t)col.index, SV_RAM_FREE)) = (int32_t)v; break;
+        default: break;
+        }
+    }
+    if (C.redo) {                                     // a re-run: the first pass left partial counts in the accumulating outputs
+        if (C.collect_hist) for (int32_t b = 0; b < AF_HIST_BINS; ++b) C.hist[W.local * AF_HIST_BINS + (uint32_t)b] = 0;
+        if (C.collect_thr) for (int32_t b = 0; b < C.horizon_s; ++b) C.thr[W.local * (uint64_t)C.horizon_s + (uint32_t)b] = 0;
+    }
+}
+
+AFL_IN void write_back(St& W, const Mem& m) {
+    const Cfg& C = AFL_C;
+    const uint64_t local = W.local;
+#pragma unroll 1
+    for (int32_t i = 0; i < C.n_edges; ++i) {
+        C.edge_sent[local * (uint64_t)C.n_edges + (uint32_t)i] = *w32(m, C.o32_sent + i);
+        C.edge_dropped[local * (uint64_t)C.n_edges + (uint32_t)i] = *w32(m, C.o32_drop + i);
+    }
+#pragma unroll 1
+    for (int32_t j = 0; j < C.n_series; ++j) {
+        C.samp_sum[local * (uint64_t)C.n_series + (uint32_t)j] = *e64(m, C.o64_ssum + j);
+        C.samp_max[local * (uint64_t)C.n_series + (uint32_t)j] = *w32(m, C.o32_smax + j);
+    }
+    AfReplicaStats st;
+    st.n_events = W.n_events; st.generated = W.generated; st.completed = W.completed;
+    st.flags = W.flags; st.n_ticks = W.n_ticks; st.peak_events = W.peak_ev; st.peak_requests = W.peak_rq;
+    st.lat_sum = W.lat_sum; st.lat_sumsq = W.lat_sumsq;
+    st.lat_min = W.completed ? W.lat_min : 0.0; st.lat_max = W.lat_max;
+    st.p50 = st.p95 = st.p99 = afr::u2d(0x7FF8000000000000ull);
+    C.stats[local] = st;
+    if (W.traced) { C.trace_counts[local * 2] = W.completed; C.trace_counts[local * 2 + 1] = W.n_ticks; }
+}
+
+// what a phase hands to the next one
+enum : uint32_t { A_NONE = 0, A_NODE, A_STEPS, A_SEND, A_TIMER };
+
+// ---------------------------------------------------------------------------------------------------
+// The lane's life: pull a replica, run it to the horizon, write it back, pull the next.  `next_index`
+// returns the next local replica index or ~0 when the launch has no more work for this lane.
+// `converge` is a warp-wide rendez-vous at the top of every iteration (device: __syncwarp).
+// ---------------------------------------------------------------------------------------------------
+template <class NextFn, class ConvFn>
+AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
+    const Cfg& C = AFL_C;
+    St W;
+    bool active = false, exhausted = false;
+#pragma unroll 1
+    for (;;) {
+        if (!converge(active || !exhausted)) break;          // all lanes of the warp are done
+        // ---- phase: lifecycle -------------------------------------------------------------------
+        if (AFL_UNLIKELY(!active)) {
+            if (exhausted) continue;
+            const uint64_t r = next_index();
+            if (r == ~0ull) { exhausted = true; continue; }
+            start_replica(W, m, r);
+            // start order of the reference (simulation_runner.py:339-342, 301-336):
+            // spike timeline, outage timeline, generator, ..., collector
+            if (C.n_spike > 0) {
+                double f = ro(C.spikes).fire;
+                bool arm = true;
+                if (f == 0.0) arm = on_spike(W, m, f);
+                if (arm && f < W.horizon) { if (f == W.now) W.busy |= 1u; heap_push(W, m, afr::d2u(f), ((uint64_t)(W.seq++) << 32) | mk_payload(K_SPIKE, 0, 0)); }
+            }
+            if (C.n_outage > 0) {
+                double f = ro(C.outages).fire;
+                bool arm = true;
+                if (f == 0.0) arm = on_outage(W, m, f);
+                if (arm && f < W.horizon) { if (f == W.now) W.busy |= 1u; heap_push(W, m, afr::d2u(f), ((uint64_t)(W.seq++) << 32) | mk_payload(K_OUTAGE, 0, 0)); }
+            }
+            W.arm_seq = W.seq++; W.need_arrival = 1;
+            W.tick_seq = W.seq++;
+            W.tick_time = 0.0 + C.sample_period;
+            active = true;
+        }
+        const bool dead = (W.flags & STOP_FLAGS) != 0;        // a pool overflowed in the last iteration: stop the replica here
+        // ---- phase: the generator's next timeout (rqs_generator.py:103-104) ------------------------------
+        if (W.need_arrival && !dead) {
+            W.need_arrival = 0;
+            double gap;
+            if (!W.g_done && gen_next_gap(W, gap)) {
+                const double t = W.now + gap;
+                if (t < W.horizon) {                         // env.run(until=T): events at >= T never fire
+                    if (AFL_UNLIKELY(t == W.now)) W.busy |= 1u;
+                    heap_push(W, m, afr::d2u(t), ((uint64_t)W.arm_seq << 32) | mk_payload(K_ARRIVAL, 0, 0));
+                }
+            } else W.g_done = 1;
+        }
+        // ---- phase: pick the next thing to run: a zero-delay item or the earliest timed event ------------
+        uint32_t word = 0;                    // item or event payload
+        bool is_item = false, finish = false, is_event = false;
+        double t_ev = 0.0; uint32_t ev_seq = 0;
+        if (AFL_UNLIKELY(dead)) finish = true;
+        else {
+            const uint32_t busy = W.busy;
+            const bool have_item = busy >= 2u;
+            if (have_item && !(busy & 1u)) {         // no heap event shares this instant: just drain
+                W.busy = busy - 2u;
+                word = nq_take(W, m);
+                is_item = true;
+            } else {
+                const bool have_ev = W.ev_n > 0;
+                uint64_t tb = 0, key = 0;
+                if (have_ev) { tb = *ev_t(m, 0); key = *ev_k(m, 0); }
+                if (have_item) {
+                    const uint64_t front = *nq_at(m, W.nq_head);
+                    const bool same_t = have_ev && tb == afr::d2u(W.now);
+                    if (!(same_t && (uint32_t)(key >> 32) < (uint32_t)(front >> 32))) {
+                        W.busy = (same_t ? busy : (busy & ~1u)) - 2u;
+                        word = nq_take(W, m);
+                        is_item = true;
+                    }
+                } else if (!have_ev) finish = true;
+                if (!is_item && !finish) {
+                    heap_pop(W, m);
+                    const bool more = W.ev_n > 0 && *ev_t(m, 0) == tb;
+                    W.busy = (W.busy & ~1u) | (more ? 1u : 0u);
+                    t_ev = afr::u2d(tb); ev_seq = (uint32_t)(key >> 32); word = (uint32_t)key;
+                    is_event = true;
+                }
+            }
+        }
+        if (finish) { t_ev = W.horizon; ev_seq = 0u; }      // ticks strictly before the horizon
+        // ---- phase: collector ticks that fall before this event ------------------------------------------------
+        if (!is_item) {
+            const double tick = W.tick_time;
+            if (tick < t_ev || (tick == t_ev && W.tick_seq < ev_seq)) take_samples(W, m, t_ev, ev_seq);
+        }
+        if (AFL_UNLIKELY(finish)) { write_back(W, m); active = false; continue; }
+        if (is_event) { W.now = t_ev; W.n_events += 1; }
+
+        // ---- phase: decode -------------------------------------------------------------------------------------
+        const uint32_t kind = word >> 29, aux = (word >> SLOT_BITS) & AUX_MASK;
+        uint32_t slot = word & SLOT_MASK;
+        uint32_t act = A_NONE;
+        uint32_t node = 0, sidx = 0, rid = 0, pack = 0, edge = 0;
+        double t0 = 0.0;
+        double tm_t = 0.0; uint32_t tm_payload = 0, tm_seq = 0;
+        AFL_TRACE("%s t=%.17g seq=%u kind=%u aux=%u slot=%u\n", is_item ? "it" : "ev", W.now, ev_seq, kind, aux, slot);
+        if (is_event) {
+            if (kind == K_DELIVER) {                          // edge.py:110-116: the edge's timeout fired
+                *w32(m, C.o32_conn + (int32_t)aux) -= 1;
+                const uint32_t meta = ro(C.edges + aux).meta;
+                pack = *rq_pack(m, slot) + 1;                  // record_hop(edge)
+                const uint32_t tk = (meta >> 3) & 3u;
+                node = tk == AF_TARGET_CLIENT ? NODE_CLIENT : (tk == AF_TARGET_LB ? NODE_LB : NODE_SERVER0 + (meta >> 5));
+                if (can_fuse(W)) {                             // (implies: every inbox empty, every consumer in get())
+                    rid = *rq_rid(m, slot); t0 = *rq_t0(m, slot);
+                    act = A_NODE;                              // put -> pending get -> resume, nothing in between
+                } else {
+                    *rq_pack(m, slot) = pack;
+                    fifo_push(m, ib_word(node, IB_HEAD), ib_word(node, IB_TAIL), slot);   // Store.put: items.append now ...
+                    nq_push(W, m, I_PUT, node, slot);                                       // ... the put event is processed later
+                }
+            } else if (kind == K_STEP_END) {
+                sidx = aux; rid = *rq_rid(m, slot);
+                pack = *rq_pack(m, slot) + (1u << 8);          // the timeout fired: next step
+                act = A_STEPS;
+            } else if (kind == K_ARRIVAL) {                   // rqs_generator.py:97-119
+                rid = ++W.generated;
+                slot = rq_alloc(W, m);
+                // the generator asks the sampler for the next gap right after transport(): its timeout is
+                // scheduled BEFORE the edge's delivery timeout.  The seq is reserved here.
+                W.arm_seq = W.seq++;
+                W.need_arrival = 1;
+                if (slot != NIL) {
+                    *rq_t0(m, slot) = W.now; *rq_rid(m, slot) = rid; *rq_pack(m, slot) = 1u;   // record_hop(generator)
+                    pack = 1u; edge = (uint32_t)C.gen_edge;
+                    act = A_SEND;
+                }
+            } else if (kind == K_SPIKE) {
+                double f;
+                if (on_spike(W, m, f)) { tm_t = f; tm_payload = mk_payload(K_SPIKE, 0, 0); tm_seq = W.seq++; act = A_TIMER; }
+            } else {
+                double f;
+                if (on_outage(W, m, f)) { tm_t = f; tm_payload = mk_payload(K_OUTAGE, 0, 0); tm_seq = W.seq++; act = A_TIMER; }
+            }
+        } else {
+            if (kind == I_GOT) {
+                node = aux; rid = *rq_rid(m, slot); t0 = *rq_t0(m, slot); pack = *rq_pack(m, slot);
+                act = A_NODE;
+            } else if (kind == I_PUT) {                        // a StorePut event is processed
+                if (*w32(m, ib_word(aux, IB_PENDING))) {
+                    *w32(m, ib_word(aux, IB_PENDING)) = 0;
+                    nq_push(W, m, I_GOT, aux, fifo_pop(m, ib_word(aux, IB_HEAD), ib_word(aux, IB_TAIL)));
+                }
+            } else if (kind == I_CLIENT_LOOP) {
+                consumer_get(W, m, NODE_CLIENT);
+            } else if (kind == I_RAM_OK) {                     // the RAM get event is processed: the handler resumes
+                sidx = aux; rid = *rq_rid(m, slot); pack = *rq_pack(m, slot);
+                *i32(m, sv_word(sidx, SV_RAM_IN_USE)) += (int32_t)ep_total_ram(m, pk_ep(pack));
+                act = A_STEPS;
+            } else if (kind == I_CPU_OK) {                     // the CPU get event is processed
+                sidx = aux; rid = *rq_rid(m, slot); pack = *rq_pack(m, slot);
+                if (pack & PK_WAIT) { pack &= ~PK_WAIT; *i32(m, sv_word(sidx, SV_READY_Q)) -= 1; }
+                pack |= PK_CORE;
+                act = A_STEPS;
+            } else if (kind == I_CPU_PUT) {                    // waiters are re-examined, then the request goes on
+                sidx = aux;
+                cpu_walk(W, m, sidx, NIL);
+                rid = *rq_rid(m, slot); pack = *rq_pack(m, slot) & ~PK_CORE;   // core_locked = False; same step again
+                act = A_STEPS;
+            } else {                                           // I_RAM_PUT: waiters first, then forward
+                sidx = aux;
+                ram_walk(W, m, sidx);
+                rid = *rq_rid(m, slot); pack = *rq_pack(m, slot);
+                edge = ro(C.servers + sidx).out_edge;
+                act = A_SEND;
+            }
+        }
+
+        // ---- phase: a node's consumer process resumes with `slot` (the StoreGet event is processed) ---------------
+        if (act == A_NODE) {
+            act = A_NONE;
+            if (node >= NODE_SERVER0) {                       // server.py:303-313, then the head of _handle_request (:88-149)
+                sidx = node - NODE_SERVER0;
+                consumer_get(W, m, node);                      // the dispatcher loops back to get() first
+                const ServerP sp = ro(C.servers + sidx);
+                pack += 1;                                     // record_hop(SERVER)
+                uint32_t epi = 0;
+                if (sp.n_ep > 1) {
+                    afr::Src src = afr::make_request(C.seed, W.replica, afr::P_SERVER, rid, pk_hops(pack));
+                    src.load(0);
+                    epi = (uint32_t)(((uint64_t)src.w.x * sp.n_ep) >> 32);
+                }
+                const uint32_t ep_global = sp.ep_begin + epi;
+                pack = (pack & 0xFFu) | (ep_global << 16);     // step 0, flags clear
+                *rq_pack(m, slot) = pack;
+                const uint32_t total_ram = ep_total_ram(m, ep_global);
+                bool go = true;
+                if (total_ram) {                               // yield RAM.get(total_ram)
+                    if (!(*w32(m, sv_word(sidx, SV_RAMQ_HEAD)) == NIL && (int32_t)total_ram <= *i32(m, sv_word(sidx, SV_RAM_FREE)) && can_fuse(W))) {
+                        // cannot be served at once: join the queue, walk it
+                        if (*w32(m, sv_word(sidx, SV_RAMQ_HEAD)) == NIL) *w32(m, sv_word(sidx, SV_RAMQ_NEED)) = total_ram;
+                        fifo_push(m, sv_word(sidx, SV_RAMQ_HEAD), sv_word(sidx, SV_RAMQ_TAIL), slot);
+                        ram_walk(W, m, sidx);
+                        go = false;
+                    } else {
+                        *i32(m, sv_word(sidx, SV_RAM_FREE)) -= (int32_t)total_ram;   // granted, and its get event would run next
+                        *i32(m, sv_word(sidx, SV_RAM_IN_USE)) += (int32_t)total_ram;
+                    }
+                }
+                if (go) act = A_STEPS;
+            } else {
+                pack += 1;                                     // record_hop(client / LB)
+                if (node == NODE_CLIENT) {
+                    if (pk_hops(pack) > 3) {                   // client.py:62: back from the servers
+                        complete(W, m, slot, t0);
+                        if (can_fuse(W)) consumer_get(W, m, NODE_CLIENT);
+                        else nq_push(W, m, I_CLIENT_LOOP, 0, 0);   // yield completed_box.put(state)
+                    } else {
+                        *rq_pack(m, slot) = pack;
+                        consumer_get(W, m, NODE_CLIENT);
+                        edge = (uint32_t)C.client_edge;
+                        act = A_SEND;
+                    }
+                } else {
+                    *rq_pack(m, slot) = pack;
+                    const int32_t lb = C.o32_lb, n = W.lb_n;
+                    // every covered server is down: the reference dies here (StopIteration inside round_robin);
+                    // the replica stops and says so (flatten() rejects timelines that can reach this state)
+                    if (AFL_UNLIKELY(n <= 0)) { W.flags |= AF_FLAG_LB_EMPTY; continue; }
+                    uint32_t pick = *w32(m, lb);
+                    if (C.lb_algo == AF_LB_ROUND_ROBIN) {      // lb_algorithms.py:22-36
+#pragma unroll 1
+                        for (int32_t i = 1; i < n; ++i) *w32(m, lb + i - 1) = *w32(m, lb + i);
+                        *w32(m, lb + n - 1) = pick;
+                    } else {                                   // least_connections, :10-20 (first min wins)
+                        uint32_t best = *w32(m, C.o32_conn + (int32_t)pick);
+#pragma unroll 1
+                        for (int32_t i = 1; i < n; ++i) {
+                            const uint32_t e2 = *w32(m, lb + i), c2 = *w32(m, C.o32_conn + (int32_t)e2);
+                            if (c2 < best) { best = c2; pick = e2; }
+                        }
+                    }
+                    consumer_get(W, m, NODE_LB);
+                    edge = pick;
+                    act = A_SEND;
+                }
+            }
+        }
+
+        // ---- phase: the `for step in endpoint.steps` loop (server.py:197-255) up to the request's next yield,
+        //      and the tail of the handler (server.py:257-276) ---------------------------------------------------------
+        if (act == A_STEPS) {
+            act = A_NONE;
+            const EndpointP ep = ro(C.endpoints + pk_ep(pack));
+#pragma unroll 1
+            for (;;) {
+                const uint32_t st = pk_step(pack);
+                if (st < ep.n_steps) {
+                    const StepP sp = ro(C.steps + ep.step_begin + st);
+                    if (sp.kind == AF_STEP_CPU) {
+                        if (pack & PK_IO) { pack &= ~PK_IO; *i32(m, sv_word(sidx, SV_IO_Q)) -= 1; }
+                        if (!(pack & PK_CORE)) {             // cpu_req = CPU.get(1); yield cpu_req
+                            if (*w32(m, sv_word(sidx, SV_CPUQ_HEAD)) == NIL && *i32(m, sv_word(sidx, SV_CPU_FREE)) > 0 && can_fuse(W)) {
+                                *i32(m, sv_word(sidx, SV_CPU_FREE)) -= 1;     // granted, and its get event would run next
+                                pack |= PK_CORE;
+                            } else {
+                                fifo_push(m, sv_word(sidx, SV_CPUQ_HEAD), sv_word(sidx, SV_CPUQ_TAIL), slot);
+                                if (!cpu_walk(W, m, sidx, slot)) { pack |= PK_WAIT; *i32(m, sv_word(sidx, SV_READY_Q)) += 1; }   // not cpu_req.triggered
+                                *rq_pack(m, slot) = pack;
+                                break;
+                            }
+                        }
+                    } else {
+                        if (pack & PK_CORE) {                // yield CPU.put(1): level rises NOW
+                            *i32(m, sv_word(sidx, SV_CPU_FREE)) += 1;
+                            if (can_fuse(W)) {
+                                if (AFL_UNLIKELY(*w32(m, sv_word(sidx, SV_CPUQ_HEAD)) != NIL)) cpu_walk(W, m, sidx, NIL);
+                                pack &= ~PK_CORE;
+                                continue;
+                            }
+                            *rq_pack(m, slot) = pack;
+                            nq_push(W, m, I_CPU_PUT, sidx, slot);
+                            break;
+                        }
+                        if (!(pack & PK_IO)) { pack |= PK_IO; *i32(m, sv_word(sidx, SV_IO_Q)) += 1; }
+                    }
+                    *rq_pack(m, slot) = pack;
+                    const double dur = sp.c_dur >= 0 ? row_val(m, sp.c_dur) : sp.dur;
+                    tm_t = W.now + dur; tm_payload = mk_payload(K_STEP_END, sidx, slot); tm_seq = W.seq++;
+                    act = A_TIMER;
+                    break;
+                }
+                // end of the endpoint (server.py:257-276)
+                if (pack & PK_CORE) {                        // yield CPU.put(1)
+                    *i32(m, sv_word(sidx, SV_CPU_FREE)) += 1;
+                    if (can_fuse(W)) {
+                        if (AFL_UNLIKELY(*w32(m, sv_word(sidx, SV_CPUQ_HEAD)) != NIL)) cpu_walk(W, m, sidx, NIL);
+                        pack &= ~PK_CORE;
+                        continue;
+                    }
+                    *rq_pack(m, slot) = pack;
+                    nq_push(W, m, I_CPU_PUT, sidx, slot);
+                    break;
+                }
+                if (pack & PK_IO) { pack &= ~PK_IO; *i32(m, sv_word(sidx, SV_IO_Q)) -= 1; }
+                *rq_pack(m, slot) = pack;
+                const uint32_t total_ram = ep.c_ram >= 0 ? (uint32_t)row_val(m, ep.c_ram) : ep.total_ram;
+                if (total_ram) {                             // yield RAM.put(total_ram): level rises NOW
+                    *i32(m, sv_word(sidx, SV_RAM_IN_USE)) -= (int32_t)total_ram;
+                    *i32(m, sv_word(sidx, SV_RAM_FREE)) += (int32_t)total_ram;
+                    if (!can_fuse(W)) { nq_push(W, m, I_RAM_PUT, sidx, slot); break; }
+                    if (AFL_UNLIKELY(*w32(m, sv_word(sidx, SV_RAMQ_HEAD)) != NIL)) ram_walk(W, m, sidx);   // the put event would run next: waiters, then forward
+                }
+                edge = ro(C.servers + sidx).out_edge;
+                act = A_SEND;
+                break;
+            }
+        }
+
+        // ---- phase: EdgeRuntime.transport -> _deliver up to its timeout (edge.py:73-107) ---------------------------
+        if (act == A_SEND) {
+            act = A_NONE;
+            const EdgeP E = ro(C.edges + edge);
+            const uint32_t s = W.seq++;                      // the timeout's place in SimPy's eid order
+            const double dropout = E.c_drop >= 0 ? row_val(m, E.c_drop) : E.dropout;
+            const double mean = E.c_mean >= 0 ? row_val(m, E.c_mean) : E.mean;
+            const double sigma = E.c_sigma >= 0 ? row_val(m, E.c_sigma) : E.sigma;
+            const afr::EdgeDraw d = afr::edge_draw(C.seed, W.replica, rid, pk_hops(pack), (int)(E.meta & 7u), mean, sigma, dropout);
+            *w32(m, C.o32_sent + (int32_t)edge) += 1;
+            if (d.u < dropout) {                            // the request vanishes (edge.py:79-86)
+                *w32(m, C.o32_drop + (int32_t)edge) += 1;
+                rq_release(W, m, slot);
+            } else {
+                *w32(m, C.o32_conn + (int32_t)edge) += 1;
+                double effective = d.transit;
+                if (C.n_spike > 0) effective = d.transit + *f64(m, C.o64_spike + (int32_t)edge);   // spike read at SEND time (edge.py:94-106)
+                else effective = d.transit + 0.0;           // (-0.0 + 0.0 = +0.0, as with a spike table of zeros)
+                tm_t = W.now + effective; tm_payload = mk_payload(K_DELIVER, edge, slot); tm_seq = s;
+                act = A_TIMER;
+            }
+        }
+
+        // ---- phase: schedule the timeout ------------------------------------------------------------------------------
+        if (act == A_TIMER) {
+            if (tm_t < W.horizon) {                          // env.run(until=T): events at >= T never fire
+                if (AFL_UNLIKELY(tm_t == W.now)) W.busy |= 1u;   // a zero-delay timeout: it competes with the now-queue
+                heap_push(W, m, afr::d2u(tm_t), ((uint64_t)tm_seq << 32) | tm_payload);
+            }
+        }
+
+    }
+}
+
+}  // namespace afl

@@ -1,0 +1,163 @@
+// Host side of the thread-per-replica engine (af_lane.cuh): the read-only scenario tables with the
+// sweep's column map folded in, and the launch configuration (shared-memory layout of a warp, tier
+// sizes).  Shared by the CUDA engine (af_engine.cu) and the CPU-only debugging twin (tests/host_twin).
+#pragma once
+#include <string>
+#include <vector>
+#include "af_lane.cuh"
+
+namespace aflh {
+
+struct Tables {
+    std::vector<afl::EdgeP> edges; std::vector<afl::ServerP> servers; std::vector<afl::EndpointP> endpoints;
+    std::vector<afl::StepP> steps; std::vector<afl::SpikeP> spikes; std::vector<afl::OutageP> outages;
+    std::vector<int32_t> lb; std::vector<afl::ColP> cols;
+    int32_t n_row = 0;
+};
+
+// Scenario (+ the sweep's columns) -> the kernel's read-only tables.  A column over a field the kernel
+// looks up during the run (edge latency parameters, step durations, endpoint RAM, spike amplitudes) gets a
+// slot in the lane's row copy; a column over a field consumed at the start of a replica (users, cores, RAM)
+// does not.  Two columns over the same (field, index): the later one wins, as in af_core.cuh::load_params.
+inline bool build_tables(const AfScenario& s, const AfSweepColumn* cols, int32_t n_cols, Tables& t, std::string& err) {
+    t = Tables();
+    t.edges.resize((size_t)s.n_edges);
+    for (int i = 0; i < s.n_edges; ++i) {
+        const AfEdge& a = s.edges[i]; afl::EdgeP& e = t.edges[(size_t)i];
+        e.mean = a.mean; e.sigma = a.sigma; e.dropout = a.dropout;
+        e.meta = (uint32_t)a.dist | ((uint32_t)a.target_kind << 3) | ((uint32_t)a.target_index << 5);
+        e.c_mean = e.c_sigma = e.c_drop = -1; e.pad = 0; e.pad2[0] = e.pad2[1] = 0;
+    }
+    t.servers.resize((size_t)s.n_servers);
+    for (int i = 0; i < s.n_servers; ++i) {
+        const AfServer& a = s.servers[i]; afl::ServerP& v = t.servers[(size_t)i];
+        v.cpu_cores = a.cpu_cores; v.ram_mb = a.ram_mb; v.out_edge = (uint32_t)a.out_edge;
+        v.ep_begin = (uint32_t)a.endpoint_begin; v.n_ep = (uint32_t)a.n_endpoints; v.c_cores = v.c_ram = -1; v.pad = 0;
+    }
+    t.endpoints.resize((size_t)s.n_endpoints);
+    for (int i = 0; i < s.n_endpoints; ++i) {
+        const AfEndpoint& a = s.endpoints[i]; afl::EndpointP& p = t.endpoints[(size_t)i];
+        p.step_begin = (uint32_t)a.step_begin; p.n_steps = (uint32_t)a.n_steps; p.total_ram = (uint32_t)a.total_ram; p.c_ram = -1;
+    }
+    t.steps.resize((size_t)s.n_steps);
+    for (int i = 0; i < s.n_steps; ++i) { t.steps[(size_t)i].dur = s.steps[i].duration; t.steps[(size_t)i].kind = (uint32_t)s.steps[i].kind; t.steps[(size_t)i].c_dur = -1; }
+    t.spikes.resize((size_t)s.n_spike_marks);
+    for (int i = 0; i < s.n_spike_marks; ++i) {
+        afl::SpikeP& p = t.spikes[(size_t)i];
+        p.fire = s.spike_marks[i].fire_time; p.delta = s.spike_marks[i].delta; p.edge = (uint32_t)s.spike_marks[i].edge; p.c_delta = -1; p.pad[0] = p.pad[1] = 0;
+    }
+    t.outages.resize((size_t)s.n_outage_marks);
+    for (int i = 0; i < s.n_outage_marks; ++i) { t.outages[(size_t)i].fire = s.outage_marks[i].fire_time; t.outages[(size_t)i].lb_edge = s.outage_marks[i].lb_edge; t.outages[(size_t)i].down = s.outage_marks[i].down; }
+    t.lb.assign(s.lb_edges, s.lb_edges + s.n_lb_edges);
+    t.cols.resize((size_t)n_cols);
+    int32_t n_row = 0;
+    for (int32_t c = 0; c < n_cols; ++c) {
+        afl::ColP& k = t.cols[(size_t)c];
+        k.field = cols[c].field; k.index = cols[c].index; k.slot = -1; k.pad = 0; k.base = 0.0;
+        const int32_t i = k.index;
+        switch (k.field) {
+        case AF_FIELD_USERS_MEAN: k.base = s.users_mean; break;
+        case AF_FIELD_USERS_SIGMA: k.base = s.users_sigma; break;
+        case AF_FIELD_RATE_PER_USER: k.base = s.rate_per_user; break;
+        case AF_FIELD_SERVER_CPU_CORES: k.base = s.servers[i].cpu_cores; break;
+        case AF_FIELD_SERVER_RAM_MB: k.base = s.servers[i].ram_mb; break;
+        case AF_FIELD_EDGE_MEAN: k.slot = n_row++; k.base = s.edges[i].mean; t.edges[(size_t)i].c_mean = (int16_t)k.slot; break;
+        case AF_FIELD_EDGE_SIGMA: k.slot = n_row++; k.base = s.edges[i].sigma; t.edges[(size_t)i].c_sigma = (int16_t)k.slot; break;
+        case AF_FIELD_EDGE_DROPOUT: k.slot = n_row++; k.base = s.edges[i].dropout; t.edges[(size_t)i].c_drop = (int16_t)k.slot; break;
+        case AF_FIELD_STEP_DURATION: k.slot = n_row++; k.base = s.steps[i].duration; t.steps[(size_t)i].c_dur = k.slot; break;
+        case AF_FIELD_ENDPOINT_RAM: k.slot = n_row++; k.base = s.endpoints[i].total_ram; t.endpoints[(size_t)i].c_ram = k.slot; break;
+        case AF_FIELD_SPIKE_DELTA: k.slot = n_row++; k.base = s.spike_marks[i].delta < 0.0 ? -s.spike_marks[i].delta : s.spike_marks[i].delta;
+                                   t.spikes[(size_t)i].c_delta = k.slot; break;
+        default: err = "sweep: unknown field id"; return false;
+        }
+    }
+    if (n_row > 32000) { err = "sweep: too many looked-up columns for the lane engine"; return false; }
+    t.n_row = n_row;
+    return true;
+}
+
+constexpr int32_t LANE_EVENT_CAPACITY = 512;      // defaults of the lane engine's global tiers (AfOptions fields <= 0)
+constexpr int32_t LANE_REQUEST_CAPACITY = 2048;
+
+// smallest per-lane budget make_cfg() accepts for this scenario (5 events, 2 requests, 4 items + the fixed tables)
+inline int32_t min_lane_bytes(const AfScenario& s, const Tables& t) {
+    const int32_t n_series = 3 * s.n_servers + s.n_edges;
+    const int32_t fix64 = (s.n_spike_marks > 0 ? s.n_edges : 0) + n_series + t.n_row;
+    const int32_t fix32 = 3 * s.n_edges + afl::SV_WORDS * s.n_servers + afl::IB_WORDS * (s.n_servers + 2) + s.n_lb_edges + n_series;
+    return 8 * fix64 + 4 * fix32 + 8 * 4 + 16 * 6 + 20 * 3;
+}
+
+// The launch configuration for a budget of `lane_bytes` of shared memory per lane (= per replica in
+// flight).  Returns false when even the smallest tiers do not fit: the topology is too wide for this
+// engine at this occupancy (the caller lowers the occupancy or takes the warp-per-replica engine).
+inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, int32_t lane_bytes, int32_t trace_tick_cap, afl::Cfg& C) {
+    C.n_edges = s.n_edges; C.n_servers = s.n_servers; C.n_endpoints = s.n_endpoints; C.n_steps = s.n_steps;
+    C.n_lb_edges = s.n_lb_edges; C.lb_algo = s.lb_algo; C.gen_edge = s.gen_edge; C.client_edge = s.client_edge;
+    C.n_spike = s.n_spike_marks; C.n_outage = s.n_outage_marks;
+    C.users_dist = s.users_dist; C.window_s = s.window_s; C.horizon_s = s.horizon_s; C.metrics_mask = s.metrics_mask;
+    C.users_mean = s.users_mean; C.users_sigma = s.users_sigma; C.rate_per_user = s.rate_per_user; C.sample_period = s.sample_period;
+    C.n_series = 3 * s.n_servers + s.n_edges;
+    C.n_sweep_cols = (int32_t)t.cols.size(); C.n_row = t.n_row;
+    C.collect_hist = o.collect_histogram; C.collect_thr = o.collect_throughput;
+    C.trace_replicas = o.trace_replicas; C.trace_clock_cap = o.trace_clock_capacity; C.trace_tick_cap = trace_tick_cap;
+    C.redo = 0;
+    int32_t ev_total = o.event_capacity > 0 ? o.event_capacity : LANE_EVENT_CAPACITY;
+    int32_t rq_total = o.request_capacity > 0 ? o.request_capacity : LANE_REQUEST_CAPACITY;
+    if (rq_total > (int32_t)afl::SLOT_MASK) rq_total = (int32_t)afl::SLOT_MASK;
+    // fixed part of a lane's shared memory
+    const int32_t fix64 = (C.n_spike > 0 ? C.n_edges : 0) + C.n_series + C.n_row;
+    const int32_t fix32 = 3 * C.n_edges + afl::SV_WORDS * C.n_servers + afl::IB_WORDS * (C.n_servers + 2) + C.n_lb_edges + C.n_series;
+    int32_t nq_s = 4;
+    int32_t rest = lane_bytes - 8 * fix64 - 4 * fix32 - 8 * nq_s;
+    // split the rest between pending events (16 B) and request records (20 B): at nominal load a request in
+    // flight owns one pending event, plus the arrival and the two timelines
+    int32_t rq_s = (rest - 16 * 4) / 36;
+    if (rq_s > rq_total) rq_s = rq_total;
+    int32_t ev_s = rq_s < 0 ? 0 : (rest - 20 * rq_s) / 16;
+    if (ev_s > ev_total) { ev_s = ev_total; rq_s = (rest - 16 * ev_s) / 20; if (rq_s > rq_total) rq_s = rq_total; }
+    if (rq_s < (rq_total < 2 ? rq_total : 2) || ev_s < (ev_total < 5 ? ev_total : 5)) return false;
+    {   // what is left over goes to the now-queue's shared-memory end
+        const int32_t left = rest - 16 * ev_s - 20 * rq_s;
+        nq_s += left / 8;
+        if (nq_s > afl::NQ_TOTAL) nq_s = afl::NQ_TOTAL;
+    }
+    C.ev_s = ev_s; C.ev_total = ev_total; C.rq_s = rq_s; C.rq_total = rq_total; C.nq_s = nq_s;
+    int32_t e = 0;
+    C.o64_evt = e; e += ev_s;
+    C.o64_evk = e; e += ev_s;
+    C.o64_t0 = e; e += rq_s;
+    C.o64_nq = e; e += nq_s;
+    C.o64_spike = e; e += C.n_spike > 0 ? C.n_edges : 0;
+    C.o64_ssum = e; e += C.n_series;
+    C.o64_row = e; e += C.n_row;
+    C.n64 = e;
+    int32_t w = 0;
+    C.o32_rid = w; w += rq_s;
+    C.o32_pack = w; w += rq_s;
+    C.o32_next = w; w += rq_s;
+    C.o32_conn = w; w += C.n_edges;
+    C.o32_sent = w; w += C.n_edges;
+    C.o32_drop = w; w += C.n_edges;
+    C.o32_srv = w; w += afl::SV_WORDS * C.n_servers;
+    C.o32_inbox = w; w += afl::IB_WORDS * (C.n_servers + 2);
+    C.o32_lb = w; w += C.n_lb_edges;
+    C.o32_smax = w; w += C.n_series;
+    C.n32 = w;
+    C.warp_bytes = C.n64 * afl::STRIDE64 + C.n32 * afl::STRIDE32;
+    // global tier
+    int32_t g = 0;
+    C.g64_evt = g; g += ev_total - ev_s;
+    C.g64_evk = g; g += ev_total - ev_s;
+    C.g64_t0 = g; g += rq_total - rq_s;
+    C.g64_nq = g; g += afl::NQ_TOTAL - nq_s;
+    C.gn64 = g;
+    int32_t h = 0;
+    C.g32_rid = h; h += rq_total - rq_s;
+    C.g32_pack = h; h += rq_total - rq_s;
+    C.g32_next = h; h += rq_total - rq_s;
+    C.gn32 = h;
+    C.gwarp_bytes = (uint64_t)C.gn64 * afl::STRIDE64 + (uint64_t)C.gn32 * afl::STRIDE32;
+    return true;
+}
+
+}  // namespace aflh

@@ -128,6 +128,12 @@ def run_sharded(runner, *, with_histogram: bool = True):
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
     begin, end = shard_bounds(runner.n_replicas, rank, world)
+    if end <= begin:
+        # more ranks than replicas: nothing to launch here, but the collective must still complete
+        from . import _capi as K  # noqa: PLC0415
+        res = None
+        ints, flts = summary_block(np.zeros(0, dtype=K.STATS_DTYPE), None)
+        return res, all_gather_summary(ints, flts)
     res = runner.run(begin, end)
     hist = runner.engine().reduced_histogram() if (with_histogram and runner.histogram) else None
     ints, flts = summary_block(res.stats, hist)

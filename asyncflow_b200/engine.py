@@ -64,6 +64,12 @@ class Engine:
                                 int(histogram), int(throughput), trace_replicas, trace_clock_capacity)
         self._check(self._lib.af_engine_configure(self._h, C.byref(self._opt)), "af_engine_configure")
 
+    def set_mode(self, mode: str | int) -> None:
+        """Pass structure of :meth:`run`: ``"auto"`` (thread-per-replica kernel, flagged replicas re-run one per
+        warp), ``"warp"`` or ``"lane"`` (one kernel only) -- ``af_engine_set_mode``."""
+        m = K.MODES[mode] if isinstance(mode, str) else int(mode)
+        self._check(self._lib.af_engine_set_mode(self._h, m), "af_engine_set_mode")
+
     def upload(self, flat: FlatScenario) -> None:
         self._check(self._lib.af_scenario_upload(self._h, C.byref(flat.pod)), "af_scenario_upload")
         self.flat = flat
@@ -90,6 +96,20 @@ class Engine:
         a, b = C.c_float(), C.c_float()
         self._check(self._lib.af_last_run_ms(self._h, C.byref(a), C.byref(b)), "af_last_run_ms")
         return a.value, b.value
+
+    def selftest_rng(self, kind: int, n: int, *, seed: int, replica: int, dist: int = 0, mean: float = 0.0,
+                     sigma: float = 0.0, hop: int = 1) -> tuple[np.ndarray, np.ndarray]:
+        """AF-RNG known-answer hook (``af_selftest_rng``): ``n`` device draws of ``kind`` as two f64 arrays."""
+        a, b = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.float64)
+        self._check(self._lib.af_selftest_rng(self._h, int(seed), int(replica), int(kind), int(dist), float(mean),
+                                              float(sigma), int(hop), int(n), a.ctypes.data, b.ctypes.data), "af_selftest_rng")
+        return a, b
+
+    def last_run_passes(self) -> dict:
+        """What the last run did: which kernels, the lane pass's occupancy and pool sizes, replicas per pass."""
+        p = K.AfRunPasses()
+        self._check(self._lib.af_last_run_passes(self._h, C.byref(p)), "af_last_run_passes")
+        return {k: int(getattr(p, k)) for k, _ in K.AfRunPasses._fields_}
 
     @property
     def launch_count(self) -> int:

@@ -231,8 +231,19 @@ def flatten(payload: Any) -> FlatScenario:
         amp = spike_of[(m[1], m[2])]
         c_spikes[i] = K.AfSpikeMark(fire, amp if m[3] == "start" else -amp, eidx[m[2]], 0)
     c_out = (K.AfOutageMark * max(1, len(s_tl)))()
+    pool = set(lb_edges)                                # replay of the outage marks over the LB's edge set
     for i, (m, fire) in enumerate(zip(s_tl, _timeline(s_tl))):
-        c_out[i] = K.AfOutageMark(fire, edge_by_server.get(m[2], -1), 1 if m[3] == "start" else 0)
+        le = edge_by_server.get(m[2], -1)
+        c_out[i] = K.AfOutageMark(fire, le, 1 if m[3] == "start" else 0)
+        if le >= 0:
+            pool.discard(le) if m[3] == "start" else pool.add(le)
+            if lb_edges and not pool and fire < horizon:
+                # The reference only rejects "all servers down" (schemas/payload.py:145-252); servers chained BEHIND a
+                # covered one keep that check quiet while the LB's own dict runs empty, and the first request that
+                # then reaches the LB dies in round_robin (routing/lb_algorithms.py:22-36).  Say so up front.
+                msg = (f"event injection: at t={fire:g}s every server behind the load balancer is down "
+                       f"(mark {m[1]!r} on {m[2]!r}); the reference's load balancer raises on an empty edge set")
+                raise ValueError(msg)
 
     pod = K.AfScenario()
     pod.users_dist = K.DIST[udist]

@@ -12,7 +12,8 @@
  *   runtime/actors/server.py:79-313          server event loop
  *   runtime/events/injection.py:35-226       spikes / outages
  *   metrics/collector.py:50-66               sampled metrics
- * for MANY independent replicas at once (one replica per warp).
+ * for MANY independent replicas at once (one replica per GPU thread; replicas whose
+ * queues outgrow the nominal-load pools are re-run one per warp with large HBM pools).
  *
  * The reference is pure Python and has no FFI; the two seams a maintainer binds
  * are documented in INTEGRATION.md:
@@ -175,7 +176,9 @@ typedef struct AfOptions {
 
 /* AfReplicaStats.flags */
 enum { AF_FLAG_EVENT_OVERFLOW = 1, AF_FLAG_REQUEST_OVERFLOW = 2, AF_FLAG_TRACE_TRUNCATED = 4,
-       AF_FLAG_NOWQ_OVERFLOW = 8 /* > 128 zero-delay continuations pending at one instant */ };
+       AF_FLAG_NOWQ_OVERFLOW = 8, /* > 128 zero-delay continuations pending at one instant */
+       AF_FLAG_LB_EMPTY = 16      /* a request reached the load balancer while every covered server was down:
+                                   * the reference raises here (routing/lb_algorithms.py:22-36 on an empty dict) */ };
 
 typedef struct AfReplicaStats {
     uint64_t n_events;           /* timed events processed                          */
@@ -200,6 +203,12 @@ void af_engine_destroy(af_engine* e);
 const char* af_last_error(const af_engine* e);   /* e may be NULL: create errors  */
 
 int af_engine_configure(af_engine* e, const AfOptions* opt);
+/* Pass structure of af_run.  AUTO (default): every replica runs on the thread-per-replica kernel, whose
+ * per-replica pools are sized for nominal load (512 pending events, 2048 requests in flight); the replicas
+ * it flags are re-run by the warp-per-replica kernel with AfOptions' capacities, inside the same af_run.
+ * WARP / LANE pin one kernel (LANE takes AfOptions' capacities as they are and only reports overflows). */
+enum { AF_MODE_AUTO = 0, AF_MODE_WARP = 1, AF_MODE_LANE = 2 };
+int af_engine_set_mode(af_engine* e, int mode);
 int af_scenario_upload(af_engine* e, const AfScenario* host_pod);
 /* rows cover replicas [first_replica, first_replica + sweep->n_rows); pass NULL to clear */
 int af_sweep_upload(af_engine* e, const AfSweep* sweep, uint64_t first_replica);
@@ -212,6 +221,16 @@ int af_sync(af_engine* e);
 int af_last_run_ms(af_engine* e, float* ms_total, float* ms_sim_kernel);
 /* kernels launched by this engine so far                                          */
 uint64_t af_launch_count(const af_engine* e);
+/* what the last af_run did */
+typedef struct AfRunPasses {
+    int32_t lane_pass, warp_pass;        /* which kernels ran                                            */
+    int32_t lane_warps_per_sm;           /* occupancy the lane pass chose                                */
+    int32_t lane_bytes;                  /* shared memory per replica in flight                          */
+    int32_t lane_events_smem, lane_requests_smem;   /* pool entries kept in shared memory               */
+    uint64_t lane_replicas;              /* replicas the thread-per-replica pass ran                     */
+    uint64_t warp_replicas;              /* replicas the warp-per-replica pass ran (AUTO: the flagged)   */
+} AfRunPasses;
+int af_last_run_passes(af_engine* e, AfRunPasses* out);
 
 /* Results of the last af_run, n = replica_end - replica_begin entries each.       */
 int af_fetch_stats(af_engine* e, AfReplicaStats* out, uint64_t n);
@@ -229,6 +248,19 @@ int af_fetch_trace_clocks(af_engine* e, uint64_t local_replica, double* start_fi
                           uint64_t capacity_pairs, uint64_t* n_pairs);
 int af_fetch_trace_series(af_engine* e, uint64_t local_replica, uint32_t* values,
                           uint64_t capacity_ticks, uint64_t* n_ticks); /* [series][capacity_ticks] */
+
+/* AF-RNG known-answer hook: the device's random numbers outside the state machine, n values per call
+ * (the streams of oracle/afrng.py; tests/test_gpu_rng.py compares them bit for bit with oracle/afrng_c):
+ *   EDGE         request ids 1..n on (replica, hop): a = dropout uniform, b = latency variate of `dist`
+ *                (reference runtime/actors/edge.py:78,90 + samplers/common_helpers.py:49-89)
+ *   GEN_UNIFORM  positions 0..n-1 of the replica's generator stream: a = u, b = -ln(1 - max(u, 1e-15))
+ *                (samplers/poisson_poisson.py:72-74)
+ *   GEN_USERS    replicas replica..replica+n-1, first window draw: a = users (`dist` = AF_DIST_POISSON or
+ *                AF_DIST_NORMAL), b = stream position after the draw (poisson_poisson.py:58, gaussian_poisson.py:70)
+ *   ENDPOINT     request ids 1..n: a = endpoint picked among `dist` endpoints (runtime/actors/server.py:101)   */
+enum { AF_SELFTEST_EDGE = 0, AF_SELFTEST_GEN_UNIFORM = 1, AF_SELFTEST_GEN_USERS = 2, AF_SELFTEST_ENDPOINT = 3 };
+int af_selftest_rng(af_engine* e, uint64_t seed, uint64_t replica, int kind, int dist, double mean, double sigma,
+                    uint32_t hop, uint64_t n, double* out_a, double* out_b);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,7 @@
 #include <string.h>
 #include <vector>
 #include "../../asyncflow_b200/csrc/af_host_common.h"
+#include "../../asyncflow_b200/csrc/af_lane_host.h"
 
 extern "C" const char* af_twin_last_error() {
     static thread_local std::string e;
@@ -66,6 +67,42 @@ extern "C" int af_twin_run(const AfScenario* sc, const AfSweep* sw, uint64_t swe
             stats[r].p99 = afh::hist_percentile(hist + r * AF_HIST_BINS, stats[r].completed, 99.0);
         }
     }
+    return AF_OK;
+}
+
+// The thread-per-replica engine (af_lane.cuh) as a "warp" of one lane.  `lane_bytes` = the lane's share of
+// shared memory: small values push the tiered tables (events, requests, now-queue) into their second tier.
+extern "C" int af_twin_run_lane(const AfScenario* sc, const AfSweep* sw, uint64_t sweep_first, const AfOptions* opt,
+                                int32_t lane_bytes, uint64_t seed, uint64_t replica_begin, uint64_t n,
+                                AfReplicaStats* stats, uint32_t* sent, uint32_t* dropped, uint32_t* hist,
+                                uint32_t* thr, uint64_t* samp_sum, uint32_t* samp_max, double* trace_clocks,
+                                uint32_t* trace_series, uint32_t* trace_counts) {
+    if (!afh::validate(*sc, g_err)) return AF_ERR_INVALID;
+    aflh::Tables T;
+    if (!aflh::build_tables(*sc, sw ? sw->columns : nullptr, sw ? sw->n_columns : 0, T, g_err)) return AF_ERR_INVALID;
+    afl::Cfg& C = afl::h_cfg;
+    memset(&C, 0, sizeof C);
+    if (lane_bytes < aflh::min_lane_bytes(*sc, T)) lane_bytes = aflh::min_lane_bytes(*sc, T);   // (the engine lowers its occupancy instead)
+    if (!aflh::make_cfg(*sc, *opt, T, lane_bytes, afh::trace_tick_capacity(*sc), C)) { g_err = "lane engine: tables do not fit the lane's shared memory"; return AF_ERR_INVALID; }
+    C.edges = T.edges.data(); C.servers = T.servers.data(); C.endpoints = T.endpoints.data(); C.steps = T.steps.data();
+    C.spikes = T.spikes.data(); C.outages = T.outages.data(); C.lb_edges = T.lb.data(); C.cols = T.cols.data();
+    if (sw) { C.sweep_vals = sw->values; C.sweep_first = sweep_first; C.sweep_rows = sw->n_rows; }
+    C.stats = stats; C.edge_sent = sent; C.edge_dropped = dropped; C.hist = hist; C.thr = thr;
+    C.samp_sum = samp_sum; C.samp_max = samp_max; C.trace_clocks = trace_clocks; C.trace_series = trace_series;
+    C.trace_counts = trace_counts;
+    C.seed = seed; C.replica_begin = replica_begin; C.n_replicas = n;
+    std::vector<uint64_t> smem((size_t)C.warp_bytes / 8 + 2), glob((size_t)(C.gwarp_bytes / 8) + 2);
+    afl::Mem m;
+    m.s64 = (unsigned char*)smem.data(); m.s32 = m.s64 + (size_t)C.n64 * afl::STRIDE64;
+    m.g64 = (unsigned char*)glob.data(); m.g32 = m.g64 + (size_t)C.gn64 * afl::STRIDE64;
+    uint64_t next = 0;
+    afl::run_lane(m, [&]() -> uint64_t { return next < n ? next++ : ~0ull; }, [](bool alive) { return alive; });
+    if (C.collect_hist && stats)
+        for (uint64_t r = 0; r < n; ++r) {
+            stats[r].p50 = afh::hist_percentile(hist + r * AF_HIST_BINS, stats[r].completed, 50.0);
+            stats[r].p95 = afh::hist_percentile(hist + r * AF_HIST_BINS, stats[r].completed, 95.0);
+            stats[r].p99 = afh::hist_percentile(hist + r * AF_HIST_BINS, stats[r].completed, 99.0);
+        }
     return AF_OK;
 }
 

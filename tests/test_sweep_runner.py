@@ -169,3 +169,38 @@ def test_frame_lists_parameters_next_to_statistics():
     assert list(dfp["row"]) == sw.order[2:5].tolist()
     assert list(dfp["users_mean"]) == [USERS[r] for r in sw.order[2:5]]
     assert isinstance(df, pd.DataFrame)
+
+
+def test_from_yaml_mirrors_the_reference_constructor(monkeypatch, tmp_path):
+    """GpuSimulationRunner.from_yaml(env=, yaml_path=) -- the reference's convenience constructor
+    (runtime/simulation_runner.py:381-398): reads the YAML, builds the runner, run() gives analyzer-shaped
+    results equal to the oracle's on the same payload."""
+    import asyncflow_b200.runner as R
+    import yaml
+    monkeypatch.setattr(R, "Engine", lambda device=0: TwinEngine(device))
+    payload = load_scenario("c1_my_service.yml", 12)
+    path = tmp_path / "scenario.yml"
+    path.write_text(yaml.safe_dump(payload))
+    env = object()                                      # accepted and kept, like simpy.Environment there
+    runner = R.GpuSimulationRunner.from_yaml(env=env, yaml_path=path, seed=SEED, replica=3)
+    assert runner.env is env
+    res = runner.run()
+    o = des_port.simulate(payload, seed=SEED, replica=3)
+    assert [tuple(x) for x in res.clocks.tolist()] == [tuple(c) for c in o["clocks"]]
+    lat = res.get_latency_stats()
+    assert lat["total_requests"] == o["completed"]
+    assert str(path) and R.GpuSimulationRunner.from_yaml(yaml_path=str(path)).simulation_input is not None   # str paths too
+
+
+def test_results_of_two_shards_do_not_share_memory():
+    """run(begin, end) per shard, then concatenate: the second collect() must not overwrite the first
+    (the staging buffers are reused; results own their arrays)."""
+    from asyncflow_b200.results import SweepResults
+    sw = runner()
+    a = sw.run(0, 2)
+    before = a.completed.copy()
+    b = sw.run(2, 4)
+    assert not np.shares_memory(a.stats, b.stats) and not np.shares_memory(a.edge_sent, b.edge_sent)
+    assert a.completed.tolist() == before.tolist()
+    both = SweepResults.concatenate([a, b])
+    assert both.completed.tolist() == before.tolist() + b.completed.tolist()

@@ -8,6 +8,7 @@ oracle.  Never imported by the product package.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -60,13 +61,28 @@ def lib(variant: str | None = None) -> C.CDLL:
         L.af_twin_run.argtypes = [
             C.POINTER(K.AfScenario), C.POINTER(K.AfSweep), C.c_uint64, C.POINTER(K.AfOptions),
             C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 10
+        L.af_twin_run_lane.argtypes = [
+            C.POINTER(K.AfScenario), C.POINTER(K.AfSweep), C.c_uint64, C.POINTER(K.AfOptions), C.c_int32,
+            C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 10
         _libs[variant] = L
     return _libs[variant]
 
 
+#: which state machine run() drives when the caller does not say: "lane" = af_lane.cuh (thread per replica, the
+#: product's first pass), "warp" = af_core.cuh (warp per replica, the product's pass for flagged replicas)
+DEFAULT_ENGINE = os.environ.get("AF_TWIN_ENGINE", "lane")
+#: the lane's share of shared memory in the twin (the CUDA engine derives it from the occupancy it picks)
+DEFAULT_LANE_BYTES = int(os.environ.get("AF_TWIN_LANE_BYTES", "1816"))
+
+
 def run(flat, *, seed: int, replica_begin: int = 0, n: int = 1, sweep=None, sweep_first: int = 0, trace: int = 0,
-        clock_cap: int = 0, event_capacity: int = 0, request_capacity: int = 0, variant: str | None = None) -> dict:
+        clock_cap: int = 0, event_capacity: int = 0, request_capacity: int = 0, variant: str | None = None,
+        engine: str | None = None, lane_bytes: int | None = None) -> dict:
     L = lib(variant)
+    engine = engine or ("warp" if variant is not None else DEFAULT_ENGINE)
+    if engine == "lane":      # same default capacities as the warp engine (the CUDA lane pass has smaller ones and escalates)
+        event_capacity = event_capacity or 2048
+        request_capacity = request_capacity or 16384
     opt = K.AfOptions(event_capacity, request_capacity, 0, 0, 1, 1, trace, clock_cap)
     T = flat.horizon_s
     ne, nser = flat.n_edges, flat.n_series
@@ -88,10 +104,13 @@ def run(flat, *, seed: int, replica_begin: int = 0, n: int = 1, sweep=None, swee
         # rows [sweep_first, end) of the table describe replicas sweep_first, sweep_first+1, ...
         sw, keep = sweep.pod(sweep_first, None)
         sw_p = C.byref(sw)
-    rc = L.af_twin_run(C.byref(flat.pod), sw_p, sweep_first, C.byref(opt), seed, replica_begin, n,
-                       *[out[k].ctypes.data for k in ("stats", "sent", "dropped", "hist", "thr",
-                                                      "samp_sum", "samp_max", "trace_clocks",
-                                                      "trace_series", "trace_counts")])
+    bufs = [out[k].ctypes.data for k in ("stats", "sent", "dropped", "hist", "thr", "samp_sum", "samp_max",
+                                         "trace_clocks", "trace_series", "trace_counts")]
+    if engine == "lane":
+        rc = L.af_twin_run_lane(C.byref(flat.pod), sw_p, sweep_first, C.byref(opt), lane_bytes or DEFAULT_LANE_BYTES,
+                                seed, replica_begin, n, *bufs)
+    else:
+        rc = L.af_twin_run(C.byref(flat.pod), sw_p, sweep_first, C.byref(opt), seed, replica_begin, n, *bufs)
     if rc != 0:
         raise RuntimeError(L.af_twin_error().decode())
     del keep

@@ -17,6 +17,9 @@ ap.add_argument("--sweep", default="rtt")
 ap.add_argument("--no-metrics", action="store_true")
 ap.add_argument("--users", type=float, default=0.0)
 ap.add_argument("--balance", action="store_true", help="launch heaviest rows first (SweepRunner(balance=True))")
+ap.add_argument("--mode", default="", help="auto | warp | lane (af_engine_set_mode); default: the library's")
+ap.add_argument("--event-capacity", type=int, default=0)
+ap.add_argument("--request-capacity", type=int, default=None)
 a = ap.parse_args()
 d = yaml.safe_load((ROOT / "tests" / "scenarios" / a.scenario).read_text())
 d["sim_settings"]["total_simulation_time"] = a.horizon
@@ -32,7 +35,10 @@ if a.sweep == "rtt":
     sweep = {("edge_mean", e): rtt for e in flat.edge_ids}
 elif a.sweep == "users":
     sweep = {("users_mean",): np.linspace(10, 1000, n)}
-sw = SweepRunner(flat, n, sweep, warps_per_block=a.wpb, blocks_per_sm=a.bps, balance=a.balance)
+sw = SweepRunner(flat, n, sweep, warps_per_block=a.wpb, blocks_per_sm=a.bps, balance=a.balance,
+                 event_capacity=a.event_capacity, request_capacity=a.request_capacity)
+if a.mode:
+    sw.engine().set_mode(a.mode)
 for i in range(a.reps):
     t = time.time(); res = sw.run(); wall = time.time() - t
     ms_total, ms_sim = sw.last_ms
@@ -41,3 +47,7 @@ for i in range(a.reps):
           f"completed {s['completed']:.3e}, events {s['events']:.3e}, "
           f"{s['completed']/ms_sim*1e3:.3e} compl/s, {s['events']/ms_sim*1e3:.3e} events/s, overflow {s['overflowed']}, "
           f"peak_ev {res.stats['peak_events'].max()} peak_rq {res.stats['peak_requests'].max()} mean_lat {s['mean_latency']:.5f}", flush=True)
+try:
+    print("passes:", sw.engine().last_run_passes(), flush=True)
+except AttributeError:
+    pass
