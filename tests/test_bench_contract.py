@@ -52,3 +52,32 @@ def test_gpu_arm_fails_loudly_without_cuda():
                        capture_output=True, text=True, timeout=300)
     assert p.returncode != 0 and p.stdout.strip() == ""
     assert "no CPU fallback" in p.stderr
+
+
+def test_every_config_builds_rows_that_are_a_pure_function_of_the_global_id():
+    """--config c2|c3|c4|c5: the sweep row of a replica depends on its global id only, every rank's contiguous id
+    range covers the whole grid (equal work per rank), and SweepSpec accepts the columns."""
+    import numpy as np
+
+    import bench
+    from asyncflow_b200 import SweepSpec, flatten
+    for key in ("c2", "c3", "c4", "c5"):
+        w = bench.make_workload(key, horizon=5, replicas=4000)
+        flat = flatten(w.payload)
+        ids = np.arange(0, 4000, dtype=np.int64)
+        a = SweepSpec(flat, 4000, w.columns(flat, ids, 4000))
+        b = SweepSpec(flat, 4000, w.columns(flat, ids + 3 * 4000, 4000))      # rank 3 of a larger job: same grid
+        assert np.array_equal(a.values, b.values) and a.n_columns >= 1, key
+        sub = SweepSpec(flat, 7, w.columns(flat, ids[100:107], 4000))
+        assert np.array_equal(sub.values, a.values[100:107]), key
+        assert w.bytes_per_completion == 96.0 * w.events_per_completion + 8.0
+        p = a.payload_for(w.payload, 1234)                                    # the reference-side view of one row
+        assert p["sim_settings"]["total_simulation_time"] == 5
+
+
+def test_effective_cores_respects_affinity_and_quota():
+    import bench
+    n, info = bench.effective_cores()
+    assert 1 <= n <= (info["os_cpu_count"] or 1) and n <= info["affinity"]
+    if info["cgroup_quota_cpus"]:
+        assert n <= max(1, round(info["cgroup_quota_cpus"]))

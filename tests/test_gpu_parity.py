@@ -21,6 +21,18 @@ def eng():
         yield e
 
 
+#: pass structures of af_run (af_engine_set_mode): the product default, and each kernel pinned.  The pinned lane
+#: kernel takes the capacities as given (no escalation), so it gets the warp engine's defaults.
+MODES = {"auto": {}, "lane": {"event_capacity": 2048, "request_capacity": 16384}, "warp": {}}
+
+
+@pytest.fixture(params=sorted(MODES))
+def mode(request, eng):
+    eng.set_mode(request.param)
+    yield request.param
+    eng.set_mode("auto")
+
+
 def run_traced(eng, flat, begin, n, clock_cap=200000, **kw):
     eng.upload(flat)
     eng.configure(trace_replicas=n, trace_clock_capacity=clock_cap, **kw)
@@ -31,12 +43,14 @@ def run_traced(eng, flat, begin, n, clock_cap=200000, **kw):
 
 
 @pytest.mark.parametrize("name", sorted(PARITY_CASES))
-def test_engine_reproduces_golden_vectors(eng, name):
+def test_engine_reproduces_golden_vectors(eng, mode, name):
     gold = load_golden(name)
     flat = flatten(load_scenario(name, gold["horizon"]))
     for vec in gold["vectors"]:
-        st, sent, dropped = run_traced(eng, flat, vec["replica"], 1)
+        st, sent, dropped = run_traced(eng, flat, vec["replica"], 1, **MODES[mode])
         assert st[0]["flags"] == 0
+        passes = eng.last_run_passes()
+        assert passes["lane_pass"] == (mode != "warp") and passes["warp_pass"] == (mode != "lane")
         check_against_golden(
             vec, generated=int(st[0]["generated"]), completed=int(st[0]["completed"]),
             clocks=eng.trace_clocks(0), edge_sent=dict(zip(flat.edge_ids, map(int, sent[0]))),
@@ -45,13 +59,13 @@ def test_engine_reproduces_golden_vectors(eng, name):
 
 
 @pytest.mark.parametrize("name", sorted(PARITY_CASES))
-def test_engine_matches_oracle_on_fresh_replicas(eng, name):
+def test_engine_matches_oracle_on_fresh_replicas(eng, mode, name):
     horizon = {"c1_my_service.yml": 10, "c3_lb_two_servers.yml": 12, "c4_lb8_events.yml": 245,
                "c5_multihop32.yml": 6}.get(name)
     payload = load_scenario(name, horizon)
     flat = flatten(payload)
     reps = [21, 22, 23] if not name.startswith("c4") else [21]
-    st, sent, dropped = run_traced(eng, flat, reps[0], len(reps))
+    st, sent, dropped = run_traced(eng, flat, reps[0], len(reps), **MODES[mode])
     thr, hist = eng.throughput(), eng.histograms()
     ssum, smax = eng.sampled()
     for i, rep in enumerate(reps):
@@ -237,3 +251,93 @@ def test_two_engines_on_one_device_do_not_disturb_each_other():
         np.testing.assert_array_equal(a.stats(), sa)
         np.testing.assert_array_equal(b.stats(), sb)
     assert sa["completed"].sum() > 0 and sb["completed"].sum() > 0
+
+
+def test_the_timed_workload_is_pinned_to_the_oracle(eng, mode):
+    """bench.py's exact workload (configs[2]: C3, every edge normal(mean = RTT, sigma = jitter x RTT), the row a
+    GLOBAL replica id gets from bench.sweep_rows, horizon 60 s): first, middle and last replica of the 100 000,
+    every (start, finish), counter, per-second bucket and sampled series against the oracle on the payload the
+    sweep row stands for."""
+    import bench
+    total = 100_000
+    payload = bench.workload(total, 60)
+    flat = flatten(payload)
+    ids = np.arange(total, dtype=np.int64)
+    rtt, sig = bench.sweep_rows(ids, total)
+    cols = {}
+    for e in flat.edge_ids:
+        cols[("edge_mean", e)] = rtt
+        cols[("edge_sigma", e)] = sig
+    spec = SweepSpec(flat, total, cols)
+    eng.upload(flat)
+    for rid in (0, total // 2 - 1, total - 1):
+        eng.configure(trace_replicas=1, trace_clock_capacity=20000, throughput=True, **MODES[mode])
+        eng.upload_sweep(spec, rid, row_first=rid, row_count=1)
+        eng.run(bench.SEED, rid, rid + 1)
+        st = eng.stats()
+        sent, dropped = eng.edge_counts()
+        assert st[0]["flags"] == 0
+        o = des_port.simulate(spec.payload_for(payload, rid), seed=bench.SEED, replica=rid)
+        assert o["completed"] > 7000
+        assert_matches_oracle(o, flat, stats=st[0], clocks=eng.trace_clocks(0), sent=sent[0], dropped=dropped[0],
+                              series=eng.trace_series(0), throughput=eng.throughput()[0], hist=eng.histograms()[0])
+    eng.upload_sweep(None)
+
+
+def test_every_bench_config_row_matches_the_oracle(eng):
+    """One sweep row of each bench.py --config (c2, c4, c5 at their BASELINE shapes, shortened horizons): the
+    engine in its product mode against the oracle on SweepSpec.payload_for(row)."""
+    import bench
+    for cfg, horizon, rows in (("c2", 20, (0, 9_999)), ("c4", 125, (123_456,)), ("c5", 6, (3_999_999,))):
+        w = bench.make_workload(cfg, horizon=horizon)
+        flat = flatten(w.payload)
+        spec = SweepSpec(flat, len(rows), w.columns(flat, np.asarray(rows, dtype=np.int64), w.replicas))
+        eng.upload(flat)
+        for i, rid in enumerate(rows):
+            eng.configure(trace_replicas=1, trace_clock_capacity=400000, request_capacity=400000, throughput=True)
+            eng.upload_sweep(spec, rid, row_first=i, row_count=1)
+            eng.run(bench.SEED, rid, rid + 1)
+            st = eng.stats()
+            sent, dropped = eng.edge_counts()
+            assert st[0]["flags"] == 0, (cfg, rid, int(st[0]["flags"]))
+            o = des_port.simulate(spec.payload_for(w.payload, i), seed=bench.SEED, replica=rid)
+            assert_matches_oracle(o, flat, stats=st[0], clocks=eng.trace_clocks(0), sent=sent[0], dropped=dropped[0],
+                                  series=eng.trace_series(0), throughput=eng.throughput()[0])
+    eng.upload_sweep(None)
+
+
+def test_from_yaml_on_the_device(eng, tmp_path):
+    """GpuSimulationRunner.from_yaml(env=, yaml_path=): reference runtime/simulation_runner.py:381-398."""
+    import yaml
+    payload = load_scenario("c3_lb_two_servers.yml", 10)
+    path = tmp_path / "two_servers_lb.yml"
+    path.write_text(yaml.safe_dump(payload))
+    res = GpuSimulationRunner.from_yaml(env=None, yaml_path=path, seed=SEED, replica=2).run()
+    o = des_port.simulate(payload, seed=SEED, replica=2)
+    np.testing.assert_array_equal(res.clocks, np.array(o["clocks"]).reshape(-1, 2))
+    assert res.get_latency_stats()["total_requests"] == o["completed"]
+
+
+def test_flagged_replicas_are_rerun_inside_af_run(eng):
+    """AUTO mode: the thread-per-replica pass has nominal-load pools; the saturated rows of a users sweep overflow
+    them and are re-run one per warp inside the same af_run -- results complete, flags clear, rows exact."""
+    base = load_scenario("c1_my_service.yml", 20)
+    flat = flatten(base)
+    users = [30.0, 900.0, 40.0, 1000.0, 850.0, 20.0, 100.0, 700.0]
+    spec = SweepSpec(flat, len(users), {("users_mean",): users})
+    eng.set_mode("auto")
+    eng.upload(flat)
+    eng.configure(trace_replicas=len(users), trace_clock_capacity=40000, request_capacity=40000, throughput=True)
+    eng.upload_sweep(spec, 0)
+    eng.run(SEED, 0, len(users))
+    st = eng.stats()
+    sent, dropped = eng.edge_counts()
+    passes = eng.last_run_passes()
+    assert passes["lane_replicas"] == len(users) and 3 <= passes["warp_replicas"] <= 4, passes
+    assert (st["flags"] == 0).all()
+    assert int(st["peak_requests"].max()) > 2048
+    for i in range(len(users)):
+        o = des_port.simulate(spec.payload_for(base, i), seed=SEED, replica=i)
+        assert_matches_oracle(o, flat, stats=st[i], clocks=eng.trace_clocks(i), sent=sent[i], dropped=dropped[i],
+                              series=eng.trace_series(i), throughput=eng.throughput()[i], hist=eng.histograms()[i])
+    eng.upload_sweep(None)
