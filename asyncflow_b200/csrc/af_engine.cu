@@ -480,7 +480,7 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
         // fewer warps per SM when the topology's fixed tables need a larger share of shared memory
         while (lane_warps > 1 && lane_budget(e, lane_warps) < aflh::min_lane_bytes(e->sc, e->lt) + 256) lane_warps /= 2;
         memset(&C, 0, sizeof C);
-        if (!aflh::make_cfg(e->sc, o, e->lt, lane_budget(e, lane_warps), afh::trace_tick_capacity(e->sc), C)) {
+        if (!aflh::make_cfg(e->sc, o, e->lt, lane_budget(e, lane_warps), afh::trace_tick_capacity(e->sc), 32, C)) {
             if (e->mode == AF_MODE_LANE) return e->fail(AF_ERR_INVALID, "scenario tables do not fit a lane's shared memory (thread-per-replica engine)");
             lane = false;
         }

@@ -90,7 +90,9 @@ inline int32_t min_lane_bytes(const AfScenario& s, const Tables& t) {
 // The launch configuration for a budget of `lane_bytes` of shared memory per lane (= per replica in
 // flight).  Returns false when even the smallest tiers do not fit: the topology is too wide for this
 // engine at this occupancy (the caller lowers the occupancy or takes the warp-per-replica engine).
-inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, int32_t lane_bytes, int32_t trace_tick_cap, afl::Cfg& C) {
+// `lanes` = lanes of a warp in the code that will RUN the configuration: 32 for the CUDA kernel, 1 for the host twin
+// (afl::LANES is a property of the compilation pass, and the host pass of a .cu file sees 1).
+inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, int32_t lane_bytes, int32_t trace_tick_cap, int32_t lanes, afl::Cfg& C) {
     C.n_edges = s.n_edges; C.n_servers = s.n_servers; C.n_endpoints = s.n_endpoints; C.n_steps = s.n_steps;
     C.n_lb_edges = s.n_lb_edges; C.lb_algo = s.lb_algo; C.gen_edge = s.gen_edge; C.client_edge = s.client_edge;
     C.n_spike = s.n_spike_marks; C.n_outage = s.n_outage_marks;
@@ -143,7 +145,7 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     C.o32_lb = w; w += C.n_lb_edges;
     C.o32_smax = w; w += C.n_series;
     C.n32 = w;
-    C.warp_bytes = C.n64 * afl::STRIDE64 + C.n32 * afl::STRIDE32;
+    C.warp_bytes = (C.n64 * 8 + C.n32 * 4) * lanes;
     // global tier
     int32_t g = 0;
     C.g64_evt = g; g += ev_total - ev_s;
@@ -156,7 +158,7 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     C.g32_pack = h; h += rq_total - rq_s;
     C.g32_next = h; h += rq_total - rq_s;
     C.gn32 = h;
-    C.gwarp_bytes = (uint64_t)C.gn64 * afl::STRIDE64 + (uint64_t)C.gn32 * afl::STRIDE32;
+    C.gwarp_bytes = ((uint64_t)C.gn64 * 8 + (uint64_t)C.gn32 * 4) * (uint64_t)lanes;
     return true;
 }
 

@@ -83,7 +83,7 @@ extern "C" int af_twin_run_lane(const AfScenario* sc, const AfSweep* sw, uint64_
     afl::Cfg& C = afl::h_cfg;
     memset(&C, 0, sizeof C);
     if (lane_bytes < aflh::min_lane_bytes(*sc, T)) lane_bytes = aflh::min_lane_bytes(*sc, T);   // (the engine lowers its occupancy instead)
-    if (!aflh::make_cfg(*sc, *opt, T, lane_bytes, afh::trace_tick_capacity(*sc), C)) { g_err = "lane engine: tables do not fit the lane's shared memory"; return AF_ERR_INVALID; }
+    if (!aflh::make_cfg(*sc, *opt, T, lane_bytes, afh::trace_tick_capacity(*sc), afl::LANES, C)) { g_err = "lane engine: tables do not fit the lane's shared memory"; return AF_ERR_INVALID; }
     C.edges = T.edges.data(); C.servers = T.servers.data(); C.endpoints = T.endpoints.data(); C.steps = T.steps.data();
     C.spikes = T.spikes.data(); C.outages = T.outages.data(); C.lb_edges = T.lb.data(); C.cols = T.cols.data();
     if (sw) { C.sweep_vals = sw->values; C.sweep_first = sweep_first; C.sweep_rows = sw->n_rows; }

@@ -1,0 +1,109 @@
+"""CPU tier: the thread-per-replica state machine (asyncflow_b200/csrc/af_lane.cuh, compiled for the host as a warp of
+one lane) against the oracle, against the warp-per-replica state machine (af_core.cuh), and across its memory tiers."""
+
+from __future__ import annotations
+
+import des_port
+import fuzz
+import numpy as np
+import pytest
+import twin
+from helpers import PARITY_CASES, SEED, assert_matches_oracle, load_scenario
+
+from asyncflow_b200 import _capi as K
+from asyncflow_b200 import SweepSpec, flatten
+
+FIELDS = ("n_events", "generated", "completed", "flags", "n_ticks", "peak_events", "peak_requests",
+          "lat_sum", "lat_sumsq", "lat_min", "lat_max", "p50", "p95", "p99")
+
+
+def _same(a: dict, b: dict) -> None:
+    for f in FIELDS:
+        np.testing.assert_array_equal(a["stats"][f], b["stats"][f], err_msg=f)
+    for k in ("sent", "dropped", "hist", "thr", "samp_sum", "samp_max", "trace_counts"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
+@pytest.mark.parametrize("name", sorted(PARITY_CASES))
+def test_lane_and_warp_state_machines_agree_on_everything(name):
+    """Same stats block (incl. peaks and event counts), counters, histograms, buckets, sampled aggregates and traces."""
+    flat = flatten(load_scenario(name, PARITY_CASES[name]))
+    kw = dict(seed=SEED, replica_begin=40, n=3, trace=3, clock_cap=300000, request_capacity=400000, event_capacity=8192)
+    lane = twin.run(flat, engine="lane", **kw)
+    warp = twin.run(flat, engine="warp", **kw)
+    _same(lane, warp)
+    for j in range(3):
+        n, nt = int(lane["stats"][j]["completed"]), int(lane["stats"][j]["n_ticks"])
+        np.testing.assert_array_equal(lane["trace_clocks"][j, :n], warp["trace_clocks"][j, :n])
+        np.testing.assert_array_equal(lane["trace_series"][j][:, :nt], warp["trace_series"][j][:, :nt])
+
+
+@pytest.mark.parametrize("lane_bytes", [0, 300, 908, 1816, 7000])
+def test_results_do_not_depend_on_the_shared_memory_tier_split(lane_bytes):
+    """lane_bytes = the lane's share of shared memory (0: the smallest the scenario admits): however the events,
+    requests and now-queue items are split between the two tiers, the replica is the same."""
+    for name in ("c3_lb_two_servers.yml", "overload_single.yml", "poisson_ties.yml", "c5_multihop32.yml"):
+        payload = load_scenario(name, PARITY_CASES[name])
+        flat = flatten(payload)
+        r = twin.run(flat, engine="lane", lane_bytes=lane_bytes or 1, seed=SEED, replica_begin=11, n=1, trace=1, clock_cap=300000)
+        o = des_port.simulate(payload, seed=SEED, replica=11)
+        n, nt = int(r["stats"][0]["completed"]), int(r["stats"][0]["n_ticks"])
+        assert r["stats"][0]["flags"] == 0
+        assert_matches_oracle(o, flat, stats=r["stats"][0], clocks=r["trace_clocks"][0, :n], sent=r["sent"][0],
+                              dropped=r["dropped"][0], series=r["trace_series"][0][:, :nt], throughput=r["thr"][0],
+                              hist=r["hist"][0])
+
+
+def test_random_sweeps_on_the_lane_engine_match_the_oracle_row_by_row():
+    """Every AF_FIELD_* of the C ABI as a sweep column (fields read at the start of a replica and fields looked up
+    through the lane's row copy), tiny shared-memory tier."""
+    for seed in range(900, 912):
+        payload = fuzz.scenario(seed)
+        flat = flatten(payload)
+        n = 3
+        spec = SweepSpec(flat, n, fuzz.sweep_columns(seed, payload, n))
+        r = twin.run(flat, engine="lane", lane_bytes=400, seed=SEED, n=n, sweep=spec, trace=n, clock_cap=100000,
+                     request_capacity=200000)
+        for i in range(n):
+            p = spec.payload_for(payload, i)
+            o = des_port.simulate(p, seed=SEED, replica=i)
+            m = int(r["stats"][i]["completed"])
+            assert r["stats"][i]["flags"] == 0
+            assert_matches_oracle(o, flatten(p), stats=r["stats"][i], clocks=r["trace_clocks"][i, :m], sent=r["sent"][i],
+                                  dropped=r["dropped"][i])
+
+
+def test_lane_pool_overflow_is_flagged():
+    flat = flatten(load_scenario("overload_single.yml"))
+    r = twin.run(flat, engine="lane", seed=SEED, n=1, request_capacity=200)
+    assert r["stats"][0]["flags"] & K.FLAG_REQUEST_OVERFLOW
+    r = twin.run(flat, engine="lane", seed=SEED, n=1, event_capacity=4)
+    assert r["stats"][0]["flags"] & K.FLAG_EVENT_OVERFLOW
+
+
+def _lb_empty_payload(horizon: int = 6):
+    """The LB covers only srv-1, srv-1 chains to srv-2; an outage takes srv-1 down.  The reference's validator accepts
+    it (srv-2 is still up) and its load balancer then raises on an empty edge set."""
+    p = load_scenario("c3_lb_two_servers.yml", horizon)
+    topo = p["topology_graph"]
+    topo["nodes"]["load_balancer"]["server_covered"] = ["srv-1"]
+    topo["edges"] = [e for e in topo["edges"] if e["id"] not in ("lb-srv2", "srv1-client")]
+    topo["edges"].append({"id": "srv1-srv2", "source": "srv-1", "target": "srv-2",
+                          "latency": {"mean": 0.001, "distribution": "exponential"}})
+    p["events"] = [{"event_id": "down-1", "target_id": "srv-1", "start": {"kind": "server_down", "t_start": 2.0},
+                    "end": {"kind": "server_up", "t_end": 4.0}}]
+    return p
+
+
+def test_an_outage_that_empties_the_lb_pool_is_rejected_up_front_and_flagged_by_the_engines():
+    with pytest.raises(ValueError, match="every server behind the load balancer is down"):
+        flatten(_lb_empty_payload())
+    # the engines themselves stop the replica instead of reading lb[-1]: a horizon that ends before the outage
+    # passes the host check; then the POD's horizon is put back
+    flat = flatten(_lb_empty_payload(1))
+    flat.pod.horizon_s = 6
+    flat.horizon_s = 6
+    for engine in ("lane", "warp"):
+        r = twin.run(flat, engine=engine, seed=SEED, n=2)
+        assert (r["stats"]["flags"] & K.FLAG_LB_EMPTY).all(), engine
+        assert (r["stats"]["completed"] > 0).all()

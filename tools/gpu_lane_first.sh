@@ -4,7 +4,8 @@
 #   gpurun --timeout 1500 -- 'bash tools/gpu_lane_first.sh > gpurun_out/lane_first.log 2>&1'
 cd "$(dirname "$0")/.." || exit 1
 QB="timeout 200 python tools/quick_bench.py"
-echo "=== parity, product library, mode auto"; timeout 400 python tools/check_variant_gpu.py || echo "PARITY FAILED (auto)"
+echo "=== smoke"; timeout 300 python __graft_entry__.py --smoke || { echo "SMOKE FAILED: stopping"; exit 1; }
+echo "=== parity, product library, mode auto"; timeout 400 python tools/check_variant_gpu.py || { echo "PARITY FAILED (auto): stopping"; exit 1; }
 echo "=== parity, product library, mode lane"; ASYNCFLOW_B200_ENGINE=lane timeout 400 python tools/check_variant_gpu.py || echo "PARITY FAILED (lane)"
 echo "=== parity, product library, mode warp"; ASYNCFLOW_B200_ENGINE=warp timeout 400 python tools/check_variant_gpu.py || echo "PARITY FAILED (warp)"
 for mode in auto warp; do
