@@ -79,13 +79,12 @@ __global__ void AF_LAUNCH_BOUNDS af_sim_kernel() {
 #define AF_LANE_MAX_THREADS 512
 #endif
 __global__ void __launch_bounds__(AF_LANE_MAX_THREADS, 1) af_lane_kernel() {
-    extern __shared__ __align__(16) unsigned char af_smem[];
     const afl::Cfg& C = afl::c_cfg;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    unsigned char* ws = af_smem + (size_t)warp * (size_t)C.warp_bytes;
+    const uint32_t ws = warp * (uint32_t)C.warp_bytes;
     unsigned char* gs = C.gtier + ((uint64_t)blockIdx.x * (blockDim.x >> 5) + warp) * C.gwarp_bytes;
     afl::Mem m;
-    m.s64 = ws + lane * 8u; m.s32 = ws + (size_t)C.n64 * afl::STRIDE64 + lane * 4u;
+    m.s64 = ws + lane * 8u; m.s32 = ws + (uint32_t)C.n64 * (uint32_t)afl::STRIDE64 + lane * 4u;
     m.g64 = gs + lane * 8u; m.g32 = gs + (size_t)C.gn64 * afl::STRIDE64 + lane * 4u;
     afl::run_lane(m,
         [&]() -> uint64_t {

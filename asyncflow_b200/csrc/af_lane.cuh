@@ -131,7 +131,7 @@ struct Cfg {
     int32_t ev_s, ev_total, rq_s, rq_total, nq_s;
     // shared-memory layout of a warp: 64-bit region (element offsets), then 32-bit region (word offsets)
     int32_t o64_evt, o64_evk, o64_t0, o64_nq, o64_spike, o64_ssum, o64_row, n64;
-    int32_t o32_rid, o32_pack, o32_next, o32_conn, o32_sent, o32_drop, o32_srv, o32_inbox, o32_lb, o32_smax, n32;
+    int32_t o32_rid, o32_pack, o32_next, o32_conn, o32_sent, o32_drop, o32_srv, o32_inbox, o32_lb, o32_smax, o32_dirty, n_dirty, n32;
     int32_t warp_bytes;                             // n64 * 256 + n32 * 128
     // global tier of a warp (same interleave): element / word offsets, sizes
     int32_t g64_evt, g64_evk, g64_t0, g64_nq, gn64;
@@ -176,22 +176,41 @@ template <class T> AFL_IN T ro(const T* p) {
 }
 
 // ---- the lane's memory ------------------------------------------------------------------------------
+// Shared memory is addressed by 32-bit byte offsets into ONE array the compiler knows to be shared (LDS / STS with
+// 32-bit address arithmetic; a generic 64-bit pointer costs twice the integer work per access -- ncu r02a: 36 % of
+// the executed instructions were address arithmetic).  A tiered table takes a BRANCH on "is it in shared memory",
+// not a pointer select: the shared side stays an LDS.
+#if AFL_DEVICE
+extern __shared__ __align__(16) unsigned char afl_smem[];
+#define AFL_SM afl_smem
+#else
+static unsigned char* afl_smem_host = nullptr;     // the twin's stand-in for the SM's shared memory
+#define AFL_SM afl_smem_host
+#endif
 struct Mem {
-    unsigned char* s64; unsigned char* s32;     // shared-memory regions of the warp, already offset by the lane
+    uint32_t s64, s32;                          // shared-memory regions of the warp (byte offsets, the lane's column)
     unsigned char* g64; unsigned char* g32;     // global tier of the warp, already offset by the lane
 };
-AFL_IN uint64_t* e64(const Mem& m, int32_t elem) { return reinterpret_cast<uint64_t*>(m.s64 + (size_t)elem * STRIDE64); }
-AFL_IN double* f64(const Mem& m, int32_t elem) { return reinterpret_cast<double*>(m.s64 + (size_t)elem * STRIDE64); }
-AFL_IN uint32_t* w32(const Mem& m, int32_t word) { return reinterpret_cast<uint32_t*>(m.s32 + (size_t)word * STRIDE32); }
-AFL_IN int32_t* i32(const Mem& m, int32_t word) { return reinterpret_cast<int32_t*>(m.s32 + (size_t)word * STRIDE32); }
+AFL_IN uint64_t* e64(const Mem& m, int32_t elem) { return reinterpret_cast<uint64_t*>(AFL_SM + (m.s64 + (uint32_t)elem * (uint32_t)STRIDE64)); }
+AFL_IN double* f64(const Mem& m, int32_t elem) { return reinterpret_cast<double*>(AFL_SM + (m.s64 + (uint32_t)elem * (uint32_t)STRIDE64)); }
+AFL_IN uint32_t* w32(const Mem& m, int32_t word) { return reinterpret_cast<uint32_t*>(AFL_SM + (m.s32 + (uint32_t)word * (uint32_t)STRIDE32)); }
+AFL_IN int32_t* i32(const Mem& m, int32_t word) { return reinterpret_cast<int32_t*>(AFL_SM + (m.s32 + (uint32_t)word * (uint32_t)STRIDE32)); }
+AFL_IN uint64_t* g64p(const Mem& m, int32_t elem) { return reinterpret_cast<uint64_t*>(m.g64 + (size_t)(uint32_t)elem * STRIDE64); }
+AFL_IN uint32_t* g32p(const Mem& m, int32_t word) { return reinterpret_cast<uint32_t*>(m.g32 + (size_t)(uint32_t)word * STRIDE32); }
 // tiered: entry idx of a table whose first `split` entries are in shared memory
-AFL_IN uint64_t* t64(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split) {
-    return reinterpret_cast<uint64_t*>(AFL_LIKELY(idx < split) ? m.s64 + (size_t)(os + idx) * STRIDE64
-                                                               : m.g64 + (size_t)(og + idx - split) * STRIDE64);
+AFL_IN uint64_t ld_t64(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split) {
+    if (AFL_LIKELY(idx < split)) return *e64(m, os + idx);
+    return *g64p(m, og + idx - split);
 }
-AFL_IN uint32_t* t32(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split) {
-    return reinterpret_cast<uint32_t*>(AFL_LIKELY(idx < split) ? m.s32 + (size_t)(os + idx) * STRIDE32
-                                                               : m.g32 + (size_t)(og + idx - split) * STRIDE32);
+AFL_IN void st_t64(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split, uint64_t v) {
+    if (AFL_LIKELY(idx < split)) *e64(m, os + idx) = v; else *g64p(m, og + idx - split) = v;
+}
+AFL_IN uint32_t ld_t32(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split) {
+    if (AFL_LIKELY(idx < split)) return *w32(m, os + idx);
+    return *g32p(m, og + idx - split);
+}
+AFL_IN void st_t32(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split, uint32_t v) {
+    if (AFL_LIKELY(idx < split)) *w32(m, os + idx) = v; else *g32p(m, og + idx - split) = v;
 }
 
 // the replica's scalar state: registers (nothing here is indexed dynamically)
@@ -222,40 +241,47 @@ AFL_IN uint32_t ep_total_ram(const Mem& m, uint32_t ep) {
 }
 
 // ---- request records (tiered): t0 | rid, pack, next ----------------------------------------------
-AFL_IN double* rq_t0(const Mem& m, uint32_t s) { return reinterpret_cast<double*>(t64(m, AFL_C.o64_t0, AFL_C.g64_t0, (int32_t)s, AFL_C.rq_s)); }
-AFL_IN uint32_t* rq_rid(const Mem& m, uint32_t s) { return t32(m, AFL_C.o32_rid, AFL_C.g32_rid, (int32_t)s, AFL_C.rq_s); }
-AFL_IN uint32_t* rq_pack(const Mem& m, uint32_t s) { return t32(m, AFL_C.o32_pack, AFL_C.g32_pack, (int32_t)s, AFL_C.rq_s); }
-AFL_IN uint32_t* rq_next(const Mem& m, uint32_t s) { return t32(m, AFL_C.o32_next, AFL_C.g32_next, (int32_t)s, AFL_C.rq_s); }
+AFL_IN double rq_t0(const Mem& m, uint32_t s) { return afr::u2d(ld_t64(m, AFL_C.o64_t0, AFL_C.g64_t0, (int32_t)s, AFL_C.rq_s)); }
+AFL_IN void rq_t0_set(const Mem& m, uint32_t s, double v) { st_t64(m, AFL_C.o64_t0, AFL_C.g64_t0, (int32_t)s, AFL_C.rq_s, afr::d2u(v)); }
+AFL_IN uint32_t rq_rid(const Mem& m, uint32_t s) { return ld_t32(m, AFL_C.o32_rid, AFL_C.g32_rid, (int32_t)s, AFL_C.rq_s); }
+AFL_IN void rq_rid_set(const Mem& m, uint32_t s, uint32_t v) { st_t32(m, AFL_C.o32_rid, AFL_C.g32_rid, (int32_t)s, AFL_C.rq_s, v); }
+AFL_IN uint32_t rq_pack(const Mem& m, uint32_t s) { return ld_t32(m, AFL_C.o32_pack, AFL_C.g32_pack, (int32_t)s, AFL_C.rq_s); }
+AFL_IN void rq_pack_set(const Mem& m, uint32_t s, uint32_t v) { st_t32(m, AFL_C.o32_pack, AFL_C.g32_pack, (int32_t)s, AFL_C.rq_s, v); }
+AFL_IN uint32_t rq_next(const Mem& m, uint32_t s) { return ld_t32(m, AFL_C.o32_next, AFL_C.g32_next, (int32_t)s, AFL_C.rq_s); }
+AFL_IN void rq_next_set(const Mem& m, uint32_t s, uint32_t v) { st_t32(m, AFL_C.o32_next, AFL_C.g32_next, (int32_t)s, AFL_C.rq_s, v); }
 
 AFL_IN uint32_t rq_alloc(St& W, const Mem& m) {
     uint32_t s;
-    if (W.rq_free != NIL) { s = W.rq_free; W.rq_free = *rq_next(m, s); }
+    if (W.rq_free != NIL) { s = W.rq_free; W.rq_free = rq_next(m, s); }
     else if ((int32_t)W.rq_hw < AFL_C.rq_total) { s = W.rq_hw++; }
     else { W.flags |= AF_FLAG_REQUEST_OVERFLOW; return NIL; }
     const uint32_t live = ++W.rq_live;
     if (live > W.peak_rq) W.peak_rq = live;
     return s;
 }
-AFL_IN void rq_release(St& W, const Mem& m, uint32_t s) { *rq_next(m, s) = W.rq_free; W.rq_free = s; --W.rq_live; }
+AFL_IN void rq_release(St& W, const Mem& m, uint32_t s) { rq_next_set(m, s, W.rq_free); W.rq_free = s; --W.rq_live; }
 
 // intrusive FIFOs through the `next` links; head / tail are words of the 32-bit region
 AFL_IN void fifo_push(const Mem& m, int32_t w_head, int32_t w_tail, uint32_t s) {
-    *rq_next(m, s) = NIL;
+    rq_next_set(m, s, NIL);
     const uint32_t tail = *w32(m, w_tail);
-    if (tail == NIL) *w32(m, w_head) = s; else *rq_next(m, tail) = s;
+    if (tail == NIL) *w32(m, w_head) = s; else rq_next_set(m, tail, s);
     *w32(m, w_tail) = s;
 }
 AFL_IN uint32_t fifo_pop(const Mem& m, int32_t w_head, int32_t w_tail) {
     const uint32_t s = *w32(m, w_head);
-    const uint32_t h = *rq_next(m, s);
+    const uint32_t h = rq_next(m, s);
     *w32(m, w_head) = h;
     if (h == NIL) *w32(m, w_tail) = NIL;
     return s;
 }
 
 // ---- pending timed events: 4-ary min-heap on (time bits, seq), tiered ---------------------------------
-AFL_IN uint64_t* ev_t(const Mem& m, int32_t i) { return t64(m, AFL_C.o64_evt, AFL_C.g64_evt, i, AFL_C.ev_s); }
-AFL_IN uint64_t* ev_k(const Mem& m, int32_t i) { return t64(m, AFL_C.o64_evk, AFL_C.g64_evk, i, AFL_C.ev_s); }
+AFL_IN uint64_t ev_t(const Mem& m, int32_t i) { return ld_t64(m, AFL_C.o64_evt, AFL_C.g64_evt, i, AFL_C.ev_s); }
+AFL_IN uint64_t ev_k(const Mem& m, int32_t i) { return ld_t64(m, AFL_C.o64_evk, AFL_C.g64_evk, i, AFL_C.ev_s); }
+AFL_IN void ev_set(const Mem& m, int32_t i, uint64_t t, uint64_t k) {
+    st_t64(m, AFL_C.o64_evt, AFL_C.g64_evt, i, AFL_C.ev_s, t); st_t64(m, AFL_C.o64_evk, AFL_C.g64_evk, i, AFL_C.ev_s, k);
+}
 AFL_IN bool ev_less(uint64_t ta, uint64_t ka, uint64_t tb, uint64_t kb) {       // times are non-negative doubles: bit order = value order
     return ta < tb || (ta == tb && (uint32_t)(ka >> 32) < (uint32_t)(kb >> 32));
 }
@@ -267,53 +293,52 @@ AFL_IN void heap_push(St& W, const Mem& m, uint64_t tb, uint64_t key) {
 #pragma unroll 1
     while (i > 0) {
         const int32_t p = (i - 1) >> 2;
-        const uint64_t tp = *ev_t(m, p), kp = *ev_k(m, p);
+        const uint64_t tp = ev_t(m, p), kp = ev_k(m, p);
         if (!ev_less(tb, key, tp, kp)) break;
-        *ev_t(m, i) = tp; *ev_k(m, i) = kp;
+        ev_set(m, i, tp, kp);
         i = p;
     }
-    *ev_t(m, i) = tb; *ev_k(m, i) = key;
+    ev_set(m, i, tb, key);
 }
 // remove the root (the caller has read it)
 AFL_IN void heap_pop(St& W, const Mem& m) {
     const int32_t n = --W.ev_n;
     if (n == 0) return;
-    const uint64_t tl = *ev_t(m, n), kl = *ev_k(m, n);
+    const uint64_t tl = ev_t(m, n), kl = ev_k(m, n);
     int32_t i = 0;
 #pragma unroll 1
     for (;;) {
         const int32_t c = 4 * i + 1;
         if (c >= n) break;
         int32_t b = c;
-        uint64_t tbst = *ev_t(m, c), kbst = *ev_k(m, c);
-#pragma unroll
-        for (int32_t j = 1; j < 4; ++j) {
-            if (c + j < n) {
-                const uint64_t tj = *ev_t(m, c + j), kj = *ev_k(m, c + j);
-                if (ev_less(tj, kj, tbst, kbst)) { tbst = tj; kbst = kj; b = c + j; }
-            }
+        uint64_t tbst = ev_t(m, c), kbst = ev_k(m, c);
+#pragma unroll 1
+        for (int32_t j = c + 1; j < c + 4 && j < n; ++j) {
+            const uint64_t tj = ev_t(m, j), kj = ev_k(m, j);
+            if (ev_less(tj, kj, tbst, kbst)) { tbst = tj; kbst = kj; b = j; }
         }
         if (!ev_less(tbst, kbst, tl, kl)) break;
-        *ev_t(m, i) = tbst; *ev_k(m, i) = kbst;
+        ev_set(m, i, tbst, kbst);
         i = b;
     }
-    *ev_t(m, i) = tl; *ev_k(m, i) = kl;
+    ev_set(m, i, tl, kl);
 }
 
 // ---- now-queue (tiered ring of NQ_TOTAL items: seq << 32 | kind:3 aux:9 slot:20) ---------------------
-AFL_IN uint64_t* nq_at(const Mem& m, uint32_t pos) {
-    return t64(m, AFL_C.o64_nq, AFL_C.g64_nq, (int32_t)(pos & (uint32_t)(NQ_TOTAL - 1)), AFL_C.nq_s);
+AFL_IN uint64_t nq_ld(const Mem& m, uint32_t pos) {
+    return ld_t64(m, AFL_C.o64_nq, AFL_C.g64_nq, (int32_t)(pos & (uint32_t)(NQ_TOTAL - 1)), AFL_C.nq_s);
 }
 AFL_IN bool can_fuse(const St& W) { return AFL_LIKELY(W.busy == 0); }
 AFL_IN void nq_push(St& W, const Mem& m, uint32_t kind, uint32_t aux, uint32_t slot) {
     const uint32_t tail = W.nq_tail;
     if (tail - W.nq_head >= (uint32_t)NQ_TOTAL) { W.flags |= AF_FLAG_NOWQ_OVERFLOW; return; }
-    *nq_at(m, tail) = ((uint64_t)(W.seq++) << 32) | mk_payload(kind, aux, slot);
+    st_t64(m, AFL_C.o64_nq, AFL_C.g64_nq, (int32_t)(tail & (uint32_t)(NQ_TOTAL - 1)), AFL_C.nq_s,
+           ((uint64_t)(W.seq++) << 32) | mk_payload(kind, aux, slot));
     W.nq_tail = tail + 1;
     W.busy += 2u;
 }
 AFL_IN uint32_t nq_take(St& W, const Mem& m) {      // (the caller has adjusted `busy`)
-    const uint32_t item = (uint32_t)*nq_at(m, W.nq_head);
+    const uint32_t item = (uint32_t)nq_ld(m, W.nq_head);
     W.nq_head += 1;
     if (W.nq_head == W.nq_tail) { W.nq_head = 0; W.nq_tail = 0; }   // empty: restart at the shared-memory end of the ring
     return item;
@@ -351,10 +376,72 @@ AFL_IN bool gen_next_gap(St& W, double& gap) {
     return ok;
 }
 
-// ---- Stores (mailboxes), Containers: as af_core.cuh ----------------------------------------------------
+// ---- sampled metrics (metrics/collector.py:50-66), LAZILY --------------------------------------------------------
+// The collector reads every gauge at every tick.  Done literally, that loop (n_series loads, 64-bit adds, maxima) runs
+// in every iteration of the warp -- with 32 replicas in a warp some lane always has a tick due.  A gauge only changes
+// inside an event, so the tick loop here just counts ticks, and the per-series aggregates are settled when a gauge
+// CHANGES:  sum over ticks of v  =  n_ticks * v_final - sum over changes of (delta * ticks taken before the change)
+// (u64 modular arithmetic: exact), and the maximum over ticks takes the OLD value at a change iff a tick has seen it
+// (one "changed since the last tick" bit per series, cleared by a tick).  Traced replicas also store every reading.
+AFL_IN void gauge_touch(const St& W, const Mem& m, int32_t j, uint32_t v_old, int32_t delta) {
+    uint64_t* acc = e64(m, AFL_C.o64_ssum + j);
+    *acc = *acc + (uint64_t)(int64_t)delta * (uint64_t)W.n_ticks;
+    uint32_t* dw = w32(m, AFL_C.o32_dirty + (j >> 5));
+    const uint32_t d = *dw, bit = 1u << (j & 31);
+    if (!(d & bit)) {
+        uint32_t* mx = w32(m, AFL_C.o32_smax + j);
+        if (v_old > *mx) *mx = v_old;
+        *dw = d | bit;
+    }
+}
+AFL_IN void conn_add(const St& W, const Mem& m, uint32_t edge, int32_t delta) {
+    uint32_t* p = w32(m, AFL_C.o32_conn + (int32_t)edge);
+    const uint32_t v = *p;
+    if (AFL_C.metrics_mask & AF_METRIC_EDGE_CONN) gauge_touch(W, m, 3 * AFL_C.n_servers + (int32_t)edge, v, delta);
+    *p = v + (uint32_t)delta;
+}
 AFL_IN int32_t ib_word(uint32_t node, int32_t f) { return AFL_C.o32_inbox + (int32_t)node * IB_WORDS + f; }
 AFL_IN int32_t sv_word(uint32_t sidx, int32_t f) { return AFL_C.o32_srv + (int32_t)sidx * SV_WORDS + f; }
+// field = SV_READY_Q / SV_IO_Q / SV_RAM_IN_USE (series 3 * sidx + 0 / 1 / 2)
+AFL_IN void srv_gauge_add(const St& W, const Mem& m, uint32_t sidx, int32_t field, int32_t delta) {
+    int32_t* p = i32(m, sv_word(sidx, field));
+    const int32_t v = *p;
+    if ((AFL_C.metrics_mask & 7u) == 7u) gauge_touch(W, m, 3 * (int32_t)sidx + (field - SV_READY_Q), (uint32_t)v, delta);
+    *p = v + delta;
+}
+AFL_IN uint32_t gauge_value(const Mem& m, int32_t j) {
+    const int32_t ns3 = 3 * AFL_C.n_servers;
+    if (j < ns3) { const int32_t mt = j % 3; return *w32(m, sv_word((uint32_t)(j / 3), mt == 0 ? SV_READY_Q : (mt == 1 ? SV_IO_Q : SV_RAM_IN_USE))); }
+    return *w32(m, AFL_C.o32_conn + (j - ns3));
+}
+AFL_IN bool gauge_on(int32_t j) {
+    return j < 3 * AFL_C.n_servers ? (AFL_C.metrics_mask & 7u) == 7u          // collector.py:60-63
+                                   : (AFL_C.metrics_mask & AF_METRIC_EDGE_CONN) != 0;
+}
+// every collector tick ordered before (t, ev_seq)
+AFL_IN void take_ticks(St& W, const Mem& m, double t, uint32_t ev_seq) {
+    double tick = W.tick_time;
+    uint32_t tseq = W.tick_seq, nt = W.n_ticks, seq = W.seq;
+    const double horizon = W.horizon;
+#pragma unroll 1
+    while ((tick < t || (tick == t && tseq < ev_seq)) && tick < horizon) {
+        if (AFL_UNLIKELY(W.traced != 0) && (int32_t)nt < AFL_C.trace_tick_cap) {
+#pragma unroll 1
+            for (int32_t j = 0; j < AFL_C.n_series; ++j)
+                if (gauge_on(j)) AFL_C.trace_series[(W.local * (uint64_t)AFL_C.n_series + (uint32_t)j) * (uint64_t)AFL_C.trace_tick_cap + nt] = gauge_value(m, j);
+        }
+        nt += 1;
+        tseq = seq++;                                 // the collector re-arms its timeout here
+        tick = tick + AFL_C.sample_period;
+    }
+    if (nt != W.n_ticks) {                            // every gauge has now been read at its current value
+#pragma unroll 1
+        for (int32_t w = 0; w < AFL_C.n_dirty; ++w) *w32(m, AFL_C.o32_dirty + w) = 0u;
+    }
+    W.tick_time = tick; W.tick_seq = tseq; W.n_ticks = nt; W.seq = seq;
+}
 
+// ---- Stores (mailboxes), Containers: as af_core.cuh ----------------------------------------------------
 // `yield box.get()` of the node's consumer process
 AFL_IN void consumer_get(St& W, const Mem& m, uint32_t node) {
     if (AFL_UNLIKELY(*w32(m, ib_word(node, IB_HEAD)) != NIL)) {
@@ -383,7 +470,7 @@ AFL_IN void ram_walk(St& W, const Mem& m, uint32_t sidx) {
         if ((int32_t)need > *i32(m, sv_word(sidx, SV_RAM_FREE))) break;
         const uint32_t w = fifo_pop(m, sv_word(sidx, SV_RAMQ_HEAD), sv_word(sidx, SV_RAMQ_TAIL));
         const uint32_t h = *w32(m, sv_word(sidx, SV_RAMQ_HEAD));
-        if (h != NIL) *w32(m, sv_word(sidx, SV_RAMQ_NEED)) = ep_total_ram(m, pk_ep(*rq_pack(m, h)));
+        if (h != NIL) *w32(m, sv_word(sidx, SV_RAMQ_NEED)) = ep_total_ram(m, pk_ep(rq_pack(m, h)));
         *i32(m, sv_word(sidx, SV_RAM_FREE)) -= (int32_t)need;
         nq_push(W, m, I_RAM_OK, sidx, w);
     }
@@ -432,40 +519,6 @@ AFL_IN bool on_outage(St& W, const Mem& m, double& next_fire) {
     W.outage_cur = cur;
     if (cur < AFL_C.n_outage) { next_fire = ro(AFL_C.outages + cur).fire; return true; }
     return false;
-}
-
-// ---- sampled metrics: every collector tick ordered before (t, ev_seq) (collector.py:50-66) ----------------
-AFL_IN void take_samples(St& W, const Mem& m, double t, uint32_t ev_seq) {
-    const int32_t n_series = AFL_C.n_series, ns3 = 3 * AFL_C.n_servers;
-    const bool srv_on = (AFL_C.metrics_mask & 7u) == 7u;          // collector.py:60-63
-    const bool edge_on = (AFL_C.metrics_mask & AF_METRIC_EDGE_CONN) != 0;
-    double tick = W.tick_time;
-    uint32_t tseq = W.tick_seq, nt = W.n_ticks, seq = W.seq;
-    const double horizon = W.horizon;
-    const bool traced = W.traced != 0;
-#pragma unroll 1
-    while ((tick < t || (tick == t && tseq < ev_seq)) && tick < horizon) {
-#pragma unroll 1
-        for (int32_t j = 0; j < n_series; ++j) {
-            uint32_t v;
-            if (j < ns3) {
-                if (!srv_on) continue;
-                const int32_t mt = j % 3;
-                v = *w32(m, sv_word((uint32_t)(j / 3), mt == 0 ? SV_READY_Q : (mt == 1 ? SV_IO_Q : SV_RAM_IN_USE)));
-            } else {
-                if (!edge_on) continue;
-                v = *w32(m, AFL_C.o32_conn + (j - ns3));
-            }
-            *e64(m, AFL_C.o64_ssum + j) += v;
-            if (v > *w32(m, AFL_C.o32_smax + j)) *w32(m, AFL_C.o32_smax + j) = v;
-            if (traced && (int32_t)nt < AFL_C.trace_tick_cap)
-                AFL_C.trace_series[(W.local * (uint64_t)n_series + (uint32_t)j) * (uint64_t)AFL_C.trace_tick_cap + nt] = v;
-        }
-        nt += 1;
-        tseq = seq++;                                 // the collector re-arms its timeout here
-        tick = tick + AFL_C.sample_period;
-    }
-    W.tick_time = tick; W.tick_seq = tseq; W.n_ticks = nt; W.seq = seq;
 }
 
 #if AFL_DEVICE
@@ -540,6 +593,8 @@ AFL_IN void start_replica(St& W, const Mem& m, uint64_t local_index) {
     for (int32_t i = 0; i < C.n_lb_edges; ++i) *w32(m, C.o32_lb + i) = (uint32_t)C.lb_edges[i];
 #pragma unroll 1
     for (int32_t j = 0; j < C.n_series; ++j) { *e64(m, C.o64_ssum + j) = 0; *w32(m, C.o32_smax + j) = 0; }
+#pragma unroll 1
+    for (int32_t w = 0; w < C.n_dirty; ++w) *w32(m, C.o32_dirty + w) = 0xFFFFFFFFu;      // no tick has read anything yet
     // sweep overrides of this replica: fields consumed here, fields looked up during the run (row copy)
     const bool has_row = C.n_sweep_cols > 0 && W.replica >= C.sweep_first && W.replica - C.sweep_first < C.sweep_rows;
     const double* row = C.sweep_vals + (has_row ? (W.replica - C.sweep_first) * (uint64_t)C.n_sweep_cols : 0);
@@ -573,9 +628,16 @@ AFL_IN void write_back(St& W, const Mem& m) {
         C.edge_dropped[local * (uint64_t)C.n_edges + (uint32_t)i] = *w32(m, C.o32_drop + i);
     }
 #pragma unroll 1
-    for (int32_t j = 0; j < C.n_series; ++j) {
-        C.samp_sum[local * (uint64_t)C.n_series + (uint32_t)j] = *e64(m, C.o64_ssum + j);
-        C.samp_max[local * (uint64_t)C.n_series + (uint32_t)j] = *w32(m, C.o32_smax + j);
+    for (int32_t j = 0; j < C.n_series; ++j) {       // settle the lazy aggregates (see gauge_touch)
+        uint64_t sum = 0; uint32_t mx = 0;
+        if (gauge_on(j)) {
+            const uint32_t v = gauge_value(m, j);
+            sum = (uint64_t)W.n_ticks * (uint64_t)v - *e64(m, C.o64_ssum + j);
+            mx = *w32(m, C.o32_smax + j);
+            if (!((*w32(m, C.o32_dirty + (j >> 5)) >> (j & 31)) & 1u) && v > mx) mx = v;
+        }
+        C.samp_sum[local * (uint64_t)C.n_series + (uint32_t)j] = sum;
+        C.samp_max[local * (uint64_t)C.n_series + (uint32_t)j] = mx;
     }
     AfReplicaStats st;
     st.n_events = W.n_events; st.generated = W.generated; st.completed = W.completed;
@@ -590,10 +652,20 @@ AFL_IN void write_back(St& W, const Mem& m) {
 // what a phase hands to the next one
 enum : uint32_t { A_NONE = 0, A_NODE, A_STEPS, A_SEND, A_TIMER };
 
+// Warp-wide rendez-vous between two phases.  Without it the lanes that split on the event kind stay split until
+// the top of the loop (the compiler's reconvergence point of a branch inside a loop with early exits is the loop
+// header): ncu r02a showed 4.3 active lanes in the SEND phase that 18 lanes need.  Every lane passes every
+// AFL_SYNC of an iteration -- no `continue` below.
+#if AFL_DEVICE
+#define AFL_SYNC() __syncwarp()
+#else
+#define AFL_SYNC() ((void)0)
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // The lane's life: pull a replica, run it to the horizon, write it back, pull the next.  `next_index`
 // returns the next local replica index or ~0 when the launch has no more work for this lane.
-// `converge` is a warp-wide rendez-vous at the top of every iteration (device: __syncwarp).
+// `converge` is a warp-wide rendez-vous at the top of every iteration (device: __any_sync).
 // ---------------------------------------------------------------------------------------------------
 template <class NextFn, class ConvFn>
 AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
@@ -604,33 +676,36 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
     for (;;) {
         if (!converge(active || !exhausted)) break;          // all lanes of the warp are done
         // ---- phase: lifecycle -------------------------------------------------------------------
-        if (AFL_UNLIKELY(!active)) {
-            if (exhausted) continue;
+        if (AFL_UNLIKELY(!active && !exhausted)) {
             const uint64_t r = next_index();
-            if (r == ~0ull) { exhausted = true; continue; }
-            start_replica(W, m, r);
-            // start order of the reference (simulation_runner.py:339-342, 301-336):
-            // spike timeline, outage timeline, generator, ..., collector
-            if (C.n_spike > 0) {
-                double f = ro(C.spikes).fire;
-                bool arm = true;
-                if (f == 0.0) arm = on_spike(W, m, f);
-                if (arm && f < W.horizon) { if (f == W.now) W.busy |= 1u; heap_push(W, m, afr::d2u(f), ((uint64_t)(W.seq++) << 32) | mk_payload(K_SPIKE, 0, 0)); }
+            if (r == ~0ull) exhausted = true;
+            else {
+                start_replica(W, m, r);
+                // start order of the reference (simulation_runner.py:339-342, 301-336):
+                // spike timeline, outage timeline, generator, ..., collector
+                if (C.n_spike > 0) {
+                    double f = ro(C.spikes).fire;
+                    bool arm = true;
+                    if (f == 0.0) arm = on_spike(W, m, f);
+                    if (arm && f < W.horizon) { if (f == W.now) W.busy |= 1u; heap_push(W, m, afr::d2u(f), ((uint64_t)(W.seq++) << 32) | mk_payload(K_SPIKE, 0, 0)); }
+                }
+                if (C.n_outage > 0) {
+                    double f = ro(C.outages).fire;
+                    bool arm = true;
+                    if (f == 0.0) arm = on_outage(W, m, f);
+                    if (arm && f < W.horizon) { if (f == W.now) W.busy |= 1u; heap_push(W, m, afr::d2u(f), ((uint64_t)(W.seq++) << 32) | mk_payload(K_OUTAGE, 0, 0)); }
+                }
+                W.arm_seq = W.seq++; W.need_arrival = 1;
+                W.tick_seq = W.seq++;
+                W.tick_time = 0.0 + C.sample_period;
+                active = true;
             }
-            if (C.n_outage > 0) {
-                double f = ro(C.outages).fire;
-                bool arm = true;
-                if (f == 0.0) arm = on_outage(W, m, f);
-                if (arm && f < W.horizon) { if (f == W.now) W.busy |= 1u; heap_push(W, m, afr::d2u(f), ((uint64_t)(W.seq++) << 32) | mk_payload(K_OUTAGE, 0, 0)); }
-            }
-            W.arm_seq = W.seq++; W.need_arrival = 1;
-            W.tick_seq = W.seq++;
-            W.tick_time = 0.0 + C.sample_period;
-            active = true;
         }
-        const bool dead = (W.flags & STOP_FLAGS) != 0;        // a pool overflowed in the last iteration: stop the replica here
+        AFL_SYNC();
+        const bool run = active;                              // a lane without a replica idles through the phases
+        const bool dead = run && (W.flags & STOP_FLAGS) != 0; // a pool overflowed in the last iteration: stop the replica here
         // ---- phase: the generator's next timeout (rqs_generator.py:103-104) ------------------------------
-        if (W.need_arrival && !dead) {
+        if (run && W.need_arrival && !dead) {
             W.need_arrival = 0;
             double gap;
             if (!W.g_done && gen_next_gap(W, gap)) {
@@ -641,47 +716,52 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 }
             } else W.g_done = 1;
         }
+        AFL_SYNC();
         // ---- phase: pick the next thing to run: a zero-delay item or the earliest timed event ------------
         uint32_t word = 0;                    // item or event payload
         bool is_item = false, finish = false, is_event = false;
         double t_ev = 0.0; uint32_t ev_seq = 0;
-        if (AFL_UNLIKELY(dead)) finish = true;
-        else {
-            const uint32_t busy = W.busy;
-            const bool have_item = busy >= 2u;
-            if (have_item && !(busy & 1u)) {         // no heap event shares this instant: just drain
-                W.busy = busy - 2u;
-                word = nq_take(W, m);
-                is_item = true;
-            } else {
-                const bool have_ev = W.ev_n > 0;
-                uint64_t tb = 0, key = 0;
-                if (have_ev) { tb = *ev_t(m, 0); key = *ev_k(m, 0); }
-                if (have_item) {
-                    const uint64_t front = *nq_at(m, W.nq_head);
-                    const bool same_t = have_ev && tb == afr::d2u(W.now);
-                    if (!(same_t && (uint32_t)(key >> 32) < (uint32_t)(front >> 32))) {
-                        W.busy = (same_t ? busy : (busy & ~1u)) - 2u;
-                        word = nq_take(W, m);
-                        is_item = true;
+        if (run) {
+            if (AFL_UNLIKELY(dead)) finish = true;
+            else {
+                const uint32_t busy = W.busy;
+                const bool have_item = busy >= 2u;
+                if (have_item && !(busy & 1u)) {         // no heap event shares this instant: just drain
+                    W.busy = busy - 2u;
+                    word = nq_take(W, m);
+                    is_item = true;
+                } else {
+                    const bool have_ev = W.ev_n > 0;
+                    uint64_t tb = 0, key = 0;
+                    if (have_ev) { tb = ev_t(m, 0); key = ev_k(m, 0); }
+                    if (have_item) {
+                        const uint64_t front = nq_ld(m, W.nq_head);
+                        const bool same_t = have_ev && tb == afr::d2u(W.now);
+                        if (!(same_t && (uint32_t)(key >> 32) < (uint32_t)(front >> 32))) {
+                            W.busy = (same_t ? busy : (busy & ~1u)) - 2u;
+                            word = nq_take(W, m);
+                            is_item = true;
+                        }
+                    } else if (!have_ev) finish = true;
+                    if (!is_item && !finish) {
+                        heap_pop(W, m);
+                        const bool more = W.ev_n > 0 && ev_t(m, 0) == tb;
+                        W.busy = (W.busy & ~1u) | (more ? 1u : 0u);
+                        t_ev = afr::u2d(tb); ev_seq = (uint32_t)(key >> 32); word = (uint32_t)key;
+                        is_event = true;
                     }
-                } else if (!have_ev) finish = true;
-                if (!is_item && !finish) {
-                    heap_pop(W, m);
-                    const bool more = W.ev_n > 0 && *ev_t(m, 0) == tb;
-                    W.busy = (W.busy & ~1u) | (more ? 1u : 0u);
-                    t_ev = afr::u2d(tb); ev_seq = (uint32_t)(key >> 32); word = (uint32_t)key;
-                    is_event = true;
                 }
             }
+            if (finish) { t_ev = W.horizon; ev_seq = 0u; }      // ticks strictly before the horizon
         }
-        if (finish) { t_ev = W.horizon; ev_seq = 0u; }      // ticks strictly before the horizon
+        AFL_SYNC();
         // ---- phase: collector ticks that fall before this event ------------------------------------------------
-        if (!is_item) {
+        if (run && !is_item) {
             const double tick = W.tick_time;
-            if (tick < t_ev || (tick == t_ev && W.tick_seq < ev_seq)) take_samples(W, m, t_ev, ev_seq);
+            if (tick < t_ev || (tick == t_ev && W.tick_seq < ev_seq)) take_ticks(W, m, t_ev, ev_seq);
         }
-        if (AFL_UNLIKELY(finish)) { write_back(W, m); active = false; continue; }
+        if (AFL_UNLIKELY(finish)) { write_back(W, m); active = false; }
+        AFL_SYNC();
         if (is_event) { W.now = t_ev; W.n_events += 1; }
 
         // ---- phase: decode -------------------------------------------------------------------------------------
@@ -692,24 +772,25 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
         double t0 = 0.0;
         double tm_t = 0.0; uint32_t tm_payload = 0, tm_seq = 0;
         AFL_TRACE("%s t=%.17g seq=%u kind=%u aux=%u slot=%u\n", is_item ? "it" : "ev", W.now, ev_seq, kind, aux, slot);
+        // everything that names a request reads its record here, once, for all kinds
+        const bool names_request = is_event ? (kind == K_DELIVER || kind == K_STEP_END) : (is_item && kind != I_CLIENT_LOOP && kind != I_PUT);
+        if (names_request) { rid = rq_rid(m, slot); pack = rq_pack(m, slot); t0 = rq_t0(m, slot); }
         if (is_event) {
             if (kind == K_DELIVER) {                          // edge.py:110-116: the edge's timeout fired
-                *w32(m, C.o32_conn + (int32_t)aux) -= 1;
+                conn_add(W, m, aux, -1);
                 const uint32_t meta = ro(C.edges + aux).meta;
-                pack = *rq_pack(m, slot) + 1;                  // record_hop(edge)
+                pack += 1;                                     // record_hop(edge)
                 const uint32_t tk = (meta >> 3) & 3u;
                 node = tk == AF_TARGET_CLIENT ? NODE_CLIENT : (tk == AF_TARGET_LB ? NODE_LB : NODE_SERVER0 + (meta >> 5));
-                if (can_fuse(W)) {                             // (implies: every inbox empty, every consumer in get())
-                    rid = *rq_rid(m, slot); t0 = *rq_t0(m, slot);
-                    act = A_NODE;                              // put -> pending get -> resume, nothing in between
-                } else {
-                    *rq_pack(m, slot) = pack;
+                if (can_fuse(W)) act = A_NODE;                 // put -> pending get -> resume, nothing in between
+                else {                                         // (fused implies: every inbox empty, every consumer in get())
+                    rq_pack_set(m, slot, pack);
                     fifo_push(m, ib_word(node, IB_HEAD), ib_word(node, IB_TAIL), slot);   // Store.put: items.append now ...
                     nq_push(W, m, I_PUT, node, slot);                                       // ... the put event is processed later
                 }
             } else if (kind == K_STEP_END) {
-                sidx = aux; rid = *rq_rid(m, slot);
-                pack = *rq_pack(m, slot) + (1u << 8);          // the timeout fired: next step
+                sidx = aux;
+                pack += (1u << 8);                             // the timeout fired: next step
                 act = A_STEPS;
             } else if (kind == K_ARRIVAL) {                   // rqs_generator.py:97-119
                 rid = ++W.generated;
@@ -719,7 +800,7 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 W.arm_seq = W.seq++;
                 W.need_arrival = 1;
                 if (slot != NIL) {
-                    *rq_t0(m, slot) = W.now; *rq_rid(m, slot) = rid; *rq_pack(m, slot) = 1u;   // record_hop(generator)
+                    rq_t0_set(m, slot, W.now); rq_rid_set(m, slot, rid);   // record_hop(generator): pack = 1 (stored by SEND)
                     pack = 1u; edge = (uint32_t)C.gen_edge;
                     act = A_SEND;
                 }
@@ -730,9 +811,9 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 double f;
                 if (on_outage(W, m, f)) { tm_t = f; tm_payload = mk_payload(K_OUTAGE, 0, 0); tm_seq = W.seq++; act = A_TIMER; }
             }
-        } else {
+        } else if (is_item) {
             if (kind == I_GOT) {
-                node = aux; rid = *rq_rid(m, slot); t0 = *rq_t0(m, slot); pack = *rq_pack(m, slot);
+                node = aux;
                 act = A_NODE;
             } else if (kind == I_PUT) {                        // a StorePut event is processed
                 if (*w32(m, ib_word(aux, IB_PENDING))) {
@@ -742,27 +823,27 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
             } else if (kind == I_CLIENT_LOOP) {
                 consumer_get(W, m, NODE_CLIENT);
             } else if (kind == I_RAM_OK) {                     // the RAM get event is processed: the handler resumes
-                sidx = aux; rid = *rq_rid(m, slot); pack = *rq_pack(m, slot);
-                *i32(m, sv_word(sidx, SV_RAM_IN_USE)) += (int32_t)ep_total_ram(m, pk_ep(pack));
+                sidx = aux;
+                srv_gauge_add(W, m, sidx, SV_RAM_IN_USE, (int32_t)ep_total_ram(m, pk_ep(pack)));
                 act = A_STEPS;
             } else if (kind == I_CPU_OK) {                     // the CPU get event is processed
-                sidx = aux; rid = *rq_rid(m, slot); pack = *rq_pack(m, slot);
-                if (pack & PK_WAIT) { pack &= ~PK_WAIT; *i32(m, sv_word(sidx, SV_READY_Q)) -= 1; }
+                sidx = aux;
+                if (pack & PK_WAIT) { pack &= ~PK_WAIT; srv_gauge_add(W, m, sidx, SV_READY_Q, -1); }
                 pack |= PK_CORE;
                 act = A_STEPS;
             } else if (kind == I_CPU_PUT) {                    // waiters are re-examined, then the request goes on
                 sidx = aux;
                 cpu_walk(W, m, sidx, NIL);
-                rid = *rq_rid(m, slot); pack = *rq_pack(m, slot) & ~PK_CORE;   // core_locked = False; same step again
+                pack &= ~PK_CORE;                              // core_locked = False; same step again
                 act = A_STEPS;
             } else {                                           // I_RAM_PUT: waiters first, then forward
                 sidx = aux;
                 ram_walk(W, m, sidx);
-                rid = *rq_rid(m, slot); pack = *rq_pack(m, slot);
                 edge = ro(C.servers + sidx).out_edge;
                 act = A_SEND;
             }
         }
+        AFL_SYNC();
 
         // ---- phase: a node's consumer process resumes with `slot` (the StoreGet event is processed) ---------------
         if (act == A_NODE) {
@@ -780,7 +861,7 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 }
                 const uint32_t ep_global = sp.ep_begin + epi;
                 pack = (pack & 0xFFu) | (ep_global << 16);     // step 0, flags clear
-                *rq_pack(m, slot) = pack;
+                rq_pack_set(m, slot, pack);
                 const uint32_t total_ram = ep_total_ram(m, ep_global);
                 bool go = true;
                 if (total_ram) {                               // yield RAM.get(total_ram)
@@ -792,7 +873,7 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                         go = false;
                     } else {
                         *i32(m, sv_word(sidx, SV_RAM_FREE)) -= (int32_t)total_ram;   // granted, and its get event would run next
-                        *i32(m, sv_word(sidx, SV_RAM_IN_USE)) += (int32_t)total_ram;
+                        srv_gauge_add(W, m, sidx, SV_RAM_IN_USE, (int32_t)total_ram);
                     }
                 }
                 if (go) act = A_STEPS;
@@ -804,36 +885,37 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                         if (can_fuse(W)) consumer_get(W, m, NODE_CLIENT);
                         else nq_push(W, m, I_CLIENT_LOOP, 0, 0);   // yield completed_box.put(state)
                     } else {
-                        *rq_pack(m, slot) = pack;
                         consumer_get(W, m, NODE_CLIENT);
                         edge = (uint32_t)C.client_edge;
                         act = A_SEND;
                     }
                 } else {
-                    *rq_pack(m, slot) = pack;
                     const int32_t lb = C.o32_lb, n = W.lb_n;
                     // every covered server is down: the reference dies here (StopIteration inside round_robin);
                     // the replica stops and says so (flatten() rejects timelines that can reach this state)
-                    if (AFL_UNLIKELY(n <= 0)) { W.flags |= AF_FLAG_LB_EMPTY; continue; }
-                    uint32_t pick = *w32(m, lb);
-                    if (C.lb_algo == AF_LB_ROUND_ROBIN) {      // lb_algorithms.py:22-36
+                    if (AFL_UNLIKELY(n <= 0)) { rq_pack_set(m, slot, pack); W.flags |= AF_FLAG_LB_EMPTY; }
+                    else {
+                        uint32_t pick = *w32(m, lb);
+                        if (C.lb_algo == AF_LB_ROUND_ROBIN) {      // lb_algorithms.py:22-36
 #pragma unroll 1
-                        for (int32_t i = 1; i < n; ++i) *w32(m, lb + i - 1) = *w32(m, lb + i);
-                        *w32(m, lb + n - 1) = pick;
-                    } else {                                   // least_connections, :10-20 (first min wins)
-                        uint32_t best = *w32(m, C.o32_conn + (int32_t)pick);
+                            for (int32_t i = 1; i < n; ++i) *w32(m, lb + i - 1) = *w32(m, lb + i);
+                            *w32(m, lb + n - 1) = pick;
+                        } else {                                   // least_connections, :10-20 (first min wins)
+                            uint32_t best = *w32(m, C.o32_conn + (int32_t)pick);
 #pragma unroll 1
-                        for (int32_t i = 1; i < n; ++i) {
-                            const uint32_t e2 = *w32(m, lb + i), c2 = *w32(m, C.o32_conn + (int32_t)e2);
-                            if (c2 < best) { best = c2; pick = e2; }
+                            for (int32_t i = 1; i < n; ++i) {
+                                const uint32_t e2 = *w32(m, lb + i), c2 = *w32(m, C.o32_conn + (int32_t)e2);
+                                if (c2 < best) { best = c2; pick = e2; }
+                            }
                         }
+                        consumer_get(W, m, NODE_LB);
+                        edge = pick;
+                        act = A_SEND;
                     }
-                    consumer_get(W, m, NODE_LB);
-                    edge = pick;
-                    act = A_SEND;
                 }
             }
         }
+        AFL_SYNC();
 
         // ---- phase: the `for step in endpoint.steps` loop (server.py:197-255) up to the request's next yield,
         //      and the tail of the handler (server.py:257-276) ---------------------------------------------------------
@@ -846,15 +928,15 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 if (st < ep.n_steps) {
                     const StepP sp = ro(C.steps + ep.step_begin + st);
                     if (sp.kind == AF_STEP_CPU) {
-                        if (pack & PK_IO) { pack &= ~PK_IO; *i32(m, sv_word(sidx, SV_IO_Q)) -= 1; }
+                        if (pack & PK_IO) { pack &= ~PK_IO; srv_gauge_add(W, m, sidx, SV_IO_Q, -1); }
                         if (!(pack & PK_CORE)) {             // cpu_req = CPU.get(1); yield cpu_req
                             if (*w32(m, sv_word(sidx, SV_CPUQ_HEAD)) == NIL && *i32(m, sv_word(sidx, SV_CPU_FREE)) > 0 && can_fuse(W)) {
                                 *i32(m, sv_word(sidx, SV_CPU_FREE)) -= 1;     // granted, and its get event would run next
                                 pack |= PK_CORE;
                             } else {
                                 fifo_push(m, sv_word(sidx, SV_CPUQ_HEAD), sv_word(sidx, SV_CPUQ_TAIL), slot);
-                                if (!cpu_walk(W, m, sidx, slot)) { pack |= PK_WAIT; *i32(m, sv_word(sidx, SV_READY_Q)) += 1; }   // not cpu_req.triggered
-                                *rq_pack(m, slot) = pack;
+                                if (!cpu_walk(W, m, sidx, slot)) { pack |= PK_WAIT; srv_gauge_add(W, m, sidx, SV_READY_Q, 1); }   // not cpu_req.triggered
+                                rq_pack_set(m, slot, pack);
                                 break;
                             }
                         }
@@ -866,13 +948,13 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                                 pack &= ~PK_CORE;
                                 continue;
                             }
-                            *rq_pack(m, slot) = pack;
+                            rq_pack_set(m, slot, pack);
                             nq_push(W, m, I_CPU_PUT, sidx, slot);
                             break;
                         }
-                        if (!(pack & PK_IO)) { pack |= PK_IO; *i32(m, sv_word(sidx, SV_IO_Q)) += 1; }
+                        if (!(pack & PK_IO)) { pack |= PK_IO; srv_gauge_add(W, m, sidx, SV_IO_Q, 1); }
                     }
-                    *rq_pack(m, slot) = pack;
+                    rq_pack_set(m, slot, pack);
                     const double dur = sp.c_dur >= 0 ? row_val(m, sp.c_dur) : sp.dur;
                     tm_t = W.now + dur; tm_payload = mk_payload(K_STEP_END, sidx, slot); tm_seq = W.seq++;
                     act = A_TIMER;
@@ -886,17 +968,16 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                         pack &= ~PK_CORE;
                         continue;
                     }
-                    *rq_pack(m, slot) = pack;
+                    rq_pack_set(m, slot, pack);
                     nq_push(W, m, I_CPU_PUT, sidx, slot);
                     break;
                 }
-                if (pack & PK_IO) { pack &= ~PK_IO; *i32(m, sv_word(sidx, SV_IO_Q)) -= 1; }
-                *rq_pack(m, slot) = pack;
+                if (pack & PK_IO) { pack &= ~PK_IO; srv_gauge_add(W, m, sidx, SV_IO_Q, -1); }
                 const uint32_t total_ram = ep.c_ram >= 0 ? (uint32_t)row_val(m, ep.c_ram) : ep.total_ram;
                 if (total_ram) {                             // yield RAM.put(total_ram): level rises NOW
-                    *i32(m, sv_word(sidx, SV_RAM_IN_USE)) -= (int32_t)total_ram;
+                    srv_gauge_add(W, m, sidx, SV_RAM_IN_USE, -(int32_t)total_ram);
                     *i32(m, sv_word(sidx, SV_RAM_FREE)) += (int32_t)total_ram;
-                    if (!can_fuse(W)) { nq_push(W, m, I_RAM_PUT, sidx, slot); break; }
+                    if (!can_fuse(W)) { rq_pack_set(m, slot, pack); nq_push(W, m, I_RAM_PUT, sidx, slot); break; }
                     if (AFL_UNLIKELY(*w32(m, sv_word(sidx, SV_RAMQ_HEAD)) != NIL)) ram_walk(W, m, sidx);   // the put event would run next: waiters, then forward
                 }
                 edge = ro(C.servers + sidx).out_edge;
@@ -904,6 +985,7 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 break;
             }
         }
+        AFL_SYNC();
 
         // ---- phase: EdgeRuntime.transport -> _deliver up to its timeout (edge.py:73-107) ---------------------------
         if (act == A_SEND) {
@@ -919,7 +1001,8 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 *w32(m, C.o32_drop + (int32_t)edge) += 1;
                 rq_release(W, m, slot);
             } else {
-                *w32(m, C.o32_conn + (int32_t)edge) += 1;
+                rq_pack_set(m, slot, pack);                  // (the one store of the record on the request's way out of a node)
+                conn_add(W, m, edge, 1);
                 double effective = d.transit;
                 if (C.n_spike > 0) effective = d.transit + *f64(m, C.o64_spike + (int32_t)edge);   // spike read at SEND time (edge.py:94-106)
                 else effective = d.transit + 0.0;           // (-0.0 + 0.0 = +0.0, as with a spike table of zeros)
@@ -927,6 +1010,7 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 act = A_TIMER;
             }
         }
+        AFL_SYNC();
 
         // ---- phase: schedule the timeout ------------------------------------------------------------------------------
         if (act == A_TIMER) {
@@ -935,7 +1019,6 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 heap_push(W, m, afr::d2u(tm_t), ((uint64_t)tm_seq << 32) | tm_payload);
             }
         }
-
     }
 }
 

@@ -83,7 +83,7 @@ constexpr int32_t LANE_REQUEST_CAPACITY = 2048;
 inline int32_t min_lane_bytes(const AfScenario& s, const Tables& t) {
     const int32_t n_series = 3 * s.n_servers + s.n_edges;
     const int32_t fix64 = (s.n_spike_marks > 0 ? s.n_edges : 0) + n_series + t.n_row;
-    const int32_t fix32 = 3 * s.n_edges + afl::SV_WORDS * s.n_servers + afl::IB_WORDS * (s.n_servers + 2) + s.n_lb_edges + n_series;
+    const int32_t fix32 = 3 * s.n_edges + afl::SV_WORDS * s.n_servers + afl::IB_WORDS * (s.n_servers + 2) + s.n_lb_edges + n_series + (n_series + 31) / 32;
     return 8 * fix64 + 4 * fix32 + 8 * 4 + 16 * 6 + 20 * 3;
 }
 
@@ -108,7 +108,8 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     if (rq_total > (int32_t)afl::SLOT_MASK) rq_total = (int32_t)afl::SLOT_MASK;
     // fixed part of a lane's shared memory
     const int32_t fix64 = (C.n_spike > 0 ? C.n_edges : 0) + C.n_series + C.n_row;
-    const int32_t fix32 = 3 * C.n_edges + afl::SV_WORDS * C.n_servers + afl::IB_WORDS * (C.n_servers + 2) + C.n_lb_edges + C.n_series;
+    C.n_dirty = (C.n_series + 31) / 32;
+    const int32_t fix32 = 3 * C.n_edges + afl::SV_WORDS * C.n_servers + afl::IB_WORDS * (C.n_servers + 2) + C.n_lb_edges + C.n_series + C.n_dirty;
     int32_t nq_s = 4;
     int32_t rest = lane_bytes - 8 * fix64 - 4 * fix32 - 8 * nq_s;
     // split the rest between pending events (16 B) and request records (20 B): at nominal load a request in
@@ -144,6 +145,7 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     C.o32_inbox = w; w += afl::IB_WORDS * (C.n_servers + 2);
     C.o32_lb = w; w += C.n_lb_edges;
     C.o32_smax = w; w += C.n_series;
+    C.o32_dirty = w; w += C.n_dirty;
     C.n32 = w;
     C.warp_bytes = (C.n64 * 8 + C.n32 * 4) * lanes;
     // global tier

@@ -93,7 +93,8 @@ extern "C" int af_twin_run_lane(const AfScenario* sc, const AfSweep* sw, uint64_
     C.seed = seed; C.replica_begin = replica_begin; C.n_replicas = n;
     std::vector<uint64_t> smem((size_t)C.warp_bytes / 8 + 2), glob((size_t)(C.gwarp_bytes / 8) + 2);
     afl::Mem m;
-    m.s64 = (unsigned char*)smem.data(); m.s32 = m.s64 + (size_t)C.n64 * afl::STRIDE64;
+    afl::afl_smem_host = (unsigned char*)smem.data();
+    m.s64 = 0u; m.s32 = (uint32_t)((size_t)C.n64 * afl::STRIDE64);
     m.g64 = (unsigned char*)glob.data(); m.g32 = m.g64 + (size_t)C.gn64 * afl::STRIDE64;
     uint64_t next = 0;
     afl::run_lane(m, [&]() -> uint64_t { return next < n ? next++ : ~0ull; }, [](bool alive) { return alive; });
