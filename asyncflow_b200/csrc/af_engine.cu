@@ -255,6 +255,7 @@ struct af_engine {
     // sweep
     int32_t sweep_cols = 0; uint64_t sweep_rows = 0, sweep_first = 0;
     std::vector<AfSweepColumn> h_sweep_cols;
+    std::vector<int32_t> h_sweep_alias;            // aflh::column_aliases of the uploaded values
     DevBuf d_sweep_cols, d_sweep_vals;
     // thread-per-replica pass: read-only tables (af_lane_host.h), global tiers, the list of flagged replicas
     int mode = AF_MODE_AUTO;
@@ -433,6 +434,7 @@ int af_sweep_upload(af_engine* e, const AfSweep* sw, uint64_t first_replica) {
             }
         }
     e->h_sweep_cols.assign(sw->columns, sw->columns + sw->n_columns);
+    e->h_sweep_alias = aflh::column_aliases(sw->values, sw->n_rows, sw->n_columns);
     size_t cb = (size_t)sw->n_columns * sizeof(AfSweepColumn), vb = (size_t)sw->n_columns * sw->n_rows * sizeof(double);
     AF_CUDA(e, e->d_sweep_cols.ensure(cb), "sweep columns");
     AF_CUDA(e, e->d_sweep_vals.ensure(vb), "sweep values");
@@ -444,7 +446,11 @@ int af_sweep_upload(af_engine* e, const AfSweep* sw, uint64_t first_replica) {
 }
 
 // shared-memory budget of one lane when the CTA has `warps` warps (one CTA per SM)
-static int32_t lane_budget(const af_engine* e, int warps) { return (int32_t)((e->max_smem_optin / (warps * 32)) & ~3); }
+static int32_t lane_budget(const af_engine* e, int warps) {
+    int32_t b = (int32_t)((e->max_smem_optin / (warps * 32)) & ~3);
+    if (const char* cap = getenv("ASYNCFLOW_B200_LANE_BYTES")) { const int32_t c = atoi(cap) & ~3; if (c > 0 && c < b) b = c; }   // experiments: leave more of the SM's 256 KB to L1
+    return b;
+}
 
 int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     if (!e) return AF_ERR_INVALID;
@@ -463,7 +469,10 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     int lane_warps = 0;
     if (lane) {
         std::string why;
-        if (!aflh::build_tables(e->sc, e->h_sweep_cols.data(), e->sweep_cols, e->lt, why)) {
+        // columns that repeat an earlier column share its slot -- only when every replica of this run has a sweep row
+        // (a replica outside the sweep takes each column's own base value)
+        const bool all_rows = e->sweep_cols > 0 && begin >= e->sweep_first && end - e->sweep_first <= e->sweep_rows;
+        if (!aflh::build_tables(e->sc, e->h_sweep_cols.data(), e->sweep_cols, all_rows ? e->h_sweep_alias.data() : nullptr, e->lt, why)) {
             if (e->mode == AF_MODE_LANE) return e->fail(AF_ERR_INVALID, why);
             lane = false;
         }
@@ -477,7 +486,8 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
         lane_warps = e->opt.warps_per_block > 0 ? e->opt.warps_per_block : AF_LANE_DEFAULT_WARPS;
         if (lane_warps > AF_LANE_MAX_THREADS / 32) lane_warps = AF_LANE_MAX_THREADS / 32;
         // fewer warps per SM when the topology's fixed tables need a larger share of shared memory
-        while (lane_warps > 1 && lane_budget(e, lane_warps) < aflh::min_lane_bytes(e->sc, e->lt) + 256) lane_warps /= 2;
+        while (lane_warps > 1 && lane_budget(e, lane_warps) < aflh::min_lane_bytes(e->sc, e->lt) + 64)
+            lane_warps -= lane_warps > 8 ? 4 : (lane_warps > 4 ? 2 : 1);
         memset(&C, 0, sizeof C);
         if (!aflh::make_cfg(e->sc, o, e->lt, lane_budget(e, lane_warps), afh::trace_tick_capacity(e->sc), 32, C)) {
             if (e->mode == AF_MODE_LANE) return e->fail(AF_ERR_INVALID, "scenario tables do not fit a lane's shared memory (thread-per-replica engine)");

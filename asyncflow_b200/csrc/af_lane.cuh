@@ -113,8 +113,9 @@ struct alignas(16) OutageP { double fire; int32_t lb_edge, down; };             
 struct ColP { int32_t field, index, slot, pad; double base; };     // one sweep column: slot = index into the lane's row copy (-1: consumed at start)
 
 // words of a server's mutable record (32-bit region)
-enum : int32_t { SV_CPU_FREE = 0, SV_RAM_FREE, SV_READY_Q, SV_IO_Q, SV_RAM_IN_USE, SV_RAMQ_HEAD, SV_RAMQ_TAIL,
-                 SV_CPUQ_HEAD, SV_CPUQ_TAIL, SV_RAMQ_NEED, SV_WORDS };
+enum : int32_t { SV_CPU_FREE = 0, SV_RAM_FREE, SV_READY_Q, SV_IO_Q, SV_RAM_IN_USE, SV_WORDS };
+// ... and of its cold record (global tier): the intrusive FIFOs of the RAM / CPU Containers' waiters
+enum : int32_t { SQ_RAMQ_HEAD = 0, SQ_RAMQ_TAIL, SQ_CPUQ_HEAD, SQ_CPUQ_TAIL, SQ_RAMQ_NEED, SQ_WORDS };
 enum : int32_t { IB_HEAD = 0, IB_TAIL, IB_PENDING, IB_WORDS };
 
 // Everything the kernel needs to know about one launch; built on the host (af_lane_host.h).
@@ -131,11 +132,12 @@ struct Cfg {
     int32_t ev_s, ev_total, rq_s, rq_total, nq_s;
     // shared-memory layout of a warp: 64-bit region (element offsets), then 32-bit region (word offsets)
     int32_t o64_evt, o64_evk, o64_t0, o64_nq, o64_spike, o64_ssum, o64_row, n64;
-    int32_t o32_rid, o32_pack, o32_next, o32_conn, o32_sent, o32_drop, o32_srv, o32_inbox, o32_lb, o32_smax, o32_dirty, n_dirty, n32;
+    int32_t o32_rid, o32_pack, o32_next, o32_conn, o32_sent, o32_srv, o32_lb, o32_smax, o32_dirty, n_dirty, n32;
     int32_t warp_bytes;                             // n64 * 256 + n32 * 128
     // global tier of a warp (same interleave): element / word offsets, sizes
     int32_t g64_evt, g64_evk, g64_t0, g64_nq, gn64;
-    int32_t g32_rid, g32_pack, g32_next, gn32;
+    int32_t g32_rid, g32_pack, g32_next, g32_cold, gn32;
+    int32_t c_srvq, c_inbox, c_drop;                // cold words (offsets from g32_cold): waiter FIFOs, mailboxes, drop counters
     uint64_t gwarp_bytes;                           // gn64 * 256 + gn32 * 128
     // device pointers
     const EdgeP* edges; const ServerP* servers; const EndpointP* endpoints; const StepP* steps;
@@ -176,41 +178,57 @@ template <class T> AFL_IN T ro(const T* p) {
 }
 
 // ---- the lane's memory ------------------------------------------------------------------------------
-// Shared memory is addressed by 32-bit byte offsets into ONE array the compiler knows to be shared (LDS / STS with
-// 32-bit address arithmetic; a generic 64-bit pointer costs twice the integer work per access -- ncu r02a: 36 % of
-// the executed instructions were address arithmetic).  A tiered table takes a BRANCH on "is it in shared memory",
-// not a pointer select: the shared side stays an LDS.
-#if AFL_DEVICE
-extern __shared__ __align__(16) unsigned char afl_smem[];
-#define AFL_SM afl_smem
-#else
-static unsigned char* afl_smem_host = nullptr;     // the twin's stand-in for the SM's shared memory
-#define AFL_SM afl_smem_host
-#endif
+// Shared memory is addressed by absolute 32-bit shared-window addresses through ld.shared / st.shared (one LDS /
+// STS, 32-bit address arithmetic).  Going through a pointer into an `extern __shared__` array costs four extra
+// instructions per access on sm_100a (S2R SR_CgaCtaId + MOV + LEA + IADD rebuild the window base every time:
+// ncu r02b, 33 % of the executed instructions), a generic pointer costs 64-bit arithmetic.  A tiered table takes a
+// BRANCH on "is it in shared memory", not a select.  All shared accesses are volatile asm: they keep program order.
 struct Mem {
-    uint32_t s64, s32;                          // shared-memory regions of the warp (byte offsets, the lane's column)
+    uint32_t s64, s32;                          // shared-memory regions of the warp (window addresses, the lane's column)
     unsigned char* g64; unsigned char* g32;     // global tier of the warp, already offset by the lane
 };
-AFL_IN uint64_t* e64(const Mem& m, int32_t elem) { return reinterpret_cast<uint64_t*>(AFL_SM + (m.s64 + (uint32_t)elem * (uint32_t)STRIDE64)); }
-AFL_IN double* f64(const Mem& m, int32_t elem) { return reinterpret_cast<double*>(AFL_SM + (m.s64 + (uint32_t)elem * (uint32_t)STRIDE64)); }
-AFL_IN uint32_t* w32(const Mem& m, int32_t word) { return reinterpret_cast<uint32_t*>(AFL_SM + (m.s32 + (uint32_t)word * (uint32_t)STRIDE32)); }
-AFL_IN int32_t* i32(const Mem& m, int32_t word) { return reinterpret_cast<int32_t*>(AFL_SM + (m.s32 + (uint32_t)word * (uint32_t)STRIDE32)); }
+#if AFL_DEVICE
+AFL_IN uint32_t sm_ld32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+AFL_IN void sm_st32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v)); }
+AFL_IN uint64_t sm_ld64(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+AFL_IN void sm_st64(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" :: "r"(a), "l"(v)); }
+#else
+static unsigned char* afl_smem_host = nullptr;     // the twin's stand-in for the SM's shared memory
+AFL_IN uint32_t sm_ld32(uint32_t a) { uint32_t v; memcpy(&v, afl_smem_host + a, 4); return v; }
+AFL_IN void sm_st32(uint32_t a, uint32_t v) { memcpy(afl_smem_host + a, &v, 4); }
+AFL_IN uint64_t sm_ld64(uint32_t a) { uint64_t v; memcpy(&v, afl_smem_host + a, 8); return v; }
+AFL_IN void sm_st64(uint32_t a, uint64_t v) { memcpy(afl_smem_host + a, &v, 8); }
+#endif
+AFL_IN uint32_t a64(const Mem& m, int32_t elem) { return m.s64 + (uint32_t)elem * (uint32_t)STRIDE64; }
+AFL_IN uint32_t a32(const Mem& m, int32_t word) { return m.s32 + (uint32_t)word * (uint32_t)STRIDE32; }
+AFL_IN uint64_t e64_ld(const Mem& m, int32_t elem) { return sm_ld64(a64(m, elem)); }
+AFL_IN void e64_st(const Mem& m, int32_t elem, uint64_t v) { sm_st64(a64(m, elem), v); }
+AFL_IN double f64_ld(const Mem& m, int32_t elem) { return afr::u2d(sm_ld64(a64(m, elem))); }
+AFL_IN void f64_st(const Mem& m, int32_t elem, double v) { sm_st64(a64(m, elem), afr::d2u(v)); }
+AFL_IN uint32_t w32_ld(const Mem& m, int32_t word) { return sm_ld32(a32(m, word)); }
+AFL_IN void w32_st(const Mem& m, int32_t word, uint32_t v) { sm_st32(a32(m, word), v); }
+AFL_IN int32_t i32_ld(const Mem& m, int32_t word) { return (int32_t)sm_ld32(a32(m, word)); }
+AFL_IN void i32_st(const Mem& m, int32_t word, int32_t v) { sm_st32(a32(m, word), (uint32_t)v); }
 AFL_IN uint64_t* g64p(const Mem& m, int32_t elem) { return reinterpret_cast<uint64_t*>(m.g64 + (size_t)(uint32_t)elem * STRIDE64); }
 AFL_IN uint32_t* g32p(const Mem& m, int32_t word) { return reinterpret_cast<uint32_t*>(m.g32 + (size_t)(uint32_t)word * STRIDE32); }
+// cold words (global tier only): queue links of the Stores and Containers, drop counters -- touched at ties, under
+// contention, on a dropped request
+AFL_IN uint32_t c32_ld(const Mem& m, int32_t word) { return *g32p(m, AFL_C.g32_cold + word); }
+AFL_IN void c32_st(const Mem& m, int32_t word, uint32_t v) { *g32p(m, AFL_C.g32_cold + word) = v; }
 // tiered: entry idx of a table whose first `split` entries are in shared memory
 AFL_IN uint64_t ld_t64(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split) {
-    if (AFL_LIKELY(idx < split)) return *e64(m, os + idx);
+    if (AFL_LIKELY(idx < split)) return e64_ld(m, os + idx);
     return *g64p(m, og + idx - split);
 }
 AFL_IN void st_t64(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split, uint64_t v) {
-    if (AFL_LIKELY(idx < split)) *e64(m, os + idx) = v; else *g64p(m, og + idx - split) = v;
+    if (AFL_LIKELY(idx < split)) e64_st(m, os + idx, v); else *g64p(m, og + idx - split) = v;
 }
 AFL_IN uint32_t ld_t32(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split) {
-    if (AFL_LIKELY(idx < split)) return *w32(m, os + idx);
+    if (AFL_LIKELY(idx < split)) return w32_ld(m, os + idx);
     return *g32p(m, og + idx - split);
 }
 AFL_IN void st_t32(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split, uint32_t v) {
-    if (AFL_LIKELY(idx < split)) *w32(m, os + idx) = v; else *g32p(m, og + idx - split) = v;
+    if (AFL_LIKELY(idx < split)) w32_st(m, os + idx, v); else *g32p(m, og + idx - split) = v;
 }
 
 // the replica's scalar state: registers (nothing here is indexed dynamically)
@@ -220,6 +238,7 @@ struct St {
     uint32_t seq; int32_t ev_n; uint32_t peak_ev;
     uint32_t nq_head, nq_tail, busy;            // busy = 2 * (items in the now-queue) + (the heap may hold an event of this instant)
     uint32_t rq_free, rq_hw, rq_live, peak_rq;
+    uint32_t n_waiting;                         // requests parked in a RAM / CPU waiter FIFO (0: every such FIFO is empty, no need to look)
     double g_vnow, g_wend, g_lam;               // generator: the sampler's virtual clock (the simulation's is `now`)
     uint32_t g_pos, generated, g_done, need_arrival, arm_seq;
     double users_mean, users_sigma, rate_per_user;
@@ -234,7 +253,7 @@ struct St {
 constexpr uint32_t STOP_FLAGS = AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW | AF_FLAG_NOWQ_OVERFLOW | AF_FLAG_LB_EMPTY;
 
 // ---- swept parameters ----------------------------------------------------------------------------
-AFL_IN double row_val(const Mem& m, int32_t c) { return *f64(m, AFL_C.o64_row + c); }
+AFL_IN double row_val(const Mem& m, int32_t c) { return f64_ld(m, AFL_C.o64_row + c); }
 AFL_IN uint32_t ep_total_ram(const Mem& m, uint32_t ep) {
     const EndpointP p = ro(AFL_C.endpoints + ep);
     return p.c_ram >= 0 ? (uint32_t)row_val(m, p.c_ram) : p.total_ram;
@@ -261,18 +280,18 @@ AFL_IN uint32_t rq_alloc(St& W, const Mem& m) {
 }
 AFL_IN void rq_release(St& W, const Mem& m, uint32_t s) { rq_next_set(m, s, W.rq_free); W.rq_free = s; --W.rq_live; }
 
-// intrusive FIFOs through the `next` links; head / tail are words of the 32-bit region
+// intrusive FIFOs through the `next` links; head / tail are COLD words
 AFL_IN void fifo_push(const Mem& m, int32_t w_head, int32_t w_tail, uint32_t s) {
     rq_next_set(m, s, NIL);
-    const uint32_t tail = *w32(m, w_tail);
-    if (tail == NIL) *w32(m, w_head) = s; else rq_next_set(m, tail, s);
-    *w32(m, w_tail) = s;
+    const uint32_t tail = c32_ld(m, w_tail);
+    if (tail == NIL) c32_st(m, w_head, s); else rq_next_set(m, tail, s);
+    c32_st(m, w_tail, s);
 }
 AFL_IN uint32_t fifo_pop(const Mem& m, int32_t w_head, int32_t w_tail) {
-    const uint32_t s = *w32(m, w_head);
+    const uint32_t s = c32_ld(m, w_head);
     const uint32_t h = rq_next(m, s);
-    *w32(m, w_head) = h;
-    if (h == NIL) *w32(m, w_tail) = NIL;
+    c32_st(m, w_head, h);
+    if (h == NIL) c32_st(m, w_tail, NIL);
     return s;
 }
 
@@ -384,35 +403,36 @@ AFL_IN bool gen_next_gap(St& W, double& gap) {
 // (u64 modular arithmetic: exact), and the maximum over ticks takes the OLD value at a change iff a tick has seen it
 // (one "changed since the last tick" bit per series, cleared by a tick).  Traced replicas also store every reading.
 AFL_IN void gauge_touch(const St& W, const Mem& m, int32_t j, uint32_t v_old, int32_t delta) {
-    uint64_t* acc = e64(m, AFL_C.o64_ssum + j);
-    *acc = *acc + (uint64_t)(int64_t)delta * (uint64_t)W.n_ticks;
-    uint32_t* dw = w32(m, AFL_C.o32_dirty + (j >> 5));
-    const uint32_t d = *dw, bit = 1u << (j & 31);
+    const uint32_t aa = a64(m, AFL_C.o64_ssum + j);
+    sm_st64(aa, sm_ld64(aa) + (uint64_t)(int64_t)delta * (uint64_t)W.n_ticks);
+    const uint32_t da = a32(m, AFL_C.o32_dirty + (j >> 5));
+    const uint32_t d = sm_ld32(da), bit = 1u << (j & 31);
     if (!(d & bit)) {
-        uint32_t* mx = w32(m, AFL_C.o32_smax + j);
-        if (v_old > *mx) *mx = v_old;
-        *dw = d | bit;
+        const uint32_t ma = a32(m, AFL_C.o32_smax + j);
+        if (v_old > sm_ld32(ma)) sm_st32(ma, v_old);
+        sm_st32(da, d | bit);
     }
 }
 AFL_IN void conn_add(const St& W, const Mem& m, uint32_t edge, int32_t delta) {
-    uint32_t* p = w32(m, AFL_C.o32_conn + (int32_t)edge);
-    const uint32_t v = *p;
+    const uint32_t pa = a32(m, AFL_C.o32_conn + (int32_t)edge);
+    const uint32_t v = sm_ld32(pa);
     if (AFL_C.metrics_mask & AF_METRIC_EDGE_CONN) gauge_touch(W, m, 3 * AFL_C.n_servers + (int32_t)edge, v, delta);
-    *p = v + (uint32_t)delta;
+    sm_st32(pa, v + (uint32_t)delta);
 }
-AFL_IN int32_t ib_word(uint32_t node, int32_t f) { return AFL_C.o32_inbox + (int32_t)node * IB_WORDS + f; }
+AFL_IN int32_t ib_word(uint32_t node, int32_t f) { return AFL_C.c_inbox + (int32_t)node * IB_WORDS + f; }      // cold
+AFL_IN int32_t sq_word(uint32_t sidx, int32_t f) { return AFL_C.c_srvq + (int32_t)sidx * SQ_WORDS + f; }       // cold
 AFL_IN int32_t sv_word(uint32_t sidx, int32_t f) { return AFL_C.o32_srv + (int32_t)sidx * SV_WORDS + f; }
 // field = SV_READY_Q / SV_IO_Q / SV_RAM_IN_USE (series 3 * sidx + 0 / 1 / 2)
 AFL_IN void srv_gauge_add(const St& W, const Mem& m, uint32_t sidx, int32_t field, int32_t delta) {
-    int32_t* p = i32(m, sv_word(sidx, field));
-    const int32_t v = *p;
+    const uint32_t pa = a32(m, sv_word(sidx, field));
+    const int32_t v = (int32_t)sm_ld32(pa);
     if ((AFL_C.metrics_mask & 7u) == 7u) gauge_touch(W, m, 3 * (int32_t)sidx + (field - SV_READY_Q), (uint32_t)v, delta);
-    *p = v + delta;
+    sm_st32(pa, (uint32_t)(v + delta));
 }
 AFL_IN uint32_t gauge_value(const Mem& m, int32_t j) {
     const int32_t ns3 = 3 * AFL_C.n_servers;
-    if (j < ns3) { const int32_t mt = j % 3; return *w32(m, sv_word((uint32_t)(j / 3), mt == 0 ? SV_READY_Q : (mt == 1 ? SV_IO_Q : SV_RAM_IN_USE))); }
-    return *w32(m, AFL_C.o32_conn + (j - ns3));
+    if (j < ns3) { const int32_t mt = j % 3; return w32_ld(m, sv_word((uint32_t)(j / 3), mt == 0 ? SV_READY_Q : (mt == 1 ? SV_IO_Q : SV_RAM_IN_USE))); }
+    return w32_ld(m, AFL_C.o32_conn + (j - ns3));
 }
 AFL_IN bool gauge_on(int32_t j) {
     return j < 3 * AFL_C.n_servers ? (AFL_C.metrics_mask & 7u) == 7u          // collector.py:60-63
@@ -436,27 +456,30 @@ AFL_IN void take_ticks(St& W, const Mem& m, double t, uint32_t ev_seq) {
     }
     if (nt != W.n_ticks) {                            // every gauge has now been read at its current value
 #pragma unroll 1
-        for (int32_t w = 0; w < AFL_C.n_dirty; ++w) *w32(m, AFL_C.o32_dirty + w) = 0u;
+        for (int32_t w = 0; w < AFL_C.n_dirty; ++w) w32_st(m, AFL_C.o32_dirty + w, 0u);
     }
     W.tick_time = tick; W.tick_seq = tseq; W.n_ticks = nt; W.seq = seq;
 }
 
 // ---- Stores (mailboxes), Containers: as af_core.cuh ----------------------------------------------------
+// is the waiter FIFO whose head is cold word `head` empty?  (n_waiting == 0: all of them are, without looking)
+AFL_IN bool q_empty(const St& W, const Mem& m, int32_t head) { return AFL_LIKELY(W.n_waiting == 0) || c32_ld(m, head) == NIL; }
 // `yield box.get()` of the node's consumer process
 AFL_IN void consumer_get(St& W, const Mem& m, uint32_t node) {
-    if (AFL_UNLIKELY(*w32(m, ib_word(node, IB_HEAD)) != NIL)) {
+    if (AFL_UNLIKELY(c32_ld(m, ib_word(node, IB_HEAD)) != NIL)) {
         const uint32_t it = fifo_pop(m, ib_word(node, IB_HEAD), ib_word(node, IB_TAIL));
         nq_push(W, m, I_GOT, node, it);
-    } else *w32(m, ib_word(node, IB_PENDING)) = 1;
+    } else c32_st(m, ib_word(node, IB_PENDING), 1);
 }
 // Container._trigger_get over the CPU queue: grant heads while a core is free
 // (returns true when `watch` was among the granted: its get is "triggered" at the call)
 AFL_IN bool cpu_walk(St& W, const Mem& m, uint32_t sidx, uint32_t watch) {
     bool hit = false;
 #pragma unroll 1
-    while (*w32(m, sv_word(sidx, SV_CPUQ_HEAD)) != NIL && *i32(m, sv_word(sidx, SV_CPU_FREE)) > 0) {
-        const uint32_t w = fifo_pop(m, sv_word(sidx, SV_CPUQ_HEAD), sv_word(sidx, SV_CPUQ_TAIL));
-        *i32(m, sv_word(sidx, SV_CPU_FREE)) -= 1;
+    while (!q_empty(W, m, sq_word(sidx, SQ_CPUQ_HEAD)) && i32_ld(m, sv_word(sidx, SV_CPU_FREE)) > 0) {
+        const uint32_t w = fifo_pop(m, sq_word(sidx, SQ_CPUQ_HEAD), sq_word(sidx, SQ_CPUQ_TAIL));
+        W.n_waiting -= 1;
+        i32_st(m, sv_word(sidx, SV_CPU_FREE), i32_ld(m, sv_word(sidx, SV_CPU_FREE)) - 1);
         hit = hit || w == watch;
         nq_push(W, m, I_CPU_OK, sidx, w);
     }
@@ -465,13 +488,14 @@ AFL_IN bool cpu_walk(St& W, const Mem& m, uint32_t sidx, uint32_t watch) {
 // ... over the RAM queue: grant heads while they fit, stop at the first that does not
 AFL_IN void ram_walk(St& W, const Mem& m, uint32_t sidx) {
 #pragma unroll 1
-    while (*w32(m, sv_word(sidx, SV_RAMQ_HEAD)) != NIL) {
-        const uint32_t need = *w32(m, sv_word(sidx, SV_RAMQ_NEED));
-        if ((int32_t)need > *i32(m, sv_word(sidx, SV_RAM_FREE))) break;
-        const uint32_t w = fifo_pop(m, sv_word(sidx, SV_RAMQ_HEAD), sv_word(sidx, SV_RAMQ_TAIL));
-        const uint32_t h = *w32(m, sv_word(sidx, SV_RAMQ_HEAD));
-        if (h != NIL) *w32(m, sv_word(sidx, SV_RAMQ_NEED)) = ep_total_ram(m, pk_ep(rq_pack(m, h)));
-        *i32(m, sv_word(sidx, SV_RAM_FREE)) -= (int32_t)need;
+    while (!q_empty(W, m, sq_word(sidx, SQ_RAMQ_HEAD))) {
+        const uint32_t need = c32_ld(m, sq_word(sidx, SQ_RAMQ_NEED));
+        if ((int32_t)need > i32_ld(m, sv_word(sidx, SV_RAM_FREE))) break;
+        const uint32_t w = fifo_pop(m, sq_word(sidx, SQ_RAMQ_HEAD), sq_word(sidx, SQ_RAMQ_TAIL));
+        W.n_waiting -= 1;
+        const uint32_t h = c32_ld(m, sq_word(sidx, SQ_RAMQ_HEAD));
+        if (h != NIL) c32_st(m, sq_word(sidx, SQ_RAMQ_NEED), ep_total_ram(m, pk_ep(rq_pack(m, h))));
+        i32_st(m, sv_word(sidx, SV_RAM_FREE), i32_ld(m, sv_word(sidx, SV_RAM_FREE)) - (int32_t)need);
         nq_push(W, m, I_RAM_OK, sidx, w);
     }
 }
@@ -486,8 +510,7 @@ AFL_IN bool on_spike(St& W, const Mem& m, double& next_fire) {
         if (p.fire != t) break;
         double delta = p.delta;
         if (p.c_delta >= 0) { const double v = row_val(m, p.c_delta); delta = delta < 0.0 ? -v : v; }
-        double* sp = f64(m, AFL_C.o64_spike + (int32_t)p.edge);
-        *sp = *sp + delta;
+        f64_st(m, AFL_C.o64_spike + (int32_t)p.edge, f64_ld(m, AFL_C.o64_spike + (int32_t)p.edge) + delta);
         ++cur;
     }
     W.spike_cur = cur;
@@ -507,13 +530,13 @@ AFL_IN bool on_outage(St& W, const Mem& m, double& next_fire) {
         if (p.lb_edge < 0) continue;
         int32_t at = -1;
 #pragma unroll 1
-        for (int32_t i = 0; i < n; ++i) if (*w32(m, lb + i) == (uint32_t)p.lb_edge) { at = i; break; }
+        for (int32_t i = 0; i < n; ++i) if (w32_ld(m, lb + i) == (uint32_t)p.lb_edge) { at = i; break; }
         if (at >= 0) {                               // pop (DOWN) or move_to_end (UP)
 #pragma unroll 1
-            for (int32_t i = at + 1; i < n; ++i) *w32(m, lb + i - 1) = *w32(m, lb + i);
+            for (int32_t i = at + 1; i < n; ++i) w32_st(m, lb + i - 1, w32_ld(m, lb + i));
             --n;
         }
-        if (!p.down) { *w32(m, lb + n) = (uint32_t)p.lb_edge; ++n; }
+        if (!p.down) { w32_st(m, lb + n, (uint32_t)p.lb_edge); ++n; }
     }
     W.lb_n = n;
     W.outage_cur = cur;
@@ -564,7 +587,7 @@ AFL_IN void start_replica(St& W, const Mem& m, uint64_t local_index) {
     W.now = 0.0; W.horizon = (double)C.horizon_s; W.seq = 0;
     W.ev_n = 0; W.peak_ev = 0;
     W.nq_head = 0; W.nq_tail = 0; W.busy = 0;
-    W.rq_free = NIL; W.rq_hw = 0; W.rq_live = 0; W.peak_rq = 0;
+    W.rq_free = NIL; W.rq_hw = 0; W.rq_live = 0; W.peak_rq = 0; W.n_waiting = 0;
     W.g_vnow = 0.0; W.g_wend = 0.0; W.g_lam = 0.0; W.g_pos = 0; W.generated = 0; W.g_done = 0;
     W.lb_n = C.n_lb_edges; W.spike_cur = 0; W.outage_cur = 0;
     W.n_ticks = 0; W.completed = 0; W.flags = 0; W.n_events = 0;
@@ -573,28 +596,28 @@ AFL_IN void start_replica(St& W, const Mem& m, uint64_t local_index) {
     W.users_mean = C.users_mean; W.users_sigma = C.users_sigma; W.rate_per_user = C.rate_per_user;
 #pragma unroll 1
     for (int32_t i = 0; i < C.n_edges; ++i) {
-        *w32(m, C.o32_conn + i) = 0; *w32(m, C.o32_sent + i) = 0; *w32(m, C.o32_drop + i) = 0;
-        if (C.n_spike > 0) *f64(m, C.o64_spike + i) = 0.0;
+        w32_st(m, C.o32_conn + i, 0); w32_st(m, C.o32_sent + i, 0); c32_st(m, C.c_drop + i, 0);
+        if (C.n_spike > 0) f64_st(m, C.o64_spike + i, 0.0);
     }
 #pragma unroll 1
     for (int32_t i = 0; i < C.n_servers; ++i) {
         const ServerP p = ro(C.servers + i);
-        *i32(m, sv_word((uint32_t)i, SV_CPU_FREE)) = p.cpu_cores; *i32(m, sv_word((uint32_t)i, SV_RAM_FREE)) = p.ram_mb;
-        *i32(m, sv_word((uint32_t)i, SV_READY_Q)) = 0; *i32(m, sv_word((uint32_t)i, SV_IO_Q)) = 0; *i32(m, sv_word((uint32_t)i, SV_RAM_IN_USE)) = 0;
-        *w32(m, sv_word((uint32_t)i, SV_RAMQ_HEAD)) = NIL; *w32(m, sv_word((uint32_t)i, SV_RAMQ_TAIL)) = NIL;
-        *w32(m, sv_word((uint32_t)i, SV_CPUQ_HEAD)) = NIL; *w32(m, sv_word((uint32_t)i, SV_CPUQ_TAIL)) = NIL;
-        *w32(m, sv_word((uint32_t)i, SV_RAMQ_NEED)) = 0;
+        i32_st(m, sv_word((uint32_t)i, SV_CPU_FREE), p.cpu_cores); i32_st(m, sv_word((uint32_t)i, SV_RAM_FREE), p.ram_mb);
+        i32_st(m, sv_word((uint32_t)i, SV_READY_Q), 0); i32_st(m, sv_word((uint32_t)i, SV_IO_Q), 0); i32_st(m, sv_word((uint32_t)i, SV_RAM_IN_USE), 0);
+        c32_st(m, sq_word((uint32_t)i, SQ_RAMQ_HEAD), NIL); c32_st(m, sq_word((uint32_t)i, SQ_RAMQ_TAIL), NIL);
+        c32_st(m, sq_word((uint32_t)i, SQ_CPUQ_HEAD), NIL); c32_st(m, sq_word((uint32_t)i, SQ_CPUQ_TAIL), NIL);
+        c32_st(m, sq_word((uint32_t)i, SQ_RAMQ_NEED), 0);
     }
 #pragma unroll 1
     for (int32_t i = 0; i < C.n_servers + 2; ++i) {
-        *w32(m, ib_word((uint32_t)i, IB_HEAD)) = NIL; *w32(m, ib_word((uint32_t)i, IB_TAIL)) = NIL; *w32(m, ib_word((uint32_t)i, IB_PENDING)) = 1;
+        c32_st(m, ib_word((uint32_t)i, IB_HEAD), NIL); c32_st(m, ib_word((uint32_t)i, IB_TAIL), NIL); c32_st(m, ib_word((uint32_t)i, IB_PENDING), 1);
     }
 #pragma unroll 1
-    for (int32_t i = 0; i < C.n_lb_edges; ++i) *w32(m, C.o32_lb + i) = (uint32_t)C.lb_edges[i];
+    for (int32_t i = 0; i < C.n_lb_edges; ++i) w32_st(m, C.o32_lb + i, (uint32_t)C.lb_edges[i]);
 #pragma unroll 1
-    for (int32_t j = 0; j < C.n_series; ++j) { *e64(m, C.o64_ssum + j) = 0; *w32(m, C.o32_smax + j) = 0; }
+    for (int32_t j = 0; j < C.n_series; ++j) { e64_st(m, C.o64_ssum + j, 0); w32_st(m, C.o32_smax + j, 0); }
 #pragma unroll 1
-    for (int32_t w = 0; w < C.n_dirty; ++w) *w32(m, C.o32_dirty + w) = 0xFFFFFFFFu;      // no tick has read anything yet
+    for (int32_t w = 0; w < C.n_dirty; ++w) w32_st(m, C.o32_dirty + w, 0xFFFFFFFFu);      // no tick has read anything yet
     // sweep overrides of this replica: fields consumed here, fields looked up during the run (row copy)
     const bool has_row = C.n_sweep_cols > 0 && W.replica >= C.sweep_first && W.replica - C.sweep_first < C.sweep_rows;
     const double* row = C.sweep_vals + (has_row ? (W.replica - C.sweep_first) * (uint64_t)C.n_sweep_cols : 0);
@@ -602,14 +625,14 @@ AFL_IN void start_replica(St& W, const Mem& m, uint64_t local_index) {
     for (int32_t c = 0; c < C.n_sweep_cols; ++c) {
         const ColP col = C.cols[c];
         const double v = has_row ? row[c] : col.base;
-        if (col.slot >= 0) { *f64(m, C.o64_row + col.slot) = v; continue; }
+        if (col.slot >= 0) { f64_st(m, C.o64_row + col.slot, v); continue; }
         if (!has_row) continue;
         switch (col.field) {
         case AF_FIELD_USERS_MEAN: W.users_mean = v; break;
         case AF_FIELD_USERS_SIGMA: W.users_sigma = v; break;
         case AF_FIELD_RATE_PER_USER: W.rate_per_user = v; break;
-        case AF_FIELD_SERVER_CPU_CORES: *i32(m, sv_word((uint32_t)col.index, SV_CPU_FREE)) = (int32_t)v; break;
-        case AF_FIELD_SERVER_RAM_MB: *i32(m, sv_word((uint32_t)col.index, SV_RAM_FREE)) = (int32_t)v; break;
+        case AF_FIELD_SERVER_CPU_CORES: i32_st(m, sv_word((uint32_t)col.index, SV_CPU_FREE), (int32_t)v); break;
+        case AF_FIELD_SERVER_RAM_MB: i32_st(m, sv_word((uint32_t)col.index, SV_RAM_FREE), (int32_t)v); break;
         default: break;
         }
     }
@@ -624,17 +647,17 @@ AFL_IN void write_back(St& W, const Mem& m) {
     const uint64_t local = W.local;
 #pragma unroll 1
     for (int32_t i = 0; i < C.n_edges; ++i) {
-        C.edge_sent[local * (uint64_t)C.n_edges + (uint32_t)i] = *w32(m, C.o32_sent + i);
-        C.edge_dropped[local * (uint64_t)C.n_edges + (uint32_t)i] = *w32(m, C.o32_drop + i);
+        C.edge_sent[local * (uint64_t)C.n_edges + (uint32_t)i] = w32_ld(m, C.o32_sent + i);
+        C.edge_dropped[local * (uint64_t)C.n_edges + (uint32_t)i] = c32_ld(m, C.c_drop + i);
     }
 #pragma unroll 1
     for (int32_t j = 0; j < C.n_series; ++j) {       // settle the lazy aggregates (see gauge_touch)
         uint64_t sum = 0; uint32_t mx = 0;
         if (gauge_on(j)) {
             const uint32_t v = gauge_value(m, j);
-            sum = (uint64_t)W.n_ticks * (uint64_t)v - *e64(m, C.o64_ssum + j);
-            mx = *w32(m, C.o32_smax + j);
-            if (!((*w32(m, C.o32_dirty + (j >> 5)) >> (j & 31)) & 1u) && v > mx) mx = v;
+            sum = (uint64_t)W.n_ticks * (uint64_t)v - e64_ld(m, C.o64_ssum + j);
+            mx = w32_ld(m, C.o32_smax + j);
+            if (!((w32_ld(m, C.o32_dirty + (j >> 5)) >> (j & 31)) & 1u) && v > mx) mx = v;
         }
         C.samp_sum[local * (uint64_t)C.n_series + (uint32_t)j] = sum;
         C.samp_max[local * (uint64_t)C.n_series + (uint32_t)j] = mx;
@@ -769,6 +792,7 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
         uint32_t slot = word & SLOT_MASK;
         uint32_t act = A_NONE;
         uint32_t node = 0, sidx = 0, rid = 0, pack = 0, edge = 0;
+        bool from_box = true;                  // A_NODE reached through the mailbox (an I_GOT item), not fused with the delivery
         double t0 = 0.0;
         double tm_t = 0.0; uint32_t tm_payload = 0, tm_seq = 0;
         AFL_TRACE("%s t=%.17g seq=%u kind=%u aux=%u slot=%u\n", is_item ? "it" : "ev", W.now, ev_seq, kind, aux, slot);
@@ -782,7 +806,7 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 pack += 1;                                     // record_hop(edge)
                 const uint32_t tk = (meta >> 3) & 3u;
                 node = tk == AF_TARGET_CLIENT ? NODE_CLIENT : (tk == AF_TARGET_LB ? NODE_LB : NODE_SERVER0 + (meta >> 5));
-                if (can_fuse(W)) act = A_NODE;                 // put -> pending get -> resume, nothing in between
+                if (can_fuse(W)) { act = A_NODE; from_box = false; }   // put -> pending get -> resume, nothing in between
                 else {                                         // (fused implies: every inbox empty, every consumer in get())
                     rq_pack_set(m, slot, pack);
                     fifo_push(m, ib_word(node, IB_HEAD), ib_word(node, IB_TAIL), slot);   // Store.put: items.append now ...
@@ -816,8 +840,8 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 node = aux;
                 act = A_NODE;
             } else if (kind == I_PUT) {                        // a StorePut event is processed
-                if (*w32(m, ib_word(aux, IB_PENDING))) {
-                    *w32(m, ib_word(aux, IB_PENDING)) = 0;
+                if (c32_ld(m, ib_word(aux, IB_PENDING))) {
+                    c32_st(m, ib_word(aux, IB_PENDING), 0);
                     nq_push(W, m, I_GOT, aux, fifo_pop(m, ib_word(aux, IB_HEAD), ib_word(aux, IB_TAIL)));
                 }
             } else if (kind == I_CLIENT_LOOP) {
@@ -850,7 +874,8 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
             act = A_NONE;
             if (node >= NODE_SERVER0) {                       // server.py:303-313, then the head of _handle_request (:88-149)
                 sidx = node - NODE_SERVER0;
-                consumer_get(W, m, node);                      // the dispatcher loops back to get() first
+                if (from_box) consumer_get(W, m, node);        // the dispatcher loops back to get() first (fused: the box is empty and
+                                                               // the consumer already marked as waiting -- nothing to do)
                 const ServerP sp = ro(C.servers + sidx);
                 pack += 1;                                     // record_hop(SERVER)
                 uint32_t epi = 0;
@@ -865,14 +890,15 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 const uint32_t total_ram = ep_total_ram(m, ep_global);
                 bool go = true;
                 if (total_ram) {                               // yield RAM.get(total_ram)
-                    if (!(*w32(m, sv_word(sidx, SV_RAMQ_HEAD)) == NIL && (int32_t)total_ram <= *i32(m, sv_word(sidx, SV_RAM_FREE)) && can_fuse(W))) {
+                    if (!(can_fuse(W) && (int32_t)total_ram <= i32_ld(m, sv_word(sidx, SV_RAM_FREE)) && q_empty(W, m, sq_word(sidx, SQ_RAMQ_HEAD)))) {
                         // cannot be served at once: join the queue, walk it
-                        if (*w32(m, sv_word(sidx, SV_RAMQ_HEAD)) == NIL) *w32(m, sv_word(sidx, SV_RAMQ_NEED)) = total_ram;
-                        fifo_push(m, sv_word(sidx, SV_RAMQ_HEAD), sv_word(sidx, SV_RAMQ_TAIL), slot);
+                        if (q_empty(W, m, sq_word(sidx, SQ_RAMQ_HEAD))) c32_st(m, sq_word(sidx, SQ_RAMQ_NEED), total_ram);
+                        fifo_push(m, sq_word(sidx, SQ_RAMQ_HEAD), sq_word(sidx, SQ_RAMQ_TAIL), slot);
+                        W.n_waiting += 1;
                         ram_walk(W, m, sidx);
                         go = false;
                     } else {
-                        *i32(m, sv_word(sidx, SV_RAM_FREE)) -= (int32_t)total_ram;   // granted, and its get event would run next
+                        i32_st(m, sv_word(sidx, SV_RAM_FREE), i32_ld(m, sv_word(sidx, SV_RAM_FREE)) - (int32_t)total_ram);   // granted, and its get event would run next
                         srv_gauge_add(W, m, sidx, SV_RAM_IN_USE, (int32_t)total_ram);
                     }
                 }
@@ -882,10 +908,10 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 if (node == NODE_CLIENT) {
                     if (pk_hops(pack) > 3) {                   // client.py:62: back from the servers
                         complete(W, m, slot, t0);
-                        if (can_fuse(W)) consumer_get(W, m, NODE_CLIENT);
+                        if (can_fuse(W)) { if (from_box) consumer_get(W, m, NODE_CLIENT); }
                         else nq_push(W, m, I_CLIENT_LOOP, 0, 0);   // yield completed_box.put(state)
                     } else {
-                        consumer_get(W, m, NODE_CLIENT);
+                        if (from_box) consumer_get(W, m, NODE_CLIENT);
                         edge = (uint32_t)C.client_edge;
                         act = A_SEND;
                     }
@@ -895,20 +921,20 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                     // the replica stops and says so (flatten() rejects timelines that can reach this state)
                     if (AFL_UNLIKELY(n <= 0)) { rq_pack_set(m, slot, pack); W.flags |= AF_FLAG_LB_EMPTY; }
                     else {
-                        uint32_t pick = *w32(m, lb);
+                        uint32_t pick = w32_ld(m, lb);
                         if (C.lb_algo == AF_LB_ROUND_ROBIN) {      // lb_algorithms.py:22-36
 #pragma unroll 1
-                            for (int32_t i = 1; i < n; ++i) *w32(m, lb + i - 1) = *w32(m, lb + i);
-                            *w32(m, lb + n - 1) = pick;
+                            for (int32_t i = 1; i < n; ++i) w32_st(m, lb + i - 1, w32_ld(m, lb + i));
+                            w32_st(m, lb + n - 1, pick);
                         } else {                                   // least_connections, :10-20 (first min wins)
-                            uint32_t best = *w32(m, C.o32_conn + (int32_t)pick);
+                            uint32_t best = w32_ld(m, C.o32_conn + (int32_t)pick);
 #pragma unroll 1
                             for (int32_t i = 1; i < n; ++i) {
-                                const uint32_t e2 = *w32(m, lb + i), c2 = *w32(m, C.o32_conn + (int32_t)e2);
+                                const uint32_t e2 = w32_ld(m, lb + i), c2 = w32_ld(m, C.o32_conn + (int32_t)e2);
                                 if (c2 < best) { best = c2; pick = e2; }
                             }
                         }
-                        consumer_get(W, m, NODE_LB);
+                        if (from_box) consumer_get(W, m, NODE_LB);
                         edge = pick;
                         act = A_SEND;
                     }
@@ -930,11 +956,12 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                     if (sp.kind == AF_STEP_CPU) {
                         if (pack & PK_IO) { pack &= ~PK_IO; srv_gauge_add(W, m, sidx, SV_IO_Q, -1); }
                         if (!(pack & PK_CORE)) {             // cpu_req = CPU.get(1); yield cpu_req
-                            if (*w32(m, sv_word(sidx, SV_CPUQ_HEAD)) == NIL && *i32(m, sv_word(sidx, SV_CPU_FREE)) > 0 && can_fuse(W)) {
-                                *i32(m, sv_word(sidx, SV_CPU_FREE)) -= 1;     // granted, and its get event would run next
+                            if (can_fuse(W) && i32_ld(m, sv_word(sidx, SV_CPU_FREE)) > 0 && q_empty(W, m, sq_word(sidx, SQ_CPUQ_HEAD))) {
+                                i32_st(m, sv_word(sidx, SV_CPU_FREE), i32_ld(m, sv_word(sidx, SV_CPU_FREE)) - 1);     // granted, and its get event would run next
                                 pack |= PK_CORE;
                             } else {
-                                fifo_push(m, sv_word(sidx, SV_CPUQ_HEAD), sv_word(sidx, SV_CPUQ_TAIL), slot);
+                                fifo_push(m, sq_word(sidx, SQ_CPUQ_HEAD), sq_word(sidx, SQ_CPUQ_TAIL), slot);
+                                W.n_waiting += 1;
                                 if (!cpu_walk(W, m, sidx, slot)) { pack |= PK_WAIT; srv_gauge_add(W, m, sidx, SV_READY_Q, 1); }   // not cpu_req.triggered
                                 rq_pack_set(m, slot, pack);
                                 break;
@@ -942,9 +969,9 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                         }
                     } else {
                         if (pack & PK_CORE) {                // yield CPU.put(1): level rises NOW
-                            *i32(m, sv_word(sidx, SV_CPU_FREE)) += 1;
+                            i32_st(m, sv_word(sidx, SV_CPU_FREE), i32_ld(m, sv_word(sidx, SV_CPU_FREE)) + 1);
                             if (can_fuse(W)) {
-                                if (AFL_UNLIKELY(*w32(m, sv_word(sidx, SV_CPUQ_HEAD)) != NIL)) cpu_walk(W, m, sidx, NIL);
+                                if (AFL_UNLIKELY(!q_empty(W, m, sq_word(sidx, SQ_CPUQ_HEAD)))) cpu_walk(W, m, sidx, NIL);
                                 pack &= ~PK_CORE;
                                 continue;
                             }
@@ -962,9 +989,9 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 }
                 // end of the endpoint (server.py:257-276)
                 if (pack & PK_CORE) {                        // yield CPU.put(1)
-                    *i32(m, sv_word(sidx, SV_CPU_FREE)) += 1;
+                    i32_st(m, sv_word(sidx, SV_CPU_FREE), i32_ld(m, sv_word(sidx, SV_CPU_FREE)) + 1);
                     if (can_fuse(W)) {
-                        if (AFL_UNLIKELY(*w32(m, sv_word(sidx, SV_CPUQ_HEAD)) != NIL)) cpu_walk(W, m, sidx, NIL);
+                        if (AFL_UNLIKELY(!q_empty(W, m, sq_word(sidx, SQ_CPUQ_HEAD)))) cpu_walk(W, m, sidx, NIL);
                         pack &= ~PK_CORE;
                         continue;
                     }
@@ -976,9 +1003,9 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 const uint32_t total_ram = ep.c_ram >= 0 ? (uint32_t)row_val(m, ep.c_ram) : ep.total_ram;
                 if (total_ram) {                             // yield RAM.put(total_ram): level rises NOW
                     srv_gauge_add(W, m, sidx, SV_RAM_IN_USE, -(int32_t)total_ram);
-                    *i32(m, sv_word(sidx, SV_RAM_FREE)) += (int32_t)total_ram;
+                    i32_st(m, sv_word(sidx, SV_RAM_FREE), i32_ld(m, sv_word(sidx, SV_RAM_FREE)) + (int32_t)total_ram);
                     if (!can_fuse(W)) { rq_pack_set(m, slot, pack); nq_push(W, m, I_RAM_PUT, sidx, slot); break; }
-                    if (AFL_UNLIKELY(*w32(m, sv_word(sidx, SV_RAMQ_HEAD)) != NIL)) ram_walk(W, m, sidx);   // the put event would run next: waiters, then forward
+                    if (AFL_UNLIKELY(!q_empty(W, m, sq_word(sidx, SQ_RAMQ_HEAD)))) ram_walk(W, m, sidx);   // the put event would run next: waiters, then forward
                 }
                 edge = ro(C.servers + sidx).out_edge;
                 act = A_SEND;
@@ -996,15 +1023,15 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
             const double mean = E.c_mean >= 0 ? row_val(m, E.c_mean) : E.mean;
             const double sigma = E.c_sigma >= 0 ? row_val(m, E.c_sigma) : E.sigma;
             const afr::EdgeDraw d = afr::edge_draw(C.seed, W.replica, rid, pk_hops(pack), (int)(E.meta & 7u), mean, sigma, dropout);
-            *w32(m, C.o32_sent + (int32_t)edge) += 1;
+            w32_st(m, C.o32_sent + (int32_t)edge, w32_ld(m, C.o32_sent + (int32_t)edge) + 1);
             if (d.u < dropout) {                            // the request vanishes (edge.py:79-86)
-                *w32(m, C.o32_drop + (int32_t)edge) += 1;
+                c32_st(m, C.c_drop + (int32_t)edge, c32_ld(m, C.c_drop + (int32_t)edge) + 1);
                 rq_release(W, m, slot);
             } else {
                 rq_pack_set(m, slot, pack);                  // (the one store of the record on the request's way out of a node)
                 conn_add(W, m, edge, 1);
                 double effective = d.transit;
-                if (C.n_spike > 0) effective = d.transit + *f64(m, C.o64_spike + (int32_t)edge);   // spike read at SEND time (edge.py:94-106)
+                if (C.n_spike > 0) effective = d.transit + f64_ld(m, C.o64_spike + (int32_t)edge);   // spike read at SEND time (edge.py:94-106)
                 else effective = d.transit + 0.0;           // (-0.0 + 0.0 = +0.0, as with a spike table of zeros)
                 tm_t = W.now + effective; tm_payload = mk_payload(K_DELIVER, edge, slot); tm_seq = s;
                 act = A_TIMER;

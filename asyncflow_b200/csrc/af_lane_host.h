@@ -19,7 +19,7 @@ struct Tables {
 // looks up during the run (edge latency parameters, step durations, endpoint RAM, spike amplitudes) gets a
 // slot in the lane's row copy; a column over a field consumed at the start of a replica (users, cores, RAM)
 // does not.  Two columns over the same (field, index): the later one wins, as in af_core.cuh::load_params.
-inline bool build_tables(const AfScenario& s, const AfSweepColumn* cols, int32_t n_cols, Tables& t, std::string& err) {
+inline bool build_tables(const AfScenario& s, const AfSweepColumn* cols, int32_t n_cols, const int32_t* alias, Tables& t, std::string& err) {
     t = Tables();
     t.edges.resize((size_t)s.n_edges);
     for (int i = 0; i < s.n_edges; ++i) {
@@ -55,36 +55,54 @@ inline bool build_tables(const AfScenario& s, const AfSweepColumn* cols, int32_t
         afl::ColP& k = t.cols[(size_t)c];
         k.field = cols[c].field; k.index = cols[c].index; k.slot = -1; k.pad = 0; k.base = 0.0;
         const int32_t i = k.index;
+        // a column whose values repeat an earlier looked-up column's in every row shares that column's slot
+        // (configs[2] sweeps all six edges with one RTT array and one jitter array: 2 slots, not 12)
+        const int32_t shared = alias && alias[c] >= 0 ? t.cols[(size_t)alias[c]].slot : -1;
+#define AFLH_SLOT() (shared >= 0 ? shared : n_row++)
         switch (k.field) {
         case AF_FIELD_USERS_MEAN: k.base = s.users_mean; break;
         case AF_FIELD_USERS_SIGMA: k.base = s.users_sigma; break;
         case AF_FIELD_RATE_PER_USER: k.base = s.rate_per_user; break;
         case AF_FIELD_SERVER_CPU_CORES: k.base = s.servers[i].cpu_cores; break;
         case AF_FIELD_SERVER_RAM_MB: k.base = s.servers[i].ram_mb; break;
-        case AF_FIELD_EDGE_MEAN: k.slot = n_row++; k.base = s.edges[i].mean; t.edges[(size_t)i].c_mean = (int16_t)k.slot; break;
-        case AF_FIELD_EDGE_SIGMA: k.slot = n_row++; k.base = s.edges[i].sigma; t.edges[(size_t)i].c_sigma = (int16_t)k.slot; break;
-        case AF_FIELD_EDGE_DROPOUT: k.slot = n_row++; k.base = s.edges[i].dropout; t.edges[(size_t)i].c_drop = (int16_t)k.slot; break;
-        case AF_FIELD_STEP_DURATION: k.slot = n_row++; k.base = s.steps[i].duration; t.steps[(size_t)i].c_dur = k.slot; break;
-        case AF_FIELD_ENDPOINT_RAM: k.slot = n_row++; k.base = s.endpoints[i].total_ram; t.endpoints[(size_t)i].c_ram = k.slot; break;
-        case AF_FIELD_SPIKE_DELTA: k.slot = n_row++; k.base = s.spike_marks[i].delta < 0.0 ? -s.spike_marks[i].delta : s.spike_marks[i].delta;
+        case AF_FIELD_EDGE_MEAN: k.slot = AFLH_SLOT(); k.base = s.edges[i].mean; t.edges[(size_t)i].c_mean = (int16_t)k.slot; break;
+        case AF_FIELD_EDGE_SIGMA: k.slot = AFLH_SLOT(); k.base = s.edges[i].sigma; t.edges[(size_t)i].c_sigma = (int16_t)k.slot; break;
+        case AF_FIELD_EDGE_DROPOUT: k.slot = AFLH_SLOT(); k.base = s.edges[i].dropout; t.edges[(size_t)i].c_drop = (int16_t)k.slot; break;
+        case AF_FIELD_STEP_DURATION: k.slot = AFLH_SLOT(); k.base = s.steps[i].duration; t.steps[(size_t)i].c_dur = k.slot; break;
+        case AF_FIELD_ENDPOINT_RAM: k.slot = AFLH_SLOT(); k.base = s.endpoints[i].total_ram; t.endpoints[(size_t)i].c_ram = k.slot; break;
+        case AF_FIELD_SPIKE_DELTA: k.slot = AFLH_SLOT(); k.base = s.spike_marks[i].delta < 0.0 ? -s.spike_marks[i].delta : s.spike_marks[i].delta;
                                    t.spikes[(size_t)i].c_delta = k.slot; break;
         default: err = "sweep: unknown field id"; return false;
         }
+#undef AFLH_SLOT
     }
     if (n_row > 32000) { err = "sweep: too many looked-up columns for the lane engine"; return false; }
     t.n_row = n_row;
     return true;
 }
 
+// alias[c] = the first earlier column whose values equal column c's in every row, or -1
+inline std::vector<int32_t> column_aliases(const double* values, uint64_t n_rows, int32_t n_cols) {
+    std::vector<int32_t> alias((size_t)n_cols, -1);
+    for (int32_t c = 1; c < n_cols; ++c)
+        for (int32_t a = 0; a < c && alias[(size_t)c] < 0; ++a) {
+            if (alias[(size_t)a] >= 0) continue;                 // compare with class representatives only
+            uint64_t r = 0;
+            while (r < n_rows && values[r * (uint64_t)n_cols + (uint64_t)c] == values[r * (uint64_t)n_cols + (uint64_t)a]) ++r;
+            if (r == n_rows) alias[(size_t)c] = a;
+        }
+    return alias;
+}
+
 constexpr int32_t LANE_EVENT_CAPACITY = 512;      // defaults of the lane engine's global tiers (AfOptions fields <= 0)
 constexpr int32_t LANE_REQUEST_CAPACITY = 2048;
 
-// smallest per-lane budget make_cfg() accepts for this scenario (5 events, 2 requests, 4 items + the fixed tables)
+// smallest per-lane budget make_cfg() accepts for this scenario (4 events, 2 requests + the hot fixed tables)
 inline int32_t min_lane_bytes(const AfScenario& s, const Tables& t) {
     const int32_t n_series = 3 * s.n_servers + s.n_edges;
     const int32_t fix64 = (s.n_spike_marks > 0 ? s.n_edges : 0) + n_series + t.n_row;
-    const int32_t fix32 = 3 * s.n_edges + afl::SV_WORDS * s.n_servers + afl::IB_WORDS * (s.n_servers + 2) + s.n_lb_edges + n_series + (n_series + 31) / 32;
-    return 8 * fix64 + 4 * fix32 + 8 * 4 + 16 * 6 + 20 * 3;
+    const int32_t fix32 = 2 * s.n_edges + afl::SV_WORDS * s.n_servers + s.n_lb_edges + n_series + (n_series + 31) / 32;
+    return 8 * fix64 + 4 * fix32 + 16 * 4 + 36 * 2;      // make_cfg: rq_s = (rest - 64) / 36 >= 2
 }
 
 // The launch configuration for a budget of `lane_bytes` of shared memory per lane (= per replica in
@@ -109,20 +127,20 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     // fixed part of a lane's shared memory
     const int32_t fix64 = (C.n_spike > 0 ? C.n_edges : 0) + C.n_series + C.n_row;
     C.n_dirty = (C.n_series + 31) / 32;
-    const int32_t fix32 = 3 * C.n_edges + afl::SV_WORDS * C.n_servers + afl::IB_WORDS * (C.n_servers + 2) + C.n_lb_edges + C.n_series + C.n_dirty;
-    int32_t nq_s = 4;
-    int32_t rest = lane_bytes - 8 * fix64 - 4 * fix32 - 8 * nq_s;
+    const int32_t fix32 = 2 * C.n_edges + afl::SV_WORDS * C.n_servers + C.n_lb_edges + C.n_series + C.n_dirty;
+    int32_t nq_s = 0;                                // zero-delay items: ties only -- the ring starts in the global tier
+    int32_t rest = lane_bytes - 8 * fix64 - 4 * fix32;
     // split the rest between pending events (16 B) and request records (20 B): at nominal load a request in
     // flight owns one pending event, plus the arrival and the two timelines
     int32_t rq_s = (rest - 16 * 4) / 36;
     if (rq_s > rq_total) rq_s = rq_total;
     int32_t ev_s = rq_s < 0 ? 0 : (rest - 20 * rq_s) / 16;
     if (ev_s > ev_total) { ev_s = ev_total; rq_s = (rest - 16 * ev_s) / 20; if (rq_s > rq_total) rq_s = rq_total; }
-    if (rq_s < (rq_total < 2 ? rq_total : 2) || ev_s < (ev_total < 5 ? ev_total : 5)) return false;
-    {   // what is left over goes to the now-queue's shared-memory end
-        const int32_t left = rest - 16 * ev_s - 20 * rq_s;
-        nq_s += left / 8;
+    if (rq_s < (rq_total < 2 ? rq_total : 2) || ev_s < (ev_total < 4 ? ev_total : 4)) return false;
+    if (ev_s == ev_total && rq_s == rq_total) {      // everything fits: what is left over takes the front of the now-queue
+        nq_s = (rest - 16 * ev_s - 20 * rq_s) / 8;
         if (nq_s > afl::NQ_TOTAL) nq_s = afl::NQ_TOTAL;
+        if (nq_s < 0) nq_s = 0;
     }
     C.ev_s = ev_s; C.ev_total = ev_total; C.rq_s = rq_s; C.rq_total = rq_total; C.nq_s = nq_s;
     int32_t e = 0;
@@ -140,9 +158,7 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     C.o32_next = w; w += rq_s;
     C.o32_conn = w; w += C.n_edges;
     C.o32_sent = w; w += C.n_edges;
-    C.o32_drop = w; w += C.n_edges;
     C.o32_srv = w; w += afl::SV_WORDS * C.n_servers;
-    C.o32_inbox = w; w += afl::IB_WORDS * (C.n_servers + 2);
     C.o32_lb = w; w += C.n_lb_edges;
     C.o32_smax = w; w += C.n_series;
     C.o32_dirty = w; w += C.n_dirty;
@@ -159,6 +175,9 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     C.g32_rid = h; h += rq_total - rq_s;
     C.g32_pack = h; h += rq_total - rq_s;
     C.g32_next = h; h += rq_total - rq_s;
+    C.g32_cold = h;
+    C.c_srvq = 0; C.c_inbox = C.c_srvq + afl::SQ_WORDS * C.n_servers; C.c_drop = C.c_inbox + afl::IB_WORDS * (C.n_servers + 2);
+    h += C.c_drop + C.n_edges;
     C.gn32 = h;
     C.gwarp_bytes = ((uint64_t)C.gn64 * 8 + (uint64_t)C.gn32 * 4) * (uint64_t)lanes;
     return true;

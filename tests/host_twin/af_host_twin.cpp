@@ -79,7 +79,10 @@ extern "C" int af_twin_run_lane(const AfScenario* sc, const AfSweep* sw, uint64_
                                 uint32_t* trace_series, uint32_t* trace_counts) {
     if (!afh::validate(*sc, g_err)) return AF_ERR_INVALID;
     aflh::Tables T;
-    if (!aflh::build_tables(*sc, sw ? sw->columns : nullptr, sw ? sw->n_columns : 0, T, g_err)) return AF_ERR_INVALID;
+    std::vector<int32_t> alias;
+    const bool all_rows = sw && replica_begin >= sweep_first && replica_begin + n - sweep_first <= sw->n_rows;
+    if (all_rows) alias = aflh::column_aliases(sw->values, sw->n_rows, sw->n_columns);
+    if (!aflh::build_tables(*sc, sw ? sw->columns : nullptr, sw ? sw->n_columns : 0, all_rows ? alias.data() : nullptr, T, g_err)) return AF_ERR_INVALID;
     afl::Cfg& C = afl::h_cfg;
     memset(&C, 0, sizeof C);
     if (lane_bytes < aflh::min_lane_bytes(*sc, T)) lane_bytes = aflh::min_lane_bytes(*sc, T);   // (the engine lowers its occupancy instead)

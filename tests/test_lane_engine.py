@@ -73,6 +73,33 @@ def test_random_sweeps_on_the_lane_engine_match_the_oracle_row_by_row():
                                   dropped=r["dropped"][i])
 
 
+def test_columns_that_repeat_each_other_share_a_row_slot_and_change_nothing():
+    """configs[2]'s shape: one RTT array and one jitter array over every edge (12 columns, 2 distinct value arrays).
+    The lane engine keeps one row slot per distinct array (aflh::column_aliases); rows still equal the oracle on the
+    row's own payload -- and a run that reaches past the sweep's rows (base values) does not share slots."""
+    import bench
+    payload = bench.workload(0, 6)
+    flat = flatten(payload)
+    n = 4
+    rtt = np.array([0.001, 0.013, 0.027, 0.05]); sig = np.array([0.1, 0.2, 0.35, 0.5]) * rtt
+    cols = {}
+    for e in flat.edge_ids:
+        cols[("edge_mean", e)] = rtt
+        cols[("edge_sigma", e)] = sig
+    spec = SweepSpec(flat, n, cols)
+    r = twin.run(flat, engine="lane", lane_bytes=500, seed=SEED, n=n + 1, sweep=spec, trace=n + 1, clock_cap=100000)
+    for i in range(n + 1):
+        p = spec.payload_for(payload, i) if i < n else payload
+        o = des_port.simulate(p, seed=SEED, replica=i)
+        m = int(r["stats"][i]["completed"])
+        assert_matches_oracle(o, flatten(p), stats=r["stats"][i], clocks=r["trace_clocks"][i, :m], sent=r["sent"][i],
+                              dropped=r["dropped"][i])
+    r2 = twin.run(flat, engine="lane", lane_bytes=500, seed=SEED, n=n, sweep=spec, trace=n, clock_cap=100000)
+    for i in range(n):
+        m = int(r2["stats"][i]["completed"])
+        np.testing.assert_array_equal(r2["trace_clocks"][i, :m], r["trace_clocks"][i, :m])
+
+
 def test_lane_pool_overflow_is_flagged():
     flat = flatten(load_scenario("overload_single.yml"))
     r = twin.run(flat, engine="lane", seed=SEED, n=1, request_capacity=200)

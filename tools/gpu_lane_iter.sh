@@ -6,12 +6,21 @@ cd "$(dirname "$0")/.." || exit 1
 QB="timeout 200 python tools/quick_bench.py"
 echo "=== smoke"; timeout 300 python __graft_entry__.py --smoke || { echo "SMOKE FAILED: stopping"; exit 1; }
 echo "=== parity (auto)"; timeout 400 python tools/check_variant_gpu.py || { echo "PARITY FAILED (auto): stopping"; exit 1; }
-for wpb in ${WPBS:-8 16}; do
-  echo "=== C3 rtt sweep 40000 x 20 s, lane, $wpb warps/SM"; $QB --scenario c3_lb_two_servers.yml --replicas 40000 --horizon 20 --reps 2 --mode auto --wpb $wpb | tail -2
+for wpb in ${WPBS:-8 12 16}; do
+  echo "=== C3 rtt sweep 80000 x 20 s, lane, $wpb warps/SM"; $QB --scenario c3_lb_two_servers.yml --replicas 80000 --horizon 20 --reps 2 --mode auto --wpb $wpb | tail -2
+done
+for cfg in ${CAPS:-"16 320" "12 400"}; do
+  set -- $cfg
+  echo "=== C3 rtt sweep 80000 x 20 s, lane, $1 warps/SM, at most $2 B of shared memory per lane"
+  ASYNCFLOW_B200_LANE_BYTES=$2 $QB --scenario c3_lb_two_servers.yml --replicas 80000 --horizon 20 --reps 2 --mode auto --wpb $1 | tail -2
 done
 echo "=== C1 x 40000 x 60 s"; $QB --scenario c1_my_service.yml --replicas 40000 --horizon 60 --reps 2 --sweep none | tail -2
 echo "=== C4 20000 x 120 s"; $QB --scenario c4_lb8_events.yml --replicas 20000 --horizon 120 --reps 2 --sweep none | tail -2
-echo "=== bench.py"; timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline | cut -c1-400
+for wpb in ${BENCH_WPBS:-0 12 16}; do
+  echo "=== bench.py --wpb $wpb"; timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --wpb $wpb | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline()); print({k:d[k] for k in ('value','ms_per_step','replicas_overflowed','passes')}, d['e2e']['value'])"
+done
 M=smsp__inst_executed.sum,smsp__thread_inst_executed.sum,gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active
 M=$M,smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio
 M=$M,smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio
