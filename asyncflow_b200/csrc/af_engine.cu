@@ -33,7 +33,7 @@
 
 // thread-per-replica pass: warps per SM when the caller does not say (AfOptions.warps_per_block)
 #ifndef AF_LANE_DEFAULT_WARPS
-#define AF_LANE_DEFAULT_WARPS 8
+#define AF_LANE_DEFAULT_WARPS 12
 #endif
 
 // occupancy knob: registers are capped (64/thread) so that 8 128-thread CTAs fit per SM.
@@ -84,8 +84,12 @@ __global__ void __launch_bounds__(AF_LANE_MAX_THREADS, 1) af_lane_kernel() {
     const uint32_t ws = warp * (uint32_t)C.warp_bytes;
     unsigned char* gs = C.gtier + ((uint64_t)blockIdx.x * (blockDim.x >> 5) + warp) * C.gwarp_bytes;
     afl::Mem m;
-    m.s64 = ws + lane * 8u; m.s32 = ws + (uint32_t)C.n64 * (uint32_t)afl::STRIDE64 + lane * 4u;
-    m.g64 = gs + lane * 8u; m.g32 = gs + (size_t)C.gn64 * afl::STRIDE64 + lane * 4u;
+    m.s128 = ws + lane * 16u;
+    m.s64 = ws + (uint32_t)C.n128 * (uint32_t)afl::STRIDE128 + lane * 8u;
+    m.s32 = ws + (uint32_t)C.n128 * (uint32_t)afl::STRIDE128 + (uint32_t)C.n64 * (uint32_t)afl::STRIDE64 + lane * 4u;
+    m.g128 = gs + lane * 16u;
+    m.g64 = gs + (size_t)C.gn128 * afl::STRIDE128 + lane * 8u;
+    m.g32 = gs + (size_t)C.gn128 * afl::STRIDE128 + (size_t)C.gn64 * afl::STRIDE64 + lane * 4u;
     afl::run_lane(m,
         [&]() -> uint64_t {
             const unsigned long long k = atomicAdd(C.work_counter, 1ull);

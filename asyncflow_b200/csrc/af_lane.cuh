@@ -14,11 +14,12 @@
 //                          events (the expensive ones -- the edge's variates, the heap sift -- exist
 //                          at ONE place in the code and are shared by every event kind that needs them).
 //
-// Data layout.  A lane's mutable replica state lives in shared memory, WORD-INTERLEAVED across the
-// warp: 64-bit element e of lane l at  base64 + (e * 32 + l) * 8,  32-bit word w at
-// base32 + (w * 32 + l) * 4.  Whatever index each lane uses, the 32 lanes always hit 32 different
-// banks: every access is one conflict-free wavefront (two for 64-bit), no matter how far the
-// replicas have drifted apart.  Tables whose size depends on load (pending events, request
+// Data layout.  A lane's mutable replica state lives in shared memory, ELEMENT-INTERLEAVED across the
+// warp: 128-bit element e of lane l at  base128 + (e * 32 + l) * 16  (a pending event = time | key, a request
+// record = t0 | id | pack: one LDS.128 each),  64-bit element e at  base64 + (e * 32 + l) * 8,  32-bit word w at
+// base32 + (w * 32 + l) * 4.  Whatever index each lane uses, the lanes of a quarter / half / full warp always hit
+// different banks: every access is conflict-free (4 / 2 / 1 wavefronts), no matter how far the replicas have
+// drifted apart.  Tables whose size depends on load (pending events, request
 // records, the now-queue) are TIERED: the first `*_s` entries in shared memory, the rest in a
 // per-lane region of global memory with the same interleave (L2-resident; one select per access,
 // no branch).  Read-only scenario tables are NOT replicated per replica: they are read through
@@ -80,7 +81,7 @@ constexpr int LANES = 32;
 #else
 constexpr int LANES = 1;
 #endif
-constexpr int STRIDE64 = LANES * 8, STRIDE32 = LANES * 4;
+constexpr int STRIDE128 = LANES * 16, STRIDE64 = LANES * 8, STRIDE32 = LANES * 4;
 
 constexpr uint32_t NIL = 0xFFFFFFFFu;
 constexpr uint64_t INF_BITS = 0x7FF0000000000000ull;
@@ -130,15 +131,18 @@ struct Cfg {
     int32_t redo;                                   // 1: replica indices come from redo_list (re-run of flagged replicas)
     // tiered tables: entries in shared memory / in total
     int32_t ev_s, ev_total, rq_s, rq_total, nq_s;
-    // shared-memory layout of a warp: 64-bit region (element offsets), then 32-bit region (word offsets)
-    int32_t o64_evt, o64_evk, o64_t0, o64_nq, o64_spike, o64_ssum, o64_row, n64;
-    int32_t o32_rid, o32_pack, o32_next, o32_conn, o32_sent, o32_srv, o32_lb, o32_smax, o32_dirty, n_dirty, n32;
-    int32_t warp_bytes;                             // n64 * 256 + n32 * 128
-    // global tier of a warp (same interleave): element / word offsets, sizes
-    int32_t g64_evt, g64_evk, g64_t0, g64_nq, gn64;
-    int32_t g32_rid, g32_pack, g32_next, g32_cold, gn32;
+    // shared-memory layout of a warp: 128-bit region (events, then request records), 64-bit region, 32-bit region
+    int32_t o128_ev, o128_rq, n128;
+    int32_t o64_nq, o64_spike, o64_ssum, o64_row, n64;
+    int32_t o32_next, o32_conn, o32_sent, o32_srv, o32_lb, o32_smax, o32_dirty, n_dirty, n32;
+    int32_t warp_bytes;                             // n128 * 512 + n64 * 256 + n32 * 128
+    // global tier of a warp (same interleave).  gi_* = (offset of the table in its region) - (entries kept in shared
+    // memory): entry idx >= split lives at element idx + gi_* of the region
+    int32_t gi_ev, gi_rq, gn128;
+    int32_t gi_nq, gn64;
+    int32_t gi_next, g32_cold, gn32;
     int32_t c_srvq, c_inbox, c_drop;                // cold words (offsets from g32_cold): waiter FIFOs, mailboxes, drop counters
-    uint64_t gwarp_bytes;                           // gn64 * 256 + gn32 * 128
+    uint64_t gwarp_bytes;                           // gn128 * 512 + gn64 * 256 + gn32 * 128
     // device pointers
     const EdgeP* edges; const ServerP* servers; const EndpointP* endpoints; const StepP* steps;
     const SpikeP* spikes; const OutageP* outages; const int32_t* lb_edges; const ColP* cols;
@@ -184,21 +188,30 @@ template <class T> AFL_IN T ro(const T* p) {
 // ncu r02b, 33 % of the executed instructions), a generic pointer costs 64-bit arithmetic.  A tiered table takes a
 // BRANCH on "is it in shared memory", not a select.  All shared accesses are volatile asm: they keep program order.
 struct Mem {
-    uint32_t s64, s32;                          // shared-memory regions of the warp (window addresses, the lane's column)
-    unsigned char* g64; unsigned char* g32;     // global tier of the warp, already offset by the lane
+    uint32_t s128, s64, s32;                    // shared-memory regions of the warp (window addresses, the lane's column)
+    unsigned char* g128; unsigned char* g64; unsigned char* g32;     // global tier of the warp, already offset by the lane
 };
 #if AFL_DEVICE
 AFL_IN uint32_t sm_ld32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 AFL_IN void sm_st32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v)); }
 AFL_IN uint64_t sm_ld64(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
 AFL_IN void sm_st64(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" :: "r"(a), "l"(v)); }
+AFL_IN void sm_ld128(uint32_t a, uint64_t& x, uint64_t& y) { asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(a)); }
+AFL_IN void sm_st128(uint32_t a, uint64_t x, uint64_t y) { asm volatile("st.shared.v2.u64 [%0], {%1, %2};" :: "r"(a), "l"(x), "l"(y)); }
+AFL_IN void gl_ld128(const unsigned char* p, uint64_t& x, uint64_t& y) { const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p); x = v.x; y = v.y; }
+AFL_IN void gl_st128(unsigned char* p, uint64_t x, uint64_t y) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(x, y); }
 #else
 static unsigned char* afl_smem_host = nullptr;     // the twin's stand-in for the SM's shared memory
 AFL_IN uint32_t sm_ld32(uint32_t a) { uint32_t v; memcpy(&v, afl_smem_host + a, 4); return v; }
 AFL_IN void sm_st32(uint32_t a, uint32_t v) { memcpy(afl_smem_host + a, &v, 4); }
 AFL_IN uint64_t sm_ld64(uint32_t a) { uint64_t v; memcpy(&v, afl_smem_host + a, 8); return v; }
 AFL_IN void sm_st64(uint32_t a, uint64_t v) { memcpy(afl_smem_host + a, &v, 8); }
+AFL_IN void sm_ld128(uint32_t a, uint64_t& x, uint64_t& y) { memcpy(&x, afl_smem_host + a, 8); memcpy(&y, afl_smem_host + a + 8, 8); }
+AFL_IN void sm_st128(uint32_t a, uint64_t x, uint64_t y) { memcpy(afl_smem_host + a, &x, 8); memcpy(afl_smem_host + a + 8, &y, 8); }
+AFL_IN void gl_ld128(const unsigned char* p, uint64_t& x, uint64_t& y) { memcpy(&x, p, 8); memcpy(&y, p + 8, 8); }
+AFL_IN void gl_st128(unsigned char* p, uint64_t x, uint64_t y) { memcpy(p, &x, 8); memcpy(p + 8, &y, 8); }
 #endif
+AFL_IN uint32_t a128(const Mem& m, int32_t elem) { return m.s128 + (uint32_t)elem * (uint32_t)STRIDE128; }
 AFL_IN uint32_t a64(const Mem& m, int32_t elem) { return m.s64 + (uint32_t)elem * (uint32_t)STRIDE64; }
 AFL_IN uint32_t a32(const Mem& m, int32_t word) { return m.s32 + (uint32_t)word * (uint32_t)STRIDE32; }
 AFL_IN uint64_t e64_ld(const Mem& m, int32_t elem) { return sm_ld64(a64(m, elem)); }
@@ -209,26 +222,35 @@ AFL_IN uint32_t w32_ld(const Mem& m, int32_t word) { return sm_ld32(a32(m, word)
 AFL_IN void w32_st(const Mem& m, int32_t word, uint32_t v) { sm_st32(a32(m, word), v); }
 AFL_IN int32_t i32_ld(const Mem& m, int32_t word) { return (int32_t)sm_ld32(a32(m, word)); }
 AFL_IN void i32_st(const Mem& m, int32_t word, int32_t v) { sm_st32(a32(m, word), (uint32_t)v); }
-AFL_IN uint64_t* g64p(const Mem& m, int32_t elem) { return reinterpret_cast<uint64_t*>(m.g64 + (size_t)(uint32_t)elem * STRIDE64); }
-AFL_IN uint32_t* g32p(const Mem& m, int32_t word) { return reinterpret_cast<uint32_t*>(m.g32 + (size_t)(uint32_t)word * STRIDE32); }
+// global tier: ONE 32-bit element index (table offset folded in on the host), one widening multiply-add onto the
+// lane's region pointer
+AFL_IN unsigned char* g128p(const Mem& m, int32_t elem) { return m.g128 + (uint64_t)(uint32_t)elem * (uint32_t)STRIDE128; }
+AFL_IN uint64_t* g64p(const Mem& m, int32_t elem) { return reinterpret_cast<uint64_t*>(m.g64 + (uint64_t)(uint32_t)elem * (uint32_t)STRIDE64); }
+AFL_IN uint32_t* g32p(const Mem& m, int32_t word) { return reinterpret_cast<uint32_t*>(m.g32 + (uint64_t)(uint32_t)word * (uint32_t)STRIDE32); }
 // cold words (global tier only): queue links of the Stores and Containers, drop counters -- touched at ties, under
 // contention, on a dropped request
 AFL_IN uint32_t c32_ld(const Mem& m, int32_t word) { return *g32p(m, AFL_C.g32_cold + word); }
 AFL_IN void c32_st(const Mem& m, int32_t word, uint32_t v) { *g32p(m, AFL_C.g32_cold + word) = v; }
-// tiered: entry idx of a table whose first `split` entries are in shared memory
-AFL_IN uint64_t ld_t64(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split) {
+// tiered tables: entry idx < split in shared memory (element os + idx), the rest in the global tier (element gi + idx)
+AFL_IN void ld_t128(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t& x, uint64_t& y) {
+    if (AFL_LIKELY(idx < split)) sm_ld128(a128(m, os + idx), x, y); else gl_ld128(g128p(m, gi + idx), x, y);
+}
+AFL_IN void st_t128(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t x, uint64_t y) {
+    if (AFL_LIKELY(idx < split)) sm_st128(a128(m, os + idx), x, y); else gl_st128(g128p(m, gi + idx), x, y);
+}
+AFL_IN uint64_t ld_t64(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split) {
     if (AFL_LIKELY(idx < split)) return e64_ld(m, os + idx);
-    return *g64p(m, og + idx - split);
+    return *g64p(m, gi + idx);
 }
-AFL_IN void st_t64(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split, uint64_t v) {
-    if (AFL_LIKELY(idx < split)) e64_st(m, os + idx, v); else *g64p(m, og + idx - split) = v;
+AFL_IN void st_t64(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t v) {
+    if (AFL_LIKELY(idx < split)) e64_st(m, os + idx, v); else *g64p(m, gi + idx) = v;
 }
-AFL_IN uint32_t ld_t32(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split) {
+AFL_IN uint32_t ld_t32(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split) {
     if (AFL_LIKELY(idx < split)) return w32_ld(m, os + idx);
-    return *g32p(m, og + idx - split);
+    return *g32p(m, gi + idx);
 }
-AFL_IN void st_t32(const Mem& m, int32_t os, int32_t og, int32_t idx, int32_t split, uint32_t v) {
-    if (AFL_LIKELY(idx < split)) w32_st(m, os + idx, v); else *g32p(m, og + idx - split) = v;
+AFL_IN void st_t32(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint32_t v) {
+    if (AFL_LIKELY(idx < split)) w32_st(m, os + idx, v); else *g32p(m, gi + idx) = v;
 }
 
 // the replica's scalar state: registers (nothing here is indexed dynamically)
@@ -259,15 +281,25 @@ AFL_IN uint32_t ep_total_ram(const Mem& m, uint32_t ep) {
     return p.c_ram >= 0 ? (uint32_t)row_val(m, p.c_ram) : p.total_ram;
 }
 
-// ---- request records (tiered): t0 | rid, pack, next ----------------------------------------------
-AFL_IN double rq_t0(const Mem& m, uint32_t s) { return afr::u2d(ld_t64(m, AFL_C.o64_t0, AFL_C.g64_t0, (int32_t)s, AFL_C.rq_s)); }
-AFL_IN void rq_t0_set(const Mem& m, uint32_t s, double v) { st_t64(m, AFL_C.o64_t0, AFL_C.g64_t0, (int32_t)s, AFL_C.rq_s, afr::d2u(v)); }
-AFL_IN uint32_t rq_rid(const Mem& m, uint32_t s) { return ld_t32(m, AFL_C.o32_rid, AFL_C.g32_rid, (int32_t)s, AFL_C.rq_s); }
-AFL_IN void rq_rid_set(const Mem& m, uint32_t s, uint32_t v) { st_t32(m, AFL_C.o32_rid, AFL_C.g32_rid, (int32_t)s, AFL_C.rq_s, v); }
-AFL_IN uint32_t rq_pack(const Mem& m, uint32_t s) { return ld_t32(m, AFL_C.o32_pack, AFL_C.g32_pack, (int32_t)s, AFL_C.rq_s); }
-AFL_IN void rq_pack_set(const Mem& m, uint32_t s, uint32_t v) { st_t32(m, AFL_C.o32_pack, AFL_C.g32_pack, (int32_t)s, AFL_C.rq_s, v); }
-AFL_IN uint32_t rq_next(const Mem& m, uint32_t s) { return ld_t32(m, AFL_C.o32_next, AFL_C.g32_next, (int32_t)s, AFL_C.rq_s); }
-AFL_IN void rq_next_set(const Mem& m, uint32_t s, uint32_t v) { st_t32(m, AFL_C.o32_next, AFL_C.g32_next, (int32_t)s, AFL_C.rq_s, v); }
+// ---- request records (tiered): one 128-bit element  t0 | id : pack  + the `next` link (32-bit table) ------------
+AFL_IN void rq_load(const Mem& m, uint32_t s, double& t0, uint32_t& rid, uint32_t& pack) {
+    uint64_t a, b;
+    ld_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, a, b);
+    t0 = afr::u2d(a); rid = (uint32_t)b; pack = (uint32_t)(b >> 32);
+}
+AFL_IN void rq_store(const Mem& m, uint32_t s, double t0, uint32_t rid, uint32_t pack) {
+    st_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, afr::d2u(t0), (uint64_t)rid | ((uint64_t)pack << 32));
+}
+AFL_IN uint32_t rq_pack(const Mem& m, uint32_t s) {
+    if (AFL_LIKELY((int32_t)s < AFL_C.rq_s)) return sm_ld32(a128(m, AFL_C.o128_rq + (int32_t)s) + 12u);
+    return *reinterpret_cast<const uint32_t*>(g128p(m, AFL_C.gi_rq + (int32_t)s) + 12);
+}
+AFL_IN void rq_pack_set(const Mem& m, uint32_t s, uint32_t v) {
+    if (AFL_LIKELY((int32_t)s < AFL_C.rq_s)) sm_st32(a128(m, AFL_C.o128_rq + (int32_t)s) + 12u, v);
+    else *reinterpret_cast<uint32_t*>(g128p(m, AFL_C.gi_rq + (int32_t)s) + 12) = v;
+}
+AFL_IN uint32_t rq_next(const Mem& m, uint32_t s) { return ld_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s); }
+AFL_IN void rq_next_set(const Mem& m, uint32_t s, uint32_t v) { st_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s, v); }
 
 AFL_IN uint32_t rq_alloc(St& W, const Mem& m) {
     uint32_t s;
@@ -295,11 +327,12 @@ AFL_IN uint32_t fifo_pop(const Mem& m, int32_t w_head, int32_t w_tail) {
     return s;
 }
 
-// ---- pending timed events: 4-ary min-heap on (time bits, seq), tiered ---------------------------------
-AFL_IN uint64_t ev_t(const Mem& m, int32_t i) { return ld_t64(m, AFL_C.o64_evt, AFL_C.g64_evt, i, AFL_C.ev_s); }
-AFL_IN uint64_t ev_k(const Mem& m, int32_t i) { return ld_t64(m, AFL_C.o64_evk, AFL_C.g64_evk, i, AFL_C.ev_s); }
-AFL_IN void ev_set(const Mem& m, int32_t i, uint64_t t, uint64_t k) {
-    st_t64(m, AFL_C.o64_evt, AFL_C.g64_evt, i, AFL_C.ev_s, t); st_t64(m, AFL_C.o64_evk, AFL_C.g64_evk, i, AFL_C.ev_s, k);
+// ---- pending timed events: 4-ary min-heap on (time bits, seq), tiered; one 128-bit element per event ----------
+AFL_IN void ev_get(const Mem& m, int32_t i, uint64_t& t, uint64_t& k) { ld_t128(m, AFL_C.o128_ev, AFL_C.gi_ev, i, AFL_C.ev_s, t, k); }
+AFL_IN void ev_set(const Mem& m, int32_t i, uint64_t t, uint64_t k) { st_t128(m, AFL_C.o128_ev, AFL_C.gi_ev, i, AFL_C.ev_s, t, k); }
+AFL_IN uint64_t ev_t(const Mem& m, int32_t i) {         // the time alone (root look-ahead)
+    if (AFL_LIKELY(i < AFL_C.ev_s)) return sm_ld64(a128(m, AFL_C.o128_ev + i));
+    return *reinterpret_cast<const uint64_t*>(g128p(m, AFL_C.gi_ev + i));
 }
 AFL_IN bool ev_less(uint64_t ta, uint64_t ka, uint64_t tb, uint64_t kb) {       // times are non-negative doubles: bit order = value order
     return ta < tb || (ta == tb && (uint32_t)(ka >> 32) < (uint32_t)(kb >> 32));
@@ -312,7 +345,8 @@ AFL_IN void heap_push(St& W, const Mem& m, uint64_t tb, uint64_t key) {
 #pragma unroll 1
     while (i > 0) {
         const int32_t p = (i - 1) >> 2;
-        const uint64_t tp = ev_t(m, p), kp = ev_k(m, p);
+        uint64_t tp, kp;
+        ev_get(m, p, tp, kp);
         if (!ev_less(tb, key, tp, kp)) break;
         ev_set(m, i, tp, kp);
         i = p;
@@ -323,17 +357,20 @@ AFL_IN void heap_push(St& W, const Mem& m, uint64_t tb, uint64_t key) {
 AFL_IN void heap_pop(St& W, const Mem& m) {
     const int32_t n = --W.ev_n;
     if (n == 0) return;
-    const uint64_t tl = ev_t(m, n), kl = ev_k(m, n);
+    uint64_t tl, kl;
+    ev_get(m, n, tl, kl);
     int32_t i = 0;
 #pragma unroll 1
     for (;;) {
         const int32_t c = 4 * i + 1;
         if (c >= n) break;
         int32_t b = c;
-        uint64_t tbst = ev_t(m, c), kbst = ev_k(m, c);
+        uint64_t tbst, kbst;
+        ev_get(m, c, tbst, kbst);
 #pragma unroll 1
         for (int32_t j = c + 1; j < c + 4 && j < n; ++j) {
-            const uint64_t tj = ev_t(m, j), kj = ev_k(m, j);
+            uint64_t tj, kj;
+            ev_get(m, j, tj, kj);
             if (ev_less(tj, kj, tbst, kbst)) { tbst = tj; kbst = kj; b = j; }
         }
         if (!ev_less(tbst, kbst, tl, kl)) break;
@@ -345,13 +382,13 @@ AFL_IN void heap_pop(St& W, const Mem& m) {
 
 // ---- now-queue (tiered ring of NQ_TOTAL items: seq << 32 | kind:3 aux:9 slot:20) ---------------------
 AFL_IN uint64_t nq_ld(const Mem& m, uint32_t pos) {
-    return ld_t64(m, AFL_C.o64_nq, AFL_C.g64_nq, (int32_t)(pos & (uint32_t)(NQ_TOTAL - 1)), AFL_C.nq_s);
+    return ld_t64(m, AFL_C.o64_nq, AFL_C.gi_nq, (int32_t)(pos & (uint32_t)(NQ_TOTAL - 1)), AFL_C.nq_s);
 }
 AFL_IN bool can_fuse(const St& W) { return AFL_LIKELY(W.busy == 0); }
 AFL_IN void nq_push(St& W, const Mem& m, uint32_t kind, uint32_t aux, uint32_t slot) {
     const uint32_t tail = W.nq_tail;
     if (tail - W.nq_head >= (uint32_t)NQ_TOTAL) { W.flags |= AF_FLAG_NOWQ_OVERFLOW; return; }
-    st_t64(m, AFL_C.o64_nq, AFL_C.g64_nq, (int32_t)(tail & (uint32_t)(NQ_TOTAL - 1)), AFL_C.nq_s,
+    st_t64(m, AFL_C.o64_nq, AFL_C.gi_nq, (int32_t)(tail & (uint32_t)(NQ_TOTAL - 1)), AFL_C.nq_s,
            ((uint64_t)(W.seq++) << 32) | mk_payload(kind, aux, slot));
     W.nq_tail = tail + 1;
     W.busy += 2u;
@@ -756,7 +793,7 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 } else {
                     const bool have_ev = W.ev_n > 0;
                     uint64_t tb = 0, key = 0;
-                    if (have_ev) { tb = ev_t(m, 0); key = ev_k(m, 0); }
+                    if (have_ev) ev_get(m, 0, tb, key);
                     if (have_item) {
                         const uint64_t front = nq_ld(m, W.nq_head);
                         const bool same_t = have_ev && tb == afr::d2u(W.now);
@@ -798,7 +835,7 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
         AFL_TRACE("%s t=%.17g seq=%u kind=%u aux=%u slot=%u\n", is_item ? "it" : "ev", W.now, ev_seq, kind, aux, slot);
         // everything that names a request reads its record here, once, for all kinds
         const bool names_request = is_event ? (kind == K_DELIVER || kind == K_STEP_END) : (is_item && kind != I_CLIENT_LOOP && kind != I_PUT);
-        if (names_request) { rid = rq_rid(m, slot); pack = rq_pack(m, slot); t0 = rq_t0(m, slot); }
+        if (names_request) rq_load(m, slot, t0, rid, pack);
         if (is_event) {
             if (kind == K_DELIVER) {                          // edge.py:110-116: the edge's timeout fired
                 conn_add(W, m, aux, -1);
@@ -824,8 +861,8 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 W.arm_seq = W.seq++;
                 W.need_arrival = 1;
                 if (slot != NIL) {
-                    rq_t0_set(m, slot, W.now); rq_rid_set(m, slot, rid);   // record_hop(generator): pack = 1 (stored by SEND)
-                    pack = 1u; edge = (uint32_t)C.gen_edge;
+                    pack = 1u; edge = (uint32_t)C.gen_edge;        // record_hop(generator)
+                    rq_store(m, slot, W.now, rid, pack);
                     act = A_SEND;
                 }
             } else if (kind == K_SPIKE) {

@@ -143,18 +143,14 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
         if (nq_s < 0) nq_s = 0;
     }
     C.ev_s = ev_s; C.ev_total = ev_total; C.rq_s = rq_s; C.rq_total = rq_total; C.nq_s = nq_s;
+    C.o128_ev = 0; C.o128_rq = ev_s; C.n128 = ev_s + rq_s;
     int32_t e = 0;
-    C.o64_evt = e; e += ev_s;
-    C.o64_evk = e; e += ev_s;
-    C.o64_t0 = e; e += rq_s;
     C.o64_nq = e; e += nq_s;
     C.o64_spike = e; e += C.n_spike > 0 ? C.n_edges : 0;
     C.o64_ssum = e; e += C.n_series;
     C.o64_row = e; e += C.n_row;
     C.n64 = e;
     int32_t w = 0;
-    C.o32_rid = w; w += rq_s;
-    C.o32_pack = w; w += rq_s;
     C.o32_next = w; w += rq_s;
     C.o32_conn = w; w += C.n_edges;
     C.o32_sent = w; w += C.n_edges;
@@ -163,23 +159,20 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     C.o32_smax = w; w += C.n_series;
     C.o32_dirty = w; w += C.n_dirty;
     C.n32 = w;
-    C.warp_bytes = (C.n64 * 8 + C.n32 * 4) * lanes;
-    // global tier
-    int32_t g = 0;
-    C.g64_evt = g; g += ev_total - ev_s;
-    C.g64_evk = g; g += ev_total - ev_s;
-    C.g64_t0 = g; g += rq_total - rq_s;
-    C.g64_nq = g; g += afl::NQ_TOTAL - nq_s;
-    C.gn64 = g;
-    int32_t h = 0;
-    C.g32_rid = h; h += rq_total - rq_s;
-    C.g32_pack = h; h += rq_total - rq_s;
-    C.g32_next = h; h += rq_total - rq_s;
-    C.g32_cold = h;
+    C.warp_bytes = (C.n128 * 16 + C.n64 * 8 + C.n32 * 4) * lanes;
+    // global tier: 128-bit region (events, request records), 64-bit region (now-queue), 32-bit region (links, cold words)
+    C.gi_ev = 0 - ev_s;
+    C.gi_rq = (ev_total - ev_s) - rq_s;
+    C.gn128 = (ev_total - ev_s) + (rq_total - rq_s);
+    C.gi_nq = 0 - nq_s;
+    C.gn64 = afl::NQ_TOTAL - nq_s;
+    C.gi_next = 0 - rq_s;
+    int32_t hcount = rq_total - rq_s;
+    C.g32_cold = hcount;
     C.c_srvq = 0; C.c_inbox = C.c_srvq + afl::SQ_WORDS * C.n_servers; C.c_drop = C.c_inbox + afl::IB_WORDS * (C.n_servers + 2);
-    h += C.c_drop + C.n_edges;
-    C.gn32 = h;
-    C.gwarp_bytes = ((uint64_t)C.gn64 * 8 + (uint64_t)C.gn32 * 4) * (uint64_t)lanes;
+    hcount += C.c_drop + C.n_edges;
+    C.gn32 = hcount;
+    C.gwarp_bytes = ((uint64_t)C.gn128 * 16 + (uint64_t)C.gn64 * 8 + (uint64_t)C.gn32 * 4) * (uint64_t)lanes;
     return true;
 }
 

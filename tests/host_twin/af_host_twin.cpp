@@ -97,8 +97,8 @@ extern "C" int af_twin_run_lane(const AfScenario* sc, const AfSweep* sw, uint64_
     std::vector<uint64_t> smem((size_t)C.warp_bytes / 8 + 2), glob((size_t)(C.gwarp_bytes / 8) + 2);
     afl::Mem m;
     afl::afl_smem_host = (unsigned char*)smem.data();
-    m.s64 = 0u; m.s32 = (uint32_t)((size_t)C.n64 * afl::STRIDE64);
-    m.g64 = (unsigned char*)glob.data(); m.g32 = m.g64 + (size_t)C.gn64 * afl::STRIDE64;
+    m.s128 = 0u; m.s64 = (uint32_t)((size_t)C.n128 * afl::STRIDE128); m.s32 = m.s64 + (uint32_t)((size_t)C.n64 * afl::STRIDE64);
+    m.g128 = (unsigned char*)glob.data(); m.g64 = m.g128 + (size_t)C.gn128 * afl::STRIDE128; m.g32 = m.g64 + (size_t)C.gn64 * afl::STRIDE64;
     uint64_t next = 0;
     afl::run_lane(m, [&]() -> uint64_t { return next < n ? next++ : ~0ull; }, [](bool alive) { return alive; });
     if (C.collect_hist && stats)
