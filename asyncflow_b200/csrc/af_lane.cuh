@@ -258,11 +258,13 @@ struct St {
     uint64_t replica, local;
     double now, horizon;
     uint32_t seq; int32_t ev_n; uint32_t peak_ev;
+    uint64_t arr_t; uint32_t arr_seq, arr_on;   // the generator's pending timeout: always exactly one, kept out of the heap
     uint32_t nq_head, nq_tail, busy;            // busy = 2 * (items in the now-queue) + (the heap may hold an event of this instant)
     uint32_t rq_free, rq_hw, rq_live, peak_rq;
     uint32_t n_waiting;                         // requests parked in a RAM / CPU waiter FIFO (0: every such FIFO is empty, no need to look)
     double g_vnow, g_wend, g_lam;               // generator: the sampler's virtual clock (the simulation's is `now`)
     uint32_t g_pos, generated, g_done, need_arrival, arm_seq;
+    double gap0, gap1; uint32_t gap_cnt;        // inter-arrival gaps drawn ahead (see the SEND phase)
     double users_mean, users_sigma, rate_per_user;
     int32_t lb_n, spike_cur, outage_cur;
     uint32_t tick_seq, n_ticks; double tick_time;
@@ -339,9 +341,10 @@ AFL_IN bool ev_less(uint64_t ta, uint64_t ka, uint64_t tb, uint64_t kb) {       
 }
 AFL_IN void heap_push(St& W, const Mem& m, uint64_t tb, uint64_t key) {
     int32_t i = W.ev_n;
-    if (AFL_UNLIKELY(i >= AFL_C.ev_total)) { W.flags |= AF_FLAG_EVENT_OVERFLOW; return; }
+    const int32_t pending = i + (int32_t)W.arr_on;     // the generator's timeout counts as a pending event
+    if (AFL_UNLIKELY(pending >= AFL_C.ev_total)) { W.flags |= AF_FLAG_EVENT_OVERFLOW; return; }
     W.ev_n = i + 1;
-    if ((uint32_t)(i + 1) > W.peak_ev) W.peak_ev = (uint32_t)(i + 1);
+    if ((uint32_t)(pending + 1) > W.peak_ev) W.peak_ev = (uint32_t)(pending + 1);
 #pragma unroll 1
     while (i > 0) {
         const int32_t p = (i - 1) >> 2;
@@ -622,10 +625,11 @@ AFL_IN void start_replica(St& W, const Mem& m, uint64_t local_index) {
     W.local = local_index;
     W.replica = C.replica_begin + local_index;
     W.now = 0.0; W.horizon = (double)C.horizon_s; W.seq = 0;
-    W.ev_n = 0; W.peak_ev = 0;
+    W.ev_n = 0; W.peak_ev = 0; W.arr_t = 0; W.arr_seq = 0; W.arr_on = 0;
     W.nq_head = 0; W.nq_tail = 0; W.busy = 0;
     W.rq_free = NIL; W.rq_hw = 0; W.rq_live = 0; W.peak_rq = 0; W.n_waiting = 0;
     W.g_vnow = 0.0; W.g_wend = 0.0; W.g_lam = 0.0; W.g_pos = 0; W.generated = 0; W.g_done = 0;
+    W.gap0 = 0.0; W.gap1 = 0.0; W.gap_cnt = 0;
     W.lb_n = C.n_lb_edges; W.spike_cur = 0; W.outage_cur = 0;
     W.n_ticks = 0; W.completed = 0; W.flags = 0; W.n_events = 0;
     W.lat_sum = 0.0; W.lat_sumsq = 0.0; W.lat_min = afr::u2d(INF_BITS); W.lat_max = 0.0;
@@ -767,12 +771,19 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
         // ---- phase: the generator's next timeout (rqs_generator.py:103-104) ------------------------------
         if (run && W.need_arrival && !dead) {
             W.need_arrival = 0;
-            double gap;
-            if (!W.g_done && gen_next_gap(W, gap)) {
+            double gap = 0.0;
+            bool have = false;
+            if (W.gap_cnt) { gap = W.gap0; W.gap0 = W.gap1; W.gap_cnt -= 1u; have = true; }      // drawn ahead
+            else if (!W.g_done && gen_next_gap(W, gap)) have = true;                          // (rare: see the SEND phase)
+            if (have) {
                 const double t = W.now + gap;
                 if (t < W.horizon) {                         // env.run(until=T): events at >= T never fire
                     if (AFL_UNLIKELY(t == W.now)) W.busy |= 1u;
-                    heap_push(W, m, afr::d2u(t), ((uint64_t)W.arm_seq << 32) | mk_payload(K_ARRIVAL, 0, 0));
+                    if (AFL_UNLIKELY(W.ev_n >= AFL_C.ev_total)) W.flags |= AF_FLAG_EVENT_OVERFLOW;
+                    else {
+                        W.arr_t = afr::d2u(t); W.arr_seq = W.arm_seq; W.arr_on = 1u;
+                        if ((uint32_t)W.ev_n + 1u > W.peak_ev) W.peak_ev = (uint32_t)W.ev_n + 1u;
+                    }
                 }
             } else W.g_done = 1;
         }
@@ -791,9 +802,15 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                     word = nq_take(W, m);
                     is_item = true;
                 } else {
-                    const bool have_ev = W.ev_n > 0;
+                    const bool have_heap = W.ev_n > 0, have_ev = have_heap || W.arr_on != 0;
                     uint64_t tb = 0, key = 0;
-                    if (have_ev) ev_get(m, 0, tb, key);
+                    if (have_heap) ev_get(m, 0, tb, key);
+                    const uint64_t root_t = tb;
+                    bool take_arr = false;                // the earliest timed event: the heap's root or the generator's timeout
+                    if (W.arr_on) {
+                        const uint64_t ak = ((uint64_t)W.arr_seq << 32) | mk_payload(K_ARRIVAL, 0, 0);
+                        if (!have_heap || ev_less(W.arr_t, ak, tb, key)) { tb = W.arr_t; key = ak; take_arr = true; }
+                    }
                     if (have_item) {
                         const uint64_t front = nq_ld(m, W.nq_head);
                         const bool same_t = have_ev && tb == afr::d2u(W.now);
@@ -804,8 +821,9 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                         }
                     } else if (!have_ev) finish = true;
                     if (!is_item && !finish) {
-                        heap_pop(W, m);
-                        const bool more = W.ev_n > 0 && ev_t(m, 0) == tb;
+                        bool more;
+                        if (take_arr) { W.arr_on = 0u; more = have_heap && root_t == tb; }
+                        else { heap_pop(W, m); more = (W.ev_n > 0 && ev_t(m, 0) == tb) || (W.arr_on && W.arr_t == tb); }
                         W.busy = (W.busy & ~1u) | (more ? 1u : 0u);
                         t_ev = afr::u2d(tb); ev_seq = (uint32_t)(key >> 32); word = (uint32_t)key;
                         is_event = true;
@@ -1052,26 +1070,92 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
         AFL_SYNC();
 
         // ---- phase: EdgeRuntime.transport -> _deliver up to its timeout (edge.py:73-107) ---------------------------
-        if (act == A_SEND) {
-            act = A_NONE;
-            const EdgeP E = ro(C.edges + edge);
-            const uint32_t s = W.seq++;                      // the timeout's place in SimPy's eid order
-            const double dropout = E.c_drop >= 0 ? row_val(m, E.c_drop) : E.dropout;
-            const double mean = E.c_mean >= 0 ? row_val(m, E.c_mean) : E.mean;
-            const double sigma = E.c_sigma >= 0 ? row_val(m, E.c_sigma) : E.sigma;
-            const afr::EdgeDraw d = afr::edge_draw(C.seed, W.replica, rid, pk_hops(pack), (int)(E.meta & 7u), mean, sigma, dropout);
-            w32_st(m, C.o32_sent + (int32_t)edge, w32_ld(m, C.o32_sent + (int32_t)edge) + 1);
-            if (d.u < dropout) {                            // the request vanishes (edge.py:79-86)
-                c32_st(m, C.c_drop + (int32_t)edge, c32_ld(m, C.c_drop + (int32_t)edge) + 1);
-                rq_release(W, m, slot);
-            } else {
-                rq_pack_set(m, slot, pack);                  // (the one store of the record on the request's way out of a node)
-                conn_add(W, m, edge, 1);
-                double effective = d.transit;
-                if (C.n_spike > 0) effective = d.transit + f64_ld(m, C.o64_spike + (int32_t)edge);   // spike read at SEND time (edge.py:94-106)
-                else effective = d.transit + 0.0;           // (-0.0 + 0.0 = +0.0, as with a spike table of zeros)
-                tm_t = W.now + effective; tm_payload = mk_payload(K_DELIVER, edge, slot); tm_seq = s;
-                act = A_TIMER;
+        // The edge's variates are the most expensive thing an event does (Philox, a logarithm, a division), and the
+        // lanes that do not send in this iteration would sit them out.  They ride along instead: a lane whose
+        // generator has room in its two-deep gap buffer draws its NEXT inter-arrival gap here -- same Philox, same
+        // logarithm, same division, other operands.  AF-RNG is counter-based and the generator's stream is a function
+        // of its own virtual clock alone, so WHEN a gap is drawn cannot change it.  Only the plain case is taken (one
+        // uniform, inside the current window); anything else is left to gen_next_gap at the arrival.
+        {
+            const bool send = act == A_SEND;
+            uint32_t s = 0; double dropout = 0.0, mean = 0.0, sigma = 0.0; int dist = 0;
+            if (send) {
+                act = A_NONE;
+                const EdgeP E = ro(C.edges + edge);
+                s = W.seq++;                                 // the timeout's place in SimPy's eid order
+                dropout = E.c_drop >= 0 ? row_val(m, E.c_drop) : E.dropout;
+                mean = E.c_mean >= 0 ? row_val(m, E.c_mean) : E.mean;
+                sigma = E.c_sigma >= 0 ? row_val(m, E.c_sigma) : E.sigma;
+                dist = (int)(E.meta & 7u);
+            }
+            const bool fast = send && (dist == 1 /*NORMAL*/ || dist == 3 /*EXPONENTIAL*/);
+            const bool ride = !send && (is_event || is_item) && !finish && W.gap_cnt < 2u && !W.g_done
+                              && W.g_vnow < W.horizon && W.g_vnow < W.g_wend && W.g_lam > 0.0;
+            double u = 0.0, transit = 0.0;
+            if (send && !fast) {                             // the other distributions: the general sampler, out of line
+                const afr::EdgeDraw d = afr::edge_draw(C.seed, W.replica, rid, pk_hops(pack), dist, mean, sigma, dropout);
+                u = d.u; transit = d.transit;
+            }
+            if (fast || ride) {
+                const uint32_t k0 = (uint32_t)C.seed, k1 = (uint32_t)(C.seed >> 32);
+                const uint32_t tag = (afr::P_EDGE << 24) | ((pk_hops(pack) & 0xFFFFu) << 8);
+                afr::U4 c;
+                c.x = send ? rid : (W.g_pos >> 1); c.y = send ? tag : (afr::P_GEN << 24);
+                c.z = (uint32_t)W.replica; c.w = (uint32_t)(W.replica >> 32);
+                afr::U4 w = afr::philox4x32_10(c, k0, k1);
+                double arg = 1.0, v1 = 0.0, q = 1.0;
+                bool need = true;
+                if (send) {
+                    u = afr::u53(w.x, w.y);                  // rng.uniform() < dropout_rate (edge.py:78)
+                    if (u < dropout) need = false;
+                    else if (dist == 3) arg = 1.0 - afr::u53(w.z, w.w);
+                    else {                                   // polar method: first pair from this block, more from the next ones
+                        v1 = afr::s32(w.z); const double v2 = afr::s32(w.w);
+                        q = v1 * v1 + v2 * v2;
+                        uint32_t blk = 0; bool second = true;
+#pragma unroll 1
+                        while (!(q > 0.0 && q < 1.0)) {
+                            if (second) { ++blk; c.y = tag | (blk & 0xFFu); w = afr::philox4x32_10(c, k0, k1); v1 = afr::s32(w.x); const double b = afr::s32(w.y); q = v1 * v1 + b * b; }
+                            else { v1 = afr::s32(w.z); const double b = afr::s32(w.w); q = v1 * v1 + b * b; }
+                            second = !second;
+                        }
+                        arg = q;
+                    }
+                } else {
+                    double ug = (W.g_pos & 1u) ? afr::u53(w.z, w.w) : afr::u53(w.x, w.y);
+                    if (ug < 1e-15) ug = 1e-15;             // max(u, 1e-15)
+                    arg = 1.0 - ug;
+                }
+                double L = 0.0;
+                if (need) L = afr::af_log(arg);
+                const bool divide = need && !(send && dist == 3);
+                double D = 0.0;
+                if (divide) D = send ? afr::af_div(-2.0 * L, q) : afr::af_div(-L, W.g_lam);
+                if (send) {
+                    if (need) {
+                        if (dist == 3) transit = mean * -L;
+                        else { const double v = mean + sigma * (v1 * afr::af_sqrt(D)); transit = v > 0.0 ? v : 0.0; }
+                    }
+                } else if (!(W.g_vnow + D > W.horizon) && !(W.g_vnow + D >= W.g_wend)) {       // the plain case of gen_next_gap
+                    W.g_vnow += D; W.g_pos += 1u;
+                    if (W.gap_cnt == 0u) W.gap0 = D; else W.gap1 = D;
+                    W.gap_cnt += 1u;
+                }
+            }
+            if (send) {
+                w32_st(m, C.o32_sent + (int32_t)edge, w32_ld(m, C.o32_sent + (int32_t)edge) + 1);
+                if (u < dropout) {                          // the request vanishes (edge.py:79-86)
+                    c32_st(m, C.c_drop + (int32_t)edge, c32_ld(m, C.c_drop + (int32_t)edge) + 1);
+                    rq_release(W, m, slot);
+                } else {
+                    rq_pack_set(m, slot, pack);              // (the one store of the record on the request's way out of a node)
+                    conn_add(W, m, edge, 1);
+                    double effective = transit;
+                    if (C.n_spike > 0) effective = transit + f64_ld(m, C.o64_spike + (int32_t)edge);   // spike read at SEND time (edge.py:94-106)
+                    else effective = transit + 0.0;         // (-0.0 + 0.0 = +0.0, as with a spike table of zeros)
+                    tm_t = W.now + effective; tm_payload = mk_payload(K_DELIVER, edge, slot); tm_seq = s;
+                    act = A_TIMER;
+                }
             }
         }
         AFL_SYNC();

@@ -6,14 +6,18 @@ cd "$(dirname "$0")/.." || exit 1
 QB="timeout 200 python tools/quick_bench.py"
 echo "=== smoke"; timeout 300 python __graft_entry__.py --smoke || { echo "SMOKE FAILED: stopping"; exit 1; }
 echo "=== parity (auto)"; timeout 400 python tools/check_variant_gpu.py || { echo "PARITY FAILED (auto): stopping"; exit 1; }
-for wpb in ${WPBS:-8 12}; do
+for wpb in ${WPBS:-12}; do
   echo "=== C3 rtt sweep 80000 x 20 s, lane, $wpb warps/SM"; $QB --scenario c3_lb_two_servers.yml --replicas 80000 --horizon 20 --reps 2 --mode auto --wpb $wpb | tail -2
+done
+for cap in ${CAPS:-460}; do
+  echo "=== C3 rtt sweep 80000 x 20 s, lane, 12 warps/SM, at most $cap B of shared memory per lane (rest of the 256 KB to L1)"
+  ASYNCFLOW_B200_LANE_BYTES=$cap $QB --scenario c3_lb_two_servers.yml --replicas 80000 --horizon 20 --reps 2 --mode auto --wpb 12 | tail -2
 done
 echo "=== C1 x 40000 x 60 s"; $QB --scenario c1_my_service.yml --replicas 40000 --horizon 60 --reps 2 --sweep none | tail -2
 echo "=== C4 20000 x 120 s"; $QB --scenario c4_lb8_events.yml --replicas 20000 --horizon 120 --reps 2 --sweep none | tail -2
 echo "=== C2 users sweep 10000 x 60 s"; $QB --scenario c1_my_service.yml --replicas 10000 --horizon 60 --reps 1 --sweep users | tail -2
 echo "=== C5 10000 x 10 s"; $QB --scenario c5_multihop32.yml --replicas 10000 --horizon 10 --reps 1 --sweep none | tail -2
-for wpb in ${BENCH_WPBS:-0 8}; do
+for wpb in ${BENCH_WPBS:-0}; do
   echo "=== bench.py --wpb $wpb"; timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --wpb $wpb | python -c "
 import json,sys
 d=json.loads(sys.stdin.readline()); print({k:d[k] for k in ('value','ms_per_step','replicas_overflowed','passes')}, d['e2e']['value'])"
