@@ -80,12 +80,12 @@ __global__ void AF_LAUNCH_BOUNDS af_sim_kernel() {
 #ifndef AF_LANE_MAX_THREADS
 #define AF_LANE_MAX_THREADS 384
 #endif
-__global__ void __launch_bounds__(AF_LANE_MAX_THREADS, 1) af_lane_kernel() {
+template <bool WIDE> __global__ void __launch_bounds__(AF_LANE_MAX_THREADS, 1) af_lane_kernel() {
     const afl::Cfg& C = afl::c_cfg;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t ws = warp * (uint32_t)C.warp_bytes;
     unsigned char* gs = C.gtier + ((uint64_t)blockIdx.x * (blockDim.x >> 5) + warp) * C.gwarp_bytes;
-    afl::Mem m;
+    afl::MemT<WIDE> m;
     m.s128 = ws + lane * 16u;
     m.s64 = ws + (uint32_t)C.n128 * (uint32_t)afl::STRIDE128 + lane * 8u;
     m.s32 = ws + (uint32_t)C.n128 * (uint32_t)afl::STRIDE128 + (uint32_t)C.n64 * (uint32_t)afl::STRIDE64 + lane * 4u;
@@ -491,9 +491,12 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
         }
         lane_warps = e->opt.warps_per_block > 0 ? e->opt.warps_per_block : AF_LANE_DEFAULT_WARPS;
         if (lane_warps > AF_LANE_MAX_THREADS / 32) lane_warps = AF_LANE_MAX_THREADS / 32;
-        // fewer warps per SM when the topology's fixed tables need a larger share of shared memory
-        while (lane_warps > 1 && lane_budget(e, lane_warps) < aflh::min_lane_bytes(e->sc, e->lt) + 64)
-            lane_warps -= lane_warps > 8 ? 4 : (lane_warps > 4 ? 2 : 1);
+        // A topology whose fixed tables do not fit a lane's share of shared memory at this occupancy keeps them in the
+        // global tier (make_cfg: WIDE) rather than running at a fraction of the occupancy.
+        // (experiments: ASYNCFLOW_B200_LANE_NARROW=1 lowers the occupancy until they fit, the round-2a behaviour)
+        if (getenv("ASYNCFLOW_B200_LANE_NARROW"))
+            while (lane_warps > 1 && lane_budget(e, lane_warps) < 2 * aflh::fixed_lane_bytes(e->sc, e->lt))
+                lane_warps -= lane_warps > 8 ? 4 : (lane_warps > 4 ? 2 : 1);
         memset(&C, 0, sizeof C);
         if (!aflh::make_cfg(e->sc, o, e->lt, lane_budget(e, lane_warps), afh::trace_tick_capacity(e->sc), 32, C)) {
             if (e->mode == AF_MODE_LANE) return e->fail(AF_ERR_INVALID, "scenario tables do not fit a lane's shared memory (thread-per-replica engine)");
@@ -530,7 +533,8 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     uint64_t lgrid = 0; size_t lsmem = 0;
     if (lane) {
         lsmem = (size_t)lane_warps * (size_t)C.warp_bytes;
-        AF_CUDA(e, cudaFuncSetAttribute(af_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem), "smem attribute");
+        AF_CUDA(e, C.wide ? cudaFuncSetAttribute(af_lane_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem)
+                          : cudaFuncSetAttribute(af_lane_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem), "smem attribute");
         lgrid = (uint64_t)e->sm_count;
         const uint64_t need = (n + (uint64_t)lane_warps * 32 - 1) / ((uint64_t)lane_warps * 32);
         if (lgrid > need) lgrid = need;
@@ -623,7 +627,8 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
         AF_CUDA(e, cudaMemsetAsync(e->d_counter2.p, 0, 8, e->stream), "memset");
         AF_CUDA(e, cudaMemsetAsync(e->d_redo_count.p, 0, 4, e->stream), "memset");
         AF_CUDA(e, cudaMemcpyToSymbolAsync(afl::c_cfg, &C, sizeof C, 0, cudaMemcpyHostToDevice, e->stream), "lane config -> constant memory");
-        af_lane_kernel<<<(unsigned)lgrid, lane_warps * 32, lsmem, e->stream>>>();
+        if (C.wide) af_lane_kernel<true><<<(unsigned)lgrid, lane_warps * 32, lsmem, e->stream>>>();
+        else af_lane_kernel<false><<<(unsigned)lgrid, lane_warps * 32, lsmem, e->stream>>>();
         AF_CUDA(e, cudaGetLastError(), "af_lane_kernel launch");
         e->launches += 1;
         if (redo) {

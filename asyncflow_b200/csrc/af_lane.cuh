@@ -139,8 +139,9 @@ struct Cfg {
     // global tier of a warp (same interleave).  gi_* = (offset of the table in its region) - (entries kept in shared
     // memory): entry idx >= split lives at element idx + gi_* of the region
     int32_t gi_ev, gi_rq, gn128;
-    int32_t gi_nq, gn64;
-    int32_t gi_next, g32_cold, gn32;
+    int32_t gi_nq, gf64, gn64;
+    int32_t gi_next, g32_cold, gf32, gn32;
+    int32_t wide;                                   // 1: the fixed tables live in the global tier (elements gf64 + e / words gf32 + w)
     int32_t c_srvq, c_inbox, c_drop;                // cold words (offsets from g32_cold): waiter FIFOs, mailboxes, drop counters
     uint64_t gwarp_bytes;                           // gn128 * 512 + gn64 * 256 + gn32 * 128
     // device pointers
@@ -187,9 +188,10 @@ template <class T> AFL_IN T ro(const T* p) {
 // instructions per access on sm_100a (S2R SR_CgaCtaId + MOV + LEA + IADD rebuild the window base every time:
 // ncu r02b, 33 % of the executed instructions), a generic pointer costs 64-bit arithmetic.  A tiered table takes a
 // BRANCH on "is it in shared memory", not a select.  All shared accesses are volatile asm: they keep program order.
-struct Mem {
+template <bool WIDE> struct MemT {
     uint32_t s128, s64, s32;                    // shared-memory regions of the warp (window addresses, the lane's column)
     unsigned char* g128; unsigned char* g64; unsigned char* g32;     // global tier of the warp, already offset by the lane
+    static constexpr bool wide = WIDE;          // Cfg::wide, at compile time: one kernel per value, no test per access
 };
 #if AFL_DEVICE
 AFL_IN uint32_t sm_ld32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -211,46 +213,50 @@ AFL_IN void sm_st128(uint32_t a, uint64_t x, uint64_t y) { memcpy(afl_smem_host 
 AFL_IN void gl_ld128(const unsigned char* p, uint64_t& x, uint64_t& y) { memcpy(&x, p, 8); memcpy(&y, p + 8, 8); }
 AFL_IN void gl_st128(unsigned char* p, uint64_t x, uint64_t y) { memcpy(p, &x, 8); memcpy(p + 8, &y, 8); }
 #endif
-AFL_IN uint32_t a128(const Mem& m, int32_t elem) { return m.s128 + (uint32_t)elem * (uint32_t)STRIDE128; }
-AFL_IN uint32_t a64(const Mem& m, int32_t elem) { return m.s64 + (uint32_t)elem * (uint32_t)STRIDE64; }
-AFL_IN uint32_t a32(const Mem& m, int32_t word) { return m.s32 + (uint32_t)word * (uint32_t)STRIDE32; }
-AFL_IN uint64_t e64_ld(const Mem& m, int32_t elem) { return sm_ld64(a64(m, elem)); }
-AFL_IN void e64_st(const Mem& m, int32_t elem, uint64_t v) { sm_st64(a64(m, elem), v); }
-AFL_IN double f64_ld(const Mem& m, int32_t elem) { return afr::u2d(sm_ld64(a64(m, elem))); }
-AFL_IN void f64_st(const Mem& m, int32_t elem, double v) { sm_st64(a64(m, elem), afr::d2u(v)); }
-AFL_IN uint32_t w32_ld(const Mem& m, int32_t word) { return sm_ld32(a32(m, word)); }
-AFL_IN void w32_st(const Mem& m, int32_t word, uint32_t v) { sm_st32(a32(m, word), v); }
-AFL_IN int32_t i32_ld(const Mem& m, int32_t word) { return (int32_t)sm_ld32(a32(m, word)); }
-AFL_IN void i32_st(const Mem& m, int32_t word, int32_t v) { sm_st32(a32(m, word), (uint32_t)v); }
+template <class Mem> AFL_IN uint32_t a128(const Mem& m, int32_t elem) { return m.s128 + (uint32_t)elem * (uint32_t)STRIDE128; }
+template <class Mem> AFL_IN uint32_t a64(const Mem& m, int32_t elem) { return m.s64 + (uint32_t)elem * (uint32_t)STRIDE64; }
+template <class Mem> AFL_IN uint32_t a32(const Mem& m, int32_t word) { return m.s32 + (uint32_t)word * (uint32_t)STRIDE32; }
 // global tier: ONE 32-bit element index (table offset folded in on the host), one widening multiply-add onto the
 // lane's region pointer
-AFL_IN unsigned char* g128p(const Mem& m, int32_t elem) { return m.g128 + (uint64_t)(uint32_t)elem * (uint32_t)STRIDE128; }
-AFL_IN uint64_t* g64p(const Mem& m, int32_t elem) { return reinterpret_cast<uint64_t*>(m.g64 + (uint64_t)(uint32_t)elem * (uint32_t)STRIDE64); }
-AFL_IN uint32_t* g32p(const Mem& m, int32_t word) { return reinterpret_cast<uint32_t*>(m.g32 + (uint64_t)(uint32_t)word * (uint32_t)STRIDE32); }
+template <class Mem> AFL_IN unsigned char* g128p(const Mem& m, int32_t elem) { return m.g128 + (uint64_t)(uint32_t)elem * (uint32_t)STRIDE128; }
+template <class Mem> AFL_IN uint64_t* g64p(const Mem& m, int32_t elem) { return reinterpret_cast<uint64_t*>(m.g64 + (uint64_t)(uint32_t)elem * (uint32_t)STRIDE64); }
+template <class Mem> AFL_IN uint32_t* g32p(const Mem& m, int32_t word) { return reinterpret_cast<uint32_t*>(m.g32 + (uint64_t)(uint32_t)word * (uint32_t)STRIDE32); }
+// The FIXED tables (gauges, connection / send counters, server levels, LB order, sweep-row copy, spike offsets):
+// in shared memory for a narrow topology; a WIDE one (their bytes would leave a lane no room for events at a useful
+// occupancy: 32 nodes = 2.9 KB) keeps them in the global tier, L2-resident, and shared memory goes to the heap and
+// the request records.  `wide` is a property of the launch: the kernel is compiled once per value (MemT<WIDE>), no test per access.
+template <class Mem> AFL_IN uint64_t e64_ld(const Mem& m, int32_t elem) { if (Mem::wide) return *g64p(m, AFL_C.gf64 + elem); return sm_ld64(a64(m, elem)); }
+template <class Mem> AFL_IN void e64_st(const Mem& m, int32_t elem, uint64_t v) { if (Mem::wide) *g64p(m, AFL_C.gf64 + elem) = v; else sm_st64(a64(m, elem), v); }
+template <class Mem> AFL_IN double f64_ld(const Mem& m, int32_t elem) { return afr::u2d(e64_ld(m, elem)); }
+template <class Mem> AFL_IN void f64_st(const Mem& m, int32_t elem, double v) { e64_st(m, elem, afr::d2u(v)); }
+template <class Mem> AFL_IN uint32_t w32_ld(const Mem& m, int32_t word) { if (Mem::wide) return *g32p(m, AFL_C.gf32 + word); return sm_ld32(a32(m, word)); }
+template <class Mem> AFL_IN void w32_st(const Mem& m, int32_t word, uint32_t v) { if (Mem::wide) *g32p(m, AFL_C.gf32 + word) = v; else sm_st32(a32(m, word), v); }
+template <class Mem> AFL_IN int32_t i32_ld(const Mem& m, int32_t word) { return (int32_t)w32_ld(m, word); }
+template <class Mem> AFL_IN void i32_st(const Mem& m, int32_t word, int32_t v) { w32_st(m, word, (uint32_t)v); }
 // cold words (global tier only): queue links of the Stores and Containers, drop counters -- touched at ties, under
 // contention, on a dropped request
-AFL_IN uint32_t c32_ld(const Mem& m, int32_t word) { return *g32p(m, AFL_C.g32_cold + word); }
-AFL_IN void c32_st(const Mem& m, int32_t word, uint32_t v) { *g32p(m, AFL_C.g32_cold + word) = v; }
+template <class Mem> AFL_IN uint32_t c32_ld(const Mem& m, int32_t word) { return *g32p(m, AFL_C.g32_cold + word); }
+template <class Mem> AFL_IN void c32_st(const Mem& m, int32_t word, uint32_t v) { *g32p(m, AFL_C.g32_cold + word) = v; }
 // tiered tables: entry idx < split in shared memory (element os + idx), the rest in the global tier (element gi + idx)
-AFL_IN void ld_t128(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t& x, uint64_t& y) {
+template <class Mem> AFL_IN void ld_t128(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t& x, uint64_t& y) {
     if (AFL_LIKELY(idx < split)) sm_ld128(a128(m, os + idx), x, y); else gl_ld128(g128p(m, gi + idx), x, y);
 }
-AFL_IN void st_t128(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t x, uint64_t y) {
+template <class Mem> AFL_IN void st_t128(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t x, uint64_t y) {
     if (AFL_LIKELY(idx < split)) sm_st128(a128(m, os + idx), x, y); else gl_st128(g128p(m, gi + idx), x, y);
 }
-AFL_IN uint64_t ld_t64(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split) {
-    if (AFL_LIKELY(idx < split)) return e64_ld(m, os + idx);
+template <class Mem> AFL_IN uint64_t ld_t64(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split) {
+    if (AFL_LIKELY(idx < split)) return sm_ld64(a64(m, os + idx));
     return *g64p(m, gi + idx);
 }
-AFL_IN void st_t64(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t v) {
-    if (AFL_LIKELY(idx < split)) e64_st(m, os + idx, v); else *g64p(m, gi + idx) = v;
+template <class Mem> AFL_IN void st_t64(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t v) {
+    if (AFL_LIKELY(idx < split)) sm_st64(a64(m, os + idx), v); else *g64p(m, gi + idx) = v;
 }
-AFL_IN uint32_t ld_t32(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split) {
-    if (AFL_LIKELY(idx < split)) return w32_ld(m, os + idx);
+template <class Mem> AFL_IN uint32_t ld_t32(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split) {
+    if (AFL_LIKELY(idx < split)) return sm_ld32(a32(m, os + idx));
     return *g32p(m, gi + idx);
 }
-AFL_IN void st_t32(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint32_t v) {
-    if (AFL_LIKELY(idx < split)) w32_st(m, os + idx, v); else *g32p(m, gi + idx) = v;
+template <class Mem> AFL_IN void st_t32(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint32_t v) {
+    if (AFL_LIKELY(idx < split)) sm_st32(a32(m, os + idx), v); else *g32p(m, gi + idx) = v;
 }
 
 // the replica's scalar state: registers (nothing here is indexed dynamically)
@@ -277,33 +283,33 @@ struct St {
 constexpr uint32_t STOP_FLAGS = AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW | AF_FLAG_NOWQ_OVERFLOW | AF_FLAG_LB_EMPTY;
 
 // ---- swept parameters ----------------------------------------------------------------------------
-AFL_IN double row_val(const Mem& m, int32_t c) { return f64_ld(m, AFL_C.o64_row + c); }
-AFL_IN uint32_t ep_total_ram(const Mem& m, uint32_t ep) {
+template <class Mem> AFL_IN double row_val(const Mem& m, int32_t c) { return f64_ld(m, AFL_C.o64_row + c); }
+template <class Mem> AFL_IN uint32_t ep_total_ram(const Mem& m, uint32_t ep) {
     const EndpointP p = ro(AFL_C.endpoints + ep);
     return p.c_ram >= 0 ? (uint32_t)row_val(m, p.c_ram) : p.total_ram;
 }
 
 // ---- request records (tiered): one 128-bit element  t0 | id : pack  + the `next` link (32-bit table) ------------
-AFL_IN void rq_load(const Mem& m, uint32_t s, double& t0, uint32_t& rid, uint32_t& pack) {
+template <class Mem> AFL_IN void rq_load(const Mem& m, uint32_t s, double& t0, uint32_t& rid, uint32_t& pack) {
     uint64_t a, b;
     ld_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, a, b);
     t0 = afr::u2d(a); rid = (uint32_t)b; pack = (uint32_t)(b >> 32);
 }
-AFL_IN void rq_store(const Mem& m, uint32_t s, double t0, uint32_t rid, uint32_t pack) {
+template <class Mem> AFL_IN void rq_store(const Mem& m, uint32_t s, double t0, uint32_t rid, uint32_t pack) {
     st_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, afr::d2u(t0), (uint64_t)rid | ((uint64_t)pack << 32));
 }
-AFL_IN uint32_t rq_pack(const Mem& m, uint32_t s) {
+template <class Mem> AFL_IN uint32_t rq_pack(const Mem& m, uint32_t s) {
     if (AFL_LIKELY((int32_t)s < AFL_C.rq_s)) return sm_ld32(a128(m, AFL_C.o128_rq + (int32_t)s) + 12u);
     return *reinterpret_cast<const uint32_t*>(g128p(m, AFL_C.gi_rq + (int32_t)s) + 12);
 }
-AFL_IN void rq_pack_set(const Mem& m, uint32_t s, uint32_t v) {
+template <class Mem> AFL_IN void rq_pack_set(const Mem& m, uint32_t s, uint32_t v) {
     if (AFL_LIKELY((int32_t)s < AFL_C.rq_s)) sm_st32(a128(m, AFL_C.o128_rq + (int32_t)s) + 12u, v);
     else *reinterpret_cast<uint32_t*>(g128p(m, AFL_C.gi_rq + (int32_t)s) + 12) = v;
 }
-AFL_IN uint32_t rq_next(const Mem& m, uint32_t s) { return ld_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s); }
-AFL_IN void rq_next_set(const Mem& m, uint32_t s, uint32_t v) { st_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s, v); }
+template <class Mem> AFL_IN uint32_t rq_next(const Mem& m, uint32_t s) { return ld_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s); }
+template <class Mem> AFL_IN void rq_next_set(const Mem& m, uint32_t s, uint32_t v) { st_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s, v); }
 
-AFL_IN uint32_t rq_alloc(St& W, const Mem& m) {
+template <class Mem> AFL_IN uint32_t rq_alloc(St& W, const Mem& m) {
     uint32_t s;
     if (W.rq_free != NIL) { s = W.rq_free; W.rq_free = rq_next(m, s); }
     else if ((int32_t)W.rq_hw < AFL_C.rq_total) { s = W.rq_hw++; }
@@ -312,16 +318,16 @@ AFL_IN uint32_t rq_alloc(St& W, const Mem& m) {
     if (live > W.peak_rq) W.peak_rq = live;
     return s;
 }
-AFL_IN void rq_release(St& W, const Mem& m, uint32_t s) { rq_next_set(m, s, W.rq_free); W.rq_free = s; --W.rq_live; }
+template <class Mem> AFL_IN void rq_release(St& W, const Mem& m, uint32_t s) { rq_next_set(m, s, W.rq_free); W.rq_free = s; --W.rq_live; }
 
 // intrusive FIFOs through the `next` links; head / tail are COLD words
-AFL_IN void fifo_push(const Mem& m, int32_t w_head, int32_t w_tail, uint32_t s) {
+template <class Mem> AFL_IN void fifo_push(const Mem& m, int32_t w_head, int32_t w_tail, uint32_t s) {
     rq_next_set(m, s, NIL);
     const uint32_t tail = c32_ld(m, w_tail);
     if (tail == NIL) c32_st(m, w_head, s); else rq_next_set(m, tail, s);
     c32_st(m, w_tail, s);
 }
-AFL_IN uint32_t fifo_pop(const Mem& m, int32_t w_head, int32_t w_tail) {
+template <class Mem> AFL_IN uint32_t fifo_pop(const Mem& m, int32_t w_head, int32_t w_tail) {
     const uint32_t s = c32_ld(m, w_head);
     const uint32_t h = rq_next(m, s);
     c32_st(m, w_head, h);
@@ -330,16 +336,16 @@ AFL_IN uint32_t fifo_pop(const Mem& m, int32_t w_head, int32_t w_tail) {
 }
 
 // ---- pending timed events: 4-ary min-heap on (time bits, seq), tiered; one 128-bit element per event ----------
-AFL_IN void ev_get(const Mem& m, int32_t i, uint64_t& t, uint64_t& k) { ld_t128(m, AFL_C.o128_ev, AFL_C.gi_ev, i, AFL_C.ev_s, t, k); }
-AFL_IN void ev_set(const Mem& m, int32_t i, uint64_t t, uint64_t k) { st_t128(m, AFL_C.o128_ev, AFL_C.gi_ev, i, AFL_C.ev_s, t, k); }
-AFL_IN uint64_t ev_t(const Mem& m, int32_t i) {         // the time alone (root look-ahead)
+template <class Mem> AFL_IN void ev_get(const Mem& m, int32_t i, uint64_t& t, uint64_t& k) { ld_t128(m, AFL_C.o128_ev, AFL_C.gi_ev, i, AFL_C.ev_s, t, k); }
+template <class Mem> AFL_IN void ev_set(const Mem& m, int32_t i, uint64_t t, uint64_t k) { st_t128(m, AFL_C.o128_ev, AFL_C.gi_ev, i, AFL_C.ev_s, t, k); }
+template <class Mem> AFL_IN uint64_t ev_t(const Mem& m, int32_t i) {         // the time alone (root look-ahead)
     if (AFL_LIKELY(i < AFL_C.ev_s)) return sm_ld64(a128(m, AFL_C.o128_ev + i));
     return *reinterpret_cast<const uint64_t*>(g128p(m, AFL_C.gi_ev + i));
 }
 AFL_IN bool ev_less(uint64_t ta, uint64_t ka, uint64_t tb, uint64_t kb) {       // times are non-negative doubles: bit order = value order
     return ta < tb || (ta == tb && (uint32_t)(ka >> 32) < (uint32_t)(kb >> 32));
 }
-AFL_IN void heap_push(St& W, const Mem& m, uint64_t tb, uint64_t key) {
+template <class Mem> AFL_IN void heap_push(St& W, const Mem& m, uint64_t tb, uint64_t key) {
     int32_t i = W.ev_n;
     const int32_t pending = i + (int32_t)W.arr_on;     // the generator's timeout counts as a pending event
     if (AFL_UNLIKELY(pending >= AFL_C.ev_total)) { W.flags |= AF_FLAG_EVENT_OVERFLOW; return; }
@@ -357,7 +363,7 @@ AFL_IN void heap_push(St& W, const Mem& m, uint64_t tb, uint64_t key) {
     ev_set(m, i, tb, key);
 }
 // remove the root (the caller has read it)
-AFL_IN void heap_pop(St& W, const Mem& m) {
+template <class Mem> AFL_IN void heap_pop(St& W, const Mem& m) {
     const int32_t n = --W.ev_n;
     if (n == 0) return;
     uint64_t tl, kl;
@@ -384,11 +390,11 @@ AFL_IN void heap_pop(St& W, const Mem& m) {
 }
 
 // ---- now-queue (tiered ring of NQ_TOTAL items: seq << 32 | kind:3 aux:9 slot:20) ---------------------
-AFL_IN uint64_t nq_ld(const Mem& m, uint32_t pos) {
+template <class Mem> AFL_IN uint64_t nq_ld(const Mem& m, uint32_t pos) {
     return ld_t64(m, AFL_C.o64_nq, AFL_C.gi_nq, (int32_t)(pos & (uint32_t)(NQ_TOTAL - 1)), AFL_C.nq_s);
 }
 AFL_IN bool can_fuse(const St& W) { return AFL_LIKELY(W.busy == 0); }
-AFL_IN void nq_push(St& W, const Mem& m, uint32_t kind, uint32_t aux, uint32_t slot) {
+template <class Mem> AFL_IN void nq_push(St& W, const Mem& m, uint32_t kind, uint32_t aux, uint32_t slot) {
     const uint32_t tail = W.nq_tail;
     if (tail - W.nq_head >= (uint32_t)NQ_TOTAL) { W.flags |= AF_FLAG_NOWQ_OVERFLOW; return; }
     st_t64(m, AFL_C.o64_nq, AFL_C.gi_nq, (int32_t)(tail & (uint32_t)(NQ_TOTAL - 1)), AFL_C.nq_s,
@@ -396,7 +402,7 @@ AFL_IN void nq_push(St& W, const Mem& m, uint32_t kind, uint32_t aux, uint32_t s
     W.nq_tail = tail + 1;
     W.busy += 2u;
 }
-AFL_IN uint32_t nq_take(St& W, const Mem& m) {      // (the caller has adjusted `busy`)
+template <class Mem> AFL_IN uint32_t nq_take(St& W, const Mem& m) {      // (the caller has adjusted `busy`)
     const uint32_t item = (uint32_t)nq_ld(m, W.nq_head);
     W.nq_head += 1;
     if (W.nq_head == W.nq_tail) { W.nq_head = 0; W.nq_tail = 0; }   // empty: restart at the shared-memory end of the ring
@@ -442,34 +448,32 @@ AFL_IN bool gen_next_gap(St& W, double& gap) {
 // CHANGES:  sum over ticks of v  =  n_ticks * v_final - sum over changes of (delta * ticks taken before the change)
 // (u64 modular arithmetic: exact), and the maximum over ticks takes the OLD value at a change iff a tick has seen it
 // (one "changed since the last tick" bit per series, cleared by a tick).  Traced replicas also store every reading.
-AFL_IN void gauge_touch(const St& W, const Mem& m, int32_t j, uint32_t v_old, int32_t delta) {
-    const uint32_t aa = a64(m, AFL_C.o64_ssum + j);
-    sm_st64(aa, sm_ld64(aa) + (uint64_t)(int64_t)delta * (uint64_t)W.n_ticks);
-    const uint32_t da = a32(m, AFL_C.o32_dirty + (j >> 5));
-    const uint32_t d = sm_ld32(da), bit = 1u << (j & 31);
+template <class Mem> AFL_IN void gauge_touch(const St& W, const Mem& m, int32_t j, uint32_t v_old, int32_t delta) {
+    e64_st(m, AFL_C.o64_ssum + j, e64_ld(m, AFL_C.o64_ssum + j) + (uint64_t)(int64_t)delta * (uint64_t)W.n_ticks);
+    const int32_t dw = AFL_C.o32_dirty + (j >> 5);
+    const uint32_t d = w32_ld(m, dw), bit = 1u << (j & 31);
     if (!(d & bit)) {
-        const uint32_t ma = a32(m, AFL_C.o32_smax + j);
-        if (v_old > sm_ld32(ma)) sm_st32(ma, v_old);
-        sm_st32(da, d | bit);
+        if (v_old > w32_ld(m, AFL_C.o32_smax + j)) w32_st(m, AFL_C.o32_smax + j, v_old);
+        w32_st(m, dw, d | bit);
     }
 }
-AFL_IN void conn_add(const St& W, const Mem& m, uint32_t edge, int32_t delta) {
-    const uint32_t pa = a32(m, AFL_C.o32_conn + (int32_t)edge);
-    const uint32_t v = sm_ld32(pa);
+template <class Mem> AFL_IN void conn_add(const St& W, const Mem& m, uint32_t edge, int32_t delta) {
+    const int32_t pw = AFL_C.o32_conn + (int32_t)edge;
+    const uint32_t v = w32_ld(m, pw);
     if (AFL_C.metrics_mask & AF_METRIC_EDGE_CONN) gauge_touch(W, m, 3 * AFL_C.n_servers + (int32_t)edge, v, delta);
-    sm_st32(pa, v + (uint32_t)delta);
+    w32_st(m, pw, v + (uint32_t)delta);
 }
 AFL_IN int32_t ib_word(uint32_t node, int32_t f) { return AFL_C.c_inbox + (int32_t)node * IB_WORDS + f; }      // cold
 AFL_IN int32_t sq_word(uint32_t sidx, int32_t f) { return AFL_C.c_srvq + (int32_t)sidx * SQ_WORDS + f; }       // cold
 AFL_IN int32_t sv_word(uint32_t sidx, int32_t f) { return AFL_C.o32_srv + (int32_t)sidx * SV_WORDS + f; }
 // field = SV_READY_Q / SV_IO_Q / SV_RAM_IN_USE (series 3 * sidx + 0 / 1 / 2)
-AFL_IN void srv_gauge_add(const St& W, const Mem& m, uint32_t sidx, int32_t field, int32_t delta) {
-    const uint32_t pa = a32(m, sv_word(sidx, field));
-    const int32_t v = (int32_t)sm_ld32(pa);
+template <class Mem> AFL_IN void srv_gauge_add(const St& W, const Mem& m, uint32_t sidx, int32_t field, int32_t delta) {
+    const int32_t pw = sv_word(sidx, field);
+    const int32_t v = i32_ld(m, pw);
     if ((AFL_C.metrics_mask & 7u) == 7u) gauge_touch(W, m, 3 * (int32_t)sidx + (field - SV_READY_Q), (uint32_t)v, delta);
-    sm_st32(pa, (uint32_t)(v + delta));
+    i32_st(m, pw, v + delta);
 }
-AFL_IN uint32_t gauge_value(const Mem& m, int32_t j) {
+template <class Mem> AFL_IN uint32_t gauge_value(const Mem& m, int32_t j) {
     const int32_t ns3 = 3 * AFL_C.n_servers;
     if (j < ns3) { const int32_t mt = j % 3; return w32_ld(m, sv_word((uint32_t)(j / 3), mt == 0 ? SV_READY_Q : (mt == 1 ? SV_IO_Q : SV_RAM_IN_USE))); }
     return w32_ld(m, AFL_C.o32_conn + (j - ns3));
@@ -479,7 +483,7 @@ AFL_IN bool gauge_on(int32_t j) {
                                    : (AFL_C.metrics_mask & AF_METRIC_EDGE_CONN) != 0;
 }
 // every collector tick ordered before (t, ev_seq)
-AFL_IN void take_ticks(St& W, const Mem& m, double t, uint32_t ev_seq) {
+template <class Mem> AFL_IN void take_ticks(St& W, const Mem& m, double t, uint32_t ev_seq) {
     double tick = W.tick_time;
     uint32_t tseq = W.tick_seq, nt = W.n_ticks, seq = W.seq;
     const double horizon = W.horizon;
@@ -503,9 +507,9 @@ AFL_IN void take_ticks(St& W, const Mem& m, double t, uint32_t ev_seq) {
 
 // ---- Stores (mailboxes), Containers: as af_core.cuh ----------------------------------------------------
 // is the waiter FIFO whose head is cold word `head` empty?  (n_waiting == 0: all of them are, without looking)
-AFL_IN bool q_empty(const St& W, const Mem& m, int32_t head) { return AFL_LIKELY(W.n_waiting == 0) || c32_ld(m, head) == NIL; }
+template <class Mem> AFL_IN bool q_empty(const St& W, const Mem& m, int32_t head) { return AFL_LIKELY(W.n_waiting == 0) || c32_ld(m, head) == NIL; }
 // `yield box.get()` of the node's consumer process
-AFL_IN void consumer_get(St& W, const Mem& m, uint32_t node) {
+template <class Mem> AFL_IN void consumer_get(St& W, const Mem& m, uint32_t node) {
     if (AFL_UNLIKELY(c32_ld(m, ib_word(node, IB_HEAD)) != NIL)) {
         const uint32_t it = fifo_pop(m, ib_word(node, IB_HEAD), ib_word(node, IB_TAIL));
         nq_push(W, m, I_GOT, node, it);
@@ -513,7 +517,7 @@ AFL_IN void consumer_get(St& W, const Mem& m, uint32_t node) {
 }
 // Container._trigger_get over the CPU queue: grant heads while a core is free
 // (returns true when `watch` was among the granted: its get is "triggered" at the call)
-AFL_IN bool cpu_walk(St& W, const Mem& m, uint32_t sidx, uint32_t watch) {
+template <class Mem> AFL_IN bool cpu_walk(St& W, const Mem& m, uint32_t sidx, uint32_t watch) {
     bool hit = false;
 #pragma unroll 1
     while (!q_empty(W, m, sq_word(sidx, SQ_CPUQ_HEAD)) && i32_ld(m, sv_word(sidx, SV_CPU_FREE)) > 0) {
@@ -526,7 +530,7 @@ AFL_IN bool cpu_walk(St& W, const Mem& m, uint32_t sidx, uint32_t watch) {
     return hit;
 }
 // ... over the RAM queue: grant heads while they fit, stop at the first that does not
-AFL_IN void ram_walk(St& W, const Mem& m, uint32_t sidx) {
+template <class Mem> AFL_IN void ram_walk(St& W, const Mem& m, uint32_t sidx) {
 #pragma unroll 1
     while (!q_empty(W, m, sq_word(sidx, SQ_RAMQ_HEAD))) {
         const uint32_t need = c32_ld(m, sq_word(sidx, SQ_RAMQ_NEED));
@@ -541,7 +545,7 @@ AFL_IN void ram_walk(St& W, const Mem& m, uint32_t sidx) {
 }
 
 // ---- event injection (injection.py:167-226): all marks of this instant; returns true when the timeline re-arms
-AFL_IN bool on_spike(St& W, const Mem& m, double& next_fire) {
+template <class Mem> AFL_IN bool on_spike(St& W, const Mem& m, double& next_fire) {
     int32_t cur = W.spike_cur;
     const double t = ro(AFL_C.spikes + cur).fire;
 #pragma unroll 1
@@ -557,7 +561,7 @@ AFL_IN bool on_spike(St& W, const Mem& m, double& next_fire) {
     if (cur < AFL_C.n_spike) { next_fire = ro(AFL_C.spikes + cur).fire; return true; }
     return false;
 }
-AFL_IN bool on_outage(St& W, const Mem& m, double& next_fire) {
+template <class Mem> AFL_IN bool on_outage(St& W, const Mem& m, double& next_fire) {
     int32_t cur = W.outage_cur;
     const double t = ro(AFL_C.outages + cur).fire;
     int32_t n = W.lb_n;
@@ -591,7 +595,7 @@ static inline void red_add(uint32_t* p, uint32_t v) { *p += v; }
 #endif
 
 // client: completion (client.py:62-69 + analyzer.py:83-125)
-AFL_IN void complete(St& W, const Mem& m, uint32_t slot, double t0) {
+template <class Mem> AFL_IN void complete(St& W, const Mem& m, uint32_t slot, double t0) {
     const double now = W.now;
     const double lat = now - t0;                     // finish - start (analyzer.py:86-89)
     const uint32_t done = ++W.completed;
@@ -620,7 +624,7 @@ AFL_IN void complete(St& W, const Mem& m, uint32_t slot, double t0) {
 }
 
 // ---- set-up / write-back (once per replica) -----------------------------------------------------------------
-AFL_IN void start_replica(St& W, const Mem& m, uint64_t local_index) {
+template <class Mem> AFL_IN void start_replica(St& W, const Mem& m, uint64_t local_index) {
     const Cfg& C = AFL_C;
     W.local = local_index;
     W.replica = C.replica_begin + local_index;
@@ -683,7 +687,7 @@ AFL_IN void start_replica(St& W, const Mem& m, uint64_t local_index) {
     }
 }
 
-AFL_IN void write_back(St& W, const Mem& m) {
+template <class Mem> AFL_IN void write_back(St& W, const Mem& m) {
     const Cfg& C = AFL_C;
     const uint64_t local = W.local;
 #pragma unroll 1
@@ -731,7 +735,7 @@ enum : uint32_t { A_NONE = 0, A_NODE, A_STEPS, A_SEND, A_TIMER };
 // returns the next local replica index or ~0 when the launch has no more work for this lane.
 // `converge` is a warp-wide rendez-vous at the top of every iteration (device: __any_sync).
 // ---------------------------------------------------------------------------------------------------
-template <class NextFn, class ConvFn>
+template <class Mem, class NextFn, class ConvFn>
 AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
     const Cfg& C = AFL_C;
     St W;
@@ -1096,6 +1100,9 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 const afr::EdgeDraw d = afr::edge_draw(C.seed, W.replica, rid, pk_hops(pack), dist, mean, sigma, dropout);
                 u = d.u; transit = d.transit;
             }
+            // (a rendez-vous of its own: without it the compiler specialises the block below for senders and for riders
+            //  -- `send` is known on either path -- and the two copies run one after the other: ncu r02e)
+            AFL_SYNC();
             if (fast || ride) {
                 const uint32_t k0 = (uint32_t)C.seed, k1 = (uint32_t)(C.seed >> 32);
                 const uint32_t tag = (afr::P_EDGE << 24) | ((pk_hops(pack) & 0xFFFFu) << 8);

@@ -9,12 +9,9 @@ echo "=== parity (auto)"; timeout 400 python tools/check_variant_gpu.py || { ech
 for wpb in ${WPBS:-12}; do
   echo "=== C3 rtt sweep 80000 x 20 s, lane, $wpb warps/SM"; $QB --scenario c3_lb_two_servers.yml --replicas 80000 --horizon 20 --reps 2 --mode auto --wpb $wpb | tail -2
 done
-for cap in ${CAPS:-460}; do
-  echo "=== C3 rtt sweep 80000 x 20 s, lane, 12 warps/SM, at most $cap B of shared memory per lane (rest of the 256 KB to L1)"
-  ASYNCFLOW_B200_LANE_BYTES=$cap $QB --scenario c3_lb_two_servers.yml --replicas 80000 --horizon 20 --reps 2 --mode auto --wpb 12 | tail -2
-done
 echo "=== C1 x 40000 x 60 s"; $QB --scenario c1_my_service.yml --replicas 40000 --horizon 60 --reps 2 --sweep none | tail -2
 echo "=== C4 20000 x 120 s"; $QB --scenario c4_lb8_events.yml --replicas 20000 --horizon 120 --reps 2 --sweep none | tail -2
+echo "=== C4 20000 x 120 s, fixed tables kept in shared memory (lower occupancy)"; ASYNCFLOW_B200_LANE_NARROW=1 $QB --scenario c4_lb8_events.yml --replicas 20000 --horizon 120 --reps 2 --sweep none | tail -2
 echo "=== C2 users sweep 10000 x 60 s"; $QB --scenario c1_my_service.yml --replicas 10000 --horizon 60 --reps 1 --sweep users | tail -2
 echo "=== C5 10000 x 10 s"; $QB --scenario c5_multihop32.yml --replicas 10000 --horizon 10 --reps 1 --sweep none | tail -2
 for wpb in ${BENCH_WPBS:-0}; do
