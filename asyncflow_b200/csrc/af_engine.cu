@@ -80,12 +80,12 @@ __global__ void AF_LAUNCH_BOUNDS af_sim_kernel() {
 #ifndef AF_LANE_MAX_THREADS
 #define AF_LANE_MAX_THREADS 384
 #endif
-template <bool WIDE> __global__ void __launch_bounds__(AF_LANE_MAX_THREADS, 1) af_lane_kernel() {
+__global__ void __launch_bounds__(AF_LANE_MAX_THREADS, 1) af_lane_kernel() {
     const afl::Cfg& C = afl::c_cfg;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t ws = warp * (uint32_t)C.warp_bytes;
     unsigned char* gs = C.gtier + ((uint64_t)blockIdx.x * (blockDim.x >> 5) + warp) * C.gwarp_bytes;
-    afl::MemT<WIDE> m;
+    afl::Mem m;
     m.s128 = ws + lane * 16u;
     m.s64 = ws + (uint32_t)C.n128 * (uint32_t)afl::STRIDE128 + lane * 8u;
     m.s32 = ws + (uint32_t)C.n128 * (uint32_t)afl::STRIDE128 + (uint32_t)C.n64 * (uint32_t)afl::STRIDE64 + lane * 4u;
@@ -266,7 +266,7 @@ struct af_engine {
     // thread-per-replica pass: read-only tables (af_lane_host.h), global tiers, the list of flagged replicas
     int mode = AF_MODE_AUTO;
     aflh::Tables lt;
-    DevBuf d_l_edges, d_l_servers, d_l_eps, d_l_steps, d_l_spikes, d_l_outages, d_l_lb, d_l_cols, d_gtier, d_redo_list, d_redo_count, d_counter2;
+    DevBuf d_l_edges, d_l_servers, d_l_eps, d_l_steps, d_l_spikes, d_l_outages, d_l_lb, d_l_cols, d_gtier, d_redo_list, d_redo_count, d_counter2, d_pool, d_pool_next;
     afl::Cfg C_host{};
     bool last_lane = false, last_warp = false; int last_lane_warps = 0;
     // spill + outputs
@@ -343,7 +343,7 @@ void af_engine_destroy(af_engine* e) {
         if (g_const_owner[e->device % kMaxDevices] == e) g_const_owner[e->device % kMaxDevices] = nullptr;
     }
     DevBuf* bufs[] = {&e->d_l_edges, &e->d_l_servers, &e->d_l_eps, &e->d_l_steps, &e->d_l_spikes, &e->d_l_outages, &e->d_l_lb, &e->d_l_cols,
-                      &e->d_gtier, &e->d_redo_list, &e->d_redo_count, &e->d_counter2,
+                      &e->d_gtier, &e->d_redo_list, &e->d_redo_count, &e->d_counter2, &e->d_pool, &e->d_pool_next,
                       &e->d_edges, &e->d_servers, &e->d_eps, &e->d_steps, &e->d_lb, &e->d_spikes, &e->d_outages,
                       &e->d_sweep_cols, &e->d_sweep_vals, &e->d_sp_evt, &e->d_sp_evk, &e->d_sp_rq, &e->d_sp_nx,
                       &e->d_stats, &e->d_sent, &e->d_dropped, &e->d_hist, &e->d_thr, &e->d_ssum, &e->d_smax,
@@ -483,22 +483,28 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
             lane = false;
         }
     }
+    AfOptions o = e->opt;
+    int32_t rq_static = 0;
     if (lane) {
-        AfOptions o = e->opt;
-        if (e->mode == AF_MODE_AUTO) {                 // nominal-load tiers; anything larger escalates
+        if (e->mode == AF_MODE_AUTO) {                 // nominal-load tiers per lane; request slots beyond them from the page pool
             if (o.event_capacity <= 0 || o.event_capacity > aflh::LANE_EVENT_CAPACITY) o.event_capacity = aflh::LANE_EVENT_CAPACITY;
-            if (o.request_capacity <= 0 || o.request_capacity > aflh::LANE_REQUEST_CAPACITY) o.request_capacity = aflh::LANE_REQUEST_CAPACITY;
+            if (o.request_capacity <= 0) o.request_capacity = afh::DEFAULT_REQUEST_CAPACITY;
+            if (o.request_capacity > aflh::LANE_REQUEST_CAPACITY) rq_static = aflh::LANE_REQUEST_CAPACITY;
+            if (getenv("ASYNCFLOW_B200_NO_PAGES")) { rq_static = 0; if (o.request_capacity > aflh::LANE_REQUEST_CAPACITY) o.request_capacity = aflh::LANE_REQUEST_CAPACITY; }   // experiments: the round-2a behaviour
         }
         lane_warps = e->opt.warps_per_block > 0 ? e->opt.warps_per_block : AF_LANE_DEFAULT_WARPS;
         if (lane_warps > AF_LANE_MAX_THREADS / 32) lane_warps = AF_LANE_MAX_THREADS / 32;
-        // A topology whose fixed tables do not fit a lane's share of shared memory at this occupancy keeps them in the
-        // global tier (make_cfg: WIDE) rather than running at a fraction of the occupancy.
-        // (experiments: ASYNCFLOW_B200_LANE_NARROW=1 lowers the occupancy until they fit, the round-2a behaviour)
-        if (getenv("ASYNCFLOW_B200_LANE_NARROW"))
-            while (lane_warps > 1 && lane_budget(e, lane_warps) < 2 * aflh::fixed_lane_bytes(e->sc, e->lt))
-                lane_warps -= lane_warps > 8 ? 4 : (lane_warps > 4 ? 2 : 1);
+        // fewer warps per SM when the topology's fixed tables need a larger share of shared memory (measured on B200,
+        // C4: tables in shared memory at 6 warps/SM 2.8e8 completions/s, tables in the global tier at 12 warps/SM 1.4e8)
+        while (lane_warps > 1 && lane_budget(e, lane_warps) < aflh::min_lane_bytes(e->sc, e->lt) + 128)
+            lane_warps -= lane_warps > 8 ? 4 : (lane_warps > 4 ? 2 : 1);
+        // (a topology that leaves fewer than 4 warps per SM is faster on the warp-per-replica engine: C5 before the
+        //  gauges moved out of shared memory, 2 warps/SM: 2.9e8 events/s against 5.1e8)
+        if (e->mode == AF_MODE_AUTO && lane_warps < 4) lane = false;
+    }
+    if (lane) {
         memset(&C, 0, sizeof C);
-        if (!aflh::make_cfg(e->sc, o, e->lt, lane_budget(e, lane_warps), afh::trace_tick_capacity(e->sc), 32, C)) {
+        if (!aflh::make_cfg(e->sc, o, e->lt, lane_budget(e, lane_warps), afh::trace_tick_capacity(e->sc), 32, rq_static, C)) {
             if (e->mode == AF_MODE_LANE) return e->fail(AF_ERR_INVALID, "scenario tables do not fit a lane's shared memory (thread-per-replica engine)");
             lane = false;
         }
@@ -533,8 +539,7 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     uint64_t lgrid = 0; size_t lsmem = 0;
     if (lane) {
         lsmem = (size_t)lane_warps * (size_t)C.warp_bytes;
-        AF_CUDA(e, C.wide ? cudaFuncSetAttribute(af_lane_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem)
-                          : cudaFuncSetAttribute(af_lane_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem), "smem attribute");
+        AF_CUDA(e, cudaFuncSetAttribute(af_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem), "smem attribute");
         lgrid = (uint64_t)e->sm_count;
         const uint64_t need = (n + (uint64_t)lane_warps * 32 - 1) / ((uint64_t)lane_warps * 32);
         if (lgrid > need) lgrid = need;
@@ -550,6 +555,19 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     }
     if (lane) {
         AF_CUDA(e, e->d_gtier.ensure(lgrid * (uint64_t)lane_warps * C.gwarp_bytes + 256), "lane global tiers");
+        C.pool = nullptr; C.pool_pages = 0; C.pool_next = nullptr;
+        if (C.pg_max > 0) {          // the page pool: what every resident lane could ask for, within half of the free memory
+            size_t free_b = 0, total_b = 0;
+            AF_CUDA(e, cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
+            uint64_t pages = lgrid * (uint64_t)lane_warps * 32ull * (uint64_t)C.pg_max;
+            const uint64_t have = e->d_pool.cap / afl::PG_BYTES;
+            const uint64_t afford = have + (uint64_t)(free_b / 2) / afl::PG_BYTES;
+            if (pages > afford) pages = afford;
+            if (pages > 0xFFFFFFF0ull) pages = 0xFFFFFFF0ull;
+            if (pages > have) AF_CUDA(e, e->d_pool.ensure(pages * afl::PG_BYTES), "request page pool");
+            AF_CUDA(e, e->d_pool_next.ensure(8), "request page pool");
+            C.pool = (unsigned char*)e->d_pool.p; C.pool_pages = (uint32_t)(e->d_pool.cap / afl::PG_BYTES); C.pool_next = (uint32_t*)e->d_pool_next.p;
+        }
         if ((rc = upload_vec(e, e->d_l_edges, e->lt.edges, "lane tables"))) return rc;
         if ((rc = upload_vec(e, e->d_l_servers, e->lt.servers, "lane tables"))) return rc;
         if ((rc = upload_vec(e, e->d_l_eps, e->lt.endpoints, "lane tables"))) return rc;
@@ -626,9 +644,9 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     if (lane) {
         AF_CUDA(e, cudaMemsetAsync(e->d_counter2.p, 0, 8, e->stream), "memset");
         AF_CUDA(e, cudaMemsetAsync(e->d_redo_count.p, 0, 4, e->stream), "memset");
+        if (C.pool_next) AF_CUDA(e, cudaMemsetAsync(C.pool_next, 0, 4, e->stream), "memset");
         AF_CUDA(e, cudaMemcpyToSymbolAsync(afl::c_cfg, &C, sizeof C, 0, cudaMemcpyHostToDevice, e->stream), "lane config -> constant memory");
-        if (C.wide) af_lane_kernel<true><<<(unsigned)lgrid, lane_warps * 32, lsmem, e->stream>>>();
-        else af_lane_kernel<false><<<(unsigned)lgrid, lane_warps * 32, lsmem, e->stream>>>();
+        af_lane_kernel<<<(unsigned)lgrid, lane_warps * 32, lsmem, e->stream>>>();
         AF_CUDA(e, cudaGetLastError(), "af_lane_kernel launch");
         e->launches += 1;
         if (redo) {

@@ -102,6 +102,7 @@ AFL_IN uint32_t pk_ep(uint32_t p) { return (p >> 16) & 0xFFFu; }
 enum : uint32_t { I_PUT = 0, I_GOT = 1, I_CLIENT_LOOP = 2, I_RAM_OK = 3, I_CPU_OK = 4, I_CPU_PUT = 5, I_RAM_PUT = 6 };
 constexpr uint32_t NODE_CLIENT = 0, NODE_LB = 1, NODE_SERVER0 = 2;
 constexpr int32_t NQ_TOTAL = 128;          // pending zero-delay items per replica (power of two)
+constexpr uint32_t PG_BITS = 8, PG_SLOTS = 1u << PG_BITS, PG_REC_BYTES = PG_SLOTS * 16u, PG_BYTES = PG_REC_BYTES + PG_SLOTS * 4u;   // one pool page: 256 records, then their links
 
 // ---- read-only scenario tables (global memory, shared by all replicas; 16-byte multiples so that
 //      a record is one or a few 128-bit loads).  `c_*` = index into the lane's sweep-row copy, -1 = not swept.
@@ -131,17 +132,22 @@ struct Cfg {
     int32_t redo;                                   // 1: replica indices come from redo_list (re-run of flagged replicas)
     // tiered tables: entries in shared memory / in total
     int32_t ev_s, ev_total, rq_s, rq_total, nq_s;
+    // request slots beyond rq_total: PAGES of PG_SLOTS records from one pool shared by all lanes (a saturated replica
+    // parks 10^4..10^5 requests in a RAM queue; sizing every lane's tier for that would be 100 GB).  A lane's page
+    // table (pg_max words of its 32-bit region, from gi_pt) maps page number -> pool page; pages are taken with one
+    // atomicAdd when a lane first needs them and stay with the lane for the launch.
+    int32_t rq_cap, pg_max, gi_pt;
+    unsigned char* pool; uint32_t pool_pages; uint32_t* pool_next;
     // shared-memory layout of a warp: 128-bit region (events, then request records), 64-bit region, 32-bit region
     int32_t o128_ev, o128_rq, n128;
-    int32_t o64_nq, o64_spike, o64_ssum, o64_row, n64;
-    int32_t o32_next, o32_conn, o32_sent, o32_srv, o32_lb, o32_smax, o32_dirty, n_dirty, n32;
+    int32_t o64_nq, o64_spike, o64_row, n64;
+    int32_t o32_next, o32_conn, o32_srv, o32_lb, o32_dirty, n_dirty, n32;
     int32_t warp_bytes;                             // n128 * 512 + n64 * 256 + n32 * 128
     // global tier of a warp (same interleave).  gi_* = (offset of the table in its region) - (entries kept in shared
     // memory): entry idx >= split lives at element idx + gi_* of the region
     int32_t gi_ev, gi_rq, gn128;
-    int32_t gi_nq, gf64, gn64;
-    int32_t gi_next, g32_cold, gf32, gn32;
-    int32_t wide;                                   // 1: the fixed tables live in the global tier (elements gf64 + e / words gf32 + w)
+    int32_t gi_nq, gi_acc, gn64;                    // gi_acc: the gauges' accumulators (write-only during the run: RED)
+    int32_t gi_next, g32_cold, gi_smax, gi_sent, gn32;   // ... their maxima, the per-edge send counters (RED too)
     int32_t c_srvq, c_inbox, c_drop;                // cold words (offsets from g32_cold): waiter FIFOs, mailboxes, drop counters
     uint64_t gwarp_bytes;                           // gn128 * 512 + gn64 * 256 + gn32 * 128
     // device pointers
@@ -188,10 +194,9 @@ template <class T> AFL_IN T ro(const T* p) {
 // instructions per access on sm_100a (S2R SR_CgaCtaId + MOV + LEA + IADD rebuild the window base every time:
 // ncu r02b, 33 % of the executed instructions), a generic pointer costs 64-bit arithmetic.  A tiered table takes a
 // BRANCH on "is it in shared memory", not a select.  All shared accesses are volatile asm: they keep program order.
-template <bool WIDE> struct MemT {
+struct Mem {
     uint32_t s128, s64, s32;                    // shared-memory regions of the warp (window addresses, the lane's column)
     unsigned char* g128; unsigned char* g64; unsigned char* g32;     // global tier of the warp, already offset by the lane
-    static constexpr bool wide = WIDE;          // Cfg::wide, at compile time: one kernel per value, no test per access
 };
 #if AFL_DEVICE
 AFL_IN uint32_t sm_ld32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -213,49 +218,46 @@ AFL_IN void sm_st128(uint32_t a, uint64_t x, uint64_t y) { memcpy(afl_smem_host 
 AFL_IN void gl_ld128(const unsigned char* p, uint64_t& x, uint64_t& y) { memcpy(&x, p, 8); memcpy(&y, p + 8, 8); }
 AFL_IN void gl_st128(unsigned char* p, uint64_t x, uint64_t y) { memcpy(p, &x, 8); memcpy(p + 8, &y, 8); }
 #endif
-template <class Mem> AFL_IN uint32_t a128(const Mem& m, int32_t elem) { return m.s128 + (uint32_t)elem * (uint32_t)STRIDE128; }
-template <class Mem> AFL_IN uint32_t a64(const Mem& m, int32_t elem) { return m.s64 + (uint32_t)elem * (uint32_t)STRIDE64; }
-template <class Mem> AFL_IN uint32_t a32(const Mem& m, int32_t word) { return m.s32 + (uint32_t)word * (uint32_t)STRIDE32; }
+AFL_IN uint32_t a128(const Mem& m, int32_t elem) { return m.s128 + (uint32_t)elem * (uint32_t)STRIDE128; }
+AFL_IN uint32_t a64(const Mem& m, int32_t elem) { return m.s64 + (uint32_t)elem * (uint32_t)STRIDE64; }
+AFL_IN uint32_t a32(const Mem& m, int32_t word) { return m.s32 + (uint32_t)word * (uint32_t)STRIDE32; }
 // global tier: ONE 32-bit element index (table offset folded in on the host), one widening multiply-add onto the
 // lane's region pointer
-template <class Mem> AFL_IN unsigned char* g128p(const Mem& m, int32_t elem) { return m.g128 + (uint64_t)(uint32_t)elem * (uint32_t)STRIDE128; }
-template <class Mem> AFL_IN uint64_t* g64p(const Mem& m, int32_t elem) { return reinterpret_cast<uint64_t*>(m.g64 + (uint64_t)(uint32_t)elem * (uint32_t)STRIDE64); }
-template <class Mem> AFL_IN uint32_t* g32p(const Mem& m, int32_t word) { return reinterpret_cast<uint32_t*>(m.g32 + (uint64_t)(uint32_t)word * (uint32_t)STRIDE32); }
-// The FIXED tables (gauges, connection / send counters, server levels, LB order, sweep-row copy, spike offsets):
-// in shared memory for a narrow topology; a WIDE one (their bytes would leave a lane no room for events at a useful
-// occupancy: 32 nodes = 2.9 KB) keeps them in the global tier, L2-resident, and shared memory goes to the heap and
-// the request records.  `wide` is a property of the launch: the kernel is compiled once per value (MemT<WIDE>), no test per access.
-template <class Mem> AFL_IN uint64_t e64_ld(const Mem& m, int32_t elem) { if (Mem::wide) return *g64p(m, AFL_C.gf64 + elem); return sm_ld64(a64(m, elem)); }
-template <class Mem> AFL_IN void e64_st(const Mem& m, int32_t elem, uint64_t v) { if (Mem::wide) *g64p(m, AFL_C.gf64 + elem) = v; else sm_st64(a64(m, elem), v); }
-template <class Mem> AFL_IN double f64_ld(const Mem& m, int32_t elem) { return afr::u2d(e64_ld(m, elem)); }
-template <class Mem> AFL_IN void f64_st(const Mem& m, int32_t elem, double v) { e64_st(m, elem, afr::d2u(v)); }
-template <class Mem> AFL_IN uint32_t w32_ld(const Mem& m, int32_t word) { if (Mem::wide) return *g32p(m, AFL_C.gf32 + word); return sm_ld32(a32(m, word)); }
-template <class Mem> AFL_IN void w32_st(const Mem& m, int32_t word, uint32_t v) { if (Mem::wide) *g32p(m, AFL_C.gf32 + word) = v; else sm_st32(a32(m, word), v); }
-template <class Mem> AFL_IN int32_t i32_ld(const Mem& m, int32_t word) { return (int32_t)w32_ld(m, word); }
-template <class Mem> AFL_IN void i32_st(const Mem& m, int32_t word, int32_t v) { w32_st(m, word, (uint32_t)v); }
+AFL_IN unsigned char* g128p(const Mem& m, int32_t elem) { return m.g128 + (uint64_t)(uint32_t)elem * (uint32_t)STRIDE128; }
+AFL_IN uint64_t* g64p(const Mem& m, int32_t elem) { return reinterpret_cast<uint64_t*>(m.g64 + (uint64_t)(uint32_t)elem * (uint32_t)STRIDE64); }
+AFL_IN uint32_t* g32p(const Mem& m, int32_t word) { return reinterpret_cast<uint32_t*>(m.g32 + (uint64_t)(uint32_t)word * (uint32_t)STRIDE32); }
+// fixed tables in shared memory: connection counts, server levels, LB order, sweep-row copy, spike offsets
+AFL_IN uint64_t e64_ld(const Mem& m, int32_t elem) { return sm_ld64(a64(m, elem)); }
+AFL_IN void e64_st(const Mem& m, int32_t elem, uint64_t v) { sm_st64(a64(m, elem), v); }
+AFL_IN double f64_ld(const Mem& m, int32_t elem) { return afr::u2d(e64_ld(m, elem)); }
+AFL_IN void f64_st(const Mem& m, int32_t elem, double v) { e64_st(m, elem, afr::d2u(v)); }
+AFL_IN uint32_t w32_ld(const Mem& m, int32_t word) { return sm_ld32(a32(m, word)); }
+AFL_IN void w32_st(const Mem& m, int32_t word, uint32_t v) { sm_st32(a32(m, word), v); }
+AFL_IN int32_t i32_ld(const Mem& m, int32_t word) { return (int32_t)w32_ld(m, word); }
+AFL_IN void i32_st(const Mem& m, int32_t word, int32_t v) { w32_st(m, word, (uint32_t)v); }
 // cold words (global tier only): queue links of the Stores and Containers, drop counters -- touched at ties, under
 // contention, on a dropped request
-template <class Mem> AFL_IN uint32_t c32_ld(const Mem& m, int32_t word) { return *g32p(m, AFL_C.g32_cold + word); }
-template <class Mem> AFL_IN void c32_st(const Mem& m, int32_t word, uint32_t v) { *g32p(m, AFL_C.g32_cold + word) = v; }
+AFL_IN uint32_t c32_ld(const Mem& m, int32_t word) { return *g32p(m, AFL_C.g32_cold + word); }
+AFL_IN void c32_st(const Mem& m, int32_t word, uint32_t v) { *g32p(m, AFL_C.g32_cold + word) = v; }
 // tiered tables: entry idx < split in shared memory (element os + idx), the rest in the global tier (element gi + idx)
-template <class Mem> AFL_IN void ld_t128(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t& x, uint64_t& y) {
+AFL_IN void ld_t128(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t& x, uint64_t& y) {
     if (AFL_LIKELY(idx < split)) sm_ld128(a128(m, os + idx), x, y); else gl_ld128(g128p(m, gi + idx), x, y);
 }
-template <class Mem> AFL_IN void st_t128(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t x, uint64_t y) {
+AFL_IN void st_t128(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t x, uint64_t y) {
     if (AFL_LIKELY(idx < split)) sm_st128(a128(m, os + idx), x, y); else gl_st128(g128p(m, gi + idx), x, y);
 }
-template <class Mem> AFL_IN uint64_t ld_t64(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split) {
+AFL_IN uint64_t ld_t64(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split) {
     if (AFL_LIKELY(idx < split)) return sm_ld64(a64(m, os + idx));
     return *g64p(m, gi + idx);
 }
-template <class Mem> AFL_IN void st_t64(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t v) {
+AFL_IN void st_t64(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint64_t v) {
     if (AFL_LIKELY(idx < split)) sm_st64(a64(m, os + idx), v); else *g64p(m, gi + idx) = v;
 }
-template <class Mem> AFL_IN uint32_t ld_t32(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split) {
+AFL_IN uint32_t ld_t32(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split) {
     if (AFL_LIKELY(idx < split)) return sm_ld32(a32(m, os + idx));
     return *g32p(m, gi + idx);
 }
-template <class Mem> AFL_IN void st_t32(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint32_t v) {
+AFL_IN void st_t32(const Mem& m, int32_t os, int32_t gi, int32_t idx, int32_t split, uint32_t v) {
     if (AFL_LIKELY(idx < split)) sm_st32(a32(m, os + idx), v); else *g32p(m, gi + idx) = v;
 }
 
@@ -283,51 +285,101 @@ struct St {
 constexpr uint32_t STOP_FLAGS = AF_FLAG_EVENT_OVERFLOW | AF_FLAG_REQUEST_OVERFLOW | AF_FLAG_NOWQ_OVERFLOW | AF_FLAG_LB_EMPTY;
 
 // ---- swept parameters ----------------------------------------------------------------------------
-template <class Mem> AFL_IN double row_val(const Mem& m, int32_t c) { return f64_ld(m, AFL_C.o64_row + c); }
-template <class Mem> AFL_IN uint32_t ep_total_ram(const Mem& m, uint32_t ep) {
+AFL_IN double row_val(const Mem& m, int32_t c) { return f64_ld(m, AFL_C.o64_row + c); }
+AFL_IN uint32_t ep_total_ram(const Mem& m, uint32_t ep) {
     const EndpointP p = ro(AFL_C.endpoints + ep);
     return p.c_ram >= 0 ? (uint32_t)row_val(m, p.c_ram) : p.total_ram;
 }
 
-// ---- request records (tiered): one 128-bit element  t0 | id : pack  + the `next` link (32-bit table) ------------
-template <class Mem> AFL_IN void rq_load(const Mem& m, uint32_t s, double& t0, uint32_t& rid, uint32_t& pack) {
+// ---- request records: one 128-bit element  t0 | id : pack  + the `next` link (32-bit table); three tiers:
+//      slots [0, rq_s) in shared memory, [rq_s, rq_total) in the lane's global tier, [rq_total, rq_cap) in pool pages
+AFL_IN unsigned char* pg_page(const Mem& m, uint32_t s, uint32_t& off) {
+    const uint32_t k = s - (uint32_t)AFL_C.rq_total;
+    off = k & (PG_SLOTS - 1u);
+    return AFL_C.pool + (uint64_t)(*g32p(m, AFL_C.gi_pt + (int32_t)(k >> PG_BITS))) * PG_BYTES;
+}
+AFL_IN void rq_load(const Mem& m, uint32_t s, double& t0, uint32_t& rid, uint32_t& pack) {
     uint64_t a, b;
-    ld_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, a, b);
+    if (AFL_LIKELY((int32_t)s < AFL_C.rq_total)) ld_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, a, b);
+    else { uint32_t o; const unsigned char* pg = pg_page(m, s, o); gl_ld128(pg + o * 16u, a, b); }
     t0 = afr::u2d(a); rid = (uint32_t)b; pack = (uint32_t)(b >> 32);
 }
-template <class Mem> AFL_IN void rq_store(const Mem& m, uint32_t s, double t0, uint32_t rid, uint32_t pack) {
-    st_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, afr::d2u(t0), (uint64_t)rid | ((uint64_t)pack << 32));
+AFL_IN void rq_store(const Mem& m, uint32_t s, double t0, uint32_t rid, uint32_t pack) {
+    const uint64_t a = afr::d2u(t0), b = (uint64_t)rid | ((uint64_t)pack << 32);
+    if (AFL_LIKELY((int32_t)s < AFL_C.rq_total)) st_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, a, b);
+    else { uint32_t o; unsigned char* pg = pg_page(m, s, o); gl_st128(pg + o * 16u, a, b); }
 }
-template <class Mem> AFL_IN uint32_t rq_pack(const Mem& m, uint32_t s) {
+AFL_IN uint32_t* rq_word_slow(const Mem& m, uint32_t s, uint32_t byte) {       // a 32-bit field of a record outside shared memory
+    if (AFL_LIKELY((int32_t)s < AFL_C.rq_total)) return reinterpret_cast<uint32_t*>(g128p(m, AFL_C.gi_rq + (int32_t)s) + byte);
+    uint32_t o; unsigned char* pg = pg_page(m, s, o);
+    return reinterpret_cast<uint32_t*>(pg + o * 16u + byte);
+}
+AFL_IN uint32_t rq_pack(const Mem& m, uint32_t s) {
     if (AFL_LIKELY((int32_t)s < AFL_C.rq_s)) return sm_ld32(a128(m, AFL_C.o128_rq + (int32_t)s) + 12u);
-    return *reinterpret_cast<const uint32_t*>(g128p(m, AFL_C.gi_rq + (int32_t)s) + 12);
+    return *rq_word_slow(m, s, 12u);
 }
-template <class Mem> AFL_IN void rq_pack_set(const Mem& m, uint32_t s, uint32_t v) {
+AFL_IN void rq_pack_set(const Mem& m, uint32_t s, uint32_t v) {
     if (AFL_LIKELY((int32_t)s < AFL_C.rq_s)) sm_st32(a128(m, AFL_C.o128_rq + (int32_t)s) + 12u, v);
-    else *reinterpret_cast<uint32_t*>(g128p(m, AFL_C.gi_rq + (int32_t)s) + 12) = v;
+    else *rq_word_slow(m, s, 12u) = v;
 }
-template <class Mem> AFL_IN uint32_t rq_next(const Mem& m, uint32_t s) { return ld_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s); }
-template <class Mem> AFL_IN void rq_next_set(const Mem& m, uint32_t s, uint32_t v) { st_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s, v); }
+AFL_IN uint32_t rq_next(const Mem& m, uint32_t s) {
+    if (AFL_LIKELY((int32_t)s < AFL_C.rq_total)) return ld_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s);
+    uint32_t o; const unsigned char* pg = pg_page(m, s, o);
+    return *reinterpret_cast<const uint32_t*>(pg + PG_REC_BYTES + o * 4u);
+}
+AFL_IN void rq_next_set(const Mem& m, uint32_t s, uint32_t v) {
+    if (AFL_LIKELY((int32_t)s < AFL_C.rq_total)) { st_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s, v); return; }
+    uint32_t o; unsigned char* pg = pg_page(m, s, o);
+    *reinterpret_cast<uint32_t*>(pg + PG_REC_BYTES + o * 4u) = v;
+}
 
-template <class Mem> AFL_IN uint32_t rq_alloc(St& W, const Mem& m) {
+#if AFL_DEVICE
+__device__ __forceinline__ uint32_t pool_take(uint32_t* p) { return atomicAdd(p, 1u); }
+// fire-and-forget reductions (RED.E.ADD / RED.E.MAX: no result, no scoreboard wait) and the loads that read them back
+__device__ __forceinline__ void red_add64(uint64_t* p, uint64_t v) { atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
+__device__ __forceinline__ void red_add32(uint32_t* p, uint32_t v) { atomicAdd(p, v); }
+__device__ __forceinline__ void red_max32(uint32_t* p, uint32_t v) { atomicMax(p, v); }
+__device__ __forceinline__ uint64_t ld_cg64(const uint64_t* p) { return (uint64_t)__ldcg(reinterpret_cast<const unsigned long long*>(p)); }
+__device__ __forceinline__ uint32_t ld_cg32(const uint32_t* p) { return __ldcg(p); }
+#else
+static inline uint32_t pool_take(uint32_t* p) { return (*p)++; }
+static inline void red_add64(uint64_t* p, uint64_t v) { *p += v; }
+static inline void red_add32(uint32_t* p, uint32_t v) { *p += v; }
+static inline void red_max32(uint32_t* p, uint32_t v) { if (v > *p) *p = v; }
+static inline uint64_t ld_cg64(const uint64_t* p) { return *p; }
+static inline uint32_t ld_cg32(const uint32_t* p) { return *p; }
+#endif
+AFL_IN uint32_t rq_alloc(St& W, const Mem& m) {
     uint32_t s;
     if (W.rq_free != NIL) { s = W.rq_free; W.rq_free = rq_next(m, s); }
     else if ((int32_t)W.rq_hw < AFL_C.rq_total) { s = W.rq_hw++; }
+    else if ((int32_t)W.rq_hw < AFL_C.rq_cap) {        // the paged tier: the first slot of a page the lane does not own yet takes one from the pool
+        const uint32_t k = W.rq_hw - (uint32_t)AFL_C.rq_total;
+        if ((k & (PG_SLOTS - 1u)) == 0u) {
+            uint32_t* pt = g32p(m, AFL_C.gi_pt + (int32_t)(k >> PG_BITS));
+            if (*pt == NIL) {
+                const uint32_t pid = pool_take(AFL_C.pool_next);
+                if (pid >= AFL_C.pool_pages) { W.flags |= AF_FLAG_REQUEST_OVERFLOW; return NIL; }
+                *pt = pid;
+            }
+        }
+        s = W.rq_hw++;
+    }
     else { W.flags |= AF_FLAG_REQUEST_OVERFLOW; return NIL; }
     const uint32_t live = ++W.rq_live;
     if (live > W.peak_rq) W.peak_rq = live;
     return s;
 }
-template <class Mem> AFL_IN void rq_release(St& W, const Mem& m, uint32_t s) { rq_next_set(m, s, W.rq_free); W.rq_free = s; --W.rq_live; }
+AFL_IN void rq_release(St& W, const Mem& m, uint32_t s) { rq_next_set(m, s, W.rq_free); W.rq_free = s; --W.rq_live; }
 
 // intrusive FIFOs through the `next` links; head / tail are COLD words
-template <class Mem> AFL_IN void fifo_push(const Mem& m, int32_t w_head, int32_t w_tail, uint32_t s) {
+AFL_IN void fifo_push(const Mem& m, int32_t w_head, int32_t w_tail, uint32_t s) {
     rq_next_set(m, s, NIL);
     const uint32_t tail = c32_ld(m, w_tail);
     if (tail == NIL) c32_st(m, w_head, s); else rq_next_set(m, tail, s);
     c32_st(m, w_tail, s);
 }
-template <class Mem> AFL_IN uint32_t fifo_pop(const Mem& m, int32_t w_head, int32_t w_tail) {
+AFL_IN uint32_t fifo_pop(const Mem& m, int32_t w_head, int32_t w_tail) {
     const uint32_t s = c32_ld(m, w_head);
     const uint32_t h = rq_next(m, s);
     c32_st(m, w_head, h);
@@ -336,16 +388,16 @@ template <class Mem> AFL_IN uint32_t fifo_pop(const Mem& m, int32_t w_head, int3
 }
 
 // ---- pending timed events: 4-ary min-heap on (time bits, seq), tiered; one 128-bit element per event ----------
-template <class Mem> AFL_IN void ev_get(const Mem& m, int32_t i, uint64_t& t, uint64_t& k) { ld_t128(m, AFL_C.o128_ev, AFL_C.gi_ev, i, AFL_C.ev_s, t, k); }
-template <class Mem> AFL_IN void ev_set(const Mem& m, int32_t i, uint64_t t, uint64_t k) { st_t128(m, AFL_C.o128_ev, AFL_C.gi_ev, i, AFL_C.ev_s, t, k); }
-template <class Mem> AFL_IN uint64_t ev_t(const Mem& m, int32_t i) {         // the time alone (root look-ahead)
+AFL_IN void ev_get(const Mem& m, int32_t i, uint64_t& t, uint64_t& k) { ld_t128(m, AFL_C.o128_ev, AFL_C.gi_ev, i, AFL_C.ev_s, t, k); }
+AFL_IN void ev_set(const Mem& m, int32_t i, uint64_t t, uint64_t k) { st_t128(m, AFL_C.o128_ev, AFL_C.gi_ev, i, AFL_C.ev_s, t, k); }
+AFL_IN uint64_t ev_t(const Mem& m, int32_t i) {         // the time alone (root look-ahead)
     if (AFL_LIKELY(i < AFL_C.ev_s)) return sm_ld64(a128(m, AFL_C.o128_ev + i));
     return *reinterpret_cast<const uint64_t*>(g128p(m, AFL_C.gi_ev + i));
 }
 AFL_IN bool ev_less(uint64_t ta, uint64_t ka, uint64_t tb, uint64_t kb) {       // times are non-negative doubles: bit order = value order
     return ta < tb || (ta == tb && (uint32_t)(ka >> 32) < (uint32_t)(kb >> 32));
 }
-template <class Mem> AFL_IN void heap_push(St& W, const Mem& m, uint64_t tb, uint64_t key) {
+AFL_IN void heap_push(St& W, const Mem& m, uint64_t tb, uint64_t key) {
     int32_t i = W.ev_n;
     const int32_t pending = i + (int32_t)W.arr_on;     // the generator's timeout counts as a pending event
     if (AFL_UNLIKELY(pending >= AFL_C.ev_total)) { W.flags |= AF_FLAG_EVENT_OVERFLOW; return; }
@@ -363,7 +415,7 @@ template <class Mem> AFL_IN void heap_push(St& W, const Mem& m, uint64_t tb, uin
     ev_set(m, i, tb, key);
 }
 // remove the root (the caller has read it)
-template <class Mem> AFL_IN void heap_pop(St& W, const Mem& m) {
+AFL_IN void heap_pop(St& W, const Mem& m) {
     const int32_t n = --W.ev_n;
     if (n == 0) return;
     uint64_t tl, kl;
@@ -390,11 +442,11 @@ template <class Mem> AFL_IN void heap_pop(St& W, const Mem& m) {
 }
 
 // ---- now-queue (tiered ring of NQ_TOTAL items: seq << 32 | kind:3 aux:9 slot:20) ---------------------
-template <class Mem> AFL_IN uint64_t nq_ld(const Mem& m, uint32_t pos) {
+AFL_IN uint64_t nq_ld(const Mem& m, uint32_t pos) {
     return ld_t64(m, AFL_C.o64_nq, AFL_C.gi_nq, (int32_t)(pos & (uint32_t)(NQ_TOTAL - 1)), AFL_C.nq_s);
 }
 AFL_IN bool can_fuse(const St& W) { return AFL_LIKELY(W.busy == 0); }
-template <class Mem> AFL_IN void nq_push(St& W, const Mem& m, uint32_t kind, uint32_t aux, uint32_t slot) {
+AFL_IN void nq_push(St& W, const Mem& m, uint32_t kind, uint32_t aux, uint32_t slot) {
     const uint32_t tail = W.nq_tail;
     if (tail - W.nq_head >= (uint32_t)NQ_TOTAL) { W.flags |= AF_FLAG_NOWQ_OVERFLOW; return; }
     st_t64(m, AFL_C.o64_nq, AFL_C.gi_nq, (int32_t)(tail & (uint32_t)(NQ_TOTAL - 1)), AFL_C.nq_s,
@@ -402,7 +454,7 @@ template <class Mem> AFL_IN void nq_push(St& W, const Mem& m, uint32_t kind, uin
     W.nq_tail = tail + 1;
     W.busy += 2u;
 }
-template <class Mem> AFL_IN uint32_t nq_take(St& W, const Mem& m) {      // (the caller has adjusted `busy`)
+AFL_IN uint32_t nq_take(St& W, const Mem& m) {      // (the caller has adjusted `busy`)
     const uint32_t item = (uint32_t)nq_ld(m, W.nq_head);
     W.nq_head += 1;
     if (W.nq_head == W.nq_tail) { W.nq_head = 0; W.nq_tail = 0; }   // empty: restart at the shared-memory end of the ring
@@ -448,16 +500,19 @@ AFL_IN bool gen_next_gap(St& W, double& gap) {
 // CHANGES:  sum over ticks of v  =  n_ticks * v_final - sum over changes of (delta * ticks taken before the change)
 // (u64 modular arithmetic: exact), and the maximum over ticks takes the OLD value at a change iff a tick has seen it
 // (one "changed since the last tick" bit per series, cleared by a tick).  Traced replicas also store every reading.
-template <class Mem> AFL_IN void gauge_touch(const St& W, const Mem& m, int32_t j, uint32_t v_old, int32_t delta) {
-    e64_st(m, AFL_C.o64_ssum + j, e64_ld(m, AFL_C.o64_ssum + j) + (uint64_t)(int64_t)delta * (uint64_t)W.n_ticks);
+// The accumulator and the maximum are only ever ADDED to / MAXED during the run and read at write-back: they live in
+// the lane's global tier and are updated with fire-and-forget reductions (no load, no wait, no shared memory: 12 B
+// per series -- on a 32-node topology 1.8 KB per lane, the difference between 2 and 6 warps per SM).
+AFL_IN void gauge_touch(const St& W, const Mem& m, int32_t j, uint32_t v_old, int32_t delta) {
+    red_add64(g64p(m, AFL_C.gi_acc + j), (uint64_t)(int64_t)delta * (uint64_t)W.n_ticks);
     const int32_t dw = AFL_C.o32_dirty + (j >> 5);
     const uint32_t d = w32_ld(m, dw), bit = 1u << (j & 31);
     if (!(d & bit)) {
-        if (v_old > w32_ld(m, AFL_C.o32_smax + j)) w32_st(m, AFL_C.o32_smax + j, v_old);
+        red_max32(g32p(m, AFL_C.gi_smax + j), v_old);
         w32_st(m, dw, d | bit);
     }
 }
-template <class Mem> AFL_IN void conn_add(const St& W, const Mem& m, uint32_t edge, int32_t delta) {
+AFL_IN void conn_add(const St& W, const Mem& m, uint32_t edge, int32_t delta) {
     const int32_t pw = AFL_C.o32_conn + (int32_t)edge;
     const uint32_t v = w32_ld(m, pw);
     if (AFL_C.metrics_mask & AF_METRIC_EDGE_CONN) gauge_touch(W, m, 3 * AFL_C.n_servers + (int32_t)edge, v, delta);
@@ -467,13 +522,13 @@ AFL_IN int32_t ib_word(uint32_t node, int32_t f) { return AFL_C.c_inbox + (int32
 AFL_IN int32_t sq_word(uint32_t sidx, int32_t f) { return AFL_C.c_srvq + (int32_t)sidx * SQ_WORDS + f; }       // cold
 AFL_IN int32_t sv_word(uint32_t sidx, int32_t f) { return AFL_C.o32_srv + (int32_t)sidx * SV_WORDS + f; }
 // field = SV_READY_Q / SV_IO_Q / SV_RAM_IN_USE (series 3 * sidx + 0 / 1 / 2)
-template <class Mem> AFL_IN void srv_gauge_add(const St& W, const Mem& m, uint32_t sidx, int32_t field, int32_t delta) {
+AFL_IN void srv_gauge_add(const St& W, const Mem& m, uint32_t sidx, int32_t field, int32_t delta) {
     const int32_t pw = sv_word(sidx, field);
     const int32_t v = i32_ld(m, pw);
     if ((AFL_C.metrics_mask & 7u) == 7u) gauge_touch(W, m, 3 * (int32_t)sidx + (field - SV_READY_Q), (uint32_t)v, delta);
     i32_st(m, pw, v + delta);
 }
-template <class Mem> AFL_IN uint32_t gauge_value(const Mem& m, int32_t j) {
+AFL_IN uint32_t gauge_value(const Mem& m, int32_t j) {
     const int32_t ns3 = 3 * AFL_C.n_servers;
     if (j < ns3) { const int32_t mt = j % 3; return w32_ld(m, sv_word((uint32_t)(j / 3), mt == 0 ? SV_READY_Q : (mt == 1 ? SV_IO_Q : SV_RAM_IN_USE))); }
     return w32_ld(m, AFL_C.o32_conn + (j - ns3));
@@ -483,7 +538,7 @@ AFL_IN bool gauge_on(int32_t j) {
                                    : (AFL_C.metrics_mask & AF_METRIC_EDGE_CONN) != 0;
 }
 // every collector tick ordered before (t, ev_seq)
-template <class Mem> AFL_IN void take_ticks(St& W, const Mem& m, double t, uint32_t ev_seq) {
+AFL_IN void take_ticks(St& W, const Mem& m, double t, uint32_t ev_seq) {
     double tick = W.tick_time;
     uint32_t tseq = W.tick_seq, nt = W.n_ticks, seq = W.seq;
     const double horizon = W.horizon;
@@ -507,9 +562,9 @@ template <class Mem> AFL_IN void take_ticks(St& W, const Mem& m, double t, uint3
 
 // ---- Stores (mailboxes), Containers: as af_core.cuh ----------------------------------------------------
 // is the waiter FIFO whose head is cold word `head` empty?  (n_waiting == 0: all of them are, without looking)
-template <class Mem> AFL_IN bool q_empty(const St& W, const Mem& m, int32_t head) { return AFL_LIKELY(W.n_waiting == 0) || c32_ld(m, head) == NIL; }
+AFL_IN bool q_empty(const St& W, const Mem& m, int32_t head) { return AFL_LIKELY(W.n_waiting == 0) || c32_ld(m, head) == NIL; }
 // `yield box.get()` of the node's consumer process
-template <class Mem> AFL_IN void consumer_get(St& W, const Mem& m, uint32_t node) {
+AFL_IN void consumer_get(St& W, const Mem& m, uint32_t node) {
     if (AFL_UNLIKELY(c32_ld(m, ib_word(node, IB_HEAD)) != NIL)) {
         const uint32_t it = fifo_pop(m, ib_word(node, IB_HEAD), ib_word(node, IB_TAIL));
         nq_push(W, m, I_GOT, node, it);
@@ -517,7 +572,7 @@ template <class Mem> AFL_IN void consumer_get(St& W, const Mem& m, uint32_t node
 }
 // Container._trigger_get over the CPU queue: grant heads while a core is free
 // (returns true when `watch` was among the granted: its get is "triggered" at the call)
-template <class Mem> AFL_IN bool cpu_walk(St& W, const Mem& m, uint32_t sidx, uint32_t watch) {
+AFL_IN bool cpu_walk(St& W, const Mem& m, uint32_t sidx, uint32_t watch) {
     bool hit = false;
 #pragma unroll 1
     while (!q_empty(W, m, sq_word(sidx, SQ_CPUQ_HEAD)) && i32_ld(m, sv_word(sidx, SV_CPU_FREE)) > 0) {
@@ -530,7 +585,7 @@ template <class Mem> AFL_IN bool cpu_walk(St& W, const Mem& m, uint32_t sidx, ui
     return hit;
 }
 // ... over the RAM queue: grant heads while they fit, stop at the first that does not
-template <class Mem> AFL_IN void ram_walk(St& W, const Mem& m, uint32_t sidx) {
+AFL_IN void ram_walk(St& W, const Mem& m, uint32_t sidx) {
 #pragma unroll 1
     while (!q_empty(W, m, sq_word(sidx, SQ_RAMQ_HEAD))) {
         const uint32_t need = c32_ld(m, sq_word(sidx, SQ_RAMQ_NEED));
@@ -545,7 +600,7 @@ template <class Mem> AFL_IN void ram_walk(St& W, const Mem& m, uint32_t sidx) {
 }
 
 // ---- event injection (injection.py:167-226): all marks of this instant; returns true when the timeline re-arms
-template <class Mem> AFL_IN bool on_spike(St& W, const Mem& m, double& next_fire) {
+AFL_IN bool on_spike(St& W, const Mem& m, double& next_fire) {
     int32_t cur = W.spike_cur;
     const double t = ro(AFL_C.spikes + cur).fire;
 #pragma unroll 1
@@ -561,7 +616,7 @@ template <class Mem> AFL_IN bool on_spike(St& W, const Mem& m, double& next_fire
     if (cur < AFL_C.n_spike) { next_fire = ro(AFL_C.spikes + cur).fire; return true; }
     return false;
 }
-template <class Mem> AFL_IN bool on_outage(St& W, const Mem& m, double& next_fire) {
+AFL_IN bool on_outage(St& W, const Mem& m, double& next_fire) {
     int32_t cur = W.outage_cur;
     const double t = ro(AFL_C.outages + cur).fire;
     int32_t n = W.lb_n;
@@ -595,7 +650,7 @@ static inline void red_add(uint32_t* p, uint32_t v) { *p += v; }
 #endif
 
 // client: completion (client.py:62-69 + analyzer.py:83-125)
-template <class Mem> AFL_IN void complete(St& W, const Mem& m, uint32_t slot, double t0) {
+AFL_IN void complete(St& W, const Mem& m, uint32_t slot, double t0) {
     const double now = W.now;
     const double lat = now - t0;                     // finish - start (analyzer.py:86-89)
     const uint32_t done = ++W.completed;
@@ -624,7 +679,7 @@ template <class Mem> AFL_IN void complete(St& W, const Mem& m, uint32_t slot, do
 }
 
 // ---- set-up / write-back (once per replica) -----------------------------------------------------------------
-template <class Mem> AFL_IN void start_replica(St& W, const Mem& m, uint64_t local_index) {
+AFL_IN void start_replica(St& W, const Mem& m, uint64_t local_index) {
     const Cfg& C = AFL_C;
     W.local = local_index;
     W.replica = C.replica_begin + local_index;
@@ -641,7 +696,7 @@ template <class Mem> AFL_IN void start_replica(St& W, const Mem& m, uint64_t loc
     W.users_mean = C.users_mean; W.users_sigma = C.users_sigma; W.rate_per_user = C.rate_per_user;
 #pragma unroll 1
     for (int32_t i = 0; i < C.n_edges; ++i) {
-        w32_st(m, C.o32_conn + i, 0); w32_st(m, C.o32_sent + i, 0); c32_st(m, C.c_drop + i, 0);
+        w32_st(m, C.o32_conn + i, 0); *g32p(m, C.gi_sent + i) = 0; c32_st(m, C.c_drop + i, 0);
         if (C.n_spike > 0) f64_st(m, C.o64_spike + i, 0.0);
     }
 #pragma unroll 1
@@ -660,7 +715,7 @@ template <class Mem> AFL_IN void start_replica(St& W, const Mem& m, uint64_t loc
 #pragma unroll 1
     for (int32_t i = 0; i < C.n_lb_edges; ++i) w32_st(m, C.o32_lb + i, (uint32_t)C.lb_edges[i]);
 #pragma unroll 1
-    for (int32_t j = 0; j < C.n_series; ++j) { e64_st(m, C.o64_ssum + j, 0); w32_st(m, C.o32_smax + j, 0); }
+    for (int32_t j = 0; j < C.n_series; ++j) { *g64p(m, C.gi_acc + j) = 0; *g32p(m, C.gi_smax + j) = 0; }
 #pragma unroll 1
     for (int32_t w = 0; w < C.n_dirty; ++w) w32_st(m, C.o32_dirty + w, 0xFFFFFFFFu);      // no tick has read anything yet
     // sweep overrides of this replica: fields consumed here, fields looked up during the run (row copy)
@@ -687,12 +742,12 @@ template <class Mem> AFL_IN void start_replica(St& W, const Mem& m, uint64_t loc
     }
 }
 
-template <class Mem> AFL_IN void write_back(St& W, const Mem& m) {
+AFL_IN void write_back(St& W, const Mem& m) {
     const Cfg& C = AFL_C;
     const uint64_t local = W.local;
 #pragma unroll 1
     for (int32_t i = 0; i < C.n_edges; ++i) {
-        C.edge_sent[local * (uint64_t)C.n_edges + (uint32_t)i] = w32_ld(m, C.o32_sent + i);
+        C.edge_sent[local * (uint64_t)C.n_edges + (uint32_t)i] = ld_cg32(g32p(m, C.gi_sent + i));
         C.edge_dropped[local * (uint64_t)C.n_edges + (uint32_t)i] = c32_ld(m, C.c_drop + i);
     }
 #pragma unroll 1
@@ -700,8 +755,8 @@ template <class Mem> AFL_IN void write_back(St& W, const Mem& m) {
         uint64_t sum = 0; uint32_t mx = 0;
         if (gauge_on(j)) {
             const uint32_t v = gauge_value(m, j);
-            sum = (uint64_t)W.n_ticks * (uint64_t)v - e64_ld(m, C.o64_ssum + j);
-            mx = w32_ld(m, C.o32_smax + j);
+            sum = (uint64_t)W.n_ticks * (uint64_t)v - ld_cg64(g64p(m, C.gi_acc + j));
+            mx = ld_cg32(g32p(m, C.gi_smax + j));
             if (!((w32_ld(m, C.o32_dirty + (j >> 5)) >> (j & 31)) & 1u) && v > mx) mx = v;
         }
         C.samp_sum[local * (uint64_t)C.n_series + (uint32_t)j] = sum;
@@ -735,11 +790,13 @@ enum : uint32_t { A_NONE = 0, A_NODE, A_STEPS, A_SEND, A_TIMER };
 // returns the next local replica index or ~0 when the launch has no more work for this lane.
 // `converge` is a warp-wide rendez-vous at the top of every iteration (device: __any_sync).
 // ---------------------------------------------------------------------------------------------------
-template <class Mem, class NextFn, class ConvFn>
+template <class NextFn, class ConvFn>
 AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
     const Cfg& C = AFL_C;
     St W;
     bool active = false, exhausted = false;
+#pragma unroll 1
+    for (int32_t pg = 0; pg < C.pg_max; ++pg) *g32p(m, C.gi_pt + pg) = NIL;      // the lane owns no pool page yet
 #pragma unroll 1
     for (;;) {
         if (!converge(active || !exhausted)) break;          // all lanes of the warp are done
@@ -1150,7 +1207,7 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 }
             }
             if (send) {
-                w32_st(m, C.o32_sent + (int32_t)edge, w32_ld(m, C.o32_sent + (int32_t)edge) + 1);
+                red_add32(g32p(m, C.gi_sent + (int32_t)edge), 1u);
                 if (u < dropout) {                          // the request vanishes (edge.py:79-86)
                     c32_st(m, C.c_drop + (int32_t)edge, c32_ld(m, C.c_drop + (int32_t)edge) + 1);
                     rq_release(W, m, slot);

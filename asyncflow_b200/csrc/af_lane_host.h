@@ -98,22 +98,25 @@ constexpr int32_t LANE_EVENT_CAPACITY = 512;      // defaults of the lane engine
 constexpr int32_t LANE_REQUEST_CAPACITY = 2048;
 
 // smallest per-lane budget make_cfg() accepts for this scenario (4 events, 2 requests + the hot fixed tables)
+// the lane's fixed tables in shared memory: spike offsets + sweep-row copy (64-bit), connection counts, server levels,
+// LB order, the gauges' dirty bits (32-bit).  (The gauges' sums / maxima and the send counters are write-only: global tier.)
 inline int32_t fixed_lane_bytes(const AfScenario& s, const Tables& t) {
     const int32_t n_series = 3 * s.n_servers + s.n_edges;
-    const int32_t fix64 = (s.n_spike_marks > 0 ? s.n_edges : 0) + n_series + t.n_row;
-    const int32_t fix32 = 2 * s.n_edges + afl::SV_WORDS * s.n_servers + s.n_lb_edges + n_series + (n_series + 31) / 32;
+    const int32_t fix64 = (s.n_spike_marks > 0 ? s.n_edges : 0) + t.n_row;
+    const int32_t fix32 = s.n_edges + afl::SV_WORDS * s.n_servers + s.n_lb_edges + (n_series + 31) / 32;
     return 8 * fix64 + 4 * fix32;
 }
 constexpr int32_t MIN_DYNAMIC_BYTES = 16 * 4 + 36 * 2;      // make_cfg: rq_s = (rest - 64) / 36 >= 2
-// (a topology whose fixed tables do not fit next to that goes WIDE: fixed tables in the global tier)
-inline int32_t min_lane_bytes(const AfScenario&, const Tables&) { return MIN_DYNAMIC_BYTES; }
+// smallest per-lane budget make_cfg() accepts for this scenario
+inline int32_t min_lane_bytes(const AfScenario& s, const Tables& t) { return fixed_lane_bytes(s, t) + MIN_DYNAMIC_BYTES; }
 
 // The launch configuration for a budget of `lane_bytes` of shared memory per lane (= per replica in
 // flight).  Returns false when even the smallest tiers do not fit: the topology is too wide for this
 // engine at this occupancy (the caller lowers the occupancy or takes the warp-per-replica engine).
 // `lanes` = lanes of a warp in the code that will RUN the configuration: 32 for the CUDA kernel, 1 for the host twin
 // (afl::LANES is a property of the compilation pass, and the host pass of a .cu file sees 1).
-inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, int32_t lane_bytes, int32_t trace_tick_cap, int32_t lanes, afl::Cfg& C) {
+// `rq_static` > 0: request slots beyond it come from the page pool (up to o.request_capacity); <= 0: no paging.
+inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, int32_t lane_bytes, int32_t trace_tick_cap, int32_t lanes, int32_t rq_static, afl::Cfg& C) {
     C.n_edges = s.n_edges; C.n_servers = s.n_servers; C.n_endpoints = s.n_endpoints; C.n_steps = s.n_steps;
     C.n_lb_edges = s.n_lb_edges; C.lb_algo = s.lb_algo; C.gen_edge = s.gen_edge; C.client_edge = s.client_edge;
     C.n_spike = s.n_spike_marks; C.n_outage = s.n_outage_marks;
@@ -127,15 +130,20 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     int32_t ev_total = o.event_capacity > 0 ? o.event_capacity : LANE_EVENT_CAPACITY;
     int32_t rq_total = o.request_capacity > 0 ? o.request_capacity : LANE_REQUEST_CAPACITY;
     if (rq_total > (int32_t)afl::SLOT_MASK) rq_total = (int32_t)afl::SLOT_MASK;
+    int32_t pg_max = 0;
+    if (rq_static > 0 && rq_static < rq_total) {
+        pg_max = (rq_total - rq_static + (int32_t)afl::PG_SLOTS - 1) / (int32_t)afl::PG_SLOTS;
+        if (pg_max > 4096) pg_max = 4096;
+        rq_total = rq_static;
+    }
+    C.pg_max = pg_max; C.rq_cap = rq_total + pg_max * (int32_t)afl::PG_SLOTS;
+    if (C.rq_cap > (int32_t)afl::SLOT_MASK) C.rq_cap = (int32_t)afl::SLOT_MASK;
     // fixed part of a lane's shared memory
-    const int32_t fix64 = (C.n_spike > 0 ? C.n_edges : 0) + C.n_series + C.n_row;
+    const int32_t fix64 = (C.n_spike > 0 ? C.n_edges : 0) + C.n_row;
     C.n_dirty = (C.n_series + 31) / 32;
-    const int32_t fix32 = 2 * C.n_edges + afl::SV_WORDS * C.n_servers + C.n_lb_edges + C.n_series + C.n_dirty;
+    const int32_t fix32 = C.n_edges + afl::SV_WORDS * C.n_servers + C.n_lb_edges + C.n_dirty;
     int32_t nq_s = 0;                                // zero-delay items: ties only -- the ring starts in the global tier
-    // WIDE: the fixed tables would take more than half of the lane's shared memory (or all of it): they go to the
-    // global tier and the lane keeps its shared memory for pending events and request records
-    C.wide = (8 * fix64 + 4 * fix32) * 2 > lane_bytes ? 1 : 0;
-    int32_t rest = lane_bytes - (C.wide ? 0 : 8 * fix64 + 4 * fix32);
+    int32_t rest = lane_bytes - 8 * fix64 - 4 * fix32;
     // split the rest between pending events (16 B) and request records (20 B): at nominal load a request in
     // flight owns one pending event, plus the arrival and the two timelines
     int32_t rq_s = (rest - 16 * 4) / 36;
@@ -152,40 +160,32 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     C.o128_ev = 0; C.o128_rq = ev_s; C.n128 = ev_s + rq_s;
     int32_t e = 0;
     C.o64_nq = e; e += nq_s;
-    const int32_t dyn64 = e;
-    if (C.wide) e = 0;                               // fixed tables: offsets count from gf64 / gf32 in the global tier
     C.o64_spike = e; e += C.n_spike > 0 ? C.n_edges : 0;
-    C.o64_ssum = e; e += C.n_series;
     C.o64_row = e; e += C.n_row;
-    const int32_t fixed64 = C.wide ? e : 0;
-    C.n64 = C.wide ? dyn64 : e;
+    C.n64 = e;
     int32_t w = 0;
     C.o32_next = w; w += rq_s;
-    const int32_t dyn32 = w;
-    if (C.wide) w = 0;
     C.o32_conn = w; w += C.n_edges;
-    C.o32_sent = w; w += C.n_edges;
     C.o32_srv = w; w += afl::SV_WORDS * C.n_servers;
     C.o32_lb = w; w += C.n_lb_edges;
-    C.o32_smax = w; w += C.n_series;
     C.o32_dirty = w; w += C.n_dirty;
-    const int32_t fixed32 = C.wide ? w : 0;
-    C.n32 = C.wide ? dyn32 : w;
+    C.n32 = w;
     C.warp_bytes = (C.n128 * 16 + C.n64 * 8 + C.n32 * 4) * lanes;
     // global tier: 128-bit region (events, request records), 64-bit region (now-queue), 32-bit region (links, cold words)
     C.gi_ev = 0 - ev_s;
     C.gi_rq = (ev_total - ev_s) - rq_s;
     C.gn128 = (ev_total - ev_s) + (rq_total - rq_s);
     C.gi_nq = 0 - nq_s;
-    C.gf64 = afl::NQ_TOTAL - nq_s;
-    C.gn64 = C.gf64 + fixed64;
+    C.gi_acc = afl::NQ_TOTAL - nq_s;
+    C.gn64 = C.gi_acc + C.n_series;
     C.gi_next = 0 - rq_s;
     int32_t hcount = rq_total - rq_s;
     C.g32_cold = hcount;
     C.c_srvq = 0; C.c_inbox = C.c_srvq + afl::SQ_WORDS * C.n_servers; C.c_drop = C.c_inbox + afl::IB_WORDS * (C.n_servers + 2);
     hcount += C.c_drop + C.n_edges;
-    C.gf32 = hcount;
-    hcount += fixed32;
+    C.gi_pt = hcount; hcount += C.pg_max;
+    C.gi_smax = hcount; hcount += C.n_series;
+    C.gi_sent = hcount; hcount += C.n_edges;
     C.gn32 = hcount;
     C.gwarp_bytes = ((uint64_t)C.gn128 * 16 + (uint64_t)C.gn64 * 8 + (uint64_t)C.gn32 * 4) * (uint64_t)lanes;
     return true;
