@@ -372,14 +372,20 @@ AFL_IN uint32_t rq_alloc(St& W, const Mem& m) {
 }
 AFL_IN void rq_release(St& W, const Mem& m, uint32_t s) { rq_next_set(m, s, W.rq_free); W.rq_free = s; --W.rq_live; }
 
-// intrusive FIFOs through the `next` links; head / tail are COLD words
-AFL_IN void fifo_push(const Mem& m, int32_t w_head, int32_t w_tail, uint32_t s) {
+// intrusive FIFOs through the `next` links; head / tail are COLD words.  Out of line (Mem by value: a reference across a
+// call would force it into local memory): nine call sites, all on paths taken at ties or under contention
+#if defined(__CUDACC__)
+#define AFL_COLD __host__ __device__ __noinline__
+#else
+#define AFL_COLD static __attribute__((noinline))
+#endif
+AFL_COLD void fifo_push(const Mem m, int32_t w_head, int32_t w_tail, uint32_t s) {
     rq_next_set(m, s, NIL);
     const uint32_t tail = c32_ld(m, w_tail);
     if (tail == NIL) c32_st(m, w_head, s); else rq_next_set(m, tail, s);
     c32_st(m, w_tail, s);
 }
-AFL_IN uint32_t fifo_pop(const Mem& m, int32_t w_head, int32_t w_tail) {
+AFL_COLD uint32_t fifo_pop(const Mem m, int32_t w_head, int32_t w_tail) {
     const uint32_t s = c32_ld(m, w_head);
     const uint32_t h = rq_next(m, s);
     c32_st(m, w_head, h);
@@ -1002,12 +1008,12 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 }
                 const uint32_t ep_global = sp.ep_begin + epi;
                 pack = (pack & 0xFFu) | (ep_global << 16);     // step 0, flags clear
-                rq_pack_set(m, slot, pack);
                 const uint32_t total_ram = ep_total_ram(m, ep_global);
                 bool go = true;
                 if (total_ram) {                               // yield RAM.get(total_ram)
                     if (!(can_fuse(W) && (int32_t)total_ram <= i32_ld(m, sv_word(sidx, SV_RAM_FREE)) && q_empty(W, m, sq_word(sidx, SQ_RAMQ_HEAD)))) {
                         // cannot be served at once: join the queue, walk it
+                        rq_pack_set(m, slot, pack);
                         if (q_empty(W, m, sq_word(sidx, SQ_RAMQ_HEAD))) c32_st(m, sq_word(sidx, SQ_RAMQ_NEED), total_ram);
                         fifo_push(m, sq_word(sidx, SQ_RAMQ_HEAD), sq_word(sidx, SQ_RAMQ_TAIL), slot);
                         W.n_waiting += 1;
@@ -1079,7 +1085,6 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                                 fifo_push(m, sq_word(sidx, SQ_CPUQ_HEAD), sq_word(sidx, SQ_CPUQ_TAIL), slot);
                                 W.n_waiting += 1;
                                 if (!cpu_walk(W, m, sidx, slot)) { pack |= PK_WAIT; srv_gauge_add(W, m, sidx, SV_READY_Q, 1); }   // not cpu_req.triggered
-                                rq_pack_set(m, slot, pack);
                                 break;
                             }
                         }
@@ -1091,13 +1096,11 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                                 pack &= ~PK_CORE;
                                 continue;
                             }
-                            rq_pack_set(m, slot, pack);
                             nq_push(W, m, I_CPU_PUT, sidx, slot);
                             break;
                         }
                         if (!(pack & PK_IO)) { pack |= PK_IO; srv_gauge_add(W, m, sidx, SV_IO_Q, 1); }
                     }
-                    rq_pack_set(m, slot, pack);
                     const double dur = sp.c_dur >= 0 ? row_val(m, sp.c_dur) : sp.dur;
                     tm_t = W.now + dur; tm_payload = mk_payload(K_STEP_END, sidx, slot); tm_seq = W.seq++;
                     act = A_TIMER;
@@ -1111,7 +1114,6 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                         pack &= ~PK_CORE;
                         continue;
                     }
-                    rq_pack_set(m, slot, pack);
                     nq_push(W, m, I_CPU_PUT, sidx, slot);
                     break;
                 }
@@ -1120,13 +1122,14 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 if (total_ram) {                             // yield RAM.put(total_ram): level rises NOW
                     srv_gauge_add(W, m, sidx, SV_RAM_IN_USE, -(int32_t)total_ram);
                     i32_st(m, sv_word(sidx, SV_RAM_FREE), i32_ld(m, sv_word(sidx, SV_RAM_FREE)) + (int32_t)total_ram);
-                    if (!can_fuse(W)) { rq_pack_set(m, slot, pack); nq_push(W, m, I_RAM_PUT, sidx, slot); break; }
+                    if (!can_fuse(W)) { nq_push(W, m, I_RAM_PUT, sidx, slot); break; }
                     if (AFL_UNLIKELY(!q_empty(W, m, sq_word(sidx, SQ_RAMQ_HEAD)))) ram_walk(W, m, sidx);   // the put event would run next: waiters, then forward
                 }
                 edge = ro(C.servers + sidx).out_edge;
                 act = A_SEND;
                 break;
             }
+            if (act != A_SEND) rq_pack_set(m, slot, pack);   // the request yields here: its record goes back (SEND stores its own)
         }
         AFL_SYNC();
 

@@ -11,8 +11,8 @@ for wpb in ${WPBS:-12}; do
 done
 echo "=== C1 x 40000 x 60 s"; $QB --scenario c1_my_service.yml --replicas 40000 --horizon 60 --reps 2 --sweep none | tail -2
 echo "=== C4 20000 x 120 s"; $QB --scenario c4_lb8_events.yml --replicas 20000 --horizon 120 --reps 2 --sweep none | tail -2
-echo "=== C4 20000 x 120 s, fixed tables kept in shared memory (lower occupancy)"; ASYNCFLOW_B200_LANE_NARROW=1 $QB --scenario c4_lb8_events.yml --replicas 20000 --horizon 120 --reps 2 --sweep none | tail -2
 echo "=== C2 users sweep 10000 x 60 s"; $QB --scenario c1_my_service.yml --replicas 10000 --horizon 60 --reps 1 --sweep users | tail -2
+echo "=== C2 users sweep 10000 x 60 s, no page pool (flagged replicas re-run per warp)"; ASYNCFLOW_B200_NO_PAGES=1 $QB --scenario c1_my_service.yml --replicas 10000 --horizon 60 --reps 1 --sweep users | tail -2
 echo "=== C5 10000 x 10 s"; $QB --scenario c5_multihop32.yml --replicas 10000 --horizon 10 --reps 1 --sweep none | tail -2
 for wpb in ${BENCH_WPBS:-0}; do
   echo "=== bench.py --wpb $wpb"; timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --wpb $wpb | python -c "
