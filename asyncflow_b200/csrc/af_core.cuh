@@ -59,14 +59,9 @@
 // (tests/host_twin -- a debugging twin used by the CPU-only tests; it is NOT
 // reachable from the product API).
 //
-// Build variants (all off in the product build, whose SASS they do not change; each is
-// bit-identical to it by construction and checked so on the twin, tests/test_variants.py;
-// tools/build_variants.py + tools/ab_variants.sh build and time them on the GPU):
-//   -DAF_PREDRAW      lane-parallel, memoised edge variates            (search "AF_PREDRAW")
-//   -DAF_PREGEN       lane-parallel, memoised inter-arrival logarithms (search "AF_PREGEN")
-//   -DAF_SORTED_POOL  sorted 64-entry front ring for the event pool    (search "AF_SORTED_POOL")
-//   -DAF_PIN_ACTIVE   served requests stay in the shared-memory tier   (search "AF_PIN_ACTIVE")
-//   -DAF_MIN_BLOCKS=n register budget (af_engine.cu), -DAF_PRE_MAX_ROWS / -DAF_PRE_BUDGET memo geometry
+// Round 2: this engine is the fall-back of af_run (topologies too wide for a useful occupancy of the thread-per-replica
+// engine, replicas that overflow its tiers).  Its round-1 build variants (memoised variates, sorted front ring, pinned
+// request slots) were never promoted -- the thread-per-replica engine made the question moot -- and are gone.
 #pragma once
 #include "af_rng.cuh"
 #include "../../include/asyncflow_b200.h"
@@ -127,26 +122,6 @@ AF_IN uint32_t pk_ep(uint32_t p) { return (p >> 16) & 0xFFFu; }
 
 struct ReqRec { double t0; uint32_t rid; uint32_t pack; };          // 16 B
 
-#if defined(AF_PREDRAW)
-// Build variant AF_PREDRAW -- lane-parallel, memoised edge variates.
-// An edge's random numbers are a pure function of (seed, replica, request id, hop, edge parameters)
-// (oracle/afrng.py), and on every topology the reference accepts an edge is crossed at ONE hop count
-// (generator edge 1, client edge 3, LB edges 5, a server's exit = its entry + 2).  So instead of all 32
-// lanes drawing the same variate at each send, the arrival handler lets lane l draw edge (l % rows) of
-// request id (base + 1 + l / rows): one warp-wide pass fills `chunk = 32 / rows` future requests, and
-// edge_send() reads its value from a shared-memory ring.  The ring is a MEMO, not a queue: a miss (the
-// request is older than the ring, the edge has no row, or the hop differs from the planned one) simply
-// draws as before, so results are bit-identical with or without it.
-#ifndef AF_PRE_MAX_ROWS
-#define AF_PRE_MAX_ROWS 15         /* edges that get a memo row (<= 15: 4 bits of EdgeS.meta) */
-#endif
-#ifndef AF_PRE_BUDGET
-#define AF_PRE_BUDGET 2048         /* bytes of shared memory per warp the memo may take: ring = 32, 16 or 8 ids per row */
-#endif
-constexpr int32_t PRE_MAX_ROWS = AF_PRE_MAX_ROWS;
-constexpr int32_t PRE_BUDGET = AF_PRE_BUDGET;
-static_assert(PRE_MAX_ROWS >= 1 && PRE_MAX_ROWS <= 15 && PRE_BUDGET >= 64, "memo geometry");
-#endif
 
 // ---- per-warp private tables (shared memory on the device) -------------------
 struct EdgeS {            // 48 B
@@ -183,22 +158,9 @@ struct State {
     uint32_t nq_head, nq_tail, busy;   // busy = 2 * (items in the now-queue) + (pool may hold an event of this instant)
     // request table
     uint32_t rq_free, rq_hw, rq_live, peak_rq;
-#if defined(AF_PIN_ACTIVE)
-    uint32_t rq_free_hi, rq_hw_hi;   // the HBM tier's own free list and bump pointer (rq_free / rq_hw: shared-memory tier)
-#endif
     // generator (two clocks: the sampler's virtual one and the simulation's)
     double g_vnow, g_window_end, g_lam;
     uint32_t g_pos, generated, g_done, need_arrival, arm_seq;
-#if defined(AF_PREGEN)
-    uint32_t g_lo, g_pad;      // the gap memo holds stream positions [g_lo, g_lo + 32)
-#endif
-#if defined(AF_SORTED_POOL)
-    // sorted front ring of the pending-event pool (see "AF_SORTED_POOL" below) + the result of the last
-    // unsorted scan (kept here, not in a by-reference struct, so the rare path costs the hot loop no stack)
-    uint32_t rh, rn, pmode, sc_more;
-    uint64_t sc_t, sc_k;
-    int32_t sc_slot, sc_hole;
-#endif
     // parameters that may be swept
     double users_mean, users_sigma, rate_per_user;
     // load balancer / timelines
@@ -207,11 +169,7 @@ struct State {
     uint32_t tick_seq, n_ticks;
     double tick_time;
     // results
-#if defined(AF_PREDRAW)
-    uint32_t completed, flags, traced, pre_hi;   // pre_hi: edge variates of request ids <= pre_hi have been drawn
-#else
     uint32_t completed, flags, traced, pad0;
-#endif
     uint64_t n_events;
     double lat_sum, lat_sumsq, lat_min, lat_max;
 };
@@ -233,17 +191,6 @@ struct Layout {
     int32_t off_ev_time, off_ev_key, off_rq_rec, off_rq_next, off_edge, off_server,
             off_endpoint, off_step, off_lb, off_spike, off_outage, off_samp_sum, off_samp_max, off_nq, off_inbox;
     int32_t warp_bytes;
-#if defined(AF_SORTED_POOL)
-    int32_t off_sort;              // SORT_BACK_AT x (time, key): staging for the unsorted -> sorted conversion
-#endif
-#if defined(AF_PREGEN)
-    int32_t off_gmemo;             // 32 f64: ln(1 - u) of 32 consecutive positions of the generator stream
-#endif
-#if defined(AF_PREDRAW)
-    // memoised edge variates (see pre_refill): `pre_rows` edges x `pre_ring` request ids of f64
-    int32_t off_pre, pre_rows, pre_ring, pre_chunk;
-    int32_t pre_edge[PRE_MAX_ROWS];
-#endif
 };
 
 constexpr int32_t NQ_CAP = 128;   // now-queue capacity (power of two)
@@ -267,18 +214,6 @@ inline void layout_finalize(Layout& L) {
     L.off_rq_next = o;  o += 4 * L.rq_smem;
     L.off_samp_max = o; o += 4 * L.n_series;
     L.off_lb = o;       o += 4 * L.n_lb_edges;
-#if defined(AF_SORTED_POOL)
-    o = align_up(o, 8);
-    L.off_sort = o;     o += 16 * 16;
-#endif
-#if defined(AF_PREGEN)
-    o = align_up(o, 8);
-    L.off_gmemo = o;    o += 8 * 32;
-#endif
-#if defined(AF_PREDRAW)
-    o = align_up(o, 8);
-    L.off_pre = o;      o += 8 * L.pre_rows * L.pre_ring;
-#endif
     L.warp_bytes = align_up(o, 16);
 }
 
@@ -336,15 +271,6 @@ AF_TBL(tbl_samp_sum, uint64_t, off_samp_sum)
 AF_TBL(tbl_samp_max, uint32_t, off_samp_max)
 AF_TBL(tbl_nq, uint64_t, off_nq)
 AF_TBL(tbl_inbox, InboxS, off_inbox)
-#if defined(AF_PREDRAW)
-AF_TBL(tbl_pre, double, off_pre)
-#endif
-#if defined(AF_PREGEN)
-AF_TBL(tbl_gmemo, double, off_gmemo)
-#endif
-#if defined(AF_SORTED_POOL)
-AF_TBL(tbl_sort, uint64_t, off_sort)
-#endif
 
 // ---- warp primitives (a warp of ONE lane on the host) ------------------------
 #if AF_DEVICE_CODE
@@ -370,31 +296,14 @@ static inline void red_add_u32(uint32_t* p, uint32_t v) { *p += v; }
 // storage tiers: low slot numbers live in shared memory, the rest in the warp's HBM
 // spill region (overloaded replicas queue 10^4-10^5 requests)
 // ---------------------------------------------------------------------------------
-// AF_NO_SPILL: build variant for launches whose capacities fit the shared-memory tiers
-// (every spill branch disappears; the host only selects it when ev_total <= ev_smem and
-// rq_total <= rq_smem).
-#if defined(AF_NO_SPILL)
-#define AF_IN_SMEM(idx, cap) true
-#else
 #define AF_IN_SMEM(idx, cap) AF_LIKELY((int32_t)(idx) < (cap))
-#endif
-// (host twin, -DAF_COUNT_TIERS: how many request-record accesses each tier serves -- a measurement aid)
-#if defined(AF_COUNT_TIERS) && !AF_DEVICE_CODE
-static uint64_t g_rq_tier[2];                        // [shared-memory tier, HBM tier]
-#define AF_TIER_COUNT(s) (g_rq_tier[(int32_t)(s) < AF_L.rq_smem ? 0 : 1] += 1)
-#else
-#define AF_TIER_COUNT(s) ((void)0)
-#endif
 AF_IN ReqRec rq_load(const State& W, uint32_t s) {
-    AF_TIER_COUNT(s);
     return AF_IN_SMEM(s, AF_L.rq_smem) ? tbl_rq_rec(W)[s] : W.sp_rq_rec[s - AF_L.rq_smem];
 }
 AF_IN void rq_store(State& W, uint32_t s, const ReqRec& r) {
-    AF_TIER_COUNT(s);
     if (AF_IN_SMEM(s, AF_L.rq_smem)) tbl_rq_rec(W)[s] = r; else W.sp_rq_rec[s - AF_L.rq_smem] = r;
 }
 AF_IN void rq_set_pack(State& W, uint32_t s, uint32_t pack) {
-    AF_TIER_COUNT(s);
     if (AF_IN_SMEM(s, AF_L.rq_smem)) tbl_rq_rec(W)[s].pack = pack; else W.sp_rq_rec[s - AF_L.rq_smem].pack = pack;
 }
 AF_IN uint32_t nx_load(const State& W, uint32_t s) {
@@ -411,50 +320,6 @@ AF_IN uint64_t evk_load(const State& W, int32_t k) {
 }
 
 // ---- request slots (free list threaded through rq_next) ------------------------
-#if defined(AF_PIN_ACTIVE)
-// Build variant AF_PIN_ACTIVE -- requests that are being SERVED stay in the shared-memory tier.
-// A saturated replica holds thousands of requests, almost all of them parked in a server's RAM queue
-// (17 admitted, 7x10^4 waiting); with one free list the ~20 requests that generate
-// every event end up in arbitrary slots, i.e. in the HBM tier, and each handler pays L2 round trips for
-// its record.  Here the two tiers have their own free lists: a request is moved OUT to an HBM slot when
-// it joins a RAM queue (ram_enqueue) and back IN to a shared-memory slot when it is admitted (I_RAM_OK).
-// While it waits, nothing but the queue's links refers to its slot, so renaming it is invisible: same
-// events, same order, same results; live/peak counters are not touched by a move.
-AF_IN uint32_t rq_take_lo(State& W) {
-    uint32_t s = W.rq_free;
-    if (s != NIL) { W.rq_free = nx_load(W, s); return s; }
-    if ((int32_t)W.rq_hw < AF_L.rq_smem) return W.rq_hw++;
-    return NIL;
-}
-AF_IN uint32_t rq_take_hi(State& W) {
-    uint32_t s = W.rq_free_hi;
-    if (s != NIL) { W.rq_free_hi = nx_load(W, s); return s; }
-    if ((int32_t)W.rq_hw_hi < AF_L.rq_total) return W.rq_hw_hi++;
-    return NIL;
-}
-AF_IN void rq_give(State& W, uint32_t s) {
-    if ((int32_t)s < AF_L.rq_smem) { nx_store(W, s, W.rq_free); W.rq_free = s; }
-    else { nx_store(W, s, W.rq_free_hi); W.rq_free_hi = s; }
-}
-AF_IN uint32_t rq_alloc(State& W) {
-    uint32_t s = rq_take_lo(W);
-    if (s == NIL) s = rq_take_hi(W);
-    if (s == NIL) { W.flags |= AF_FLAG_REQUEST_OVERFLOW; return NIL; }
-    uint32_t live = ++W.rq_live;
-    if (live > W.peak_rq) W.peak_rq = live;
-    return s;
-}
-AF_IN void rq_release(State& W, uint32_t s) { rq_give(W, s); --W.rq_live; }
-// rename `slot` into the other tier if that tier has room; returns the slot to use from now on
-AF_FN uint32_t rq_move(State& W, uint32_t slot, uint32_t to_lo) {
-    AF_SHARED(&W);
-    const uint32_t s2 = to_lo ? rq_take_lo(W) : rq_take_hi(W);
-    if (s2 == NIL) return slot;
-    rq_store(W, s2, rq_load(W, slot));
-    rq_give(W, slot);
-    return s2;
-}
-#else
 AF_IN uint32_t rq_alloc(State& W) {
     uint32_t s;
     if (W.rq_free != NIL) { s = W.rq_free; W.rq_free = nx_load(W, s); }
@@ -466,7 +331,6 @@ AF_IN uint32_t rq_alloc(State& W) {
 }
 AF_IN void rq_release(State& W, uint32_t s) { nx_store(W, s, W.rq_free); W.rq_free = s; --W.rq_live; }
 
-#endif
 
 // intrusive FIFOs (RAM waiters, CPU waiters) through the same `next` links
 AF_FN void fifo_push(State& W, uint32_t& head, uint32_t& tail, uint32_t s) {
@@ -521,78 +385,10 @@ AF_FN int32_t pool_find_hole(State& W) {
     return mine == 0x7FFFFFFF ? -1 : mine;
 }
 
-#if defined(AF_SORTED_POOL)
-// Build variant AF_SORTED_POOL -- while at most 64 events are pending (every nominal-load scenario: peak
-// 12-17 on C1/C2/C3, 56 on C4) the pool is a SORTED ring in the 64 shared-memory slots, lane l holding
-// logical elements l and l + 32: push inserts in (time, seq) order with one ballot per 32 elements (each
-// lane compares its element and moves it up one slot), pop reads the head.  No scan, no reductions:
-// ~90 instructions per event instead of ~160 (ncu r1i: scan + remove + push = 29 % of the executed
-// instructions).  When a 65th event arrives the 64 slots are re-interpreted as the unsorted pool below
-// (pmode 1, the round-1 code, unchanged); when that pool drains to 16 events it is sorted back into the
-// ring (pool_remove_b).  Order of pops is the same total order (time, seq) in both modes, so results are
-// bit-identical.
-constexpr uint32_t RING = 64u;                      // = the shared-memory tier of the pool (two elements per lane)
-constexpr int32_t SORT_BACK_AT = 16;
-#if !AF_DEVICE_CODE
-static uint64_t g_pool_counts[4];                    // host twin only: [ring pushes, unsorted pushes, ring -> unsorted, unsorted -> ring]
-#define AF_POOL_COUNT(i) (g_pool_counts[i] += 1)
-#else
-#define AF_POOL_COUNT(i) ((void)0)
-#endif
-#endif
 AF_FN void push_seq(State& W, double t, uint32_t payload, uint32_t s) {
     AF_SHARED(&W);
     if (!(t < W.horizon)) return;       // env.run(until=T): events at >= T never fire
     if (AF_UNLIKELY(t == W.now)) W.busy |= 1u;   // a zero-delay timeout: it competes with the now-queue
-#if defined(AF_SORTED_POOL)
-    if (AF_LIKELY(W.pmode == 0u)) {
-        const uint32_t n = W.rn, rh = W.rh;
-        if (AF_LIKELY(n < RING)) {                   // insert in (time, seq) order: one element per lane
-            const uint64_t tb = afr::d2u(t), key = ((uint64_t)s << 32) | payload;
-            double* const T = tbl_ev_time(W); uint64_t* const Kk = tbl_ev_key(W);
-#if AF_DEVICE_CODE
-            // lane l holds logical elements l and l + 32 (the second only when more than 32 are pending)
-            const uint32_t l = (uint32_t)lane_id(), ph = (rh + l) & (RING - 1u), ph2 = (ph + 32u) & (RING - 1u);
-            const bool mine = l < n, mine2 = l + 32u < n;
-            const uint64_t tl = mine ? afr::d2u(T[ph]) : 0ull, kl = mine ? Kk[ph] : 0ull;
-            const bool before = mine && (tl < tb || (tl == tb && (uint32_t)(kl >> 32) < s));
-            uint32_t pos = (uint32_t)__popc(w_ballot(before));         // sorted, so `before` is a prefix
-            uint64_t tl2 = 0ull, kl2 = 0ull;
-            if (n > 32u) {                           // (uniform)
-                if (mine2) { tl2 = afr::d2u(T[ph2]); kl2 = Kk[ph2]; }
-                const bool before2 = mine2 && (tl2 < tb || (tl2 == tb && (uint32_t)(kl2 >> 32) < s));
-                pos += (uint32_t)__popc(w_ballot(before2));
-            }
-            w_sync();                                // every lane holds its elements before any slot is rewritten
-            if (mine && l >= pos) { const uint32_t q = (ph + 1u) & (RING - 1u); T[q] = afr::u2d(tl); Kk[q] = kl; }
-            if (mine2 && l + 32u >= pos) { const uint32_t q = (ph2 + 1u) & (RING - 1u); T[q] = afr::u2d(tl2); Kk[q] = kl2; }
-#else
-            uint32_t pos = 0;
-            for (uint32_t l = 0; l < n; ++l) {
-                const uint32_t ph = (rh + l) & (RING - 1u);
-                const uint64_t tl = afr::d2u(T[ph]);
-                if (tl < tb || (tl == tb && (uint32_t)(Kk[ph] >> 32) < s)) ++pos;
-            }
-            for (uint32_t l = n; l > pos; --l) {
-                const uint32_t from = (rh + l - 1u) & (RING - 1u), to = (rh + l) & (RING - 1u);
-                T[to] = T[from]; Kk[to] = Kk[from];
-            }
-#endif
-            const uint32_t at = (rh + pos) & (RING - 1u);
-            T[at] = t; Kk[at] = key;
-            w_sync();
-            W.rn = n + 1u;
-            uint32_t live = (uint32_t)(++W.ev_live);
-            if (live > W.peak_ev) W.peak_ev = live;
-            AF_POOL_COUNT(0);
-            return;
-        }
-        // the ring is full: its 64 slots ARE a valid unsorted pool without holes; carry on below
-        W.pmode = 1u; W.ev_hw = (int32_t)RING; W.ev_last_free = -1; W.ev_hole = -1;
-        AF_POOL_COUNT(2);
-    }
-    AF_POOL_COUNT(1);
-#endif
     int32_t slot;
     if (W.ev_last_free >= 0) { slot = W.ev_last_free; W.ev_last_free = -1; }
     else if (W.ev_hole >= 0) { slot = W.ev_hole; W.ev_hole = -1; }
@@ -672,50 +468,6 @@ AF_IN void pool_remove(State& W, const PoolMin& m) {
     W.ev_hole = m.hole < nhw ? m.hole : -1;
 }
 
-#if defined(AF_SORTED_POOL)
-// pmode 1 (rare): the unsorted scan/remove behind out-of-line bodies, results through State
-AF_FN bool pool_scan_b(State& W) {
-    AF_SHARED(&W);
-    PoolMin m;
-    if (!pool_scan(W, m)) return false;
-    W.sc_t = m.tbits; W.sc_k = m.key; W.sc_slot = m.slot; W.sc_hole = m.hole; W.sc_more = m.more ? 1u : 0u;
-    return true;
-}
-AF_FN void pool_remove_b(State& W) {
-    AF_SHARED(&W);
-    PoolMin m; m.tbits = W.sc_t; m.key = W.sc_k; m.slot = W.sc_slot; m.hole = W.sc_hole; m.more = W.sc_more != 0u;
-    pool_remove(W, m);
-    if (W.ev_live > SORT_BACK_AT || AF_L.ev_smem < (int32_t)RING) return;
-    // few events left: extract them in order into the staging area, then lay them out as the ring
-    uint64_t* const st = tbl_sort(W);
-    const int32_t n = W.ev_live;
-#pragma unroll 1
-    for (int32_t i = 0; i < n; ++i) {
-        pool_scan_b(W);
-        m.tbits = W.sc_t; m.key = W.sc_k; m.slot = W.sc_slot; m.hole = W.sc_hole;
-        pool_remove(W, m);
-        st[2 * i] = m.tbits; st[2 * i + 1] = m.key;
-        w_sync();
-    }
-#pragma unroll 1
-    for (int32_t i = 0; i < n; ++i) { tbl_ev_time(W)[i] = afr::u2d(st[2 * i]); tbl_ev_key(W)[i] = st[2 * i + 1]; }
-    w_sync();
-    W.rh = 0u; W.rn = (uint32_t)n; W.pmode = 0u;
-    W.ev_live = n; W.ev_hw = 0; W.ev_last_free = -1; W.ev_hole = -1;
-    AF_POOL_COUNT(3);
-}
-// pmode 0: the head of the ring is the minimum
-AF_IN bool ring_peek(const State& W, uint64_t& tbits, uint64_t& key, bool& more) {
-    const uint32_t n = W.rn;
-    if (n == 0u) return false;
-    const uint32_t p = W.rh;
-    tbits = afr::d2u(tbl_ev_time(W)[p]);
-    key = tbl_ev_key(W)[p];
-    more = n > 1u && afr::d2u(tbl_ev_time(W)[(p + 1u) & (RING - 1u)]) == tbits;
-    return true;
-}
-AF_IN void ring_pop(State& W) { W.rh = (W.rh + 1u) & (RING - 1u); W.rn -= 1u; W.ev_live -= 1; }
-#endif
 
 // ---- now-queue: FIFO of zero-delay continuation items (seq << 32 | kind:3 aux:9 slot:20) ----
 enum : uint32_t { I_PUT = 0, I_GOT = 1, I_CLIENT_LOOP = 2, I_RAM_OK = 3, I_CPU_OK = 4, I_CPU_PUT = 5, I_RAM_PUT = 6 };
@@ -739,27 +491,6 @@ AF_FN void nq_push(State& W, uint32_t kind, uint32_t aux, uint32_t slot) {
 // generator: samplers/poisson_poisson.py:52-82 / gaussian_poisson.py:64-94.
 // Returns false when the sampler is exhausted; otherwise the next yielded gap.
 // ---------------------------------------------------------------------------------
-#if defined(AF_PREGEN)
-// Build variant AF_PREGEN -- the inter-arrival gaps' logarithms, 32 stream positions per warp pass.
-// A gap is -ln(1 - max(u_pos, 1e-15)) / lambda with u_pos the pos-th uniform of the replica's
-// generator stream (a pure function of pos, oracle/afrng.py GenStream); the user draws that share the
-// stream only move `pos`.  Lane l computes position pos + l; gen_next_gap() then reads ln(1 - u) from
-// shared memory.  Same operations on the same operands as the direct path: bit-identical results.
-AF_FN void gen_refill(State& W, uint32_t pos) {
-    AF_SHARED(&W);
-    double* memo = tbl_gmemo(W);
-#pragma unroll 1
-    for (int32_t l = lane_id(); l < 32; l += WARP) {
-        const uint32_t p = pos + (uint32_t)l;
-        afr::Src s = afr::make_gen(AF_G.seed, W.replica, p);
-        double u = s.next53();
-        if (u < 1e-15) u = 1e-15;                   // max(u, 1e-15)
-        memo[p & 31u] = afr::af_log(1.0 - u);
-    }
-    w_sync();
-    W.g_lo = pos;
-}
-#endif
 
 AF_IN bool gen_next_gap(State& W, double& gap) {
     const double T = W.horizon;
@@ -775,17 +506,11 @@ AF_IN bool gen_next_gap(State& W, double& gap) {
             lam = d.value * W.rate_per_user;
         }
         if (lam <= 0.0) { vnow = wend; continue; }
-#if defined(AF_PREGEN)
-        if (pos - W.g_lo >= 32u) gen_refill(W, pos);
-        double dt = afr::af_div(-tbl_gmemo(W)[pos & 31u], lam);
-        pos += 1u;
-#else
         afr::Src s = afr::make_gen(AF_G.seed, W.replica, pos);
         double u = s.next53();
         pos = s.pos;
         if (u < 1e-15) u = 1e-15;                   // max(u, 1e-15)
         double dt = afr::af_div(-afr::af_log(1.0 - u), lam);
-#endif
         if (vnow + dt > T) break;
         if (vnow + dt >= wend) { vnow = wend; continue; }
         vnow += dt;
@@ -808,60 +533,12 @@ AF_IN void arm_generator(State& W) {
 // edges: EdgeRuntime.transport -> Initialize (URGENT) -> _deliver up to its timeout
 // (edge.py:73-107).  Called at the END of the item that called transport().
 // ---------------------------------------------------------------------------------
-#if defined(AF_PREDRAW)
-// EdgeS.meta carries the plan: row + 1 in [16:20) (0 = this edge is not memoised), planned hop in [20:28)
-AF_IN uint32_t meta_row1(uint32_t meta) { return (meta >> 16) & 15u; }
-AF_IN uint32_t meta_hop(uint32_t meta) { return (meta >> 20) & 0xFFu; }
-AF_IN double pre_encode(const afr::EdgeDraw& d, double dropout) { return d.u < dropout ? -1.0 : d.transit; }  // transit >= 0 always
-
-#if !AF_DEVICE_CODE
-static uint64_t g_pre_lookups[2];                    // [miss, hit]
-#endif
-// Draw the edge variates of the next `pre_chunk` request ids, one (request, edge) pair per lane.
-AF_FN void pre_refill(State& W) {
-    AF_SHARED(&W);
-    const uint32_t base = W.pre_hi;
-    const int32_t rows = AF_L.pre_rows, n = rows * AF_L.pre_chunk;
-    const uint32_t ring = (uint32_t)AF_L.pre_ring;
-    double* pre = tbl_pre(W);
-#pragma unroll 1
-    for (int32_t l = lane_id(); l < n; l += WARP) {
-        const uint32_t row = (uint32_t)(l % rows), rid = base + 1u + (uint32_t)(l / rows);
-        const EdgeS& E = tbl_edge(W)[AF_L.pre_edge[row]];
-        const double dropout = E.dropout;
-        afr::EdgeDraw d = afr::edge_draw(AF_G.seed, W.replica, rid, meta_hop(E.meta), (int)(E.meta & 7u), E.mean, E.sigma, dropout);
-        pre[row * ring + (rid & (ring - 1u))] = pre_encode(d, dropout);
-    }
-    w_sync();
-    W.pre_hi = base + (uint32_t)AF_L.pre_chunk;
-}
-#endif
 
 AF_FN void edge_send(State& W, uint32_t slot, uint32_t e, uint32_t rid, uint32_t hops) {
     AF_SHARED(&W);
     EdgeS& E = tbl_edge(W)[e];
     uint32_t s = W.seq++;                            // the timeout's place in SimPy's eid order
     const double dropout = E.dropout;
-#if defined(AF_PREDRAW)
-    const uint32_t meta = E.meta, row1 = meta_row1(meta), hi = W.pre_hi, ring = (uint32_t)AF_L.pre_ring;
-    double v;                                        // < 0: dropped, else the transit time
-    const bool memo = AF_LIKELY(row1 != 0u && hops == meta_hop(meta) && rid <= hi && rid + ring > hi);
-#if !AF_DEVICE_CODE
-    g_pre_lookups[memo ? 1 : 0] += 1;                // host twin only: lets the tests see that the memo is live
-#endif
-    if (memo)
-        v = tbl_pre(W)[(row1 - 1u) * ring + (rid & (ring - 1u))];
-    else
-        v = pre_encode(afr::edge_draw(AF_G.seed, W.replica, rid, hops, (int)(meta & 7u), E.mean, E.sigma, dropout), dropout);
-    E.sent += 1;
-    if (v < 0.0) {                                  // the request vanishes (edge.py:79-86)
-        E.dropped += 1;
-        rq_release(W, slot);
-        return;
-    }
-    E.conn += 1;
-    double effective = v + E.spike;                // spike read at SEND time (edge.py:94-106)
-#else
     afr::EdgeDraw d = afr::edge_draw(AF_G.seed, W.replica, rid, hops, (int)(E.meta & 7u), E.mean, E.sigma, dropout);
     E.sent += 1;
     if (d.u < dropout) {                            // the request vanishes (edge.py:79-86)
@@ -871,7 +548,6 @@ AF_FN void edge_send(State& W, uint32_t slot, uint32_t e, uint32_t rid, uint32_t
     }
     E.conn += 1;
     double effective = d.transit + E.spike;        // spike read at SEND time (edge.py:94-106)
-#endif
     push_seq(W, W.now + effective, mk_payload(K_DELIVER, e, slot), s);
 }
 
@@ -925,10 +601,6 @@ AF_FN void ram_walk(State& W, ServerS& S, uint32_t sidx) {
 }
 // RAM.get(total_ram) of a request that cannot be served at once: join the queue, walk it
 AF_IN void ram_enqueue(State& W, ServerS& S, uint32_t sidx, uint32_t slot, uint32_t total_ram) {
-#if defined(AF_PIN_ACTIVE)
-    // it will wait unless the walk below admits it at once (queue empty and it fits): park it in the HBM tier
-    if ((int32_t)slot < AF_L.rq_smem && !(S.ramq_head == NIL && (int32_t)total_ram <= S.ram_free)) slot = rq_move(W, slot, 0u);
-#endif
     if (S.ramq_head == NIL) S.ramq_head_need = total_ram;
     fifo_push(W, S.ramq_head, S.ramq_tail, slot);
     ram_walk(W, S, sidx);
@@ -1128,9 +800,6 @@ AF_IN void run_item(State& W, uint32_t item) {
         consumer_get(W, NODE_CLIENT);
     } else if (kind == I_RAM_OK) {                   // the RAM get event is processed: the handler resumes
         ServerS& S = tbl_server(W)[aux];
-#if defined(AF_PIN_ACTIVE)
-        if ((int32_t)slot >= AF_L.rq_smem) slot = rq_move(W, slot, 1u);   // admitted: back into the fast tier
-#endif
         ReqRec r = rq_load(W, slot);
         S.ram_in_use += (int32_t)tbl_endpoint(W)[pk_ep(r.pack)].total_ram;
         run_steps(W, slot, aux, r.rid, r.pack);
@@ -1160,11 +829,7 @@ AF_IN void on_deliver(State& W, uint32_t slot, uint32_t e) {
     ReqRec r = rq_load(W, slot);
     r.pack += 1;                                     // record_hop(edge)
     const uint32_t tk = (meta >> 3) & 3u;
-    #if defined(AF_PREDRAW)
-    const uint32_t node = tk == AF_TARGET_CLIENT ? NODE_CLIENT : (tk == AF_TARGET_LB ? NODE_LB : NODE_SERVER0 + ((meta >> 5) & 0xFFu));
-#else
     const uint32_t node = tk == AF_TARGET_CLIENT ? NODE_CLIENT : (tk == AF_TARGET_LB ? NODE_LB : NODE_SERVER0 + (meta >> 5));
-#endif
     if (can_fuse(W)) {                               // (implies: every inbox empty, every consumer in get())
         node_got(W, node, slot, r.t0, r.rid, r.pack);   // put -> pending get -> resume, nothing in between
         return;                                      // (the consumer stores the record's new pack itself)
@@ -1187,9 +852,6 @@ AF_IN void on_arrival(State& W) {
     if (slot == NIL) return;
     ReqRec r; r.t0 = W.now; r.rid = rid; r.pack = 1;  // record_hop(generator)
     rq_store(W, slot, r);
-#if defined(AF_PREDRAW)
-    if (AF_L.pre_rows > 0 && rid > W.pre_hi) pre_refill(W);
-#endif
     edge_send(W, slot, (uint32_t)AF_L.gen_edge, rid, 1u);
 }
 
@@ -1296,9 +958,6 @@ AF_FN void load_params(State& W) {
         EdgeS e;
         e.mean = a.mean; e.sigma = a.sigma; e.dropout = a.dropout; e.spike = 0.0;
         e.meta = (uint32_t)a.dist | ((uint32_t)a.target_kind << 3) | ((uint32_t)a.target_index << 5);
-#if defined(AF_PREDRAW)
-        e.meta |= (uint32_t)a.reserved << 16;        // the host's plan (afh::predraw_plan): row + 1 | hop << 4
-#endif
         e.conn = 0; e.sent = 0; e.dropped = 0;
         tbl_edge(W)[i] = e;
     }
@@ -1415,22 +1074,10 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
     W.ev_hw = 0; W.ev_live = 0; W.ev_last_free = -1; W.ev_hole = -1; W.peak_ev = 0;
     W.nq_head = 0; W.nq_tail = 0; W.busy = 0;
     W.rq_free = NIL; W.rq_hw = 0; W.rq_live = 0; W.peak_rq = 0;
-#if defined(AF_PIN_ACTIVE)
-    W.rq_free_hi = NIL; W.rq_hw_hi = (uint32_t)AF_L.rq_smem;
-#endif
     W.g_vnow = 0.0; W.g_window_end = 0.0; W.g_lam = 0.0; W.g_pos = 0; W.generated = 0; W.g_done = 0;
     W.lb_n = AF_L.n_lb_edges;
     W.spike_cur = 0; W.outage_cur = 0;
     W.n_ticks = 0; W.completed = 0; W.flags = 0; W.n_events = 0;
-#if defined(AF_PREDRAW)
-    W.pre_hi = 0;
-#endif
-#if defined(AF_PREGEN)
-    W.g_lo = 0x80000000u;                            // nothing memoised yet
-#endif
-#if defined(AF_SORTED_POOL)
-    W.rh = 0u; W.rn = 0u; W.pmode = AF_L.ev_smem >= (int32_t)RING ? 0u : 1u; W.sc_more = 0u;
-#endif
     W.lat_sum = 0.0; W.lat_sumsq = 0.0; W.lat_min = afr::u2d(INF_BITS); W.lat_max = 0.0;
     W.traced = (int64_t)local_index < (int64_t)AF_L.trace_replicas ? 1u : 0u;
     w_sync();
@@ -1462,16 +1109,7 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
             continue;
         }
         PoolMin m;
-#if defined(AF_SORTED_POOL)
-        bool have_ev;
-        if (AF_LIKELY(W.pmode == 0u)) have_ev = ring_peek(W, m.tbits, m.key, m.more);
-        else {
-            have_ev = pool_scan_b(W);
-            m.tbits = W.sc_t; m.key = W.sc_k; m.more = W.sc_more != 0u;
-        }
-#else
         const bool have_ev = pool_scan(W, m);
-#endif
         if (have_item) {
             const uint64_t front = tbl_nq(W)[W.nq_head & (NQ_CAP - 1)];
             const bool same_t = have_ev && m.tbits == afr::d2u(W.now);
@@ -1483,11 +1121,7 @@ AF_IN void run_replica(State& W, uint64_t local_index) {
                 continue;
             }
         } else if (!have_ev) break;
-#if defined(AF_SORTED_POOL)
-        if (AF_LIKELY(W.pmode == 0u)) ring_pop(W); else pool_remove_b(W);
-#else
         pool_remove(W, m);
-#endif
         const double t = afr::u2d(m.tbits);
         const uint32_t payload = (uint32_t)m.key, ev_seq = (uint32_t)(m.key >> 32);
         W.busy = (W.busy & ~1u) | (m.more ? 1u : 0u);

@@ -372,9 +372,6 @@ int af_scenario_upload(af_engine* e, const AfScenario* s) {
     AF_CUDA(e, cudaStreamSynchronize(e->stream), "sync before upload");
     e->sc = *s;
     e->h_edges.assign(s->edges, s->edges + s->n_edges);
-#if defined(AF_PREDRAW)
-    afh::predraw_annotate(*s, e->h_edges.data());
-#endif
     e->h_servers.assign(s->servers, s->servers + s->n_servers);
     e->h_eps.assign(s->endpoints, s->endpoints + s->n_endpoints);
     e->h_steps.assign(s->steps, s->steps + s->n_steps);

@@ -80,53 +80,8 @@ inline int32_t trace_tick_capacity(const AfScenario& s) {
     return (int32_t)n + 2;
 }
 
-#if defined(AF_PREDRAW)
-// The AF_PREDRAW plan (af_core.cuh): at which hop count each edge is crossed and which edges get a
-// row of the memo ring.  hop = length of the request's history when transport() is called:
-// generator 1 (rqs_generator.py:113), client 3 (client.py:55-60), then +2 per node (the edge's and
-// the node's record_hop).  First assignment wins; the kernel compares the planned hop with the actual
-// one at every send, so an edge reachable at two depths only loses memo hits, never correctness.
-struct PredrawPlan { std::vector<int32_t> hop, row; int32_t rows = 0, ring = 0, chunk = 0; int32_t edge_of_row[afc::PRE_MAX_ROWS]; };
-inline PredrawPlan predraw_plan(const AfScenario& s) {
-    PredrawPlan p;
-    p.hop.assign((size_t)s.n_edges, -1); p.row.assign((size_t)s.n_edges, -1);
-    std::vector<int32_t> order;
-    auto set = [&](int32_t e, int32_t h) { if (p.hop[(size_t)e] < 0 && h <= 255) { p.hop[(size_t)e] = h; order.push_back(e); } };
-    set(s.gen_edge, 1);
-    set(s.client_edge, 3);
-    for (size_t i = 0; i < order.size(); ++i) {
-        const int32_t e = order[i], h = p.hop[(size_t)e];
-        const AfEdge& E = s.edges[e];
-        if (E.target_kind == AF_TARGET_LB) { for (int k = 0; k < s.n_lb_edges; ++k) set(s.lb_edges[k], h + 2); }
-        else if (E.target_kind == AF_TARGET_SERVER) set(s.servers[E.target_index].out_edge, h + 2);
-    }
-    // geometry: as many rows as edges (<= PRE_MAX_ROWS), as deep a ring as the byte budget allows (32, 16, 8
-    // request ids per row), then fewer rows if even 8 do not fit
-    int32_t rows = (int32_t)order.size() < afc::PRE_MAX_ROWS ? (int32_t)order.size() : afc::PRE_MAX_ROWS;
-    int32_t ring = 32;
-    while (ring > 8 && 8 * rows * ring > afc::PRE_BUDGET) ring /= 2;
-    while (rows > 0 && 8 * rows * ring > afc::PRE_BUDGET) --rows;
-    p.rows = rows; p.ring = ring;
-    p.chunk = rows ? (32 / rows < ring ? 32 / rows : ring) : 0;          // one pass must not lap the ring
-    for (int32_t r = 0; r < rows; ++r) { p.row[(size_t)order[(size_t)r]] = r; p.edge_of_row[r] = order[(size_t)r]; }
-    return p;
-}
-// what af_scenario_upload writes into AfEdge.reserved (bits [16:28) of the kernel's EdgeS.meta)
-inline void predraw_annotate(const AfScenario& s, AfEdge* edges) {
-    PredrawPlan p = predraw_plan(s);
-    for (int32_t e = 0; e < s.n_edges; ++e)
-        edges[e].reserved = p.row[(size_t)e] < 0 ? 0 : ((p.row[(size_t)e] + 1) | (p.hop[(size_t)e] << 4));
-}
-#endif
 
 inline void make_layout(const AfScenario& s, const AfOptions& o, int32_t n_sweep_cols, afc::Layout& L) {
-#if defined(AF_PREDRAW)
-    {
-        PredrawPlan p = predraw_plan(s);
-        L.pre_rows = p.rows; L.pre_ring = p.ring; L.pre_chunk = p.chunk;
-        for (int r = 0; r < afc::PRE_MAX_ROWS; ++r) L.pre_edge[r] = r < p.rows ? p.edge_of_row[r] : 0;
-    }
-#endif
     L.n_edges = s.n_edges; L.n_servers = s.n_servers; L.n_endpoints = s.n_endpoints; L.n_steps = s.n_steps;
     L.n_lb_edges = s.n_lb_edges; L.lb_algo = s.lb_algo; L.gen_edge = s.gen_edge; L.client_edge = s.client_edge;
     L.n_spike = s.n_spike_marks; L.n_outage = s.n_outage_marks;

@@ -36,13 +36,7 @@ extern "C" int af_twin_run(const AfScenario* sc, const AfSweep* sw, uint64_t swe
     afh::make_layout(*sc, *opt, sw ? sw->n_columns : 0, L);
     afc::Globals& G = afc::h_G;
     memset(&G, 0, sizeof G);
-#if defined(AF_PREDRAW)
-    std::vector<AfEdge> planned(sc->edges, sc->edges + sc->n_edges);
-    afh::predraw_annotate(*sc, planned.data());
-    G.edges = planned.data(); G.servers = sc->servers;
-#else
     G.edges = sc->edges; G.servers = sc->servers;
-#endif
     G.endpoints = sc->endpoints; G.steps = sc->steps;
     G.lb_edges = sc->lb_edges; G.spikes = sc->spike_marks; G.outages = sc->outage_marks;
     if (sw) { G.sweep_cols = sw->columns; G.sweep_vals = sw->values; G.sweep_first = sweep_first; G.sweep_rows = sw->n_rows; }
@@ -133,34 +127,4 @@ extern "C" int af_twin_sizeof(int which) {
     case 10: return (int)sizeof(AfReplicaStats);
     default: return -1;
     }
-}
-
-// memo statistics of the AF_PREDRAW build variant (zeros in the default build): [misses, hits] since the last call
-extern "C" void af_twin_pre_lookups(uint64_t* out) {
-#if defined(AF_PREDRAW)
-    out[0] = afc::g_pre_lookups[0]; out[1] = afc::g_pre_lookups[1];
-    afc::g_pre_lookups[0] = afc::g_pre_lookups[1] = 0;
-#else
-    out[0] = out[1] = 0;
-#endif
-}
-
-// pool statistics of the AF_SORTED_POOL build variant (zeros otherwise), since the last call:
-// [ring pushes, unsorted pushes, ring -> unsorted switches, unsorted -> ring switches]
-extern "C" void af_twin_pool_counts(uint64_t* out) {
-#if defined(AF_SORTED_POOL)
-    for (int i = 0; i < 4; ++i) { out[i] = afc::g_pool_counts[i]; afc::g_pool_counts[i] = 0; }
-#else
-    for (int i = 0; i < 4; ++i) out[i] = 0;
-#endif
-}
-
-// request-record accesses per tier since the last call (twin built with -DAF_COUNT_TIERS; zeros otherwise)
-extern "C" void af_twin_tier_counts(uint64_t* out) {
-#if defined(AF_COUNT_TIERS)
-    out[0] = afc::g_rq_tier[0]; out[1] = afc::g_rq_tier[1];
-    afc::g_rq_tier[0] = afc::g_rq_tier[1] = 0;
-#else
-    out[0] = out[1] = 0;
-#endif
 }

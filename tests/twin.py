@@ -19,31 +19,16 @@ from asyncflow_b200 import _capi as K
 _DIR = Path(__file__).resolve().parent / "host_twin"
 _SO = _DIR / "_build" / "libaf_host_twin.so"
 _SRC = [_DIR / "af_host_twin.cpp"] + sorted((_DIR.parent.parent / "asyncflow_b200" / "csrc").glob("*.*h")) \
-    + [_DIR.parent.parent / "include" / "asyncflow_b200.h", _DIR.parent.parent / "asyncflow_b200" / "csrc" / "ENGINE_DEFINES"]
+    + [_DIR.parent.parent / "include" / "asyncflow_b200.h"]
 
 
-VARIANTS = {None: [], "predraw": ["-DAF_PREDRAW"], "pregen": ["-DAF_PREGEN"],
-            "memo": ["-DAF_PREDRAW", "-DAF_PREGEN"], "sorted": ["-DAF_SORTED_POOL"],
-            "all": ["-DAF_PREDRAW", "-DAF_PREGEN", "-DAF_SORTED_POOL"],
-            "pin": ["-DAF_PIN_ACTIVE"],
-            "count": ["-DAF_COUNT_TIERS"], "pin_count": ["-DAF_PIN_ACTIVE", "-DAF_COUNT_TIERS"],
-            "all4": ["-DAF_PREDRAW", "-DAF_PREGEN", "-DAF_SORTED_POOL", "-DAF_PIN_ACTIVE"],
-            "narrow": ["-DAF_PREDRAW", "-DAF_PRE_MAX_ROWS=6", "-DAF_PRE_BUDGET=1536"],   # other memo geometries
-            "tiny": ["-DAF_PREDRAW", "-DAF_PRE_MAX_ROWS=3", "-DAF_PRE_BUDGET=64"]}      # build variants of the engine core (af_core.cuh)
-
-
-def product_defines() -> list[str]:
-    f = _DIR.parent.parent / "asyncflow_b200" / "csrc" / "ENGINE_DEFINES"
-    return [ln.strip() for ln in f.read_text().splitlines() if ln.strip() and not ln.startswith("#")] if f.exists() else []
-
-
-def build(variant: str | None = None) -> Path:
-    so = _SO if variant is None else _SO.with_name(f"libaf_host_twin_{variant}.so")
+def build() -> Path:
+    so = _SO
     newest = max(p.stat().st_mtime for p in _SRC)
     if not so.exists() or so.stat().st_mtime < newest:
         so.parent.mkdir(exist_ok=True)
         subprocess.run(
-            ["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", *(product_defines() if variant is None else VARIANTS[variant]), "-x", "c++",
+            ["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-x", "c++",
              "-o", str(so), str(_DIR / "af_host_twin.cpp")], check=True)
     return so
 
@@ -51,9 +36,9 @@ def build(variant: str | None = None) -> Path:
 _libs: dict = {}
 
 
-def lib(variant: str | None = None) -> C.CDLL:
-    if variant not in _libs:
-        L = C.CDLL(str(build(variant)))
+def lib() -> C.CDLL:
+    if None not in _libs:
+        L = C.CDLL(str(build()))
         L.af_twin_error.restype = C.c_char_p
         L.af_twin_hist_percentile.restype = C.c_double
         L.af_twin_hist_percentile.argtypes = [C.c_void_p, C.c_uint64, C.c_double]
@@ -64,8 +49,8 @@ def lib(variant: str | None = None) -> C.CDLL:
         L.af_twin_run_lane.argtypes = [
             C.POINTER(K.AfScenario), C.POINTER(K.AfSweep), C.c_uint64, C.POINTER(K.AfOptions), C.c_int32,
             C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 10
-        _libs[variant] = L
-    return _libs[variant]
+        _libs[None] = L
+    return _libs[None]
 
 
 #: which state machine run() drives when the caller does not say: "lane" = af_lane.cuh (thread per replica, the
@@ -76,10 +61,10 @@ DEFAULT_LANE_BYTES = int(os.environ.get("AF_TWIN_LANE_BYTES", "1816"))
 
 
 def run(flat, *, seed: int, replica_begin: int = 0, n: int = 1, sweep=None, sweep_first: int = 0, trace: int = 0,
-        clock_cap: int = 0, event_capacity: int = 0, request_capacity: int = 0, variant: str | None = None,
+        clock_cap: int = 0, event_capacity: int = 0, request_capacity: int = 0,
         engine: str | None = None, lane_bytes: int | None = None, lane_static_requests: int = 0) -> dict:
-    L = lib(variant)
-    engine = engine or ("warp" if variant is not None else DEFAULT_ENGINE)
+    L = lib()
+    engine = engine or DEFAULT_ENGINE
     if engine == "lane":      # same default capacities as the warp engine (the CUDA lane pass has smaller ones and escalates)
         event_capacity = event_capacity or 2048
         request_capacity = request_capacity or 16384

@@ -13,9 +13,8 @@ from asyncflow_b200 import _capi as K
 
 
 class TwinEngine:
-    def __init__(self, device: int = 0, variant: str | None = None) -> None:
+    def __init__(self, device: int = 0) -> None:
         self.device = device
-        self.variant = variant
         self.flat = None
         self.opt: dict = {}
         self.sweep = None
@@ -51,8 +50,7 @@ class TwinEngine:
         self._n = end - begin
         self._r = twin.run(self.flat, seed=seed, replica_begin=begin, n=self._n, sweep=self.sweep, sweep_first=begin,
                            trace=o.get("trace_replicas", 0), clock_cap=o.get("trace_clock_capacity", 0),
-                           event_capacity=o.get("event_capacity", 0), request_capacity=o.get("request_capacity", 0),
-                           variant=self.variant)
+                           event_capacity=o.get("event_capacity", 0), request_capacity=o.get("request_capacity", 0))
         self.calls.append(("run", seed, begin, end))
 
     def last_run_ms(self):

@@ -1,6 +1,6 @@
 """Offline fuzz campaign: engine state machine (CPU twin) vs the oracle on many random scenarios.
 
-    python tools/fuzz_campaign.py --first 1000 --count 2000 --jobs 8 [--variant all]
+    python tools/fuzz_campaign.py --first 1000 --count 2000 --jobs 8
 
 Test tooling (uses oracle/ and tests/host_twin); prints the failing seeds, exits non-zero on any.
 """
@@ -17,7 +17,7 @@ for p in (ROOT, ROOT / "tests", ROOT / "oracle", ROOT / "oracle" / "simpy_shim")
     sys.path.insert(0, str(p))
 
 
-VARIANT = None
+ENGINE = "lane"
 BIG = False
 
 
@@ -33,7 +33,7 @@ def one(seed: int):
         flat = flatten(payload)
         o = des_port.simulate(payload, seed=SEED, replica=seed)
         r = twin.run(flat, seed=SEED, replica_begin=seed, n=1, trace=1, clock_cap=200000, request_capacity=400000,
-                     event_capacity=8192, variant=VARIANT)
+                     event_capacity=8192, engine=ENGINE)
         st = r["stats"][0]
         n, nt = int(st["completed"]), int(st["n_ticks"])
         assert st["flags"] == 0, f"flags {int(st['flags'])}"
@@ -49,13 +49,13 @@ def main() -> None:
     ap.add_argument("--first", type=int, default=1000)
     ap.add_argument("--count", type=int, default=500)
     ap.add_argument("--jobs", type=int, default=8)
-    ap.add_argument("--variant", default=None, help="engine build variant of tests/twin.py (predraw, pregen, memo, sorted, all)")
+    ap.add_argument("--engine", default="lane", choices=["lane", "warp"], help="which state machine of tests/twin.py")
     ap.add_argument("--big", action="store_true", help="C5-shaped topologies (fuzz.big_scenario)")
     a = ap.parse_args()
-    global VARIANT, BIG
-    VARIANT, BIG = a.variant, a.big
+    global ENGINE, BIG
+    ENGINE, BIG = a.engine, a.big
     import twin
-    twin.build(a.variant)
+    twin.build()
     bad = []
     total = 0
     with mp.get_context("fork").Pool(a.jobs) as pool:
