@@ -1,6 +1,6 @@
 """Parity of ONE engine library (product or variant) on the GPU: golden vectors + fuzz vs the oracle.
 
-    ASYNCFLOW_B200_LIB=asyncflow_b200/_lib/libasyncflow_b200_memo.so python tools/check_variant_gpu.py
+    ASYNCFLOW_B200_LIB=asyncflow_b200/_lib/libasyncflow_b200_memo.so python tools/check_parity_gpu.py
 
 Test tooling for A/B sessions (uses oracle/); exits non-zero on the first mismatch.
 """

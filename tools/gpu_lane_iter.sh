@@ -5,7 +5,7 @@ tag=${1:-x}
 cd "$(dirname "$0")/.." || exit 1
 QB="timeout 200 python tools/quick_bench.py"
 echo "=== smoke"; timeout 300 python __graft_entry__.py --smoke || { echo "SMOKE FAILED: stopping"; exit 1; }
-echo "=== parity (auto)"; timeout 400 python tools/check_variant_gpu.py || { echo "PARITY FAILED (auto): stopping"; exit 1; }
+echo "=== parity (auto)"; timeout 400 python tools/check_parity_gpu.py || { echo "PARITY FAILED (auto): stopping"; exit 1; }
 for wpb in ${WPBS:-12}; do
   echo "=== C3 rtt sweep 80000 x 20 s, lane, $wpb warps/SM"; $QB --scenario c3_lb_two_servers.yml --replicas 80000 --horizon 20 --reps 2 --mode auto --wpb $wpb | tail -2
 done
