@@ -487,6 +487,7 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
             if (o.event_capacity <= 0 || o.event_capacity > aflh::LANE_EVENT_CAPACITY) o.event_capacity = aflh::LANE_EVENT_CAPACITY;
             if (o.request_capacity <= 0) o.request_capacity = afh::DEFAULT_REQUEST_CAPACITY;
             if (o.request_capacity > aflh::LANE_REQUEST_CAPACITY) rq_static = aflh::LANE_REQUEST_CAPACITY;
+            if (!AFL_PAGING) { rq_static = 0; if (o.request_capacity > aflh::LANE_REQUEST_CAPACITY) o.request_capacity = aflh::LANE_REQUEST_CAPACITY; }
             if (getenv("ASYNCFLOW_B200_NO_PAGES")) { rq_static = 0; if (o.request_capacity > aflh::LANE_REQUEST_CAPACITY) o.request_capacity = aflh::LANE_REQUEST_CAPACITY; }   // experiments: the round-2a behaviour
         }
         lane_warps = e->opt.warps_per_block > 0 ? e->opt.warps_per_block : AF_LANE_DEFAULT_WARPS;

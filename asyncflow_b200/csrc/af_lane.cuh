@@ -64,6 +64,10 @@
 #define AFL_IN static inline
 #endif
 
+// -DAFL_PAGING=0 compiles the request page pool out (A/B of its cost in the hot loop's instruction footprint)
+#ifndef AFL_PAGING
+#define AFL_PAGING 1
+#endif
 #define AFL_LIKELY(x) __builtin_expect(!!(x), 1)
 #define AFL_UNLIKELY(x) __builtin_expect(!!(x), 0)
 
@@ -300,17 +304,17 @@ AFL_IN unsigned char* pg_page(const Mem& m, uint32_t s, uint32_t& off) {
 }
 AFL_IN void rq_load(const Mem& m, uint32_t s, double& t0, uint32_t& rid, uint32_t& pack) {
     uint64_t a, b;
-    if (AFL_LIKELY((int32_t)s < AFL_C.rq_total)) ld_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, a, b);
+    if (!AFL_PAGING || AFL_LIKELY((int32_t)s < AFL_C.rq_total)) ld_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, a, b);
     else { uint32_t o; const unsigned char* pg = pg_page(m, s, o); gl_ld128(pg + o * 16u, a, b); }
     t0 = afr::u2d(a); rid = (uint32_t)b; pack = (uint32_t)(b >> 32);
 }
 AFL_IN void rq_store(const Mem& m, uint32_t s, double t0, uint32_t rid, uint32_t pack) {
     const uint64_t a = afr::d2u(t0), b = (uint64_t)rid | ((uint64_t)pack << 32);
-    if (AFL_LIKELY((int32_t)s < AFL_C.rq_total)) st_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, a, b);
+    if (!AFL_PAGING || AFL_LIKELY((int32_t)s < AFL_C.rq_total)) st_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, a, b);
     else { uint32_t o; unsigned char* pg = pg_page(m, s, o); gl_st128(pg + o * 16u, a, b); }
 }
 AFL_IN uint32_t* rq_word_slow(const Mem& m, uint32_t s, uint32_t byte) {       // a 32-bit field of a record outside shared memory
-    if (AFL_LIKELY((int32_t)s < AFL_C.rq_total)) return reinterpret_cast<uint32_t*>(g128p(m, AFL_C.gi_rq + (int32_t)s) + byte);
+    if (!AFL_PAGING || AFL_LIKELY((int32_t)s < AFL_C.rq_total)) return reinterpret_cast<uint32_t*>(g128p(m, AFL_C.gi_rq + (int32_t)s) + byte);
     uint32_t o; unsigned char* pg = pg_page(m, s, o);
     return reinterpret_cast<uint32_t*>(pg + o * 16u + byte);
 }
@@ -323,12 +327,12 @@ AFL_IN void rq_pack_set(const Mem& m, uint32_t s, uint32_t v) {
     else *rq_word_slow(m, s, 12u) = v;
 }
 AFL_IN uint32_t rq_next(const Mem& m, uint32_t s) {
-    if (AFL_LIKELY((int32_t)s < AFL_C.rq_total)) return ld_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s);
+    if (!AFL_PAGING || AFL_LIKELY((int32_t)s < AFL_C.rq_total)) return ld_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s);
     uint32_t o; const unsigned char* pg = pg_page(m, s, o);
     return *reinterpret_cast<const uint32_t*>(pg + PG_REC_BYTES + o * 4u);
 }
 AFL_IN void rq_next_set(const Mem& m, uint32_t s, uint32_t v) {
-    if (AFL_LIKELY((int32_t)s < AFL_C.rq_total)) { st_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s, v); return; }
+    if (!AFL_PAGING || AFL_LIKELY((int32_t)s < AFL_C.rq_total)) { st_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s, v); return; }
     uint32_t o; unsigned char* pg = pg_page(m, s, o);
     *reinterpret_cast<uint32_t*>(pg + PG_REC_BYTES + o * 4u) = v;
 }
@@ -353,7 +357,7 @@ AFL_IN uint32_t rq_alloc(St& W, const Mem& m) {
     uint32_t s;
     if (W.rq_free != NIL) { s = W.rq_free; W.rq_free = rq_next(m, s); }
     else if ((int32_t)W.rq_hw < AFL_C.rq_total) { s = W.rq_hw++; }
-    else if ((int32_t)W.rq_hw < AFL_C.rq_cap) {        // the paged tier: the first slot of a page the lane does not own yet takes one from the pool
+    else if (AFL_PAGING && (int32_t)W.rq_hw < AFL_C.rq_cap) {        // the paged tier: the first slot of a page the lane does not own yet takes one from the pool
         const uint32_t k = W.rq_hw - (uint32_t)AFL_C.rq_total;
         if ((k & (PG_SLOTS - 1u)) == 0u) {
             uint32_t* pt = g32p(m, AFL_C.gi_pt + (int32_t)(k >> PG_BITS));
@@ -778,6 +782,17 @@ AFL_IN void write_back(St& W, const Mem& m) {
     if (W.traced) { C.trace_counts[local * 2] = W.completed; C.trace_counts[local * 2 + 1] = W.n_ticks; }
 }
 
+// -DAFL_OUTLINE=1: a replica's set-up and write-back as real functions (once per ~10^4-10^5 iterations of the loop they
+// would otherwise sit in: ~500 instructions out of the loop's instruction footprint).  State by value: a reference
+// across a call would pin the replica's scalar state in local memory.
+#ifndef AFL_OUTLINE
+#define AFL_OUTLINE 0
+#endif
+#if AFL_OUTLINE
+AFL_COLD St start_replica_cold(const Mem m, uint64_t r) { St W; start_replica(W, m, r); return W; }
+AFL_COLD void write_back_cold(const Mem m, St W) { write_back(W, m); }
+#endif
+
 // what a phase hands to the next one
 enum : uint32_t { A_NONE = 0, A_NODE, A_STEPS, A_SEND, A_TIMER };
 
@@ -811,7 +826,11 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
             const uint64_t r = next_index();
             if (r == ~0ull) exhausted = true;
             else {
+#if AFL_OUTLINE
+                W = start_replica_cold(m, r);
+#else
                 start_replica(W, m, r);
+#endif
                 // start order of the reference (simulation_runner.py:339-342, 301-336):
                 // spike timeline, outage timeline, generator, ..., collector
                 if (C.n_spike > 0) {
@@ -905,7 +924,11 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
             const double tick = W.tick_time;
             if (tick < t_ev || (tick == t_ev && W.tick_seq < ev_seq)) take_ticks(W, m, t_ev, ev_seq);
         }
+#if AFL_OUTLINE
+        if (AFL_UNLIKELY(finish)) { write_back_cold(m, W); active = false; }
+#else
         if (AFL_UNLIKELY(finish)) { write_back(W, m); active = false; }
+#endif
         AFL_SYNC();
         if (is_event) { W.now = t_ev; W.n_events += 1; }
 
