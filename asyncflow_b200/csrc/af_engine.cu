@@ -499,6 +499,19 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
         // (a topology that leaves fewer than 4 warps per SM is faster on the warp-per-replica engine: C5 before the
         //  gauges moved out of shared memory, 2 warps/SM: 2.9e8 events/s against 5.1e8)
         if (e->mode == AF_MODE_AUTO && lane_warps < 4) lane = false;
+        // A lane runs ONE replica about ten times slower than a warp does (it shares every instruction with 31 other
+        // replicas): the thread-per-replica engine pays off when there are replicas for most lanes.  Measured on B200:
+        // C2, 10 000 replicas, 2/3 of them saturated: 3.0 s per warp, 7.7 s per lane; C1 / C3: break-even near 10^4.
+        if (e->mode == AF_MODE_AUTO && n < 3ull * (uint64_t)e->sm_count * 32ull) lane = false;
+        if (lane && e->opt.warps_per_block <= 0) {
+            // whole waves: with W warps per SM the launch takes ceil(n / lanes(W)) waves; the smallest W with that many
+            // waves leaves each lane more shared memory and each warp more issue slots (100 000 replicas: 11, not 12)
+            const uint64_t per_warp = (uint64_t)e->sm_count * 32ull;
+            const uint64_t waves = (n + per_warp * (uint64_t)lane_warps - 1) / (per_warp * (uint64_t)lane_warps);
+            int w = (int)((n + waves * per_warp - 1) / (waves * per_warp));
+            if (w < 4) w = 4;
+            if (w < lane_warps) lane_warps = w;
+        }
     }
     if (lane) {
         memset(&C, 0, sizeof C);
