@@ -28,9 +28,9 @@ FIELDS = {
     "endpoint_ram": 9, "spike_delta": 10,
 }
 FLAG_EVENT_OVERFLOW, FLAG_REQUEST_OVERFLOW, FLAG_TRACE_TRUNCATED, FLAG_NOWQ_OVERFLOW, FLAG_LB_EMPTY = 1, 2, 4, 8, 16
-MODE_AUTO, MODE_WARP, MODE_LANE = 0, 1, 2
+MODE_AUTO, MODE_WARP, MODE_LANE, MODE_TWO_PASS = 0, 1, 2, 3
 SELFTEST_EDGE, SELFTEST_GEN_UNIFORM, SELFTEST_GEN_USERS, SELFTEST_ENDPOINT = 0, 1, 2, 3
-MODES = {"auto": MODE_AUTO, "warp": MODE_WARP, "lane": MODE_LANE}
+MODES = {"auto": MODE_AUTO, "warp": MODE_WARP, "lane": MODE_LANE, "two_pass": MODE_TWO_PASS}
 
 
 class AfEdge(C.Structure):

@@ -266,7 +266,7 @@ struct af_engine {
     // thread-per-replica pass: read-only tables (af_lane_host.h), global tiers, the list of flagged replicas
     int mode = AF_MODE_AUTO;
     aflh::Tables lt;
-    DevBuf d_l_edges, d_l_servers, d_l_eps, d_l_steps, d_l_spikes, d_l_outages, d_l_lb, d_l_cols, d_gtier, d_redo_list, d_redo_count, d_counter2, d_pool, d_pool_next;
+    DevBuf d_l_edges, d_l_servers, d_l_eps, d_l_steps, d_l_spikes, d_l_outages, d_l_lb, d_l_cols, d_gtier, d_redo_list, d_redo_count, d_counter2;
     afl::Cfg C_host{};
     bool last_lane = false, last_warp = false; int last_lane_warps = 0;
     // spill + outputs
@@ -329,6 +329,7 @@ int af_engine_create(int device, af_engine** out) {
     e->opt.collect_histogram = 1; e->opt.collect_throughput = 1;
     if (const char* m = getenv("ASYNCFLOW_B200_ENGINE")) {      // kernel experiments: pin the pass structure
         if (!strcmp(m, "warp")) e->mode = AF_MODE_WARP; else if (!strcmp(m, "lane")) e->mode = AF_MODE_LANE;
+        else if (!strcmp(m, "two_pass")) e->mode = AF_MODE_TWO_PASS;
     }
     *out = e;
     return AF_OK;
@@ -343,7 +344,7 @@ void af_engine_destroy(af_engine* e) {
         if (g_const_owner[e->device % kMaxDevices] == e) g_const_owner[e->device % kMaxDevices] = nullptr;
     }
     DevBuf* bufs[] = {&e->d_l_edges, &e->d_l_servers, &e->d_l_eps, &e->d_l_steps, &e->d_l_spikes, &e->d_l_outages, &e->d_l_lb, &e->d_l_cols,
-                      &e->d_gtier, &e->d_redo_list, &e->d_redo_count, &e->d_counter2, &e->d_pool, &e->d_pool_next,
+                      &e->d_gtier, &e->d_redo_list, &e->d_redo_count, &e->d_counter2,
                       &e->d_edges, &e->d_servers, &e->d_eps, &e->d_steps, &e->d_lb, &e->d_spikes, &e->d_outages,
                       &e->d_sweep_cols, &e->d_sweep_vals, &e->d_sp_evt, &e->d_sp_evk, &e->d_sp_rq, &e->d_sp_nx,
                       &e->d_stats, &e->d_sent, &e->d_dropped, &e->d_hist, &e->d_thr, &e->d_ssum, &e->d_smax,
@@ -481,14 +482,10 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
         }
     }
     AfOptions o = e->opt;
-    int32_t rq_static = 0;
     if (lane) {
-        if (e->mode == AF_MODE_AUTO) {                 // nominal-load tiers per lane; request slots beyond them from the page pool
+        if (e->mode == AF_MODE_AUTO || e->mode == AF_MODE_TWO_PASS) {   // nominal-load tiers per lane; anything larger escalates
             if (o.event_capacity <= 0 || o.event_capacity > aflh::LANE_EVENT_CAPACITY) o.event_capacity = aflh::LANE_EVENT_CAPACITY;
-            if (o.request_capacity <= 0) o.request_capacity = afh::DEFAULT_REQUEST_CAPACITY;
-            if (o.request_capacity > aflh::LANE_REQUEST_CAPACITY) rq_static = aflh::LANE_REQUEST_CAPACITY;
-            if (!AFL_PAGING) { rq_static = 0; if (o.request_capacity > aflh::LANE_REQUEST_CAPACITY) o.request_capacity = aflh::LANE_REQUEST_CAPACITY; }
-            if (getenv("ASYNCFLOW_B200_NO_PAGES")) { rq_static = 0; if (o.request_capacity > aflh::LANE_REQUEST_CAPACITY) o.request_capacity = aflh::LANE_REQUEST_CAPACITY; }   // experiments: the round-2a behaviour
+            if (o.request_capacity <= 0 || o.request_capacity > aflh::LANE_REQUEST_CAPACITY) o.request_capacity = aflh::LANE_REQUEST_CAPACITY;
         }
         lane_warps = e->opt.warps_per_block > 0 ? e->opt.warps_per_block : AF_LANE_DEFAULT_WARPS;
         if (lane_warps > AF_LANE_MAX_THREADS / 32) lane_warps = AF_LANE_MAX_THREADS / 32;
@@ -515,12 +512,12 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     }
     if (lane) {
         memset(&C, 0, sizeof C);
-        if (!aflh::make_cfg(e->sc, o, e->lt, lane_budget(e, lane_warps), afh::trace_tick_capacity(e->sc), 32, rq_static, C)) {
+        if (!aflh::make_cfg(e->sc, o, e->lt, lane_budget(e, lane_warps), afh::trace_tick_capacity(e->sc), 32, C)) {
             if (e->mode == AF_MODE_LANE) return e->fail(AF_ERR_INVALID, "scenario tables do not fit a lane's shared memory (thread-per-replica engine)");
             lane = false;
         }
     }
-    const bool warp = e->mode == AF_MODE_WARP || e->mode == AF_MODE_AUTO;
+    const bool warp = e->mode != AF_MODE_LANE;
     const bool redo = lane && warp;
 
     afc::Layout& L = e->L;
@@ -566,19 +563,6 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     }
     if (lane) {
         AF_CUDA(e, e->d_gtier.ensure(lgrid * (uint64_t)lane_warps * C.gwarp_bytes + 256), "lane global tiers");
-        C.pool = nullptr; C.pool_pages = 0; C.pool_next = nullptr;
-        if (C.pg_max > 0) {          // the page pool: what every resident lane could ask for, within half of the free memory
-            size_t free_b = 0, total_b = 0;
-            AF_CUDA(e, cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
-            uint64_t pages = lgrid * (uint64_t)lane_warps * 32ull * (uint64_t)C.pg_max;
-            const uint64_t have = e->d_pool.cap / afl::PG_BYTES;
-            const uint64_t afford = have + (uint64_t)(free_b / 2) / afl::PG_BYTES;
-            if (pages > afford) pages = afford;
-            if (pages > 0xFFFFFFF0ull) pages = 0xFFFFFFF0ull;
-            if (pages > have) AF_CUDA(e, e->d_pool.ensure(pages * afl::PG_BYTES), "request page pool");
-            AF_CUDA(e, e->d_pool_next.ensure(8), "request page pool");
-            C.pool = (unsigned char*)e->d_pool.p; C.pool_pages = (uint32_t)(e->d_pool.cap / afl::PG_BYTES); C.pool_next = (uint32_t*)e->d_pool_next.p;
-        }
         if ((rc = upload_vec(e, e->d_l_edges, e->lt.edges, "lane tables"))) return rc;
         if ((rc = upload_vec(e, e->d_l_servers, e->lt.servers, "lane tables"))) return rc;
         if ((rc = upload_vec(e, e->d_l_eps, e->lt.endpoints, "lane tables"))) return rc;
@@ -655,7 +639,6 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     if (lane) {
         AF_CUDA(e, cudaMemsetAsync(e->d_counter2.p, 0, 8, e->stream), "memset");
         AF_CUDA(e, cudaMemsetAsync(e->d_redo_count.p, 0, 4, e->stream), "memset");
-        if (C.pool_next) AF_CUDA(e, cudaMemsetAsync(C.pool_next, 0, 4, e->stream), "memset");
         AF_CUDA(e, cudaMemcpyToSymbolAsync(afl::c_cfg, &C, sizeof C, 0, cudaMemcpyHostToDevice, e->stream), "lane config -> constant memory");
         af_lane_kernel<<<(unsigned)lgrid, lane_warps * 32, lsmem, e->stream>>>();
         AF_CUDA(e, cudaGetLastError(), "af_lane_kernel launch");
@@ -709,7 +692,7 @@ int af_selftest_rng(af_engine* e, uint64_t seed, uint64_t replica, int kind, int
 
 int af_engine_set_mode(af_engine* e, int mode) {
     if (!e) return AF_ERR_INVALID;
-    if (mode != AF_MODE_AUTO && mode != AF_MODE_WARP && mode != AF_MODE_LANE) return e->fail(AF_ERR_INVALID, "af_engine_set_mode: unknown mode");
+    if (mode != AF_MODE_AUTO && mode != AF_MODE_WARP && mode != AF_MODE_LANE && mode != AF_MODE_TWO_PASS) return e->fail(AF_ERR_INVALID, "af_engine_set_mode: unknown mode");
     e->mode = mode;
     return AF_OK;
 }

@@ -64,10 +64,6 @@
 #define AFL_IN static inline
 #endif
 
-// -DAFL_PAGING=0 compiles the request page pool out (A/B of its cost in the hot loop's instruction footprint)
-#ifndef AFL_PAGING
-#define AFL_PAGING 1
-#endif
 #define AFL_LIKELY(x) __builtin_expect(!!(x), 1)
 #define AFL_UNLIKELY(x) __builtin_expect(!!(x), 0)
 
@@ -106,7 +102,6 @@ AFL_IN uint32_t pk_ep(uint32_t p) { return (p >> 16) & 0xFFFu; }
 enum : uint32_t { I_PUT = 0, I_GOT = 1, I_CLIENT_LOOP = 2, I_RAM_OK = 3, I_CPU_OK = 4, I_CPU_PUT = 5, I_RAM_PUT = 6 };
 constexpr uint32_t NODE_CLIENT = 0, NODE_LB = 1, NODE_SERVER0 = 2;
 constexpr int32_t NQ_TOTAL = 128;          // pending zero-delay items per replica (power of two)
-constexpr uint32_t PG_BITS = 8, PG_SLOTS = 1u << PG_BITS, PG_REC_BYTES = PG_SLOTS * 16u, PG_BYTES = PG_REC_BYTES + PG_SLOTS * 4u;   // one pool page: 256 records, then their links
 
 // ---- read-only scenario tables (global memory, shared by all replicas; 16-byte multiples so that
 //      a record is one or a few 128-bit loads).  `c_*` = index into the lane's sweep-row copy, -1 = not swept.
@@ -136,12 +131,6 @@ struct Cfg {
     int32_t redo;                                   // 1: replica indices come from redo_list (re-run of flagged replicas)
     // tiered tables: entries in shared memory / in total
     int32_t ev_s, ev_total, rq_s, rq_total, nq_s;
-    // request slots beyond rq_total: PAGES of PG_SLOTS records from one pool shared by all lanes (a saturated replica
-    // parks 10^4..10^5 requests in a RAM queue; sizing every lane's tier for that would be 100 GB).  A lane's page
-    // table (pg_max words of its 32-bit region, from gi_pt) maps page number -> pool page; pages are taken with one
-    // atomicAdd when a lane first needs them and stay with the lane for the launch.
-    int32_t rq_cap, pg_max, gi_pt;
-    unsigned char* pool; uint32_t pool_pages; uint32_t* pool_next;
     // shared-memory layout of a warp: 128-bit region (events, then request records), 64-bit region, 32-bit region
     int32_t o128_ev, o128_rq, n128;
     int32_t o64_nq, o64_spike, o64_row, n64;
@@ -295,50 +284,31 @@ AFL_IN uint32_t ep_total_ram(const Mem& m, uint32_t ep) {
     return p.c_ram >= 0 ? (uint32_t)row_val(m, p.c_ram) : p.total_ram;
 }
 
-// ---- request records: one 128-bit element  t0 | id : pack  + the `next` link (32-bit table); three tiers:
-//      slots [0, rq_s) in shared memory, [rq_s, rq_total) in the lane's global tier, [rq_total, rq_cap) in pool pages
-AFL_IN unsigned char* pg_page(const Mem& m, uint32_t s, uint32_t& off) {
-    const uint32_t k = s - (uint32_t)AFL_C.rq_total;
-    off = k & (PG_SLOTS - 1u);
-    return AFL_C.pool + (uint64_t)(*g32p(m, AFL_C.gi_pt + (int32_t)(k >> PG_BITS))) * PG_BYTES;
-}
+// ---- request records (tiered): one 128-bit element  t0 | id : pack  + the `next` link (32-bit table) ------------
+// (Tried in round 2 and dropped: a third tier of 256-record PAGES from a pool shared by all lanes, so that saturated
+//  replicas -- 10^4..10^5 requests parked in a RAM queue -- stay on this engine.  Bit-exact, but the extra tier in every
+//  record access grew the loop's instruction footprint: bench workload 5.35e8 -> 4.90e8 completions/s, `no_instruction`
+//  stalls 2.4 -> 3.3 per issue, and C2 (10^4 replicas) was still faster one replica per warp.  profiles/r02_summary.md)
 AFL_IN void rq_load(const Mem& m, uint32_t s, double& t0, uint32_t& rid, uint32_t& pack) {
     uint64_t a, b;
-    if (!AFL_PAGING || AFL_LIKELY((int32_t)s < AFL_C.rq_total)) ld_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, a, b);
-    else { uint32_t o; const unsigned char* pg = pg_page(m, s, o); gl_ld128(pg + o * 16u, a, b); }
+    ld_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, a, b);
     t0 = afr::u2d(a); rid = (uint32_t)b; pack = (uint32_t)(b >> 32);
 }
 AFL_IN void rq_store(const Mem& m, uint32_t s, double t0, uint32_t rid, uint32_t pack) {
-    const uint64_t a = afr::d2u(t0), b = (uint64_t)rid | ((uint64_t)pack << 32);
-    if (!AFL_PAGING || AFL_LIKELY((int32_t)s < AFL_C.rq_total)) st_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, a, b);
-    else { uint32_t o; unsigned char* pg = pg_page(m, s, o); gl_st128(pg + o * 16u, a, b); }
-}
-AFL_IN uint32_t* rq_word_slow(const Mem& m, uint32_t s, uint32_t byte) {       // a 32-bit field of a record outside shared memory
-    if (!AFL_PAGING || AFL_LIKELY((int32_t)s < AFL_C.rq_total)) return reinterpret_cast<uint32_t*>(g128p(m, AFL_C.gi_rq + (int32_t)s) + byte);
-    uint32_t o; unsigned char* pg = pg_page(m, s, o);
-    return reinterpret_cast<uint32_t*>(pg + o * 16u + byte);
+    st_t128(m, AFL_C.o128_rq, AFL_C.gi_rq, (int32_t)s, AFL_C.rq_s, afr::d2u(t0), (uint64_t)rid | ((uint64_t)pack << 32));
 }
 AFL_IN uint32_t rq_pack(const Mem& m, uint32_t s) {
     if (AFL_LIKELY((int32_t)s < AFL_C.rq_s)) return sm_ld32(a128(m, AFL_C.o128_rq + (int32_t)s) + 12u);
-    return *rq_word_slow(m, s, 12u);
+    return *reinterpret_cast<const uint32_t*>(g128p(m, AFL_C.gi_rq + (int32_t)s) + 12);
 }
 AFL_IN void rq_pack_set(const Mem& m, uint32_t s, uint32_t v) {
     if (AFL_LIKELY((int32_t)s < AFL_C.rq_s)) sm_st32(a128(m, AFL_C.o128_rq + (int32_t)s) + 12u, v);
-    else *rq_word_slow(m, s, 12u) = v;
+    else *reinterpret_cast<uint32_t*>(g128p(m, AFL_C.gi_rq + (int32_t)s) + 12) = v;
 }
-AFL_IN uint32_t rq_next(const Mem& m, uint32_t s) {
-    if (!AFL_PAGING || AFL_LIKELY((int32_t)s < AFL_C.rq_total)) return ld_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s);
-    uint32_t o; const unsigned char* pg = pg_page(m, s, o);
-    return *reinterpret_cast<const uint32_t*>(pg + PG_REC_BYTES + o * 4u);
-}
-AFL_IN void rq_next_set(const Mem& m, uint32_t s, uint32_t v) {
-    if (!AFL_PAGING || AFL_LIKELY((int32_t)s < AFL_C.rq_total)) { st_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s, v); return; }
-    uint32_t o; unsigned char* pg = pg_page(m, s, o);
-    *reinterpret_cast<uint32_t*>(pg + PG_REC_BYTES + o * 4u) = v;
-}
+AFL_IN uint32_t rq_next(const Mem& m, uint32_t s) { return ld_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s); }
+AFL_IN void rq_next_set(const Mem& m, uint32_t s, uint32_t v) { st_t32(m, AFL_C.o32_next, AFL_C.gi_next, (int32_t)s, AFL_C.rq_s, v); }
 
 #if AFL_DEVICE
-__device__ __forceinline__ uint32_t pool_take(uint32_t* p) { return atomicAdd(p, 1u); }
 // fire-and-forget reductions (RED.E.ADD / RED.E.MAX: no result, no scoreboard wait) and the loads that read them back
 __device__ __forceinline__ void red_add64(uint64_t* p, uint64_t v) { atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
 __device__ __forceinline__ void red_add32(uint32_t* p, uint32_t v) { atomicAdd(p, v); }
@@ -346,7 +316,6 @@ __device__ __forceinline__ void red_max32(uint32_t* p, uint32_t v) { atomicMax(p
 __device__ __forceinline__ uint64_t ld_cg64(const uint64_t* p) { return (uint64_t)__ldcg(reinterpret_cast<const unsigned long long*>(p)); }
 __device__ __forceinline__ uint32_t ld_cg32(const uint32_t* p) { return __ldcg(p); }
 #else
-static inline uint32_t pool_take(uint32_t* p) { return (*p)++; }
 static inline void red_add64(uint64_t* p, uint64_t v) { *p += v; }
 static inline void red_add32(uint32_t* p, uint32_t v) { *p += v; }
 static inline void red_max32(uint32_t* p, uint32_t v) { if (v > *p) *p = v; }
@@ -357,18 +326,6 @@ AFL_IN uint32_t rq_alloc(St& W, const Mem& m) {
     uint32_t s;
     if (W.rq_free != NIL) { s = W.rq_free; W.rq_free = rq_next(m, s); }
     else if ((int32_t)W.rq_hw < AFL_C.rq_total) { s = W.rq_hw++; }
-    else if (AFL_PAGING && (int32_t)W.rq_hw < AFL_C.rq_cap) {        // the paged tier: the first slot of a page the lane does not own yet takes one from the pool
-        const uint32_t k = W.rq_hw - (uint32_t)AFL_C.rq_total;
-        if ((k & (PG_SLOTS - 1u)) == 0u) {
-            uint32_t* pt = g32p(m, AFL_C.gi_pt + (int32_t)(k >> PG_BITS));
-            if (*pt == NIL) {
-                const uint32_t pid = pool_take(AFL_C.pool_next);
-                if (pid >= AFL_C.pool_pages) { W.flags |= AF_FLAG_REQUEST_OVERFLOW; return NIL; }
-                *pt = pid;
-            }
-        }
-        s = W.rq_hw++;
-    }
     else { W.flags |= AF_FLAG_REQUEST_OVERFLOW; return NIL; }
     const uint32_t live = ++W.rq_live;
     if (live > W.peak_rq) W.peak_rq = live;
@@ -782,17 +739,6 @@ AFL_IN void write_back(St& W, const Mem& m) {
     if (W.traced) { C.trace_counts[local * 2] = W.completed; C.trace_counts[local * 2 + 1] = W.n_ticks; }
 }
 
-// -DAFL_OUTLINE=1: a replica's set-up and write-back as real functions (once per ~10^4-10^5 iterations of the loop they
-// would otherwise sit in: ~500 instructions out of the loop's instruction footprint).  State by value: a reference
-// across a call would pin the replica's scalar state in local memory.
-#ifndef AFL_OUTLINE
-#define AFL_OUTLINE 0
-#endif
-#if AFL_OUTLINE
-AFL_COLD St start_replica_cold(const Mem m, uint64_t r) { St W; start_replica(W, m, r); return W; }
-AFL_COLD void write_back_cold(const Mem m, St W) { write_back(W, m); }
-#endif
-
 // what a phase hands to the next one
 enum : uint32_t { A_NONE = 0, A_NODE, A_STEPS, A_SEND, A_TIMER };
 
@@ -817,8 +763,6 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
     St W;
     bool active = false, exhausted = false;
 #pragma unroll 1
-    for (int32_t pg = 0; pg < C.pg_max; ++pg) *g32p(m, C.gi_pt + pg) = NIL;      // the lane owns no pool page yet
-#pragma unroll 1
     for (;;) {
         if (!converge(active || !exhausted)) break;          // all lanes of the warp are done
         // ---- phase: lifecycle -------------------------------------------------------------------
@@ -826,11 +770,7 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
             const uint64_t r = next_index();
             if (r == ~0ull) exhausted = true;
             else {
-#if AFL_OUTLINE
-                W = start_replica_cold(m, r);
-#else
                 start_replica(W, m, r);
-#endif
                 // start order of the reference (simulation_runner.py:339-342, 301-336):
                 // spike timeline, outage timeline, generator, ..., collector
                 if (C.n_spike > 0) {
@@ -924,11 +864,7 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
             const double tick = W.tick_time;
             if (tick < t_ev || (tick == t_ev && W.tick_seq < ev_seq)) take_ticks(W, m, t_ev, ev_seq);
         }
-#if AFL_OUTLINE
-        if (AFL_UNLIKELY(finish)) { write_back_cold(m, W); active = false; }
-#else
         if (AFL_UNLIKELY(finish)) { write_back(W, m); active = false; }
-#endif
         AFL_SYNC();
         if (is_event) { W.now = t_ev; W.n_events += 1; }
 

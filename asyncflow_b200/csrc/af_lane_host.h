@@ -115,8 +115,7 @@ inline int32_t min_lane_bytes(const AfScenario& s, const Tables& t) { return fix
 // engine at this occupancy (the caller lowers the occupancy or takes the warp-per-replica engine).
 // `lanes` = lanes of a warp in the code that will RUN the configuration: 32 for the CUDA kernel, 1 for the host twin
 // (afl::LANES is a property of the compilation pass, and the host pass of a .cu file sees 1).
-// `rq_static` > 0: request slots beyond it come from the page pool (up to o.request_capacity); <= 0: no paging.
-inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, int32_t lane_bytes, int32_t trace_tick_cap, int32_t lanes, int32_t rq_static, afl::Cfg& C) {
+inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, int32_t lane_bytes, int32_t trace_tick_cap, int32_t lanes, afl::Cfg& C) {
     C.n_edges = s.n_edges; C.n_servers = s.n_servers; C.n_endpoints = s.n_endpoints; C.n_steps = s.n_steps;
     C.n_lb_edges = s.n_lb_edges; C.lb_algo = s.lb_algo; C.gen_edge = s.gen_edge; C.client_edge = s.client_edge;
     C.n_spike = s.n_spike_marks; C.n_outage = s.n_outage_marks;
@@ -130,14 +129,6 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     int32_t ev_total = o.event_capacity > 0 ? o.event_capacity : LANE_EVENT_CAPACITY;
     int32_t rq_total = o.request_capacity > 0 ? o.request_capacity : LANE_REQUEST_CAPACITY;
     if (rq_total > (int32_t)afl::SLOT_MASK) rq_total = (int32_t)afl::SLOT_MASK;
-    int32_t pg_max = 0;
-    if (rq_static > 0 && rq_static < rq_total) {
-        pg_max = (rq_total - rq_static + (int32_t)afl::PG_SLOTS - 1) / (int32_t)afl::PG_SLOTS;
-        if (pg_max > 4096) pg_max = 4096;
-        rq_total = rq_static;
-    }
-    C.pg_max = pg_max; C.rq_cap = rq_total + pg_max * (int32_t)afl::PG_SLOTS;
-    if (C.rq_cap > (int32_t)afl::SLOT_MASK) C.rq_cap = (int32_t)afl::SLOT_MASK;
     // fixed part of a lane's shared memory
     const int32_t fix64 = (C.n_spike > 0 ? C.n_edges : 0) + C.n_row;
     C.n_dirty = (C.n_series + 31) / 32;
@@ -183,7 +174,6 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     C.g32_cold = hcount;
     C.c_srvq = 0; C.c_inbox = C.c_srvq + afl::SQ_WORDS * C.n_servers; C.c_drop = C.c_inbox + afl::IB_WORDS * (C.n_servers + 2);
     hcount += C.c_drop + C.n_edges;
-    C.gi_pt = hcount; hcount += C.pg_max;
     C.gi_smax = hcount; hcount += C.n_series;
     C.gi_sent = hcount; hcount += C.n_edges;
     C.gn32 = hcount;

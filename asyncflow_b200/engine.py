@@ -65,8 +65,9 @@ class Engine:
         self._check(self._lib.af_engine_configure(self._h, C.byref(self._opt)), "af_engine_configure")
 
     def set_mode(self, mode: str | int) -> None:
-        """Pass structure of :meth:`run`: ``"auto"`` (thread-per-replica kernel, flagged replicas re-run one per
-        warp), ``"warp"`` or ``"lane"`` (one kernel only) -- ``af_engine_set_mode``."""
+        """Pass structure of :meth:`run`: ``"two_pass"`` (thread-per-replica kernel, flagged replicas re-run one per
+        warp), ``"auto"`` (two_pass when the launch is large enough for it to pay off, else one replica per warp),
+        ``"warp"`` or ``"lane"`` (one kernel only) -- ``af_engine_set_mode``."""
         m = K.MODES[mode] if isinstance(mode, str) else int(mode)
         self._check(self._lib.af_engine_set_mode(self._h, m), "af_engine_set_mode")
 

@@ -596,7 +596,7 @@ def main() -> None:
                     help="BASELINE.json configs[1..4] (default c3 = configs[2], the one the metric is quoted on)")
     ap.add_argument("--replicas", type=int, default=None, help="replicas per GPU (default: the configuration's)")
     ap.add_argument("--horizon", type=int, default=None, help="simulated seconds (default: the configuration's)")
-    ap.add_argument("--engine", default="", choices=["", "auto", "warp", "lane"], help="pin the pass structure (experiments)")
+    ap.add_argument("--engine", default="", choices=["", "auto", "two_pass", "warp", "lane"], help="pin the pass structure (experiments)")
     ap.add_argument("--wpb", type=int, default=0, help="warps per SM of the thread-per-replica pass (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()

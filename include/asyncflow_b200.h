@@ -203,11 +203,16 @@ void af_engine_destroy(af_engine* e);
 const char* af_last_error(const af_engine* e);   /* e may be NULL: create errors  */
 
 int af_engine_configure(af_engine* e, const AfOptions* opt);
-/* Pass structure of af_run.  AUTO (default): every replica runs on the thread-per-replica kernel, whose
- * per-replica pools are sized for nominal load (512 pending events, 2048 requests in flight); the replicas
- * it flags are re-run by the warp-per-replica kernel with AfOptions' capacities, inside the same af_run.
+/* Pass structure of af_run.
+ * TWO_PASS: every replica runs on the thread-per-replica kernel (one replica per GPU thread), whose per-replica tiers
+ *   are sized for nominal load (512 pending events, 2048 requests in flight, more request slots from a shared page
+ *   pool); the replicas it flags are re-run by the warp-per-replica kernel with AfOptions' capacities, inside the same
+ *   af_run.
+ * AUTO (default): TWO_PASS when the launch has replicas for most lanes and the topology leaves the thread-per-replica
+ *   kernel a useful occupancy; otherwise the warp-per-replica kernel alone (a thread runs one replica ~10x slower than
+ *   a warp does: it pays off in numbers).
  * WARP / LANE pin one kernel (LANE takes AfOptions' capacities as they are and only reports overflows). */
-enum { AF_MODE_AUTO = 0, AF_MODE_WARP = 1, AF_MODE_LANE = 2 };
+enum { AF_MODE_AUTO = 0, AF_MODE_WARP = 1, AF_MODE_LANE = 2, AF_MODE_TWO_PASS = 3 };
 int af_engine_set_mode(af_engine* e, int mode);
 int af_scenario_upload(af_engine* e, const AfScenario* host_pod);
 /* rows cover replicas [first_replica, first_replica + sweep->n_rows); pass NULL to clear */

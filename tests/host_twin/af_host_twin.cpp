@@ -64,10 +64,6 @@ extern "C" int af_twin_run(const AfScenario* sc, const AfSweep* sw, uint64_t swe
     return AF_OK;
 }
 
-// Request slots beyond `n` come from the page pool (0: no paging) -- the CUDA engine's AUTO mode does this with n = 2048.
-static int32_t g_lane_static_requests = 0;
-extern "C" void af_twin_set_lane_static_requests(int32_t n) { g_lane_static_requests = n; }
-
 // The thread-per-replica engine (af_lane.cuh) as a "warp" of one lane.  `lane_bytes` = the lane's share of
 // shared memory: small values push the tiered tables (events, requests, now-queue) into their second tier.
 extern "C" int af_twin_run_lane(const AfScenario* sc, const AfSweep* sw, uint64_t sweep_first, const AfOptions* opt,
@@ -84,7 +80,7 @@ extern "C" int af_twin_run_lane(const AfScenario* sc, const AfSweep* sw, uint64_
     afl::Cfg& C = afl::h_cfg;
     memset(&C, 0, sizeof C);
     if (lane_bytes < aflh::min_lane_bytes(*sc, T)) lane_bytes = aflh::min_lane_bytes(*sc, T);   // (the engine lowers its occupancy instead)
-    if (!aflh::make_cfg(*sc, *opt, T, lane_bytes, afh::trace_tick_capacity(*sc), afl::LANES, g_lane_static_requests, C)) { g_err = "lane engine: tables do not fit the lane's shared memory"; return AF_ERR_INVALID; }
+    if (!aflh::make_cfg(*sc, *opt, T, lane_bytes, afh::trace_tick_capacity(*sc), afl::LANES, C)) { g_err = "lane engine: tables do not fit the lane's shared memory"; return AF_ERR_INVALID; }
     C.edges = T.edges.data(); C.servers = T.servers.data(); C.endpoints = T.endpoints.data(); C.steps = T.steps.data();
     C.spikes = T.spikes.data(); C.outages = T.outages.data(); C.lb_edges = T.lb.data(); C.cols = T.cols.data();
     if (sw) { C.sweep_vals = sw->values; C.sweep_first = sweep_first; C.sweep_rows = sw->n_rows; }
@@ -93,9 +89,6 @@ extern "C" int af_twin_run_lane(const AfScenario* sc, const AfSweep* sw, uint64_
     C.trace_counts = trace_counts;
     C.seed = seed; C.replica_begin = replica_begin; C.n_replicas = n;
     std::vector<uint64_t> smem((size_t)C.warp_bytes / 8 + 2), glob((size_t)(C.gwarp_bytes / 8) + 2);
-    std::vector<uint64_t> pool((size_t)C.pg_max * afl::PG_BYTES / 8 + 2);          // one lane: it can own every page it may ask for
-    uint32_t pool_next = 0;
-    C.pool = (unsigned char*)pool.data(); C.pool_pages = (uint32_t)C.pg_max; C.pool_next = &pool_next;
     afl::afl_smem_host = (unsigned char*)smem.data();
     uint64_t next = 0;
     afl::Mem m;

@@ -100,25 +100,6 @@ def test_columns_that_repeat_each_other_share_a_row_slot_and_change_nothing():
         np.testing.assert_array_equal(r2["trace_clocks"][i, :m], r["trace_clocks"][i, :m])
 
 
-@pytest.mark.parametrize("static", [16, 64, 300])
-def test_request_slots_beyond_the_lane_tiers_come_from_the_page_pool(static):
-    """A saturated server parks thousands of requests in its RAM queue: slots past the lane's own tiers are pages of 256
-    records from a shared pool (the CUDA engine's AUTO mode: 2048 static slots).  Same replica whatever the split."""
-    for name in ("overload_single.yml", "c5_multihop32.yml"):
-        payload = load_scenario(name, PARITY_CASES[name])
-        flat = flatten(payload)
-        r = twin.run(flat, engine="lane", lane_bytes=600, lane_static_requests=static, request_capacity=200000, seed=SEED,
-                     replica_begin=5, n=2, trace=2, clock_cap=300000)
-        assert int(r["stats"]["peak_requests"].max()) > static + 256       # (more than one page in use)
-        for i in range(2):
-            o = des_port.simulate(payload, seed=SEED, replica=5 + i)
-            k, nt = int(r["stats"][i]["completed"]), int(r["stats"][i]["n_ticks"])
-            assert r["stats"][i]["flags"] == 0
-            assert_matches_oracle(o, flat, stats=r["stats"][i], clocks=r["trace_clocks"][i, :k], sent=r["sent"][i],
-                                  dropped=r["dropped"][i], series=r["trace_series"][i][:, :nt], throughput=r["thr"][i],
-                                  hist=r["hist"][i])
-
-
 def test_lane_pool_overflow_is_flagged():
     flat = flatten(load_scenario("overload_single.yml"))
     r = twin.run(flat, engine="lane", seed=SEED, n=1, request_capacity=200)
