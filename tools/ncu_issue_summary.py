@@ -32,8 +32,11 @@ def main() -> None:
     name_i, val_i, kern_i = H.index("Metric Name"), H.index("Metric Value"), H.index("Kernel Name")
     m, kernel = {}, None
     for r in rows[head + 1:]:
-        kernel = r[kern_i].split("(")[0]
-        m[r[name_i]] = float(r[val_i].replace(",", ""))
+        kernel = r[kern_i].split("(")[0].split("<")[0]
+        try:
+            m[r[name_i]] = float(r[val_i].replace(",", ""))
+        except ValueError:
+            continue                                  # "n/a": metric not available on this chip
     line = next(json.loads(ln) for ln in log.read_text().splitlines() if ln.startswith("{"))
     steps = line["steps"]
     events = line["events_per_s"] * line["ms_per_step"] / 1e3 / line["n_gpus"]       # timed events of one launch

@@ -5,7 +5,7 @@
 tag=${1:-rXX}
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
-for mode in auto lane warp; do
+for mode in two_pass lane warp; do
   echo "=== memcheck, mode $mode"
   ASYNCFLOW_B200_ENGINE=$mode timeout 500 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_small.py > gpurun_out/sanitize_${tag}_memcheck_${mode}.log 2>&1
   echo "exit $?"; tail -4 gpurun_out/sanitize_${tag}_memcheck_${mode}.log
