@@ -40,6 +40,12 @@ CASES = {
     "tie_cpu_io.yml": (None, [1, 6]),
     "c5_multihop32.yml": (8, [1]),
 }
+#: the BASELINE shapes at their BASELINE horizons (README my_service.yml: 60 s; the LB example's YAML: 600 s) -- long-run
+#: queue growth, u32 counters, trace capacity; hash-only, one replica each
+FULL_CASES = {
+    "c1_my_service.yml": (60, [0]),
+    "c3_lb_two_servers.yml": (600, [0]),
+}
 FULL_CLOCKS_MAX = 1500
 
 
@@ -82,12 +88,12 @@ def vector(payload: dict, replica: int) -> dict:
     return out
 
 
-def main() -> None:
+def main(only_full: bool = False) -> None:
     if not ref_harness.reference_available():
         sys.exit("needs /root/reference")
     gold = ROOT / "tests" / "golden"
     gold.mkdir(exist_ok=True)
-    for name, (horizon, replicas) in CASES.items():
+    for name, (horizon, replicas) in ({} if only_full else CASES).items():
         payload = yaml.safe_load((ROOT / "tests" / "scenarios" / name).read_text())
         if horizon is not None:
             payload["sim_settings"]["total_simulation_time"] = horizon
@@ -97,7 +103,16 @@ def main() -> None:
         path = gold / (Path(name).stem + ".json")
         path.write_text(json.dumps(doc, indent=0, separators=(",", ":")))
         print(path.name, path.stat().st_size, [v["completed"] for v in doc["vectors"]])
+    for name, (horizon, replicas) in FULL_CASES.items():
+        payload = yaml.safe_load((ROOT / "tests" / "scenarios" / name).read_text())
+        payload["sim_settings"]["total_simulation_time"] = horizon
+        doc = {"scenario": name, "horizon": horizon, "seed": SEED,
+               "generator": "oracle/make_golden.py (reference actors @ /root/reference), BASELINE horizon",
+               "vectors": [vector(payload, rep) for rep in replicas]}
+        path = gold / (Path(name).stem + "_full.json")
+        path.write_text(json.dumps(doc, indent=0, separators=(",", ":")))
+        print(path.name, path.stat().st_size, [v["completed"] for v in doc["vectors"]])
 
 
 if __name__ == "__main__":
-    main()
+    main(only_full="--full-only" in sys.argv)

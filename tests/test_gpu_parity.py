@@ -59,6 +59,21 @@ def test_engine_reproduces_golden_vectors(eng, mode, name):
             throughput=eng.throughput()[0], series=eng.trace_series(0), flat=flat)
 
 
+@pytest.mark.parametrize("name", ["c1_my_service.yml", "c3_lb_two_servers.yml"])
+def test_engine_reproduces_the_baseline_horizons(eng, mode, name):
+    """The BASELINE shapes at their BASELINE horizons (60 s / 600 s) against the unmodified reference actors."""
+    gold = load_golden(name.replace(".yml", "_full.yml"))
+    flat = flatten(load_scenario(name, gold["horizon"]))
+    for vec in gold["vectors"]:
+        st, sent, dropped = run_traced(eng, flat, vec["replica"], 1, **MODES[mode])
+        assert st[0]["flags"] == 0
+        check_against_golden(
+            vec, generated=int(st[0]["generated"]), completed=int(st[0]["completed"]),
+            clocks=eng.trace_clocks(0), edge_sent=dict(zip(flat.edge_ids, map(int, sent[0]))),
+            edge_dropped=dict(zip(flat.edge_ids, map(int, dropped[0]))),
+            throughput=eng.throughput()[0], series=eng.trace_series(0), flat=flat)
+
+
 @pytest.mark.parametrize("name", sorted(PARITY_CASES))
 def test_engine_matches_oracle_on_fresh_replicas(eng, mode, name):
     horizon = {"c1_my_service.yml": 10, "c3_lb_two_servers.yml": 12, "c4_lb8_events.yml": 245,

@@ -33,6 +33,25 @@ def test_twin_reproduces_golden_vectors(name):
             throughput=r["thr"][0], series=r["trace_series"][0][:, :nt], flat=flat)
 
 
+@pytest.mark.parametrize("engine", ["lane", "warp"])
+@pytest.mark.parametrize("name", ["c1_my_service.yml", "c3_lb_two_servers.yml"])
+def test_twin_reproduces_the_baseline_horizons(name, engine):
+    """README my_service.yml at its 60 s, the LB example at its YAML's 600 s (76 656 completions, 60 000 collector ticks):
+    both state machines against the unmodified reference actors (tests/golden/*_full.json, hash-pinned)."""
+    gold = load_golden(name.replace(".yml", "_full.yml"))
+    flat = flatten(load_scenario(name, gold["horizon"]))
+    for vec in gold["vectors"]:
+        r = twin.run(flat, seed=gold["seed"], replica_begin=vec["replica"], n=1, trace=1, clock_cap=200000, engine=engine)
+        st = r["stats"][0]
+        n, nt = int(st["completed"]), int(st["n_ticks"])
+        assert st["flags"] == 0
+        check_against_golden(
+            vec, generated=int(st["generated"]), completed=n, clocks=r["trace_clocks"][0, :n],
+            edge_sent=dict(zip(flat.edge_ids, map(int, r["sent"][0]))),
+            edge_dropped=dict(zip(flat.edge_ids, map(int, r["dropped"][0]))),
+            throughput=r["thr"][0], series=r["trace_series"][0][:, :nt], flat=flat)
+
+
 @pytest.mark.parametrize("name", ["c1_my_service.yml", "mixed_lc.yml", "poisson_ties.yml", "overload_single.yml"])
 def test_twin_matches_oracle_including_aggregates(name):
     payload = load_scenario(name, 10 if name.startswith("c1") else None)

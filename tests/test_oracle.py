@@ -12,10 +12,10 @@ import ref_harness
 from asyncflow_b200.flatten import flatten
 
 
-@pytest.mark.parametrize("name", sorted(PARITY_CASES))
+@pytest.mark.parametrize("name", sorted(PARITY_CASES) + ["c1_my_service_full.yml", "c3_lb_two_servers_full.yml"])
 def test_port_reproduces_golden_vectors(name):
-    gold = load_golden(name)
-    payload = load_scenario(name, gold["horizon"])
+    gold = load_golden(name)                       # (*_full: the BASELINE horizons, 60 s / 600 s)
+    payload = load_scenario(gold["scenario"], gold["horizon"])
     flat = flatten(payload)
     vectors = gold["vectors"] if gold["horizon"] <= 60 else gold["vectors"][:1]
     for vec in vectors:
