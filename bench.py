@@ -482,7 +482,8 @@ def run_ours(a) -> None:
     passes = eng.last_run_passes()
 
     # ---- e2e: K steps through the public API, host buffers ------------------------
-    res = e2e_step()                                    # untimed: allocates the pinned result buffers
+    if a.e2e_warm:
+        res = e2e_step()                                # untimed: allocates the pinned result buffers
     barrier()
     w0 = time.perf_counter()
     for _ in range(a.steps):
@@ -599,6 +600,8 @@ def main() -> None:
     ap.add_argument("--engine", default="", choices=["", "auto", "two_pass", "warp", "lane"], help="pin the pass structure (experiments)")
     ap.add_argument("--wpb", type=int, default=0, help="warps per SM of the thread-per-replica pass (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-warm", type=int, default=1, help="0: no untimed end-to-end step before the timed ones (the first timed "
+                    "one then also allocates the pinned result buffers; for the multi-minute BASELINE-size runs)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
     claim_stdout()
