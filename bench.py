@@ -255,6 +255,12 @@ def cpu_one_process(w: Workload, replica_ids):
     return sum(c for c, _, _ in out) / dt, sum(h for _, h, _ in out) / dt, dt
 
 
+def cpu_sample_size(cores: int, one_process_value: float, completions_per_replica: float, seconds: float) -> int:
+    """Replicas that keep `cores` processes busy for about `seconds` (the contract's bounded CPU sample: 10-30 s)."""
+    k = int(seconds * cores * one_process_value / max(completions_per_replica, 1.0))
+    return max(3 * cores, min(k, 8192))
+
+
 def spaced(total: int, k: int) -> np.ndarray:
     return np.unique(np.linspace(0, total - 1, k).astype(np.int64))
 
@@ -366,7 +372,9 @@ def run_reference(a) -> None:
     cores, info = effective_cores()
     w = make_workload(a.config, a.horizon, a.replicas)
     total = w.replicas * a.gpus
-    per_step = max(2 * cores, 4)                          # ~2 replicas per core and step
+    one = cpu_one_process(w, spaced(total, 2))
+    cpr = one[0] * one[2] / 2.0                           # completions per replica of this workload
+    per_step = cpu_sample_size(cores, one[0], cpr, seconds=10.0)      # ~10 s of all-core work per step
     ids = spaced(total, per_step * (a.steps + a.warmup))
     chunks = [ids[i::(a.steps + a.warmup)] for i in range(a.steps + a.warmup)]
     for c in chunks[: a.warmup]:
@@ -376,7 +384,6 @@ def run_reference(a) -> None:
     for c in chunks[a.warmup:]:
         n, h, t, b = cpu_path(w, c, cores)
         comp += n; ev += h; dt += t; busy += b
-    one = cpu_one_process(w, spaced(total, 2))
     value = comp / dt
     block = cpu_block(w, cores, info, comp, ev, dt, busy, len(chunks[0]), one)
     block["sample"] = f"{len(chunks[0])} replicas/step spaced over the sweep; " + block["sample"]
@@ -560,10 +567,11 @@ def run_ours(a) -> None:
         out["latency_delta_vs_reference"] = latency_delta_vs_reference(local)
     if world == 1 and not a.no_cpu_baseline:
         cores, info = effective_cores()
-        k = max(3 * cores, 4)                             # ~3 replicas per core: 10-30 s of CPU work
-        cpu_path(w, spaced(total, cores), cores)         # untimed: page in the interpreter state
+        one = cpu_one_process(w, spaced(total, 2))         # also pages in the interpreter state; calibrates the sample
+        k = cpu_sample_size(cores, one[0], per_launch_completions / n, seconds=15.0)
+        cpu_path(w, spaced(total, cores), cores)         # untimed: warm the pool
         nn, h, dt, busy = cpu_path(w, spaced(total, k), cores)
-        out["cpu_baseline"] = cpu_block(w, cores, info, nn, h, dt, busy, k, cpu_one_process(w, spaced(total, 2)))
+        out["cpu_baseline"] = cpu_block(w, cores, info, nn, h, dt, busy, k, one)
     emit(out)
     if world > 1:
         dist.destroy_process_group()
