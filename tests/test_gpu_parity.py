@@ -357,3 +357,30 @@ def test_flagged_replicas_are_rerun_inside_af_run(eng):
         assert_matches_oracle(o, flat, stats=st[i], clocks=eng.trace_clocks(i), sent=sent[i], dropped=dropped[i],
                               series=eng.trace_series(i), throughput=eng.throughput()[i], hist=eng.histograms()[i])
     eng.upload_sweep(None)
+
+
+def test_auto_mode_picks_the_kernel_by_launch_size_and_the_result_does_not_care(eng):
+    """AF_MODE_AUTO: one replica per GPU thread from 3 x SMs x 32 replicas up, one per warp below (a thread advances one
+    replica ~10x slower than a warp: it pays off in numbers) -- and every statistic of every replica is the same."""
+    flat = flatten(load_scenario("c1_my_service.yml", 3))
+    n = 20000
+
+    def run(mode, count):
+        eng.set_mode(mode)
+        eng.upload(flat)
+        eng.configure(throughput=False)
+        eng.run(SEED, 0, count)
+        return eng.stats().copy(), eng.last_run_passes()
+
+    try:
+        small, p_small = run("auto", 64)
+        big, p_big = run("auto", n)
+        warp, _ = run("warp", n)
+    finally:
+        eng.set_mode("auto")
+    assert p_small["lane_pass"] == 0 and p_small["warp_pass"] == 1
+    assert p_big["lane_pass"] == 1 and p_big["lane_replicas"] == n and 4 <= p_big["lane_warps_per_sm"] <= 12
+    for f in ("n_events", "generated", "completed", "flags", "n_ticks", "lat_sum", "lat_sumsq", "lat_min", "lat_max", "p50", "p95", "p99"):
+        np.testing.assert_array_equal(big[f], warp[f], err_msg=f)
+        np.testing.assert_array_equal(small[f], warp[f][:64], err_msg=f)
+
