@@ -12,8 +12,8 @@ import ctypes as C
 from pathlib import Path
 
 AF_ABI_VERSION = 1
-AF_HIST_BINS = 2048
-AF_HIST_SUB_BITS = 6
+AF_HIST_BINS = 4096
+AF_HIST_SUB_BITS = 7
 AF_HIST_MIN_EXP = -20
 
 DIST = {"poisson": 0, "normal": 1, "log_normal": 2, "exponential": 3, "uniform": 4}

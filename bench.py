@@ -402,7 +402,7 @@ def config_dict(w: Workload, gpus: int) -> dict:
             "replicas_per_gpu": w.replicas, "replicas_total": w.replicas * gpus, "horizon_s": w.horizon,
             "horizon_note": w.horizon_note,
             "seed": hex(SEED), "parallelism": f"replica-range x{gpus} (each rank: one Monte-Carlo repetition of the grid)",
-            "l2": "per-replica latency histograms (8 KB each) exceed the 126 MB L2 from 16 000 replicas up; "
+            "l2": "per-replica latency histograms (16 KB each) exceed the 126 MB L2 from 8 000 replicas up; "
                   "a 256 MB buffer is also overwritten between timed steps"}
 
 
@@ -552,7 +552,7 @@ def run_ours(a) -> None:
                                  "p95_s": res.global_summary.percentile(95), "p99_s": res.global_summary.percentile(99),
                                  "source": "merged (all-gathered) histogram"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(sw.spec.values.nbytes),
-                "d2h_bytes_per_step": int(sw.d2h_bytes + (2048 * 8)), "ms_per_step": wall_e2e / a.steps * 1e3},
+                "d2h_bytes_per_step": int(sw.d2h_bytes + (4096 * 8)), "ms_per_step": wall_e2e / a.steps * 1e3},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -170,8 +170,8 @@ typedef struct AfOptions {
     int32_t trace_clock_capacity;/* (start,finish) pairs per traced replica        */
 } AfOptions;
 
-#define AF_HIST_BINS 2048        /* 64 log-linear bins per octave, 2^-20 .. 2^12 s  */
-#define AF_HIST_SUB_BITS 6
+#define AF_HIST_BINS 4096        /* 128 log-linear bins per octave (<= 0.78 % wide), 2^-20 .. 2^12 s  */
+#define AF_HIST_SUB_BITS 7
 #define AF_HIST_MIN_EXP (-20)
 
 /* AfReplicaStats.flags */

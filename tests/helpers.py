@@ -122,7 +122,8 @@ def assert_matches_oracle(o: dict, flat, *, stats, clocks, sent, dropped, series
     if hist is not None:
         assert int(np.asarray(hist).sum()) == o["completed"]
         if len(lat):
-            # percentiles read off the histogram are within 2 % of numpy's exact ones
+            # percentiles read off the histogram (128 bins per octave: <= 0.78 % wide) are within 1 % of numpy's exact
+            # ones -- half of the 2 % the north star allows
             for q, key in ((50, "p50"), (95, "p95"), (99, "p99")):
                 exact = float(np.percentile(lat, q))
-                assert abs(float(stats[key]) - exact) <= 0.02 * exact, (key, float(stats[key]), exact)
+                assert abs(float(stats[key]) - exact) <= 0.01 * exact, (key, float(stats[key]), exact)

@@ -88,4 +88,4 @@ class TwinEngine:
         return self._r["trace_series"][j][:, : int(self._r["stats"][j]["n_ticks"])].copy()
 
 
-assert K.AF_HIST_BINS == 2048
+assert K.AF_HIST_BINS == 4096
