@@ -1,18 +1,18 @@
 // af_engine.cu -- sm_100a kernels and the C ABI of include/asyncflow_b200.h.
 //
 // Kernels:
-//   af_lane_kernel        one replica per THREAD (af_lane.cuh): the first pass of every run.  One
-//                         persistent CTA per SM; a lane's mutable state is word-interleaved in shared
-//                         memory (conflict-free at any divergence), deep tiers in global memory; lanes
-//                         pull replica indices from a global counter.
-//   af_flagged_kernel     compacts the replicas whose pools overflowed in the first pass (its tiers are
-//                         sized for nominal load) into a list ...
-//   af_sim_kernel         ... which the warp-per-replica engine (af_core.cuh, large HBM tiers) re-runs.
-//                         One replica per warp, persistent CTAs pulling replica
-//                         indices from a global counter (skewed sweeps balance
-//                         themselves); per-warp workspace in shared memory with
-//                         spill tiers in HBM; the replica state machine is
-//                         af_core.cuh.
+//   af_lane_kernel        one replica per THREAD (af_lane.cuh).  One persistent CTA of up to 12 warps per SM; a
+//                         lane's mutable state is element-interleaved in shared memory (conflict-free however far
+//                         the 32 replicas of a warp drift apart), deep tiers and write-only aggregates in global
+//                         memory; lanes pull replica indices from a global counter.  af_run uses it when the launch
+//                         has replicas for most lanes (AF_MODE_AUTO: n >= 3 x SMs x 32) and the topology leaves it
+//                         at least 4 warps per SM.
+//   af_flagged_kernel     compacts the replicas that overflowed the lane kernel's tiers (sized for nominal load)
+//                         into a list ...
+//   af_sim_kernel         ... which the warp-per-replica engine (af_core.cuh, large HBM tiers) re-runs; also the
+//                         whole run for small launches and very wide topologies.  One replica per warp,
+//                         persistent CTAs pulling replica indices from a global counter; per-warp workspace in
+//                         shared memory with spill tiers in HBM.
 //   af_percentile_kernel  HBM-bound pass over the per-replica latency histograms:
 //                         one warp per replica, coalesced 128-byte row reads, warp
 //                         prefix sums, numpy-"linear" p50/p95/p99.
@@ -31,7 +31,8 @@
 #include "af_host_common.h"
 #include "af_lane_host.h"
 
-// thread-per-replica pass: warps per SM when the caller does not say (AfOptions.warps_per_block)
+// thread-per-replica pass: most warps per SM when the caller does not say (AfOptions.warps_per_block); af_run lowers it
+// to whole waves and to what the topology's fixed tables leave room for
 #ifndef AF_LANE_DEFAULT_WARPS
 #define AF_LANE_DEFAULT_WARPS 12
 #endif
