@@ -115,7 +115,7 @@ inline int32_t min_lane_bytes(const AfScenario& s, const Tables& t) { return fix
 // engine at this occupancy (the caller lowers the occupancy or takes the warp-per-replica engine).
 // `lanes` = lanes of a warp in the code that will RUN the configuration: 32 for the CUDA kernel, 1 for the host twin
 // (afl::LANES is a property of the compilation pass, and the host pass of a .cu file sees 1).
-inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, int32_t lane_bytes, int32_t trace_tick_cap, int32_t lanes, afl::Cfg& C) {
+inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, int32_t lane_bytes, int32_t trace_tick_cap, int32_t lanes, afl::Cfg& C, int32_t ev_share_pct = 0) {
     C.n_edges = s.n_edges; C.n_servers = s.n_servers; C.n_endpoints = s.n_endpoints; C.n_steps = s.n_steps;
     C.n_lb_edges = s.n_lb_edges; C.lb_algo = s.lb_algo; C.gen_edge = s.gen_edge; C.client_edge = s.client_edge;
     C.n_spike = s.n_spike_marks; C.n_outage = s.n_outage_marks;
@@ -138,6 +138,11 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     // split the rest between pending events (16 B) and request records (20 B): at nominal load a request in
     // flight owns one pending event, plus the arrival and the two timelines
     int32_t rq_s = (rest - 16 * 4) / 36;
+    if (ev_share_pct > 0) {                          // experiments: events get this share of the lane's dynamic bytes
+        const int32_t ev_try = (int32_t)((int64_t)rest * ev_share_pct / 100) / 16;
+        const int32_t rq_try = (rest - 16 * ev_try) / 20;
+        if (rq_try >= 2 && ev_try >= 4) rq_s = rq_try;
+    }
     if (rq_s > rq_total) rq_s = rq_total;
     int32_t ev_s = rq_s < 0 ? 0 : (rest - 20 * rq_s) / 16;
     if (ev_s > ev_total) { ev_s = ev_total; rq_s = (rest - 16 * ev_s) / 20; if (rq_s > rq_total) rq_s = rq_total; }
