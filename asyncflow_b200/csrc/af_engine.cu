@@ -263,6 +263,7 @@ struct af_engine {
     int32_t sweep_cols = 0; uint64_t sweep_rows = 0, sweep_first = 0;
     std::vector<AfSweepColumn> h_sweep_cols;
     std::vector<int32_t> h_sweep_alias;            // aflh::column_aliases of the uploaded values
+    int32_t ev_need = 0;                           // aflh::pending_events_estimate of the scenario + sweep
     DevBuf d_sweep_cols, d_sweep_vals;
     // thread-per-replica pass: read-only tables (af_lane_host.h), global tiers, the list of flagged replicas
     int mode = AF_MODE_AUTO;
@@ -394,6 +395,7 @@ int af_scenario_upload(af_engine* e, const AfScenario* s) {
     e->sc.outage_marks = e->h_outages.data();
     e->have_scenario = true;
     e->sweep_cols = 0; e->sweep_rows = 0; e->h_sweep_cols.clear();     // a sweep belongs to the scenario it was built for
+    e->ev_need = aflh::pending_events_estimate(e->sc, nullptr);
     e->ran = false;
     return AF_OK;
 }
@@ -403,7 +405,7 @@ int af_sweep_upload(af_engine* e, const AfSweep* sw, uint64_t first_replica) {
     if (!e->have_scenario) return e->fail(AF_ERR_STATE, "af_sweep_upload before af_scenario_upload");
     AF_CUDA(e, cudaSetDevice(e->device), "cudaSetDevice");
     AF_CUDA(e, cudaStreamSynchronize(e->stream), "sync before sweep upload");
-    if (!sw || sw->n_columns == 0 || sw->n_rows == 0) { e->sweep_cols = 0; e->sweep_rows = 0; e->h_sweep_cols.clear(); return AF_OK; }
+    if (!sw || sw->n_columns == 0 || sw->n_rows == 0) { e->sweep_cols = 0; e->sweep_rows = 0; e->h_sweep_cols.clear(); e->ev_need = aflh::pending_events_estimate(e->sc, nullptr); return AF_OK; }
     if (!sw->columns || !sw->values) return e->fail(AF_ERR_INVALID, "sweep: null columns/values");
     const AfScenario& s = e->sc;
     for (int c = 0; c < sw->n_columns; ++c) {
@@ -440,6 +442,7 @@ int af_sweep_upload(af_engine* e, const AfSweep* sw, uint64_t first_replica) {
         }
     e->h_sweep_cols.assign(sw->columns, sw->columns + sw->n_columns);
     e->h_sweep_alias = aflh::column_aliases(sw->values, sw->n_rows, sw->n_columns);
+    e->ev_need = aflh::pending_events_estimate(e->sc, sw);
     size_t cb = (size_t)sw->n_columns * sizeof(AfSweepColumn), vb = (size_t)sw->n_columns * sw->n_rows * sizeof(double);
     AF_CUDA(e, e->d_sweep_cols.ensure(cb), "sweep columns");
     AF_CUDA(e, e->d_sweep_vals.ensure(vb), "sweep values");
@@ -513,7 +516,7 @@ int af_run(af_engine* e, uint64_t seed, uint64_t begin, uint64_t end) {
     }
     if (lane) {
         memset(&C, 0, sizeof C);
-        if (!aflh::make_cfg(e->sc, o, e->lt, lane_budget(e, lane_warps), afh::trace_tick_capacity(e->sc), 32, C, getenv("ASYNCFLOW_B200_EV_SHARE") ? atoi(getenv("ASYNCFLOW_B200_EV_SHARE")) : 0)) {
+        if (!aflh::make_cfg(e->sc, o, e->lt, lane_budget(e, lane_warps), afh::trace_tick_capacity(e->sc), 32, C, getenv("ASYNCFLOW_B200_EVEN_SPLIT") ? 0 : e->ev_need)) {
             if (e->mode == AF_MODE_LANE) return e->fail(AF_ERR_INVALID, "scenario tables do not fit a lane's shared memory (thread-per-replica engine)");
             lane = false;
         }

@@ -261,7 +261,7 @@ struct St {
     uint32_t seq; int32_t ev_n; uint32_t peak_ev;
     uint64_t arr_t; uint32_t arr_seq, arr_on;   // the generator's pending timeout: always exactly one, kept out of the heap
     uint32_t nq_head, nq_tail, busy;            // busy = 2 * (items in the now-queue) + (the heap may hold an event of this instant)
-    uint32_t rq_free, rq_hw, rq_live, peak_rq;
+    uint32_t rq_free, rq_free_hi, rq_hw, rq_live, peak_rq;   // two free lists: slots in shared memory / in the global tier
     uint32_t n_waiting;                         // requests parked in a RAM / CPU waiter FIFO (0: every such FIFO is empty, no need to look)
     double g_vnow, g_wend, g_lam;               // generator: the sampler's virtual clock (the simulation's is `now`)
     uint32_t g_pos, generated, g_done, need_arrival, arm_seq;
@@ -322,16 +322,25 @@ static inline void red_max32(uint32_t* p, uint32_t v) { if (v > *p) *p = v; }
 static inline uint64_t ld_cg64(const uint64_t* p) { return *p; }
 static inline uint32_t ld_cg32(const uint32_t* p) { return *p; }
 #endif
+// A request takes the LOWEST tier that has a free slot: with one LIFO list the few requests in flight after a burst
+// keep cycling through whatever slots were freed last -- often global-tier ones (C1 with 10 shared-memory slots for
+// ~3 requests in flight: -9 %).  Shared-memory slots are handed out first (free list, then fresh ones), global ones after.
 AFL_IN uint32_t rq_alloc(St& W, const Mem& m) {
     uint32_t s;
     if (W.rq_free != NIL) { s = W.rq_free; W.rq_free = rq_next(m, s); }
+    else if ((int32_t)W.rq_hw < AFL_C.rq_s) { s = W.rq_hw++; }
+    else if (W.rq_free_hi != NIL) { s = W.rq_free_hi; W.rq_free_hi = rq_next(m, s); }
     else if ((int32_t)W.rq_hw < AFL_C.rq_total) { s = W.rq_hw++; }
     else { W.flags |= AF_FLAG_REQUEST_OVERFLOW; return NIL; }
     const uint32_t live = ++W.rq_live;
     if (live > W.peak_rq) W.peak_rq = live;
     return s;
 }
-AFL_IN void rq_release(St& W, const Mem& m, uint32_t s) { rq_next_set(m, s, W.rq_free); W.rq_free = s; --W.rq_live; }
+AFL_IN void rq_release(St& W, const Mem& m, uint32_t s) {
+    if ((int32_t)s < AFL_C.rq_s) { rq_next_set(m, s, W.rq_free); W.rq_free = s; }
+    else { rq_next_set(m, s, W.rq_free_hi); W.rq_free_hi = s; }
+    --W.rq_live;
+}
 
 // intrusive FIFOs through the `next` links; head / tail are COLD words.  Out of line (Mem by value: a reference across a
 // call would force it into local memory): nine call sites, all on paths taken at ties or under contention
@@ -653,7 +662,7 @@ AFL_IN void start_replica(St& W, const Mem& m, uint64_t local_index) {
     W.now = 0.0; W.horizon = (double)C.horizon_s; W.seq = 0;
     W.ev_n = 0; W.peak_ev = 0; W.arr_t = 0; W.arr_seq = 0; W.arr_on = 0;
     W.nq_head = 0; W.nq_tail = 0; W.busy = 0;
-    W.rq_free = NIL; W.rq_hw = 0; W.rq_live = 0; W.peak_rq = 0; W.n_waiting = 0;
+    W.rq_free = NIL; W.rq_free_hi = NIL; W.rq_hw = 0; W.rq_live = 0; W.peak_rq = 0; W.n_waiting = 0;
     W.g_vnow = 0.0; W.g_wend = 0.0; W.g_lam = 0.0; W.g_pos = 0; W.generated = 0; W.g_done = 0;
     W.gap0 = 0.0; W.gap1 = 0.0; W.gap_cnt = 0;
     W.lb_n = C.n_lb_edges; W.spike_cur = 0; W.outage_cur = 0;

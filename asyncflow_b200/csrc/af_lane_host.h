@@ -94,6 +94,31 @@ inline std::vector<int32_t> column_aliases(const double* values, uint64_t n_rows
     return alias;
 }
 
+// How many pending events a replica of this launch typically holds: Little's law on the scenario (and the sweep's
+// largest values) -- requests in flight = arrival rate x time in system, one pending event each, plus the generator's
+// and the injection timelines' own.  Only used to split a lane's shared memory (a wrong guess costs speed, not results).
+inline int32_t pending_events_estimate(const AfScenario& s, const AfSweep* sw) {
+    double users = s.users_mean, rate = s.rate_per_user, edge = 0.0, steps = 0.0;
+    for (int i = 0; i < s.n_edges; ++i) if (s.edges[i].mean > edge && s.edges[i].dist != AF_DIST_LOG_NORMAL) edge = s.edges[i].mean;
+    for (int e = 0; e < s.n_endpoints; ++e) {
+        double d = 0.0;
+        for (int k = 0; k < s.endpoints[e].n_steps; ++k) d += s.steps[s.endpoints[e].step_begin + k].duration;
+        if (d > steps) steps = d;
+    }
+    if (sw)
+        for (int c = 0; c < sw->n_columns; ++c) {
+            const int f = sw->columns[c].field;
+            if (f != AF_FIELD_USERS_MEAN && f != AF_FIELD_RATE_PER_USER && f != AF_FIELD_EDGE_MEAN) continue;
+            double mx = 0.0;
+            for (uint64_t r = 0; r < sw->n_rows; ++r) { const double v = sw->values[r * (uint64_t)sw->n_columns + (uint64_t)c]; if (v > mx) mx = v; }
+            if (f == AF_FIELD_USERS_MEAN) users = mx; else if (f == AF_FIELD_RATE_PER_USER) rate = mx; else if (mx > edge) edge = mx;
+        }
+    const int hops = s.n_lb_edges > 0 ? 4 : 3;           // generator -> client -> [LB ->] server -> client
+    const double in_flight = users * rate * (hops * edge + steps);
+    const double need = in_flight + 6.0;
+    return need > 100000.0 ? 100000 : (int32_t)need;
+}
+
 constexpr int32_t LANE_EVENT_CAPACITY = 512;      // defaults of the lane engine's global tiers (AfOptions fields <= 0)
 constexpr int32_t LANE_REQUEST_CAPACITY = 2048;
 
@@ -110,12 +135,13 @@ constexpr int32_t MIN_DYNAMIC_BYTES = 16 * 4 + 36 * 2;      // make_cfg: rq_s = 
 // smallest per-lane budget make_cfg() accepts for this scenario
 inline int32_t min_lane_bytes(const AfScenario& s, const Tables& t) { return fixed_lane_bytes(s, t) + MIN_DYNAMIC_BYTES; }
 
+// `ev_need`: pending_events_estimate() of the launch (0: split evenly -- the twin's default).
 // The launch configuration for a budget of `lane_bytes` of shared memory per lane (= per replica in
 // flight).  Returns false when even the smallest tiers do not fit: the topology is too wide for this
 // engine at this occupancy (the caller lowers the occupancy or takes the warp-per-replica engine).
 // `lanes` = lanes of a warp in the code that will RUN the configuration: 32 for the CUDA kernel, 1 for the host twin
 // (afl::LANES is a property of the compilation pass, and the host pass of a .cu file sees 1).
-inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, int32_t lane_bytes, int32_t trace_tick_cap, int32_t lanes, afl::Cfg& C, int32_t ev_share_pct = 0) {
+inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, int32_t lane_bytes, int32_t trace_tick_cap, int32_t lanes, afl::Cfg& C, int32_t ev_need = 0) {
     C.n_edges = s.n_edges; C.n_servers = s.n_servers; C.n_endpoints = s.n_endpoints; C.n_steps = s.n_steps;
     C.n_lb_edges = s.n_lb_edges; C.lb_algo = s.lb_algo; C.gen_edge = s.gen_edge; C.client_edge = s.client_edge;
     C.n_spike = s.n_spike_marks; C.n_outage = s.n_outage_marks;
@@ -138,8 +164,14 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     // split the rest between pending events (16 B) and request records (20 B): at nominal load a request in
     // flight owns one pending event, plus the arrival and the two timelines
     int32_t rq_s = (rest - 16 * 4) / 36;
-    if (ev_share_pct > 0) {                          // experiments: events get this share of the lane's dynamic bytes
-        const int32_t ev_try = (int32_t)((int64_t)rest * ev_share_pct / 100) / 16;
+    if (ev_need > 0) {
+        // Heap entries are touched ~20 times per event, a request record twice: the events a replica typically holds go
+        // to shared memory first, the records take what is left (at least 4 slots).  Measured on B200, bench workload
+        // (11 warps/SM): 18 events + 14 records 5.45e8 completions/s, 31 + 3: 6.14e8; C4 (5 warps/SM) the other way
+        // round: 31 + 27: 3.97e8, 56 + 7: 3.73e8 -- hence "what it needs", not "as much as fits".
+        int32_t ev_try = ev_need, ev_max = (rest - 20 * 4) / 16;
+        if (ev_try > ev_max) ev_try = ev_max;
+        if (ev_try > ev_total) ev_try = ev_total;
         const int32_t rq_try = (rest - 16 * ev_try) / 20;
         if (rq_try >= 2 && ev_try >= 4) rq_s = rq_try;
     }

@@ -104,6 +104,21 @@ extern "C" int af_twin_run_lane(const AfScenario* sc, const AfSweep* sw, uint64_
     return AF_OK;
 }
 
+// the host-side estimate that splits a lane's shared memory between events and request records (af_run)
+extern "C" int af_twin_pending_events_estimate(const AfScenario* sc, const AfSweep* sw) { return aflh::pending_events_estimate(*sc, sw); }
+// ... and the split it leads to for a given per-lane budget: out = {ev_s, rq_s}
+extern "C" int af_twin_lane_split(const AfScenario* sc, const AfSweep* sw, int32_t lane_bytes, int32_t use_estimate, int32_t* out) {
+    aflh::Tables T; std::string err;
+    std::vector<int32_t> alias;
+    if (sw) alias = aflh::column_aliases(sw->values, sw->n_rows, sw->n_columns);
+    if (!aflh::build_tables(*sc, sw ? sw->columns : nullptr, sw ? sw->n_columns : 0, sw ? alias.data() : nullptr, T, err)) return -1;
+    AfOptions o; memset(&o, 0, sizeof o); o.event_capacity = aflh::LANE_EVENT_CAPACITY; o.request_capacity = aflh::LANE_REQUEST_CAPACITY;
+    afl::Cfg C; memset(&C, 0, sizeof C);
+    if (!aflh::make_cfg(*sc, o, T, lane_bytes, 0, 32, C, use_estimate ? aflh::pending_events_estimate(*sc, sw) : 0)) return -2;
+    out[0] = C.ev_s; out[1] = C.rq_s;
+    return 0;
+}
+
 // sizeof() of every ABI struct as the C++ compiler lays it out (tests/test_capi.py)
 extern "C" int af_twin_sizeof(int which) {
     switch (which) {
