@@ -165,15 +165,20 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     // flight owns one pending event, plus the arrival and the two timelines
     int32_t rq_s = (rest - 16 * 4) / 36;
     if (ev_need > 0) {
-        // Heap entries are touched ~20 times per event, a request record twice: the events a replica typically holds go
-        // to shared memory first, the records take what is left (at least 4 slots).  Measured on B200, bench workload
-        // (11 warps/SM): 18 events + 14 records 5.45e8 completions/s, 31 + 3: 6.14e8; C4 (5 warps/SM) the other way
-        // round: 31 + 27: 3.97e8, 56 + 7: 3.73e8 -- hence "what it needs", not "as much as fits".
-        int32_t ev_try = ev_need, ev_max = (rest - 20 * 4) / 16;
+        // Heap entries are touched ~20 times per event, a request record twice: when a replica typically holds more
+        // pending events than the even split keeps in shared memory, the events get the bytes, down to half of the
+        // even split's record slots (at least 4).  Measured on B200, bench workload (11 warps/SM, up to 60 pending
+        // events): 18 events + 14 records 5.45e8 completions/s, 24 + 9 5.94e8, 31 + 3 6.14e8.  Never BELOW the even
+        // split: C4 31 + 27 4.03e8, 19 + 36 3.89e8; C1 30 + 26 5.58e8, 10 + 42 5.50e8.
+        const int32_t ev_even = (rest - 20 * rq_s) / 16;
+        const int32_t rq_min = rq_s / 2 > 4 ? rq_s / 2 : 4;
+        int32_t ev_try = ev_need, ev_max = (rest - 20 * rq_min) / 16;
         if (ev_try > ev_max) ev_try = ev_max;
         if (ev_try > ev_total) ev_try = ev_total;
-        const int32_t rq_try = (rest - 16 * ev_try) / 20;
-        if (rq_try >= 2 && ev_try >= 4) rq_s = rq_try;
+        if (ev_try > ev_even) {
+            const int32_t rq_try = (rest - 16 * ev_try) / 20;
+            if (rq_try >= 2) rq_s = rq_try;
+        }
     }
     if (rq_s > rq_total) rq_s = rq_total;
     int32_t ev_s = rq_s < 0 ? 0 : (rest - 20 * rq_s) / 16;
