@@ -8,23 +8,26 @@
 //                          redundantly; ncu (profiles/r01i_*): ~560 warp-instructions per timed event,
 //                          issue-slot bound, 31 % of them 32-way-redundant random-number code.
 //   this file              one replica per LANE: every warp instruction advances up to 32 replicas.
-//                          The loop body is written as a fixed sequence of PHASES (pick -> sample ->
-//                          decode -> node -> steps -> send -> timer); a lane skips the phases its
-//                          event does not need, so the warp pays each phase at most once per 32
-//                          events (the expensive ones -- the edge's variates, the heap sift -- exist
-//                          at ONE place in the code and are shared by every event kind that needs them).
+//                          The loop body is a fixed sequence of PHASES (lifecycle -> gap -> pick -> ticks ->
+//                          decode -> node -> steps -> send -> timer) with a warp rendez-vous between them; a
+//                          lane skips the phases its event does not need, so the warp pays each phase at most
+//                          once per 32 events (the expensive ones -- the edge's variates, the heap sift --
+//                          exist at ONE place in the code and are shared by every event kind that needs
+//                          them).  ~76 warp-instructions per timed event, 12 of 32 lanes active on average
+//                          (profiles/r02_summary.md).
 //
 // Data layout.  A lane's mutable replica state lives in shared memory, ELEMENT-INTERLEAVED across the
 // warp: 128-bit element e of lane l at  base128 + (e * 32 + l) * 16  (a pending event = time | key, a request
 // record = t0 | id | pack: one LDS.128 each),  64-bit element e at  base64 + (e * 32 + l) * 8,  32-bit word w at
 // base32 + (w * 32 + l) * 4.  Whatever index each lane uses, the lanes of a quarter / half / full warp always hit
 // different banks: every access is conflict-free (4 / 2 / 1 wavefronts), no matter how far the replicas have
-// drifted apart.  Tables whose size depends on load (pending events, request
-// records, the now-queue) are TIERED: the first `*_s` entries in shared memory, the rest in a
-// per-lane region of global memory with the same interleave (L2-resident; one select per access,
-// no branch).  Read-only scenario tables are NOT replicated per replica: they are read through
-// the read-only data path (128-bit __ldg) and a swept field is an index into the lane's copy of its
-// sweep row.
+// drifted apart.  Tables whose size depends on load (pending events, request records, the now-queue) are TIERED:
+// the first `*_s` entries in shared memory, the rest in a per-lane region of global memory with the same
+// interleave (L2-resident; a branch per access, so that the shared side stays an LDS).  The same region holds the
+// cold words (waiter FIFOs, mailboxes, drop counters) and the write-only aggregates (the gauges' sums and
+// maxima, the send counters: fire-and-forget REDs).  Read-only scenario tables are NOT replicated per replica:
+// they are read through the read-only data path (128-bit __ldg) and a swept field is an index into the lane's
+// copy of its sweep row.
 //
 //   code here           reference being replaced
 //   ------------------  ---------------------------------------------------------
@@ -37,7 +40,7 @@
 //   phase STEPS         server.py:197-276 (lazy CPU lock, IO queue, release, forward)
 //   cpu_walk, ram_walk  simpy Container._trigger_get (FIFO, head-of-line blocking)
 //   on_spike/on_outage  runtime/events/injection.py:167-226
-//   take_samples        metrics/collector.py:50-66
+//   take_ticks, gauge_touch   metrics/collector.py:50-66 (lazily: settled when a gauge changes)
 //   complete            client.py:62-69 + metrics/analyzer.py:83-125
 //
 // Ordering rule: identical to af_core.cuh (DESIGN.md "tie rule"): timed events pop by (time, seq)
