@@ -134,3 +134,41 @@ def test_an_outage_that_empties_the_lb_pool_is_rejected_up_front_and_flagged_by_
         r = twin.run(flat, engine=engine, seed=SEED, n=2)
         assert (r["stats"]["flags"] & K.FLAG_LB_EMPTY).all(), engine
         assert (r["stats"]["completed"] > 0).all()
+
+
+def test_shared_memory_split_follows_the_estimated_need_but_never_starves_a_table():
+    """af_run splits a lane's dynamic shared memory between pending events and request records by the number of events a
+    replica of the launch typically holds (aflh::pending_events_estimate: Little's law on the scenario and the sweep's
+    maxima).  Properties: never fewer events than the even split, never fewer records than half of it (>= 4), and the
+    bench workload (RTT up to 50 ms: ~30 requests in flight) does get more events than the even split."""
+    import ctypes as C
+
+    import bench
+    L = twin.lib()
+
+    def split(w, budget, with_sweep=True):
+        flat = flatten(w.payload)
+        sw_p, keep = None, None
+        if with_sweep:
+            ids = np.arange(0, 2000, dtype=np.int64) * (w.replicas // 2000)
+            spec = SweepSpec(flat, len(ids), w.columns(flat, ids, w.replicas))
+            sw, keep = spec.pod(0, None)
+            sw_p = C.byref(sw)
+        out = (C.c_int32 * 2)()
+        assert L.af_twin_lane_split(C.byref(flat.pod), sw_p, budget, 0, out) == 0
+        even = tuple(out)
+        assert L.af_twin_lane_split(C.byref(flat.pod), sw_p, budget, 1, out) == 0
+        need = tuple(out)
+        est = L.af_twin_pending_events_estimate(C.byref(flat.pod), sw_p)
+        del keep
+        return est, even, need
+
+    for key, budget in (("c3", 660), ("c3", 904), ("c2", 660), ("c4", 1036), ("c4", 1452), ("c5", 1204)):
+        est, even, need = split(bench.make_workload(key), budget)
+        assert need[0] >= even[0] and need[1] >= max(4, even[1] // 2) or need == even, (key, budget, est, even, need)
+        assert 16 * need[0] + 20 * need[1] <= 16 * even[0] + 20 * even[1] + 36, (key, budget, even, need)
+    est, even, need = split(bench.make_workload("c3"), 660)
+    assert est >= 25 and need[0] > even[0], (est, even, need)
+    est, even, need = split(bench.make_workload("c2"), 1036, with_sweep=False)      # README my_service.yml: ~3 in flight
+    assert est <= 12 and need == even, (est, even, need)
+
