@@ -181,6 +181,7 @@ class SweepResults:
         self.replica_begin = replica_begin
         self.rows: np.ndarray | None = None      # sweep row of each result row (set by SweepRunner)
         self.traced: list[ReplicaResults] = []    # full clocks + sampled series of the first `trace_replicas` replica ids
+        self.exact: np.ndarray | None = None      # rows whose p50/p95/p99 are exact (SweepRunner.exact_percentiles)
 
     def __len__(self) -> int:
         return int(self.stats.shape[0])

@@ -384,3 +384,30 @@ def test_auto_mode_picks_the_kernel_by_launch_size_and_the_result_does_not_care(
         np.testing.assert_array_equal(big[f], warp[f], err_msg=f)
         np.testing.assert_array_equal(small[f], warp[f][:64], err_msg=f)
 
+
+def test_exact_percentiles_on_the_device():
+    """SweepRunner.exact_percentiles: rows re-simulated with their clock lists kept, numpy.percentile on them == the
+    oracle's latencies' percentiles, bit for bit; the other rows keep the histogram values (within 1 %)."""
+    from asyncflow_b200 import SweepRunner
+    base = load_scenario("c1_my_service.yml", 6)
+    n = 300
+    users = np.linspace(20.0, 200.0, n)
+    sw = SweepRunner(base, n, {("users_mean",): users}, seed=SEED)
+    try:
+        res = sw.run()
+        coarse = res.stats[["p50", "p95", "p99"]].copy()
+        rows = [0, 1, 150, 299]
+        sw.exact_percentiles(res, rows, chunk=2)
+        for row in rows + [7]:
+            o = des_port.simulate(sw.payload_for(row), seed=SEED, replica=row)
+            lat = np.array([b - a for a, b in o["clocks"]])
+            for q, key in ((50, "p50"), (95, "p95"), (99, "p99")):
+                exact = float(np.percentile(lat, q))
+                if row in rows:
+                    assert float(res.stats[key][row]) == exact, (row, key)
+                else:
+                    assert float(res.stats[key][row]) == float(coarse[key][row])
+                    assert abs(float(res.stats[key][row]) - exact) <= 0.01 * exact
+    finally:
+        sw.close()
+

@@ -204,3 +204,27 @@ def test_results_of_two_shards_do_not_share_memory():
     assert a.completed.tolist() == before.tolist()
     both = SweepResults.concatenate([a, b])
     assert both.completed.tolist() == before.tolist() + b.completed.tolist()
+
+
+def test_exact_percentiles_replace_the_histogram_ones_for_the_rows_asked_for():
+    """SweepRunner.exact_percentiles(res, rows): the rows are simulated again with their (start, finish) lists kept and
+    numpy.percentile applied -- the reference analyzer's arithmetic (metrics/analyzer.py:93-103) -- also under
+    balance=True, where a row's replica id is not its row number."""
+    for kw in ({}, {"balance": True}):
+        sw = runner(**kw)
+        res = sw.run()
+        coarse = res.stats[["p50", "p95", "p99"]].copy()
+        rows = [1, 2, 5]
+        sw.exact_percentiles(res, rows, chunk=2)
+        assert res.exact.tolist() == [i in rows for i in range(len(USERS))]
+        for row in range(len(USERS)):
+            o = oracle_row(sw, row)
+            lat = np.array([b - a for a, b in o["clocks"]])
+            for q, key in ((50, "p50"), (95, "p95"), (99, "p99")):
+                exact = float(np.percentile(lat, q))
+                if row in rows:
+                    assert float(res.stats[key][row]) == exact, (kw, row, key)
+                else:
+                    assert float(res.stats[key][row]) == float(coarse[key][row])
+                    assert abs(float(res.stats[key][row]) - exact) <= 0.01 * exact
+
