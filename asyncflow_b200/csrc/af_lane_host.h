@@ -2,7 +2,6 @@
 // sweep's column map folded in, and the launch configuration (shared-memory layout of a warp, tier
 // sizes).  Shared by the CUDA engine (af_engine.cu) and the CPU-only debugging twin (tests/host_twin).
 #pragma once
-#include <stdlib.h>
 #include <string>
 #include <vector>
 #include "af_lane.cuh"
@@ -172,7 +171,7 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
         // events): 18 events + 14 records 5.45e8 completions/s, 24 + 9 5.94e8, 31 + 3 6.14e8.  Never BELOW the even
         // split: C4 31 + 27 4.03e8, 19 + 36 3.89e8; C1 30 + 26 5.58e8, 10 + 42 5.50e8.
         const int32_t ev_even = (rest - 20 * rq_s) / 16;
-        const int32_t rq_min = getenv("ASYNCFLOW_B200_RQ_MIN_HALF") ? (rq_s / 2 > 4 ? rq_s / 2 : 4) : 4;
+        const int32_t rq_min = rq_s / 2 > 4 ? rq_s / 2 : 4;
         int32_t ev_try = ev_need, ev_max = (rest - 20 * rq_min) / 16;
         if (ev_try > ev_max) ev_try = ev_max;
         if (ev_try > ev_total) ev_try = ev_total;
