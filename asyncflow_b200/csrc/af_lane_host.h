@@ -166,12 +166,13 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     int32_t rq_s = (rest - 16 * 4) / 36;
     if (ev_need > 0) {
         // Heap entries are touched ~20 times per event, a request record twice: when a replica typically holds more
-        // pending events than the even split keeps in shared memory, the events get the bytes, down to half of the
-        // even split's record slots (at least 4).  Measured on B200, bench workload (11 warps/SM, up to 60 pending
-        // events): 18 events + 14 records 5.45e8 completions/s, 24 + 9 5.94e8, 31 + 3 6.14e8.  Never BELOW the even
-        // split: C4 31 + 27 4.03e8, 19 + 36 3.89e8; C1 30 + 26 5.58e8, 10 + 42 5.50e8.
+        // pending events than the even split keeps in shared memory, the events get the bytes, down to 4 record slots.
+        // Measured on B200, bench workload (11 warps/SM, up to 60 pending events; profiles/r02j_ab_split_shares.log,
+        // r02j_ab_split_policy.log): 18 events + 14 records 5.45e8 completions/s, 24 + 9 5.94e8, 26 + 7 5.86e8,
+        // 30 + 4 6.03e8, 31 + 3 6.14e8; C5 (5 warps/SM, ~85 pending events) 17 + 13 7.17e7, 29 + 4 7.37e7.  Never BELOW
+        // the even split: C4 31 + 27 4.03e8, 19 + 36 3.89e8; C1 30 + 26 5.58e8, 10 + 42 5.50e8.
         const int32_t ev_even = (rest - 20 * rq_s) / 16;
-        const int32_t rq_min = rq_s / 2 > 4 ? rq_s / 2 : 4;
+        const int32_t rq_min = 4;
         int32_t ev_try = ev_need, ev_max = (rest - 20 * rq_min) / 16;
         if (ev_try > ev_max) ev_try = ev_max;
         if (ev_try > ev_total) ev_try = ev_total;

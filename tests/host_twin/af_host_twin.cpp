@@ -64,6 +64,11 @@ extern "C" int af_twin_run(const AfScenario* sc, const AfSweep* sw, uint64_t swe
     return AF_OK;
 }
 
+// af_run splits a lane's shared memory by aflh::pending_events_estimate(); the twin splits evenly unless a test sets
+// the estimate it wants the next af_twin_run_lane calls to use (0 = even split)
+static int32_t g_ev_need = 0;
+extern "C" void af_twin_set_ev_need(int32_t ev_need) { g_ev_need = ev_need < 0 ? 0 : ev_need; }
+
 // The thread-per-replica engine (af_lane.cuh) as a "warp" of one lane.  `lane_bytes` = the lane's share of
 // shared memory: small values push the tiered tables (events, requests, now-queue) into their second tier.
 extern "C" int af_twin_run_lane(const AfScenario* sc, const AfSweep* sw, uint64_t sweep_first, const AfOptions* opt,
@@ -80,7 +85,7 @@ extern "C" int af_twin_run_lane(const AfScenario* sc, const AfSweep* sw, uint64_
     afl::Cfg& C = afl::h_cfg;
     memset(&C, 0, sizeof C);
     if (lane_bytes < aflh::min_lane_bytes(*sc, T)) lane_bytes = aflh::min_lane_bytes(*sc, T);   // (the engine lowers its occupancy instead)
-    if (!aflh::make_cfg(*sc, *opt, T, lane_bytes, afh::trace_tick_capacity(*sc), afl::LANES, C)) { g_err = "lane engine: tables do not fit the lane's shared memory"; return AF_ERR_INVALID; }
+    if (!aflh::make_cfg(*sc, *opt, T, lane_bytes, afh::trace_tick_capacity(*sc), afl::LANES, C, g_ev_need)) { g_err = "lane engine: tables do not fit the lane's shared memory"; return AF_ERR_INVALID; }
     C.edges = T.edges.data(); C.servers = T.servers.data(); C.endpoints = T.endpoints.data(); C.steps = T.steps.data();
     C.spikes = T.spikes.data(); C.outages = T.outages.data(); C.lb_edges = T.lb.data(); C.cols = T.cols.data();
     if (sw) { C.sweep_vals = sw->values; C.sweep_first = sweep_first; C.sweep_rows = sw->n_rows; }

@@ -62,7 +62,9 @@ DEFAULT_LANE_BYTES = int(os.environ.get("AF_TWIN_LANE_BYTES", "1816"))
 
 def run(flat, *, seed: int, replica_begin: int = 0, n: int = 1, sweep=None, sweep_first: int = 0, trace: int = 0,
         clock_cap: int = 0, event_capacity: int = 0, request_capacity: int = 0,
-        engine: str | None = None, lane_bytes: int | None = None) -> dict:
+        engine: str | None = None, lane_bytes: int | None = None, ev_need: int = 0) -> dict:
+    """``ev_need``: the pending-events estimate the lane engine splits its shared memory by (af_run computes it from the
+    scenario and the sweep; 0 = the even split)."""
     L = lib()
     engine = engine or DEFAULT_ENGINE
     if engine == "lane":      # same default capacities as the warp engine (the CUDA lane pass has smaller ones and escalates)
@@ -92,6 +94,7 @@ def run(flat, *, seed: int, replica_begin: int = 0, n: int = 1, sweep=None, swee
     bufs = [out[k].ctypes.data for k in ("stats", "sent", "dropped", "hist", "thr", "samp_sum", "samp_max",
                                          "trace_clocks", "trace_series", "trace_counts")]
     if engine == "lane":
+        L.af_twin_set_ev_need(int(ev_need))
         rc = L.af_twin_run_lane(C.byref(flat.pod), sw_p, sweep_first, C.byref(opt), lane_bytes or DEFAULT_LANE_BYTES,
                                 seed, replica_begin, n, *bufs)
     else:

@@ -19,6 +19,18 @@ for p in (ROOT, ROOT / "tests", ROOT / "oracle", ROOT / "oracle" / "simpy_shim")
 
 ENGINE = "lane"
 BIG = False
+LAYOUTS = False
+
+
+def layout_for(seed: int) -> dict:
+    """A per-seed shared-memory layout for the lane engine: the budget of one lane (the CUDA engine runs 600-1800 B per
+    lane, depending on the occupancy it picks) and the pending-events estimate that splits it (af_run: Little's law)."""
+    if not LAYOUTS or ENGINE != "lane":
+        return {}
+    import random
+    r = random.Random(seed * 7919 + 13)
+    return {"lane_bytes": r.choice([1, 300, 420, 520, 604, 648, 660, 900, 1200, 1816]),     # 1: the smallest the scenario fits in
+            "ev_need": r.choice([0, 0, 4, 12, 26, 60, 200, 100000])}
 
 
 def one(seed: int):
@@ -33,7 +45,7 @@ def one(seed: int):
         flat = flatten(payload)
         o = des_port.simulate(payload, seed=SEED, replica=seed)
         r = twin.run(flat, seed=SEED, replica_begin=seed, n=1, trace=1, clock_cap=200000, request_capacity=400000,
-                     event_capacity=8192, engine=ENGINE)
+                     event_capacity=8192, engine=ENGINE, **layout_for(seed))
         st = r["stats"][0]
         n, nt = int(st["completed"]), int(st["n_ticks"])
         assert st["flags"] == 0, f"flags {int(st['flags'])}"
@@ -51,9 +63,11 @@ def main() -> None:
     ap.add_argument("--jobs", type=int, default=8)
     ap.add_argument("--engine", default="lane", choices=["lane", "warp"], help="which state machine of tests/twin.py")
     ap.add_argument("--big", action="store_true", help="C5-shaped topologies (fuzz.big_scenario)")
+    ap.add_argument("--layouts", action="store_true",
+                    help="lane engine: a random per-lane shared-memory budget and split per seed (both tiers of every table)")
     a = ap.parse_args()
-    global ENGINE, BIG
-    ENGINE, BIG = a.engine, a.big
+    global ENGINE, BIG, LAYOUTS
+    ENGINE, BIG, LAYOUTS = a.engine, a.big, a.layouts
     import twin
     twin.build()
     bad = []
