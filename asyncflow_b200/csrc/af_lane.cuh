@@ -366,13 +366,10 @@ AFL_COLD uint32_t fifo_pop(const Mem m, int32_t w_head, int32_t w_tail) {
     return s;
 }
 
-// ---- pending timed events: 4-ary min-heap on (time bits, seq), tiered; one 128-bit element per event ----------
+// ---- pending timed events: 4-ary min-heap on (time bits, seq), tiered; one 128-bit element per event.  The root is
+//      always in shared memory (make_cfg: ev_s >= 1): the loop reads it with a plain LDS ------------------------------
 AFL_IN void ev_get(const Mem& m, int32_t i, uint64_t& t, uint64_t& k) { ld_t128(m, AFL_C.o128_ev, AFL_C.gi_ev, i, AFL_C.ev_s, t, k); }
 AFL_IN void ev_set(const Mem& m, int32_t i, uint64_t t, uint64_t k) { st_t128(m, AFL_C.o128_ev, AFL_C.gi_ev, i, AFL_C.ev_s, t, k); }
-AFL_IN uint64_t ev_t(const Mem& m, int32_t i) {         // the time alone (root look-ahead)
-    if (AFL_LIKELY(i < AFL_C.ev_s)) return sm_ld64(a128(m, AFL_C.o128_ev + i));
-    return *reinterpret_cast<const uint64_t*>(g128p(m, AFL_C.gi_ev + i));
-}
 AFL_IN bool ev_less(uint64_t ta, uint64_t ka, uint64_t tb, uint64_t kb) {       // times are non-negative doubles: bit order = value order
     return ta < tb || (ta == tb && (uint32_t)(ka >> 32) < (uint32_t)(kb >> 32));
 }
@@ -394,27 +391,36 @@ AFL_IN void heap_push(St& W, const Mem& m, uint64_t tb, uint64_t key) {
     ev_set(m, i, tb, key);
 }
 // remove the root (the caller has read it)
+// One sift-down level = the four children fetched TOGETHER (indices past the end clamped onto the last child: a
+// duplicate never wins a strict comparison), one tier test for the group instead of one per child, the minimum picked
+// with selects.  The lanes of a warp sit at different depths with different child counts; this way a level costs every
+// lane the same straight-line code and its four loads are in flight at once.
 AFL_IN void heap_pop(St& W, const Mem& m) {
     const int32_t n = --W.ev_n;
     if (n == 0) return;
     uint64_t tl, kl;
     ev_get(m, n, tl, kl);
+    const int32_t last = n - 1;
     int32_t i = 0;
 #pragma unroll 1
     for (;;) {
         const int32_t c = 4 * i + 1;
         if (c >= n) break;
-        int32_t b = c;
-        uint64_t tbst, kbst;
-        ev_get(m, c, tbst, kbst);
-#pragma unroll 1
-        for (int32_t j = c + 1; j < c + 4 && j < n; ++j) {
-            uint64_t tj, kj;
-            ev_get(m, j, tj, kj);
-            if (ev_less(tj, kj, tbst, kbst)) { tbst = tj; kbst = kj; b = j; }
+        const int32_t c1 = c + 1 < last ? c + 1 : last, c3 = c + 3 < last ? c + 3 : last;
+        int32_t c2 = c + 2 < last ? c + 2 : last;
+        uint64_t t0, k0, t1, k1, t2, k2, t3, k3;
+        if (AFL_LIKELY(c3 < AFL_C.ev_s)) {
+            sm_ld128(a128(m, AFL_C.o128_ev + c), t0, k0); sm_ld128(a128(m, AFL_C.o128_ev + c1), t1, k1);
+            sm_ld128(a128(m, AFL_C.o128_ev + c2), t2, k2); sm_ld128(a128(m, AFL_C.o128_ev + c3), t3, k3);
+        } else {
+            ev_get(m, c, t0, k0); ev_get(m, c1, t1, k1); ev_get(m, c2, t2, k2); ev_get(m, c3, t3, k3);
         }
-        if (!ev_less(tbst, kbst, tl, kl)) break;
-        ev_set(m, i, tbst, kbst);
+        int32_t b = c;
+        if (ev_less(t1, k1, t0, k0)) { t0 = t1; k0 = k1; b = c1; }
+        if (ev_less(t3, k3, t2, k2)) { t2 = t3; k2 = k3; c2 = c3; }
+        if (ev_less(t2, k2, t0, k0)) { t0 = t2; k0 = k2; b = c2; }
+        if (!ev_less(t0, k0, tl, kl)) break;
+        ev_set(m, i, t0, k0);
         i = b;
     }
     ev_set(m, i, tl, kl);
@@ -842,7 +848,7 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                 } else {
                     const bool have_heap = W.ev_n > 0, have_ev = have_heap || W.arr_on != 0;
                     uint64_t tb = 0, key = 0;
-                    if (have_heap) ev_get(m, 0, tb, key);
+                    if (have_heap) sm_ld128(a128(m, AFL_C.o128_ev), tb, key);      // the root is always in shared memory (ev_s >= 1)
                     const uint64_t root_t = tb;
                     bool take_arr = false;                // the earliest timed event: the heap's root or the generator's timeout
                     if (W.arr_on) {
@@ -861,7 +867,7 @@ AFL_IN void run_lane(const Mem& m, NextFn next_index, ConvFn converge) {
                     if (!is_item && !finish) {
                         bool more;
                         if (take_arr) { W.arr_on = 0u; more = have_heap && root_t == tb; }
-                        else { heap_pop(W, m); more = (W.ev_n > 0 && ev_t(m, 0) == tb) || (W.arr_on && W.arr_t == tb); }
+                        else { heap_pop(W, m); more = (W.ev_n > 0 && sm_ld64(a128(m, AFL_C.o128_ev)) == tb) || (W.arr_on && W.arr_t == tb); }
                         W.busy = (W.busy & ~1u) | (more ? 1u : 0u);
                         t_ev = afr::u2d(tb); ev_seq = (uint32_t)(key >> 32); word = (uint32_t)key;
                         is_event = true;

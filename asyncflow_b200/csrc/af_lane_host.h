@@ -135,13 +135,14 @@ constexpr int32_t MIN_DYNAMIC_BYTES = 16 * 4 + 36 * 2;      // make_cfg: rq_s = 
 // smallest per-lane budget make_cfg() accepts for this scenario
 inline int32_t min_lane_bytes(const AfScenario& s, const Tables& t) { return fixed_lane_bytes(s, t) + MIN_DYNAMIC_BYTES; }
 
-// `ev_need`: pending_events_estimate() of the launch (0: split evenly -- the twin's default).
+// `ev_need`: pending_events_estimate() of the launch (0: split evenly -- the twin's default); `rq_min`: the record slots
+// that stay in shared memory when the events take the rest.
 // The launch configuration for a budget of `lane_bytes` of shared memory per lane (= per replica in
 // flight).  Returns false when even the smallest tiers do not fit: the topology is too wide for this
 // engine at this occupancy (the caller lowers the occupancy or takes the warp-per-replica engine).
 // `lanes` = lanes of a warp in the code that will RUN the configuration: 32 for the CUDA kernel, 1 for the host twin
 // (afl::LANES is a property of the compilation pass, and the host pass of a .cu file sees 1).
-inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, int32_t lane_bytes, int32_t trace_tick_cap, int32_t lanes, afl::Cfg& C, int32_t ev_need = 0) {
+inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, int32_t lane_bytes, int32_t trace_tick_cap, int32_t lanes, afl::Cfg& C, int32_t ev_need = 0, int32_t rq_min = 2) {
     C.n_edges = s.n_edges; C.n_servers = s.n_servers; C.n_endpoints = s.n_endpoints; C.n_steps = s.n_steps;
     C.n_lb_edges = s.n_lb_edges; C.lb_algo = s.lb_algo; C.gen_edge = s.gen_edge; C.client_edge = s.client_edge;
     C.n_spike = s.n_spike_marks; C.n_outage = s.n_outage_marks;
@@ -166,13 +167,15 @@ inline bool make_cfg(const AfScenario& s, const AfOptions& o, const Tables& t, i
     int32_t rq_s = (rest - 16 * 4) / 36;
     if (ev_need > 0) {
         // Heap entries are touched ~20 times per event, a request record twice: when a replica typically holds more
-        // pending events than the even split keeps in shared memory, the events get the bytes, down to 4 record slots.
-        // Measured on B200, bench workload (11 warps/SM, up to 60 pending events; profiles/r02j_ab_split_shares.log,
-        // r02j_ab_split_policy.log): 18 events + 14 records 5.45e8 completions/s, 24 + 9 5.94e8, 26 + 7 5.86e8,
-        // 30 + 4 6.03e8, 31 + 3 6.14e8; C5 (5 warps/SM, ~85 pending events) 17 + 13 7.17e7, 29 + 4 7.37e7.  Never BELOW
-        // the even split: C4 31 + 27 4.03e8, 19 + 36 3.89e8; C1 30 + 26 5.58e8, 10 + 42 5.50e8.
+        // pending events than the even split keeps in shared memory, the events get the bytes, down to `rq_min` (2)
+        // record slots.  Measured on B200, bench workload (11 warps/SM, up to 60 pending events), events + records in
+        // shared memory: 18 + 14 5.45e8 completions/s, 24 + 9 5.94e8, 26 + 7 5.86e8, 30 + 4 6.03e8 (profiles/
+        // r02j_ab_split_*.log); with the grouped sift-down 30 + 4 6.42e8, 31 + 3 6.48e8, 33 + 2 6.55e8 (profiles/
+        // r02k_ab_final.log); C5 (5 warps/SM, ~85 pending events) 17 + 13 7.17e7, 29 + 4 7.37e7; C4 at 7 warps/SM
+        // 32 + 4 6.00e8, 29 + 7 6.02e8.  Never BELOW the even split: C4 31 + 27 4.03e8, 19 + 36 3.89e8; C1 30 + 26
+        // 5.58e8, 10 + 42 5.50e8.
         const int32_t ev_even = (rest - 20 * rq_s) / 16;
-        const int32_t rq_min = 4;
+        if (rq_min < 2) rq_min = 2;
         int32_t ev_try = ev_need, ev_max = (rest - 20 * rq_min) / 16;
         if (ev_try > ev_max) ev_try = ev_max;
         if (ev_try > ev_total) ev_try = ev_total;

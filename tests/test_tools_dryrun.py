@@ -31,6 +31,14 @@ def test_quick_bench(twin_backed, monkeypatch, capsys, args):
     assert "compl/s" in out and "overflow 0.0" in out
 
 
+def test_ab_lane_lib(twin_backed, monkeypatch, capsys):
+    import json
+    monkeypatch.setattr(sys, "argv", ["ab_lane_lib.py", "--replicas", "6", "--horizon", "4", "--reps", "1"])
+    runpy.run_path(str(ROOT / "tools" / "ab_lane_lib.py"), run_name="__main__")
+    row = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert row["checksum"][0] > 0 and row["flags"] == 0 and row["ms"] > 0
+
+
 def test_drilldown_example(twin_backed, monkeypatch, capsys):
     monkeypatch.setattr(sys, "argv", ["sweep_users_drilldown.py", "24"])
     runpy.run_path(str(ROOT / "examples" / "sweep_users_drilldown.py"), run_name="__main__")

@@ -23,6 +23,8 @@ _SRC = [_DIR / "af_host_twin.cpp"] + sorted((_DIR.parent.parent / "asyncflow_b20
 
 
 def build() -> Path:
+    if os.environ.get("AF_TWIN_SO"):          # experiments: a twin built by hand (e.g. with a -D of a kernel variant)
+        return Path(os.environ["AF_TWIN_SO"])
     so = _SO
     newest = max(p.stat().st_mtime for p in _SRC)
     if not so.exists() or so.stat().st_mtime < newest:

@@ -53,8 +53,15 @@ class TwinEngine:
                            event_capacity=o.get("event_capacity", 0), request_capacity=o.get("request_capacity", 0))
         self.calls.append(("run", seed, begin, end))
 
+    def sync(self) -> None:
+        pass
+
     def last_run_ms(self):
         return (1.0, 1.0)
+
+    def last_run_passes(self) -> dict:
+        return {"lane_pass": 1, "warp_pass": 0, "lane_warps_per_sm": 0, "lane_bytes": twin.DEFAULT_LANE_BYTES,
+                "lane_events_smem": 0, "lane_requests_smem": 0, "lane_replicas": self._n, "warp_replicas": 0}
 
     # -- fetchers ---------------------------------------------------------------
     def _into(self, out, arr):
