@@ -77,7 +77,7 @@ __global__ void AF_LAUNCH_BOUNDS af_sim_kernel() {
 // One replica per thread.  Compiled for one CTA of up to 384 threads per SM (the shared-memory budget of a
 // lane decides the CTA size at launch).  Measured on B200 (bench workload): 8 warps 4.5e8 completions/s, 12 warps
 // 5.3e8, 16 warps no better than 12 (each lane's share of shared memory shrinks, more of the heap lives in L2) --
-// so the register budget is spent at 12 warps: 144 registers, no spills (128 at 512 threads spilled 40 B).
+// so the register budget is spent at 12 warps: 150 registers, no spills (128 at 512 threads spilled 40 B).
 #ifndef AF_LANE_MAX_THREADS
 #define AF_LANE_MAX_THREADS 384
 #endif
