@@ -54,19 +54,19 @@ def test_results_do_not_depend_on_the_shared_memory_tier_split(lane_bytes):
                               hist=r["hist"][0])
 
 
-@pytest.mark.parametrize("ev_need", [0, 4, 26, 60, 100000])
-def test_results_do_not_depend_on_the_split_between_events_and_records(ev_need):
+@pytest.mark.parametrize("name,lane_bytes", [("c3_lb_two_servers.yml", 648), ("c4_lb8_events.yml", 1036),
+                                             ("c5_multihop32.yml", 1444), ("overload_single.yml", 660)])
+def test_results_do_not_depend_on_the_split_between_events_and_records(name, lane_bytes):
     """ev_need = the pending-events estimate af_run splits a lane's shared memory by (0: evenly): events first, records
     down to 2 slots -- at the budgets the CUDA engine really runs (600-1450 B per lane) the replica is the same."""
-    for name, lane_bytes in (("c3_lb_two_servers.yml", 648), ("c4_lb8_events.yml", 1036), ("c5_multihop32.yml", 1444),
-                             ("overload_single.yml", 660)):
-        payload = load_scenario(name, PARITY_CASES[name])
-        flat = flatten(payload)
+    payload = load_scenario(name, PARITY_CASES[name])
+    flat = flatten(payload)
+    o = des_port.simulate(payload, seed=SEED, replica=23)
+    for ev_need in (0, 4, 26, 60, 100000):
         r = twin.run(flat, engine="lane", lane_bytes=lane_bytes, ev_need=ev_need, seed=SEED, replica_begin=23, n=1, trace=1,
                      clock_cap=300000)
-        o = des_port.simulate(payload, seed=SEED, replica=23)
         n, nt = int(r["stats"][0]["completed"]), int(r["stats"][0]["n_ticks"])
-        assert r["stats"][0]["flags"] == 0
+        assert r["stats"][0]["flags"] == 0, ev_need
         assert_matches_oracle(o, flat, stats=r["stats"][0], clocks=r["trace_clocks"][0, :n], sent=r["sent"][0],
                               dropped=r["dropped"][0], series=r["trace_series"][0][:, :nt], throughput=r["thr"][0],
                               hist=r["hist"][0])
