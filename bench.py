@@ -533,7 +533,7 @@ def run_ours(a) -> None:
     issue = {"events_per_s_one_gpu": per_launch_events / sim_s,
              "peak_slots_per_s": slots, "peak_source": "148 SMs x 4 SMSPs x the SM clock sampled during the run",
              "warp_inst_per_event": prof.get("warp_inst_per_event"), "issue_active_pct": prof.get("issue_active_pct"),
-             "source": prof.get("source")}
+             "source": prof.get("source"), "profiled_build": prof.get("build")}
     if prof.get("warp_inst_per_event"):
         issue["achieved_slots_per_s"] = per_launch_events / sim_s * prof["warp_inst_per_event"]
         issue["frac"] = issue["achieved_slots_per_s"] / slots
